@@ -1,0 +1,247 @@
+/*
+ * vpt.h — C ABI of libvpt.so: the B200-native (sm_100a) voxel path-tracing + denoising hot path.
+ *
+ * The reference (wangkepfe/Real-time-path-tracing-voxel-blocks) has no FFI; its hot path sits behind C++
+ * singletons called from one host thread. Each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference). Conventions: opaque handle, int status (0 = ok, non-zero =
+ * error, text via vpt_last_error()), no exceptions across the boundary, caller-owned host memory, library-owned
+ * device memory, one context per GPU, calls on a context serialised by the caller. There is NO CPU fallback:
+ * every compute entry point fails with VPT_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef VPT_H
+#define VPT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPT_OK 0
+#define VPT_ERR_ARG 1
+#define VPT_ERR_CUDA 2
+#define VPT_ERR_STATE 3
+#define VPT_ERR_IO 4
+#define VPT_ERR_NCCL 5
+
+typedef struct vpt_ctx vpt_ctx;
+
+/* renderer/shaders/Camera.h:6-28 — same field order, 212 bytes. Matrices are 3x3, column storage
+ * (m00,m10,m20, m01,m11,m21, m02,m12,m22) as renderer/shaders/LinearMath.h:1040-1050. */
+typedef struct VptCamera
+{
+    float resolution[2];
+    float inversedResolution[2];
+    float tanHalfFov[2];
+    float pos[3];
+    float dir[3];
+    float posDelta[3];
+    float yaw;
+    float pitch;
+    float uvToWorld[9];
+    float worldToUv[9];
+    float uvToView[9];
+    float viewToUv[9];
+} VptCamera;
+
+/* renderer/shaders/SystemParameter.h:11-38 (MaterialParameter) without the texture handles. */
+typedef struct VptMaterial
+{
+    float albedo[3];
+    float roughness;
+    float translucency;
+    float uvScale;
+    int32_t metallic;
+    int32_t materialId;
+    int32_t useWorldGridUV;
+    int32_t isEmissive;
+    int32_t isThinfilm;
+    int32_t pad;
+} VptMaterial;
+
+/* renderer/shaders/AliasTable.h:11-16 */
+typedef struct VptAliasBin
+{
+    float q;
+    float p;
+    int32_t alias;
+} VptAliasBin;
+
+/* renderer/shaders/RestirCommon.h:6-13 (DIReservoir, 20 bytes) */
+typedef struct VptReservoir
+{
+    uint32_t lightData;
+    uint32_t uvData;
+    float weightSum;
+    float targetPdf;
+    float M;
+} VptReservoir;
+
+/* renderer/core/GlobalSettings.h:82-141 (DenoisingParams) */
+typedef struct VptDenoisingParams
+{
+    int32_t enableHitDistanceReconstruction;
+    int32_t enablePrePass;
+    int32_t enableTemporalAccumulation;
+    int32_t enableHistoryFix;
+    int32_t enableHistoryClamping;
+    int32_t enableSpatialFiltering;
+    int32_t enableFireflyFilter;
+    float maxAccumulatedFrameNum;
+    float maxFastAccumulatedFrameNum;
+    float phiLuminance;
+    float lobeAngleFraction;
+    float roughnessFraction;
+    float depthThreshold;
+    int32_t atrousIterationNum;
+    float disocclusionThreshold;
+    float disocclusionThresholdAlternate;
+    float denoisingRange;
+} VptDenoisingParams;
+
+/* Subset of renderer/core/BufferManager.h:8-46 (Buffer2DName). F4 = float4 per pixel, F1 = float per pixel. */
+typedef enum VptBufferName
+{
+    VPT_BUF_Illumination = 0,          /* F4 noisy radiance rgb + primary hit distance (RayGen.cu:181) */
+    VPT_BUF_IlluminationOutput = 1,    /* F4 denoised, albedo re-applied (BufferCopy.h:36-116) */
+    VPT_BUF_IlluminationPing = 2,      /* F4 */
+    VPT_BUF_IlluminationPong = 3,      /* F4 */
+    VPT_BUF_NormalRoughness = 4,       /* F4 */
+    VPT_BUF_Depth = 5,                 /* F1 */
+    VPT_BUF_Material = 6,              /* F1 */
+    VPT_BUF_Albedo = 7,                /* F4 */
+    VPT_BUF_HistoryLength = 8,         /* F1 */
+    VPT_BUF_PrevDepth = 9,             /* F1 */
+    VPT_BUF_PrevMaterial = 10,         /* F1 */
+    VPT_BUF_PrevIllumination = 11,     /* F4 */
+    VPT_BUF_PrevFastIllumination = 12, /* F4 */
+    VPT_BUF_PrevHistoryLength = 13,    /* F1 */
+    VPT_BUF_PrevNormalRoughness = 14,  /* F4 */
+    VPT_BUF_GeoNormalThinfilm = 15,    /* F4 */
+    VPT_BUF_MaterialParameter = 16,    /* F4 */
+    VPT_BUF_PrevMaterialParameter = 17,/* F4 */
+    VPT_BUF_PrevGeoNormalThinfilm = 18,/* F4 */
+    VPT_BUF_PrevAlbedo = 19,           /* F4 */
+    VPT_BUF_PrimaryHits = 22           /* int4 per pixel: voxel x,y,z and face id (-1 = miss); new in this build */
+} VptBufferName;
+
+/* Per-stage device timings of the last vpt_render / vpt_denoise call, CUDA events on the context stream (ms). */
+typedef struct VptTimings
+{
+    float trace_ms;
+    float resolve_ms;
+    float firefly_ms;
+    float temporal_ms;
+    float history_fix_ms;
+    float history_clamp_ms;
+    float atrous_smem_ms;
+    float atrous_ms;        /* sum over the Atrous passes */
+    float composite_ms;     /* BufferCopySky + BufferCopyNonSky */
+    float denoise_total_ms; /* whole chain, first launch to last */
+    int32_t atrous_passes;
+    int32_t kernel_launches; /* kernels launched by the last render + denoise calls */
+} VptTimings;
+
+/* ---- lifetime. Replaces OfflineBackend::init + BufferManager::init + OptixRenderer::init
+ * (renderer/core/OfflineBackend.cpp:26-44, BufferManager.cpp:107-241, OptixRenderer.cpp:928-1366). */
+int vpt_create(int device, int width, int height, vpt_ctx **out);
+void vpt_destroy(vpt_ctx *ctx);
+const char *vpt_last_error(void);
+int vpt_sync(vpt_ctx *ctx);
+/* cudaStream_t of the context (OfflineBackend::getCudaStream, OfflineBackend.h:41) as an opaque pointer. */
+void *vpt_stream(vpt_ctx *ctx);
+
+/* ---- inputs */
+/* util/RandGenHost.cpp:5-20 (BlueNoiseRandGeneratorHost::init): sobol[65536], scrambling[131072], ranking[131072]. */
+int vpt_set_tables(vpt_ctx *ctx, const uint8_t *sobol, const uint8_t *scrambling, const uint8_t *ranking);
+/* VoxelEngine::voxelChunks (voxelengine/VoxelEngine.h:25-76): ids are chunk-major, chunk index
+ * cx + CX*(cz + CZ*cy) (VoxelEngine.cu:221-224), 32768 bytes per chunk in GetLinearId order (VoxelMath.h:120-127). */
+int vpt_set_grid(vpt_ctx *ctx, int chunksX, int chunksY, int chunksZ, const uint8_t *ids);
+int vpt_get_grid(vpt_ctx *ctx, uint8_t *ids_out, size_t bytes);
+/* VoxelEngine::setVoxelAtGlobal (VoxelEngine.cu:265-276). */
+int vpt_set_voxel(vpt_ctx *ctx, int x, int y, int z, int blockId);
+/* initVoxelsMultiChunk + GenerateVoxelChunk (voxelengine/VoxelSceneGen.cu:341-388, 61-165): noise is
+ * chunks x 32 x 32 floats, noise[chunk][z][x]. Runs on the device. */
+int vpt_generate_terrain(vpt_ctx *ctx, int chunksX, int chunksY, int chunksZ, const float *noise);
+/* MaterialManager (renderer/assets/MaterialManager.cpp:85-120): material table + block id -> material index. */
+int vpt_set_materials(vpt_ctx *ctx, const VptMaterial *materials, int count, const uint16_t *blockToMaterial /*[256]*/);
+/* SkyModel buffers (renderer/sky/Sky.cu:355-396): RGBA32F sky (equal-area sphere map) and sun-disk maps with
+ * their alias tables (shaders/AliasTable.cu:66-153) and the sun direction. */
+int vpt_set_sky(vpt_ctx *ctx, const float *skyRGBA, int skyW, int skyH, const float *sunRGBA, int sunW, int sunH,
+                const VptAliasBin *skyAlias, const VptAliasBin *sunAlias, const float *sunDir /*[3]*/);
+/* New parameters of this build (SURVEY "five facts" #2); the reference is spp=1, limits 3/1, ReSTIR on
+ * (renderer/shaders/RayGen.cu:146-147). */
+int vpt_set_trace_params(vpt_ctx *ctx, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir);
+
+/* ---- the hot path */
+/* OptixRenderer::render (renderer/core/OptixRenderer.cpp:411-485) == __raygen__pathtracer over W x H
+ * (renderer/shaders/RayGen.cu:102-181). iterationIndex is the pre-increment value the reference stores in
+ * sysParam (OptixRenderer.cpp:419-420). Asynchronous on the context stream; vpt_sync/vpt_read_buffer wait. */
+int vpt_render(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamera, int iterationIndex);
+/* Sample-sharded form (multi-GPU): renders samples k = sampleBegin, sampleBegin+sampleStep, ... < spp and leaves
+ * the un-normalised radiance SUM in Illumination; vpt_resolve divides by spp (after the cross-GPU sum). */
+int vpt_render_shard(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamera, int iterationIndex,
+                     int sampleBegin, int sampleStep);
+int vpt_resolve(vpt_ctx *ctx);
+/* Denoiser::run (renderer/denoising/Denoiser.cu:24-408). frameNum == OfflineBackend::getFrameNum();
+ * iterationIndex is the POST-increment GlobalSettings::iterationIndex the reference reads there (:37,296). */
+int vpt_denoise(vpt_ctx *ctx, const VptDenoisingParams *params, const VptCamera *camera, const VptCamera *prevCamera,
+                int frameNum, int iterationIndex);
+/* Denoiser on caller-supplied inputs (config 3): flips the G-buffer ping-pong like a render would; the caller
+ * then uploads Illumination/Depth/NormalRoughness/Material/Albedo with vpt_write_buffer and calls vpt_denoise. */
+int vpt_begin_external_frame(vpt_ctx *ctx);
+/* One call = H2D of the five G-buffer planes + vpt_denoise + D2H of IlluminationOutput (the e2e path of cfg 3). */
+int vpt_denoise_external(vpt_ctx *ctx, const VptDenoisingParams *params, const VptCamera *camera, const VptCamera *prevCamera,
+                         int frameNum, int iterationIndex, const float *illumination, const float *depth,
+                         const float *normalRoughness, const float *material, const float *albedo, float *outputRGBA);
+
+/* ---- outputs. BufferManager::GetBuffer2D (renderer/core/BufferManager.h:84) + OfflineBackend::storeFrameInBatch. */
+int vpt_read_buffer(vpt_ctx *ctx, VptBufferName name, void *host, size_t bytes);
+int vpt_write_buffer(vpt_ctx *ctx, VptBufferName name, const void *host, size_t bytes);
+/* BufferManager::reservoirBuffer (BufferManager.cpp:206-207): plane `parity` of the 2 x W x H reservoir array. */
+int vpt_read_reservoirs(vpt_ctx *ctx, int parity, VptReservoir *host, size_t bytes);
+int vpt_write_reservoirs(vpt_ctx *ctx, int parity, const VptReservoir *host, size_t bytes);
+/* Device pointer of a buffer (for callers that own a CUDA context in the same process, e.g. NCCL plumbing). */
+void *vpt_device_ptr(vpt_ctx *ctx, VptBufferName name);
+/* Device-side counters of the last render: traversal calls (rays) and voxel steps. */
+int vpt_get_counters(vpt_ctx *ctx, uint64_t *rays, uint64_t *steps);
+int vpt_get_timings(vpt_ctx *ctx, VptTimings *out);
+/* Toggle CUDA-event stage timing (default on; adds event records between kernels). */
+int vpt_set_profiling(vpt_ctx *ctx, int enabled);
+
+/* ---- multi-GPU: one context per rank, NCCL communicator owned by the library. */
+/* 128-byte ncclUniqueId, created on rank 0 and broadcast by the caller's own plumbing. */
+int vpt_comm_unique_id(uint8_t *id128);
+int vpt_comm_init(vpt_ctx *ctx, int rank, int nranks, const uint8_t *id128);
+/* ncclAllReduce(sum) of the W*H*4 float accumulation buffer (spp sharding), then every rank may vpt_resolve. */
+int vpt_comm_allreduce_illumination(vpt_ctx *ctx);
+/* Broadcast the sample-0 G-buffer, depth and current reservoir plane from rank 0 (so any rank can denoise). */
+int vpt_comm_broadcast_gbuffer(vpt_ctx *ctx, int iterationIndex);
+/* Row-band sharded denoiser (config 3): this rank owns rows [rowBegin,rowEnd) (multiples of 4); halo rows are
+ * exchanged with the neighbouring bands by ncclSend/ncclRecv between passes. */
+int vpt_denoise_band(vpt_ctx *ctx, const VptDenoisingParams *params, const VptCamera *camera, const VptCamera *prevCamera,
+                     int frameNum, int iterationIndex, int rowBegin, int rowEnd);
+
+/* ---- host-side helpers mirroring the reference's host code (no device work) */
+/* Camera::init / Camera::update (renderer/shaders/Camera.h:29-99). */
+void vpt_camera_init(VptCamera *cam, int width, int height);
+void vpt_camera_update(VptCamera *cam);
+/* mainOffline.cpp:227-247: position, direction (normalised like SceneConfigParser does) and horizontal fov in degrees. */
+void vpt_camera_from_scene(VptCamera *cam, int width, int height, const float *position, const float *direction, float fovDegrees);
+/* initVoxelsMultiChunk's CPU noise maps (VoxelSceneGen.cu:358-376): PerlinNoiseGenerator(4 octaves, seed), chunks x 32 x 32. */
+void vpt_perlin_noise_chunks(int chunksX, int chunksY, int chunksZ, unsigned seed, float *out);
+/* AliasTable::update, CPU build path (renderer/shaders/AliasTable.cu:66-153). */
+void vpt_build_alias_table(const float *weights, unsigned n, VptAliasBin *bins);
+/* GlobalSettings::LoadFromYAML (renderer/core/GlobalSettings.cpp:69-138), "denoising" section -> params. Returns
+ * VPT_ERR_IO when the file cannot be opened (values stay default), like the reference returns false. */
+int vpt_load_denoising_settings(const char *yamlPath, VptDenoisingParams *params);
+void vpt_default_denoising_params(VptDenoisingParams *params);
+/* SceneConfigParser::LoadFromFile (renderer/core/SceneConfig.cpp:6-114): camera position/direction(normalised)/up/fov
+ * and chunk_config. out9 = pos[3], dir[3], up[3]. */
+int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigned *chunks3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPT_H */

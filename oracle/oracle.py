@@ -1,0 +1,252 @@
+"""ORACLE — test infrastructure only.
+
+ctypes binding of oracle/liboracle.so (the CPU restatement of the reference's traversal, shading and
+denoiser code; see the headers of oracle/orc_*.h for the reference file:line each function follows).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg import this
+module; the product path (libvpt.so) never does.
+
+The object model mirrors the product binding (python/vpt.py) on purpose so parity tests drive both with
+the same bytes: Oracle(width, height).set_tables/.set_grid/.set_materials/.set_sky/.render/.denoise/.read.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# buffer names shared with include/vpt.h (VptBufferName)
+BUF = dict(
+    Illumination=0, IlluminationOutput=1, IlluminationPing=2, IlluminationPong=3, NormalRoughness=4, Depth=5,
+    Material=6, Albedo=7, HistoryLength=8, PrevDepth=9, PrevMaterial=10, PrevIllumination=11,
+    PrevFastIllumination=12, PrevHistoryLength=13, PrevNormalRoughness=14, GeoNormalThinfilm=15,
+    MaterialParameter=16, PrevMaterialParameter=17, PrevGeoNormalThinfilm=18, PrevAlbedo=19, PrimaryHits=22)
+_F1 = {"Depth", "Material", "HistoryLength", "PrevDepth", "PrevMaterial", "PrevHistoryLength"}
+
+RESERVOIR_DTYPE = np.dtype([("lightData", "<u4"), ("uvData", "<u4"), ("weightSum", "<f4"), ("targetPdf", "<f4"), ("M", "<f4")])
+ALIAS_DTYPE = np.dtype([("q", "<f4"), ("p", "<f4"), ("alias", "<i4")])
+MATERIAL_DTYPE = np.dtype([("albedo", "<f4", 3), ("roughness", "<f4"), ("translucency", "<f4"), ("uvScale", "<f4"),
+                           ("metallic", "<i4"), ("materialId", "<i4"), ("useWorldGridUV", "<i4"), ("isEmissive", "<i4"),
+                           ("isThinfilm", "<i4"), ("pad", "<i4")])
+DENOISE_DTYPE = np.dtype([("enableHitDistanceReconstruction", "<i4"), ("enablePrePass", "<i4"), ("enableTemporalAccumulation", "<i4"),
+                          ("enableHistoryFix", "<i4"), ("enableHistoryClamping", "<i4"), ("enableSpatialFiltering", "<i4"),
+                          ("enableFireflyFilter", "<i4"), ("maxAccumulatedFrameNum", "<f4"), ("maxFastAccumulatedFrameNum", "<f4"),
+                          ("phiLuminance", "<f4"), ("lobeAngleFraction", "<f4"), ("roughnessFraction", "<f4"), ("depthThreshold", "<f4"),
+                          ("atrousIterationNum", "<i4"), ("disocclusionThreshold", "<f4"), ("disocclusionThresholdAlternate", "<f4"),
+                          ("denoisingRange", "<f4")])
+assert RESERVOIR_DTYPE.itemsize == 20 and ALIAS_DTYPE.itemsize == 12 and MATERIAL_DTYPE.itemsize == 48 and DENOISE_DTYPE.itemsize == 68
+CAMERA_FLOATS = 53  # 212-byte POD (Camera.h:6-28)
+
+
+def build(force=False):
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.startswith("orc_")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/voxelengine"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_perlin_noise.restype = C.c_float
+        L.orc_perlin_noise.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_float]
+        L.orc_rand.restype = C.c_float
+        L.orc_rand.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_uv_to_world_direction.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        L.orc_camera_from_scene.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float]
+        L.orc_dda.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_disney_evaluate.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_disney_sample.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        for name in ("orc_read_buffer", "orc_write_buffer"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        for name in ("orc_read_reservoirs", "orc_write_reservoirs"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.orc_get_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def camera_init(width, height):
+    cam = np.zeros(CAMERA_FLOATS, np.float32)
+    lib().orc_camera_init(_p(cam), width, height)
+    return cam
+
+
+def camera_update(cam):
+    lib().orc_camera_update(_p(cam))
+    return cam
+
+
+def camera_from_scene(width, height, pos, direction, fov_deg):
+    cam = np.zeros(CAMERA_FLOATS, np.float32)
+    pos = np.asarray(pos, np.float32)
+    direction = np.asarray(direction, np.float32)
+    lib().orc_camera_from_scene(_p(cam), width, height, _p(pos), _p(direction), float(fov_deg))
+    return cam
+
+
+def uv_to_world_direction(cam, u, v):
+    out = np.zeros(3, np.float32)
+    lib().orc_uv_to_world_direction(_p(cam), float(u), float(v), _p(out))
+    return out
+
+
+def world_direction_to_uv(cam, d):
+    out = np.zeros(2, np.float32)
+    d = np.asarray(d, np.float32)
+    lib().orc_world_direction_to_uv(_p(cam), _p(d), _p(out))
+    return out
+
+
+def perlin_noise_chunks(cx, cy, cz, seed=124):
+    out = np.zeros((cx * cy * cz, 32, 32), np.float32)
+    lib().orc_perlin_noise_chunks(cx, cy, cz, seed, _p(out))
+    return out
+
+
+def build_alias_table(weights):
+    w = np.ascontiguousarray(weights, np.float32).ravel()
+    bins = np.zeros(w.size, ALIAS_DTYPE)
+    lib().orc_build_alias_table(_p(w), w.size, _p(bins))
+    return bins
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
+class Oracle:
+    def __init__(self, width, height):
+        self.L = lib()
+        self.w, self.h = width, height
+        self.ctx = C.c_void_p(self.L.orc_create(width, height))
+
+    def close(self):
+        if self.ctx:
+            self.L.orc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tables(self, tables):
+        t = np.ascontiguousarray(tables, np.uint8)
+        assert t.size == 327680
+        self.L.orc_set_tables(self.ctx, _p(t[:65536]), _p(t[65536:196608]), _p(t[196608:]))
+
+    def set_grid(self, cx, cy, cz, ids):
+        ids = np.ascontiguousarray(ids, np.uint8)
+        assert ids.size == cx * cy * cz * 32768
+        self.L.orc_set_grid(self.ctx, cx, cy, cz, _p(ids))
+        self.chunks = (cx, cy, cz)
+
+    def generate_terrain(self, cx, cy, cz, noise):
+        noise = np.ascontiguousarray(noise, np.float32)
+        self.L.orc_generate_terrain(self.ctx, cx, cy, cz, _p(noise))
+        self.chunks = (cx, cy, cz)
+
+    def get_grid(self):
+        cx, cy, cz = self.chunks
+        out = np.zeros(cx * cy * cz * 32768, np.uint8)
+        assert self.L.orc_get_grid(self.ctx, _p(out), out.size) == 0
+        return out
+
+    def set_voxel(self, x, y, z, block_id):
+        return self.L.orc_set_voxel(self.ctx, x, y, z, block_id)
+
+    def set_materials(self, materials, block_to_material):
+        m = np.ascontiguousarray(materials, MATERIAL_DTYPE)
+        b = np.ascontiguousarray(block_to_material, np.uint16)
+        assert b.size == 256
+        self.L.orc_set_materials(self.ctx, _p(m), m.size, _p(b))
+
+    def set_sky(self, sky, sun, sky_alias, sun_alias, sun_dir):
+        sky = np.ascontiguousarray(sky, np.float32)
+        sun = np.ascontiguousarray(sun, np.float32)
+        sd = np.asarray(sun_dir, np.float32)
+        sa = np.ascontiguousarray(sky_alias, ALIAS_DTYPE)
+        su = np.ascontiguousarray(sun_alias, ALIAS_DTYPE)
+        self.L.orc_set_sky(self.ctx, _p(sky), sky.shape[1], sky.shape[0], _p(sun), sun.shape[1], sun.shape[0], _p(sa), _p(su), _p(sd))
+
+    def set_trace_params(self, spp=1, total_bounce_limit=3, diffuse_bounce_limit=1, enable_restir=1):
+        self.L.orc_set_trace_params(self.ctx, spp, total_bounce_limit, diffuse_bounce_limit, enable_restir)
+
+    def render(self, cam, prev_cam, iteration_index):
+        self.L.orc_render(self.ctx, _p(cam), _p(prev_cam), iteration_index)
+
+    def render_shard(self, cam, prev_cam, iteration_index, sample_begin, sample_step):
+        self.L.orc_render_shard(self.ctx, _p(cam), _p(prev_cam), iteration_index, sample_begin, sample_step)
+
+    def resolve(self):
+        self.L.orc_resolve(self.ctx)
+
+    def begin_external_frame(self):
+        self.L.orc_begin_external_frame(self.ctx)
+
+    def denoise(self, params, cam, prev_cam, frame_num, iteration_index):
+        p = np.ascontiguousarray(params, DENOISE_DTYPE)
+        self.L.orc_denoise(self.ctx, _p(p), _p(cam), _p(prev_cam), frame_num, iteration_index)
+
+    def read(self, name):
+        n = self.w * self.h
+        if name == "PrimaryHits":
+            out = np.zeros((self.h, self.w, 4), np.int32)
+        elif name in _F1:
+            out = np.zeros((self.h, self.w), np.float32)
+        else:
+            out = np.zeros((self.h, self.w, 4), np.float32)
+        rc = self.L.orc_read_buffer(self.ctx, BUF[name], _p(out), out.nbytes)
+        assert rc == 0, name
+        return out
+
+    def write(self, name, arr):
+        dt = np.int32 if name == "PrimaryHits" else np.float32
+        a = np.ascontiguousarray(arr, dt)
+        rc = self.L.orc_write_buffer(self.ctx, BUF[name], _p(a), a.nbytes)
+        assert rc == 0, name
+
+    def read_reservoirs(self, parity):
+        out = np.zeros((self.h, self.w), RESERVOIR_DTYPE)
+        assert self.L.orc_read_reservoirs(self.ctx, parity, _p(out), out.nbytes) == 0
+        return out
+
+    def write_reservoirs(self, parity, arr):
+        a = np.ascontiguousarray(arr, RESERVOIR_DTYPE)
+        assert self.L.orc_write_reservoirs(self.ctx, parity, _p(a), a.nbytes) == 0
+
+    def counters(self):
+        r, s = C.c_uint64(), C.c_uint64()
+        self.L.orc_get_counters(self.ctx, C.byref(r), C.byref(s))
+        return r.value, s.value
+
+    def dda(self, origin, direction, tmin=0.0, tmax=1.0e27):
+        o = np.asarray(origin, np.float32)
+        d = np.asarray(direction, np.float32)
+        out = np.zeros(7, np.int32)
+        t = C.c_float()
+        self.L.orc_dda(self.ctx, _p(o), _p(d), float(tmin), float(tmax), _p(out), C.byref(t))
+        return dict(hit=int(out[0]), voxel=(int(out[1]), int(out[2]), int(out[3])), face=int(out[4]), id=int(out[5]),
+                    steps=int(out[6]), t=t.value)

@@ -1,0 +1,745 @@
+// libvpt.so — context, device memory and the C ABI (include/vpt.h) over the sm_100a kernels.
+//
+// Replaces the reference's singleton stack on this path: OfflineBackend (renderer/core/OfflineBackend.cpp:26-131),
+// BufferManager (renderer/core/BufferManager.cpp:107-241: 34 cudaArray surfaces -> dense linear planes in HBM),
+// OptixRenderer::render (renderer/core/OptixRenderer.cpp:411-485) and Denoiser::run (renderer/denoising/Denoiser.cu:24-408).
+// Memory plan per context (fp32, W*H pixels): 2 G-buffer sets x (4+4+16+16+16+16) B, 8 float4 + 2 float denoiser
+// planes, 2 reservoir planes x 20 B, int4 primary hits  ->  ~356 B/px (0.74 GB at 1080p, 2.9 GB at 4K): trivially
+// resident in 180 GB HBM3e. The Prev* G-buffer copies of the reference (Denoiser.cu:394-407, OptixRenderer.cpp:476-478)
+// are pointer ping-pong here: the "current" set flips at every render.
+#include "vpt_kernels.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vpt;
+
+static thread_local std::string g_lastError;
+static int fail(int code, const std::string &msg) { g_lastError = msg; return code; }
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(VPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct GSet
+{
+    float *depth = nullptr, *material = nullptr;
+    float4 *normalRoughness = nullptr, *geoNormalThinfilm = nullptr, *materialParameter = nullptr, *albedo = nullptr;
+    GBufferPtrs ptrs() const { return {depth, material, normalRoughness, geoNormalThinfilm, materialParameter, albedo}; }
+};
+
+enum { EV_TRACE0, EV_TRACE1, EV_RESOLVE1, EV_DN0, EV_FIREFLY, EV_SKY, EV_TEMPORAL, EV_HFIX, EV_HCLAMP, EV_ASMEM, EV_ATROUS, EV_COMP, EV_COUNT };
+
+struct vpt_ctx
+{
+    int device = 0, width = 0, height = 0, smCount = 0;
+    size_t smemOptIn = 0;
+    cudaStream_t stream = nullptr;
+    // tables
+    uint8_t *sobol = nullptr, *scrambling = nullptr, *ranking = nullptr;
+    // grid
+    int cx = 0, cy = 0, cz = 0;
+    uint8_t *idsChunk = nullptr, *idsLinear = nullptr;
+    uint32_t *occ = nullptr;
+    // materials / sky
+    VptMaterial *materials = nullptr; int nMaterials = 0;
+    uint16_t *blockToMaterial = nullptr;
+    float4 *sky = nullptr, *sun = nullptr;
+    VptAliasBin *skyAlias = nullptr, *sunAlias = nullptr;
+    int skyW = 0, skyH = 0, sunW = 0, sunH = 0;
+    float sunDir[3] = {0, 1, 0};
+    // trace params
+    int spp = 1, totalBounceLimit = 3, diffuseBounceLimit = 1, enableRestir = 1;
+    // buffers
+    GSet gb[2];
+    int cur = 1;
+    float4 *illumination = nullptr, *illumOutput = nullptr, *ping = nullptr, *pong = nullptr, *prevIllum = nullptr, *prevFastIllum = nullptr;
+    float *historyLength = nullptr, *prevHistoryLength = nullptr;
+    VptReservoir *reservoirs = nullptr; // 2 planes
+    int4 *primaryHits = nullptr;
+    unsigned long long *counters = nullptr;
+    FireflyPatch *patches = nullptr; int *patchCount = nullptr; int maxPatches = 0;
+    // staging for vpt_denoise_external
+    void *pinned = nullptr; size_t pinnedBytes = 0;
+    // profiling
+    bool profiling = true;
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool haveTrace = false, haveDenoise = false, ranFirefly = false, ranTemporal = false, ranFix = false, ranClamp = false, ranSpatial = false, ranResolve = false;
+    int atrousPasses = 0, launchesRender = 0, launchesDenoise = 0;
+    float atrousMs = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> atrousEv;
+    // multi-GPU
+    void *ncclComm = nullptr; int rank = 0, nranks = 1;
+    size_t npix() const { return (size_t)width * height; }
+};
+
+extern "C" {
+
+const char *vpt_last_error(void) { return g_lastError.c_str(); }
+
+int vpt_create(int device, int width, int height, vpt_ctx **out)
+{
+    if (!out || width <= 0 || height <= 0) return fail(VPT_ERR_ARG, "vpt_create: bad arguments");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(VPT_ERR_CUDA, std::string("vpt_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(VPT_ERR_ARG, "vpt_create: device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(VPT_ERR_CUDA, "vpt_create: device is not sm_100-class; libvpt is built for sm_100a only");
+    vpt_ctx *c = new vpt_ctx();
+    c->device = device; c->width = width; c->height = height; c->smCount = prop.multiProcessorCount;
+    c->smemOptIn = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t n = c->npix();
+    auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
+        cudaError_t r = cudaMalloc(p, bytes);
+        if (r == cudaSuccess) r = cudaMemsetAsync(*p, 0, bytes, c->stream);
+        return r;
+    };
+    for (int s = 0; s < 2; ++s)
+    {
+        CU(alloc((void **)&c->gb[s].depth, n * 4)); CU(alloc((void **)&c->gb[s].material, n * 4));
+        CU(alloc((void **)&c->gb[s].normalRoughness, n * 16)); CU(alloc((void **)&c->gb[s].geoNormalThinfilm, n * 16));
+        CU(alloc((void **)&c->gb[s].materialParameter, n * 16)); CU(alloc((void **)&c->gb[s].albedo, n * 16));
+    }
+    CU(alloc((void **)&c->illumination, n * 16)); CU(alloc((void **)&c->illumOutput, n * 16));
+    CU(alloc((void **)&c->ping, n * 16)); CU(alloc((void **)&c->pong, n * 16));
+    CU(alloc((void **)&c->prevIllum, n * 16)); CU(alloc((void **)&c->prevFastIllum, n * 16));
+    CU(alloc((void **)&c->historyLength, n * 4)); CU(alloc((void **)&c->prevHistoryLength, n * 4));
+    CU(alloc((void **)&c->reservoirs, 2 * n * sizeof(VptReservoir)));
+    CU(alloc((void **)&c->primaryHits, n * sizeof(int4)));
+    CU(alloc((void **)&c->counters, 4 * sizeof(unsigned long long)));
+    c->maxPatches = (int)(n / 4 + 64);
+    CU(alloc((void **)&c->patches, (size_t)c->maxPatches * sizeof(FireflyPatch)));
+    CU(alloc((void **)&c->patchCount, sizeof(int)));
+    CU(alloc((void **)&c->sobol, 65536)); CU(alloc((void **)&c->scrambling, 131072)); CU(alloc((void **)&c->ranking, 131072 + 256));
+    CU(alloc((void **)&c->blockToMaterial, 256 * sizeof(uint16_t)));
+    for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return VPT_OK;
+}
+
+void vpt_destroy(vpt_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
+                    c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int s = 0; s < 2; ++s)
+    {
+        void *g[] = {c->gb[s].depth, c->gb[s].material, c->gb[s].normalRoughness, c->gb[s].geoNormalThinfilm, c->gb[s].materialParameter, c->gb[s].albedo};
+        for (void *p : g) if (p) cudaFree(p);
+    }
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (auto &p : c->atrousEv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int vpt_sync(vpt_ctx *c)
+{
+    if (!c) return fail(VPT_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+void *vpt_stream(vpt_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int vpt_set_profiling(vpt_ctx *c, int enabled) { if (!c) return VPT_ERR_ARG; c->profiling = enabled != 0; return VPT_OK; }
+
+int vpt_set_tables(vpt_ctx *c, const uint8_t *sobol, const uint8_t *scrambling, const uint8_t *ranking)
+{
+    if (!c || !sobol || !scrambling || !ranking) return fail(VPT_ERR_ARG, "vpt_set_tables: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->sobol, sobol, 65536, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->scrambling, scrambling, 131072, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ranking, ranking, 131072, cudaMemcpyHostToDevice, c->stream)); // +256 zero bytes of padding stay 0
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+
+static int allocGrid(vpt_ctx *c, int cx, int cy, int cz)
+{
+    if (cx <= 0 || cy <= 0 || cz <= 0) return fail(VPT_ERR_ARG, "grid: chunk counts must be positive");
+    if ((size_t)cx * cy * cz * 32768 > ((size_t)1 << 31)) return fail(VPT_ERR_ARG, "grid: more than 2^31 voxels");
+    if (c->cx != cx || c->cy != cy || c->cz != cz)
+    {
+        if (c->idsChunk) cudaFree(c->idsChunk);
+        if (c->idsLinear) cudaFree(c->idsLinear);
+        if (c->occ) cudaFree(c->occ);
+        c->idsChunk = c->idsLinear = nullptr; c->occ = nullptr;
+        const size_t vox = (size_t)cx * cy * cz * 32768;
+        CU(cudaMalloc((void **)&c->idsChunk, vox));
+        CU(cudaMalloc((void **)&c->idsLinear, vox));
+        CU(cudaMalloc((void **)&c->occ, vox / 8));
+        c->cx = cx; c->cy = cy; c->cz = cz;
+    }
+    return VPT_OK;
+}
+
+int vpt_set_grid(vpt_ctx *c, int cx, int cy, int cz, const uint8_t *ids)
+{
+    if (!c || !ids) return fail(VPT_ERR_ARG, "vpt_set_grid: null argument");
+    CU(cudaSetDevice(c->device));
+    int rc = allocGrid(c, cx, cy, cz);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->idsChunk, ids, (size_t)cx * cy * cz * 32768, cudaMemcpyHostToDevice, c->stream));
+    CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, cx, cy, cz, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_generate_terrain(vpt_ctx *c, int cx, int cy, int cz, const float *noise)
+{
+    if (!c || !noise) return fail(VPT_ERR_ARG, "vpt_generate_terrain: null argument");
+    CU(cudaSetDevice(c->device));
+    int rc = allocGrid(c, cx, cy, cz);
+    if (rc) return rc;
+    float *dNoise = nullptr;
+    const size_t nb = (size_t)cx * cy * cz * 1024 * sizeof(float);
+    CU(cudaMalloc((void **)&dNoise, nb));
+    CU(cudaMemcpyAsync(dNoise, noise, nb, cudaMemcpyHostToDevice, c->stream));
+    CU(launchGenerateTerrain(dNoise, c->idsChunk, cx, cy, cz, c->stream));
+    CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, cx, cy, cz, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(dNoise));
+    return VPT_OK;
+}
+int vpt_get_grid(vpt_ctx *c, uint8_t *out, size_t bytes)
+{
+    if (!c || !out) return fail(VPT_ERR_ARG, "vpt_get_grid: null argument");
+    if (!c->idsChunk) return fail(VPT_ERR_STATE, "vpt_get_grid: no grid set");
+    if (bytes != (size_t)c->cx * c->cy * c->cz * 32768) return fail(VPT_ERR_ARG, "vpt_get_grid: size mismatch");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, c->idsChunk, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_set_voxel(vpt_ctx *c, int x, int y, int z, int blockId)
+{
+    if (!c || !c->idsChunk) return fail(VPT_ERR_STATE, "vpt_set_voxel: no grid set");
+    if (x < 0 || y < 0 || z < 0 || x >= c->cx * 32 || y >= c->cy * 32 || z >= c->cz * 32) return VPT_OK; // reference ignores out-of-range edits
+    CU(cudaSetDevice(c->device));
+    CU(launchSetVoxel(c->idsChunk, c->idsLinear, c->occ, c->cx, c->cy, c->cz, x, y, z, blockId, c->stream));
+    return VPT_OK;
+}
+
+int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_t *b2m)
+{
+    if (!c || !m || !b2m || count <= 0) return fail(VPT_ERR_ARG, "vpt_set_materials: bad argument");
+    for (int i = 0; i < 256; ++i) if (b2m[i] >= count) return fail(VPT_ERR_ARG, "vpt_set_materials: blockToMaterial index out of range");
+    CU(cudaSetDevice(c->device));
+    if (c->materials) cudaFree(c->materials);
+    CU(cudaMalloc((void **)&c->materials, (size_t)count * sizeof(VptMaterial)));
+    c->nMaterials = count;
+    CU(cudaMemcpyAsync(c->materials, m, (size_t)count * sizeof(VptMaterial), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->blockToMaterial, b2m, 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+
+int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *sun, int sunW, int sunH,
+                const VptAliasBin *skyAlias, const VptAliasBin *sunAlias, const float *sunDir)
+{
+    if (!c || !sky || !sun || !skyAlias || !sunAlias || !sunDir || skyW <= 0 || skyH <= 0 || sunW <= 0 || sunH <= 0)
+        return fail(VPT_ERR_ARG, "vpt_set_sky: bad argument");
+    CU(cudaSetDevice(c->device));
+    for (void *p : {(void *)c->sky, (void *)c->sun, (void *)c->skyAlias, (void *)c->sunAlias}) if (p) cudaFree(p);
+    const size_t ns = (size_t)skyW * skyH, nu = (size_t)sunW * sunH;
+    CU(cudaMalloc((void **)&c->sky, ns * 16)); CU(cudaMalloc((void **)&c->sun, nu * 16));
+    CU(cudaMalloc((void **)&c->skyAlias, ns * sizeof(VptAliasBin))); CU(cudaMalloc((void **)&c->sunAlias, nu * sizeof(VptAliasBin)));
+    CU(cudaMemcpyAsync(c->sky, sky, ns * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->sun, sun, nu * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->skyAlias, skyAlias, ns * sizeof(VptAliasBin), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->sunAlias, sunAlias, nu * sizeof(VptAliasBin), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->skyW = skyW; c->skyH = skyH; c->sunW = sunW; c->sunH = sunH;
+    c->sunDir[0] = sunDir[0]; c->sunDir[1] = sunDir[1]; c->sunDir[2] = sunDir[2];
+    return VPT_OK;
+}
+
+int vpt_set_trace_params(vpt_ctx *c, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir)
+{
+    if (!c || spp < 1 || totalBounceLimit < 1 || diffuseBounceLimit < 1) return fail(VPT_ERR_ARG, "vpt_set_trace_params: bad argument");
+    c->spp = spp; c->totalBounceLimit = totalBounceLimit; c->diffuseBounceLimit = diffuseBounceLimit; c->enableRestir = enableRestir ? 1 : 0;
+    return VPT_OK;
+}
+
+int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
+{
+    if (!c || !cam || !prevCam || sampleBegin < 0 || sampleStep < 1) return fail(VPT_ERR_ARG, "vpt_render: bad argument");
+    if (!c->occ) return fail(VPT_ERR_STATE, "vpt_render: no voxel grid (vpt_set_grid / vpt_generate_terrain)");
+    if (!c->materials) return fail(VPT_ERR_STATE, "vpt_render: no materials (vpt_set_materials)");
+    if (!c->sky) return fail(VPT_ERR_STATE, "vpt_render: no sky (vpt_set_sky)");
+    if ((int)cam->resolution[0] != c->width || (int)cam->resolution[1] != c->height) return fail(VPT_ERR_ARG, "vpt_render: camera resolution != context size");
+    CU(cudaSetDevice(c->device));
+    c->cur ^= 1;
+    TraceArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.cam = *cam; a.prevCam = *prevCam;
+    a.width = c->width; a.height = c->height;
+    a.iterationIndex = iterationIndex; a.spp = c->spp; a.totalBounceLimit = c->totalBounceLimit; a.diffuseBounceLimit = c->diffuseBounceLimit;
+    a.enableRestir = c->enableRestir; a.sampleBegin = sampleBegin; a.sampleStep = sampleStep;
+    a.grid.W = c->cx * 32; a.grid.H = c->cy * 32; a.grid.D = c->cz * 32; a.grid.cx = c->cx; a.grid.cy = c->cy; a.grid.cz = c->cz;
+    a.grid.wordsX = c->cx; a.grid.occWords = c->cx * (c->cy * 32) * (c->cz * 32);
+    a.grid.occ = c->occ; a.grid.idsLinear = c->idsLinear;
+    // two CTAs per SM must fit next to each other (plus 1 KiB/CTA reserved by the runtime)
+    a.occInSmem = ((size_t)a.grid.occWords * 4 * 2 + 2048 <= (size_t)c->smemOptIn + 1024) && ((size_t)a.grid.occWords * 4 <= 100 * 1024) ? 1 : 0;
+    a.sobol = c->sobol; a.scrambling = c->scrambling; a.ranking = c->ranking;
+    a.materials = c->materials; a.blockToMaterial = c->blockToMaterial;
+    a.sky = c->sky; a.sun = c->sun; a.skyAlias = c->skyAlias; a.sunAlias = c->sunAlias;
+    a.skyW = c->skyW; a.skyH = c->skyH; a.sunW = c->sunW; a.sunH = c->sunH;
+    a.sunDir[0] = c->sunDir[0]; a.sunDir[1] = c->sunDir[1]; a.sunDir[2] = c->sunDir[2];
+    a.sunCosThetaMax = cosf(0.51f * 3.1415926535897932384626422832795028841971f / 180.0f / 2.0f); // miss.cu:46-47, host libm like the oracle
+    a.cur = c->gb[c->cur].ptrs(); a.prev = c->gb[c->cur ^ 1].ptrs();
+    a.illumination = c->illumination;
+    a.resCur = c->reservoirs + (size_t)(iterationIndex & 1) * c->npix();
+    a.resPrev = c->reservoirs + (size_t)((iterationIndex + 1) & 1) * c->npix();
+    a.primaryHits = c->primaryHits;
+    a.counters = c->counters;
+    CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE0], c->stream));
+    CU(launchTrace(a, c->stream, c->smCount, c->smemOptIn));
+    if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE1], c->stream));
+    c->haveTrace = c->profiling; c->ranResolve = false; c->launchesRender = 1;
+    return VPT_OK;
+}
+int vpt_resolve(vpt_ctx *c)
+{
+    if (!c) return fail(VPT_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (c->spp > 1)
+    {
+        CU(launchResolve(c->illumination, (int)c->npix(), (float)c->spp, c->stream));
+        if (c->profiling) CU(cudaEventRecord(c->ev[EV_RESOLVE1], c->stream));
+        c->ranResolve = c->profiling; c->launchesRender += 1;
+    }
+    return VPT_OK;
+}
+int vpt_render(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex)
+{
+    int rc = vpt_render_shard(c, cam, prevCam, iterationIndex, 0, 1);
+    if (rc) return rc;
+    return vpt_resolve(c);
+}
+int vpt_begin_external_frame(vpt_ctx *c) { if (!c) return VPT_ERR_ARG; c->cur ^= 1; return VPT_OK; }
+
+static int denoiseRows(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
+                       int rowBegin, int rowEnd, bool timing)
+{
+    DenoiseLaunch d;
+    d.width = c->width; d.height = c->height; d.rowBegin = rowBegin; d.rowEnd = rowEnd;
+    d.cam = *cam; d.prevCam = *prevCam; d.p = *p; d.stream = c->stream;
+    d.b.cur = c->gb[c->cur].ptrs(); d.b.prev = c->gb[c->cur ^ 1].ptrs();
+    d.b.illumination = c->illumination; d.b.illumOutput = c->illumOutput; d.b.ping = c->ping; d.b.pong = c->pong;
+    d.b.prevIllum = c->prevIllum; d.b.prevFastIllum = c->prevFastIllum; d.b.historyLength = c->historyLength; d.b.prevHistoryLength = c->prevHistoryLength;
+    const int usedIter = iterationIndex > 0 ? iterationIndex - 1 : 0;
+    d.b.reservoirs = c->reservoirs + (size_t)(usedIter & 1) * c->npix();
+    auto rec = [&](int e) -> cudaError_t { return timing ? cudaEventRecord(c->ev[e], c->stream) : cudaSuccess; };
+    int launches = 0;
+    c->ranFirefly = c->ranTemporal = c->ranFix = c->ranClamp = c->ranSpatial = false;
+    c->atrousPasses = 0;
+    CU(rec(EV_DN0));
+    if (p->enableFireflyFilter) { CU(launchFirefly(d, c->patches, c->patchCount, c->maxPatches)); launches += 2; c->ranFirefly = true; }
+    CU(rec(EV_FIREFLY));
+    CU(launchCopySky(d)); launches++;
+    if (frameNum == 0) { CU(launchFrame0Init(d)); launches++; }
+    CU(rec(EV_SKY));
+    int finalBuf = 0;
+    if (p->enableTemporalAccumulation && frameNum > 0)
+    {
+        CU(launchTemporal(d)); launches++; finalBuf = 1; c->ranTemporal = true;
+        CU(rec(EV_TEMPORAL));
+        if (p->enableHistoryFix) { CU(launchHistoryFix(d)); launches++; finalBuf = 2; c->ranFix = true; }
+        CU(rec(EV_HFIX));
+        if (p->enableHistoryClamping) { CU(launchHistoryClamping(d)); launches++; finalBuf = 3; c->ranClamp = true; }
+        CU(rec(EV_HCLAMP));
+    }
+    else { CU(rec(EV_TEMPORAL)); CU(rec(EV_HFIX)); CU(rec(EV_HCLAMP)); }
+    if (p->enableSpatialFiltering)
+    {
+        CU(launchAtrousSmem(d, c->prevIllum, c->ping)); launches++; finalBuf = 1; c->ranSpatial = true;
+        CU(rec(EV_ASMEM));
+        if (p->atrousIterationNum > 0)
+        {
+            int idx = 1, step = 1 << idx;
+            const int maxIt = p->atrousIterationNum * 2;
+            while (idx < maxIt)
+            {
+                CU(launchAtrous(d, c->ping, c->pong, (unsigned)iterationIndex, (unsigned)step)); launches++; c->atrousPasses++;
+                ++idx; step = 1 << idx;
+                CU(launchAtrous(d, c->pong, c->ping, (unsigned)iterationIndex, (unsigned)step)); launches++; c->atrousPasses++;
+                ++idx; step = 1 << idx;
+            }
+            CU(launchAtrous(d, c->ping, c->pong, (unsigned)iterationIndex, (unsigned)step)); launches++; c->atrousPasses++;
+            finalBuf = 2;
+        }
+        CU(rec(EV_ATROUS));
+    }
+    else { CU(rec(EV_ASMEM)); CU(rec(EV_ATROUS)); }
+    const float4 *fin = finalBuf == 1 ? c->ping : finalBuf == 2 ? c->pong : finalBuf == 3 ? c->prevIllum : c->illumination;
+    CU(launchCompositeNonSky(d, fin)); launches++;
+    CU(rec(EV_COMP));
+    c->launchesDenoise = launches;
+    c->haveDenoise = timing;
+    return VPT_OK;
+}
+
+int vpt_denoise(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex)
+{
+    if (!c || !p || !cam || !prevCam) return fail(VPT_ERR_ARG, "vpt_denoise: null argument");
+    if (p->enableHitDistanceReconstruction || p->enablePrePass)
+        return fail(VPT_ERR_ARG, "vpt_denoise: HitDistReconstruction / PrePass are off in the shipped settings and not built (SURVEY 8a D2/D3)");
+    CU(cudaSetDevice(c->device));
+    return denoiseRows(c, p, cam, prevCam, frameNum, iterationIndex, 0, c->height, c->profiling);
+}
+
+static int planeInfo(vpt_ctx *c, VptBufferName name, void **ptr, size_t *bytes)
+{
+    const size_t n = c->npix();
+    GSet &g = c->gb[c->cur], &pg = c->gb[c->cur ^ 1];
+    switch (name)
+    {
+    case VPT_BUF_Illumination: *ptr = c->illumination; *bytes = n * 16; break;
+    case VPT_BUF_IlluminationOutput: *ptr = c->illumOutput; *bytes = n * 16; break;
+    case VPT_BUF_IlluminationPing: *ptr = c->ping; *bytes = n * 16; break;
+    case VPT_BUF_IlluminationPong: *ptr = c->pong; *bytes = n * 16; break;
+    case VPT_BUF_NormalRoughness: *ptr = g.normalRoughness; *bytes = n * 16; break;
+    case VPT_BUF_Depth: *ptr = g.depth; *bytes = n * 4; break;
+    case VPT_BUF_Material: *ptr = g.material; *bytes = n * 4; break;
+    case VPT_BUF_Albedo: *ptr = g.albedo; *bytes = n * 16; break;
+    case VPT_BUF_HistoryLength: *ptr = c->historyLength; *bytes = n * 4; break;
+    case VPT_BUF_PrevDepth: *ptr = pg.depth; *bytes = n * 4; break;
+    case VPT_BUF_PrevMaterial: *ptr = pg.material; *bytes = n * 4; break;
+    case VPT_BUF_PrevIllumination: *ptr = c->prevIllum; *bytes = n * 16; break;
+    case VPT_BUF_PrevFastIllumination: *ptr = c->prevFastIllum; *bytes = n * 16; break;
+    case VPT_BUF_PrevHistoryLength: *ptr = c->prevHistoryLength; *bytes = n * 4; break;
+    case VPT_BUF_PrevNormalRoughness: *ptr = pg.normalRoughness; *bytes = n * 16; break;
+    case VPT_BUF_GeoNormalThinfilm: *ptr = g.geoNormalThinfilm; *bytes = n * 16; break;
+    case VPT_BUF_MaterialParameter: *ptr = g.materialParameter; *bytes = n * 16; break;
+    case VPT_BUF_PrevMaterialParameter: *ptr = pg.materialParameter; *bytes = n * 16; break;
+    case VPT_BUF_PrevGeoNormalThinfilm: *ptr = pg.geoNormalThinfilm; *bytes = n * 16; break;
+    case VPT_BUF_PrevAlbedo: *ptr = pg.albedo; *bytes = n * 16; break;
+    case VPT_BUF_PrimaryHits: *ptr = c->primaryHits; *bytes = n * 16; break;
+    default: return fail(VPT_ERR_ARG, "unknown buffer name");
+    }
+    return VPT_OK;
+}
+void *vpt_device_ptr(vpt_ctx *c, VptBufferName name)
+{
+    void *p = nullptr; size_t b = 0;
+    if (!c || planeInfo(c, name, &p, &b)) return nullptr;
+    return p;
+}
+int vpt_read_buffer(vpt_ctx *c, VptBufferName name, void *host, size_t bytes)
+{
+    if (!c || !host) return fail(VPT_ERR_ARG, "vpt_read_buffer: null argument");
+    void *p; size_t have;
+    int rc = planeInfo(c, name, &p, &have);
+    if (rc) return rc;
+    if (have != bytes) return fail(VPT_ERR_ARG, "vpt_read_buffer: size mismatch");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_write_buffer(vpt_ctx *c, VptBufferName name, const void *host, size_t bytes)
+{
+    if (!c || !host) return fail(VPT_ERR_ARG, "vpt_write_buffer: null argument");
+    void *p; size_t have;
+    int rc = planeInfo(c, name, &p, &have);
+    if (rc) return rc;
+    if (have != bytes) return fail(VPT_ERR_ARG, "vpt_write_buffer: size mismatch");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_read_reservoirs(vpt_ctx *c, int parity, VptReservoir *host, size_t bytes)
+{
+    if (!c || !host || bytes != c->npix() * sizeof(VptReservoir)) return fail(VPT_ERR_ARG, "vpt_read_reservoirs: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(host, c->reservoirs + (size_t)(parity & 1) * c->npix(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_write_reservoirs(vpt_ctx *c, int parity, const VptReservoir *host, size_t bytes)
+{
+    if (!c || !host || bytes != c->npix() * sizeof(VptReservoir)) return fail(VPT_ERR_ARG, "vpt_write_reservoirs: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->reservoirs + (size_t)(parity & 1) * c->npix(), host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+
+int vpt_denoise_external(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
+                         const float *illumination, const float *depth, const float *normalRoughness, const float *material, const float *albedo,
+                         float *outputRGBA)
+{
+    if (!c || !p || !cam || !prevCam || !illumination || !depth || !normalRoughness || !material || !albedo || !outputRGBA)
+        return fail(VPT_ERR_ARG, "vpt_denoise_external: null argument");
+    CU(cudaSetDevice(c->device));
+    c->cur ^= 1;
+    const size_t n = c->npix();
+    GSet &g = c->gb[c->cur];
+    CU(cudaMemcpyAsync(c->illumination, illumination, n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(g.depth, depth, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(g.normalRoughness, normalRoughness, n * 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(g.material, material, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(g.albedo, albedo, n * 16, cudaMemcpyHostToDevice, c->stream));
+    int rc = vpt_denoise(c, p, cam, prevCam, frameNum, iterationIndex);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(outputRGBA, c->illumOutput, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+
+int vpt_get_counters(vpt_ctx *c, uint64_t *rays, uint64_t *steps)
+{
+    if (!c || !rays || !steps) return fail(VPT_ERR_ARG, "vpt_get_counters: null argument");
+    unsigned long long h[2];
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *rays = h[0]; *steps = h[1];
+    return VPT_OK;
+}
+
+int vpt_get_timings(vpt_ctx *c, VptTimings *t)
+{
+    if (!c || !t) return fail(VPT_ERR_ARG, "vpt_get_timings: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    std::memset(t, 0, sizeof *t);
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
+    if (c->haveTrace)
+    {
+        t->trace_ms = el(EV_TRACE0, EV_TRACE1);
+        if (c->ranResolve) t->resolve_ms = el(EV_TRACE1, EV_RESOLVE1);
+    }
+    if (c->haveDenoise)
+    {
+        t->firefly_ms = el(EV_DN0, EV_FIREFLY);
+        t->composite_ms = el(EV_FIREFLY, EV_SKY) + el(EV_ATROUS, EV_COMP);
+        t->temporal_ms = el(EV_SKY, EV_TEMPORAL);
+        t->history_fix_ms = el(EV_TEMPORAL, EV_HFIX);
+        t->history_clamp_ms = el(EV_HFIX, EV_HCLAMP);
+        t->atrous_smem_ms = el(EV_HCLAMP, EV_ASMEM);
+        t->atrous_ms = el(EV_ASMEM, EV_ATROUS);
+        t->denoise_total_ms = el(EV_DN0, EV_COMP);
+        t->atrous_passes = c->atrousPasses;
+    }
+    t->kernel_launches = c->launchesRender + c->launchesDenoise;
+    return VPT_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------ multi-GPU (NCCL, dlopen'ed)
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi
+{
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+bool loadNccl()
+{
+    if (g_nccl.handle) return true;
+    // Prefer a libnccl already mapped into the process (torch's bundled 2.28) so that only one NCCL lives here.
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_lastError = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { g_lastError = std::string("libnccl: missing ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return true;
+}
+} // namespace
+#define NC(call)                                                                                                    \
+    do {                                                                                                            \
+        ncclResult_t r_ = (call);                                                                                   \
+        if (r_ != ncclSuccess) return fail(VPT_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_));    \
+    } while (0)
+
+extern "C" {
+
+int vpt_comm_unique_id(uint8_t *id128)
+{
+    if (!id128) return fail(VPT_ERR_ARG, "null id");
+    if (!loadNccl()) return VPT_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, &id, 128);
+    return VPT_OK;
+}
+int vpt_comm_init(vpt_ctx *c, int rank, int nranks, const uint8_t *id128)
+{
+    if (!c || !id128 || rank < 0 || rank >= nranks) return fail(VPT_ERR_ARG, "vpt_comm_init: bad argument");
+    if (!loadNccl()) return VPT_ERR_NCCL;
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    NC(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c->ncclComm = comm; c->rank = rank; c->nranks = nranks;
+    return VPT_OK;
+}
+int vpt_comm_allreduce_illumination(vpt_ctx *c)
+{
+    if (!c || !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_comm_allreduce_illumination: communicator not initialised");
+    CU(cudaSetDevice(c->device));
+    NC(g_nccl.AllReduce(c->illumination, c->illumination, c->npix() * 4, ncclFloat, ncclSum, (ncclComm_t)c->ncclComm, c->stream));
+    return VPT_OK;
+}
+int vpt_comm_broadcast_gbuffer(vpt_ctx *c, int iterationIndex)
+{
+    if (!c || !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_comm_broadcast_gbuffer: communicator not initialised");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->npix();
+    GSet &g = c->gb[c->cur];
+    ncclComm_t comm = (ncclComm_t)c->ncclComm;
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Broadcast(g.depth, g.depth, n, ncclFloat, 0, comm, c->stream));
+    NC(g_nccl.Broadcast(g.material, g.material, n, ncclFloat, 0, comm, c->stream));
+    NC(g_nccl.Broadcast(g.normalRoughness, g.normalRoughness, n * 4, ncclFloat, 0, comm, c->stream));
+    NC(g_nccl.Broadcast(g.geoNormalThinfilm, g.geoNormalThinfilm, n * 4, ncclFloat, 0, comm, c->stream));
+    NC(g_nccl.Broadcast(g.materialParameter, g.materialParameter, n * 4, ncclFloat, 0, comm, c->stream));
+    NC(g_nccl.Broadcast(g.albedo, g.albedo, n * 4, ncclFloat, 0, comm, c->stream));
+    VptReservoir *r = c->reservoirs + (size_t)(iterationIndex & 1) * n;
+    NC(g_nccl.Broadcast(r, r, n * 5, ncclFloat, 0, comm, c->stream));
+    NC(g_nccl.GroupEnd());
+    return VPT_OK;
+}
+
+// Halo exchange of `rows` rows of a plane with the bands above and below (elemFloats floats per pixel).
+static int haloExchange(vpt_ctx *c, void *plane, int elemFloats, int rowBegin, int rowEnd, int rows)
+{
+    if (c->nranks == 1 || rows <= 0) return VPT_OK;
+    ncclComm_t comm = (ncclComm_t)c->ncclComm;
+    const size_t rowFloats = (size_t)c->width * elemFloats;
+    float *base = (float *)plane;
+    const int up = c->rank - 1, down = c->rank + 1; // band r owns rows [r*H/n, (r+1)*H/n): "up" = lower row indices
+    NC(g_nccl.GroupStart());
+    if (up >= 0)
+    {
+        const int r = std::min(rows, rowBegin);
+        NC(g_nccl.Send(base + (size_t)rowBegin * rowFloats, (size_t)std::min(rows, rowEnd - rowBegin) * rowFloats, ncclFloat, up, comm, c->stream));
+        NC(g_nccl.Recv(base + (size_t)(rowBegin - r) * rowFloats, (size_t)r * rowFloats, ncclFloat, up, comm, c->stream));
+    }
+    if (down < c->nranks)
+    {
+        const int r = std::min(rows, c->height - rowEnd);
+        NC(g_nccl.Send(base + (size_t)(rowEnd - std::min(rows, rowEnd - rowBegin)) * rowFloats, (size_t)std::min(rows, rowEnd - rowBegin) * rowFloats, ncclFloat, down, comm, c->stream));
+        NC(g_nccl.Recv(base + (size_t)rowEnd * rowFloats, (size_t)r * rowFloats, ncclFloat, down, comm, c->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return VPT_OK;
+}
+
+// Row-band sharded Denoiser::run: every rank holds full-size planes but only its band
+// [rowBegin,rowEnd) (+ halos) is valid. Inputs (Illumination + current G-buffer) must be valid on the band plus
+// kGuard rows either side (the caller uploads them that way); history planes are exchanged as they are produced.
+int vpt_denoise_band(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
+                     int rowBegin, int rowEnd)
+{
+    if (!c || !p || !cam || !prevCam) return fail(VPT_ERR_ARG, "vpt_denoise_band: null argument");
+    if (rowBegin < 0 || rowEnd > c->height || rowBegin >= rowEnd || (rowBegin & 3)) return fail(VPT_ERR_ARG, "vpt_denoise_band: band must start on a multiple of 4 rows");
+    if (c->nranks > 1 && !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_denoise_band: communicator not initialised");
+    if (p->enableHitDistanceReconstruction || p->enablePrePass) return fail(VPT_ERR_ARG, "vpt_denoise_band: unsupported pass enabled");
+    CU(cudaSetDevice(c->device));
+    DenoiseLaunch d;
+    d.width = c->width; d.height = c->height; d.rowBegin = rowBegin; d.rowEnd = rowEnd;
+    d.cam = *cam; d.prevCam = *prevCam; d.p = *p; d.stream = c->stream;
+    d.b.cur = c->gb[c->cur].ptrs(); d.b.prev = c->gb[c->cur ^ 1].ptrs();
+    d.b.illumination = c->illumination; d.b.illumOutput = c->illumOutput; d.b.ping = c->ping; d.b.pong = c->pong;
+    d.b.prevIllum = c->prevIllum; d.b.prevFastIllum = c->prevFastIllum; d.b.historyLength = c->historyLength; d.b.prevHistoryLength = c->prevHistoryLength;
+    const int usedIter = iterationIndex > 0 ? iterationIndex - 1 : 0;
+    d.b.reservoirs = c->reservoirs + (size_t)(usedIter & 1) * c->npix();
+    int rc;
+    if (p->enableFireflyFilter)
+    {
+        CU(launchFirefly(d, c->patches, c->patchCount, c->maxPatches));
+        if ((rc = haloExchange(c, c->illumination, 4, rowBegin, rowEnd, 2))) return rc; // 5x5 noisy moments in HistoryClamping
+    }
+    CU(launchCopySky(d));
+    if (frameNum == 0)
+    {
+        CU(launchFrame0Init(d));
+        if ((rc = haloExchange(c, c->prevIllum, 4, rowBegin, rowEnd, 2))) return rc;
+    }
+    int finalBuf = 0;
+    if (p->enableTemporalAccumulation && frameNum > 0)
+    {
+        // static camera or small motion: history taps stay within the guard band exchanged at the end of the last frame
+        CU(launchTemporal(d)); finalBuf = 1;
+        if ((rc = haloExchange(c, c->historyLength, 1, rowBegin, rowEnd, 18))) return rc;
+        if ((rc = haloExchange(c, c->ping, 4, rowBegin, rowEnd, 18))) return rc; // HistoryFix stride <= 9, 2 taps
+        if ((rc = haloExchange(c, c->pong, 4, rowBegin, rowEnd, 2))) return rc;
+        if (p->enableHistoryFix)
+        {
+            CU(launchHistoryFix(d)); finalBuf = 2;
+            if ((rc = haloExchange(c, c->pong, 4, rowBegin, rowEnd, 2))) return rc;
+        }
+        if (p->enableHistoryClamping) { CU(launchHistoryClamping(d)); finalBuf = 3; }
+    }
+    if (p->enableSpatialFiltering)
+    {
+        if ((rc = haloExchange(c, c->prevIllum, 4, rowBegin, rowEnd, 2))) return rc;
+        CU(launchAtrousSmem(d, c->prevIllum, c->ping)); finalBuf = 1;
+        if (p->atrousIterationNum > 0)
+        {
+            int idx = 1, step = 1 << idx;
+            const int maxIt = p->atrousIterationNum * 2;
+            auto pass = [&](float4 *in, float4 *out) -> int {
+                const int halo = step + (step > 4 ? step / 4 + 1 : 0);
+                int r2 = haloExchange(c, in, 4, rowBegin, rowEnd, halo);
+                if (r2) return r2;
+                cudaError_t e = launchAtrous(d, in, out, (unsigned)iterationIndex, (unsigned)step);
+                if (e != cudaSuccess) return fail(VPT_ERR_CUDA, cudaGetErrorString(e));
+                return VPT_OK;
+            };
+            while (idx < maxIt)
+            {
+                if ((rc = pass(c->ping, c->pong))) return rc;
+                ++idx; step = 1 << idx;
+                if ((rc = pass(c->pong, c->ping))) return rc;
+                ++idx; step = 1 << idx;
+            }
+            if ((rc = pass(c->ping, c->pong))) return rc;
+            finalBuf = 2;
+        }
+    }
+    const float4 *fin = finalBuf == 1 ? c->ping : finalBuf == 2 ? c->pong : finalBuf == 3 ? c->prevIllum : c->illumination;
+    CU(launchCompositeNonSky(d, fin));
+    // history for the next frame's temporal pass: guard band of 32 rows (bicubic footprint + small camera motion)
+    if ((rc = haloExchange(c, c->prevIllum, 4, rowBegin, rowEnd, 32))) return rc;
+    if ((rc = haloExchange(c, c->prevFastIllum, 4, rowBegin, rowEnd, 32))) return rc;
+    if ((rc = haloExchange(c, c->prevHistoryLength, 1, rowBegin, rowEnd, 32))) return rc;
+    return VPT_OK;
+}
+
+} // extern "C"

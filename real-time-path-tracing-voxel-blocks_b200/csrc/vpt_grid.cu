@@ -1,0 +1,97 @@
+// Voxel grid producers and the device-side repack.
+//
+//  * generateTerrainKernel == GenerateVoxelChunk (/root/reference/voxelengine/VoxelSceneGen.cu:61-165):
+//    height-field terrain from a per-chunk 32x32 noise map, written in the reference's chunk-major
+//    GetLinearId order (voxelengine/VoxelMath.h:120-127). Compiled -fmad=false: the float height tests
+//    must agree with the CPU restatement for every voxel (bit-exact ids).
+//  * repackKernel builds the traversal layouts from the chunk-major bytes: a linear id volume
+//    x + W*(z + D*y) and the 1-bit occupancy mask (one warp ballot per 32 x-consecutive voxels).
+#include "vpt_kernels.h"
+
+namespace vpt {
+
+__device__ __forceinline__ float fminr_(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float fmaxr_(float a, float b) { return a > b ? a : b; }
+
+// One thread per voxel, x fastest: a warp covers 32 x-consecutive voxels of one (y,z) row of one chunk.
+__global__ void generateTerrainKernel(const float *__restrict__ noise, uint8_t *__restrict__ idsChunk, int cx, int cy, int cz)
+{
+    const size_t total = (size_t)cx * cy * cz * 32768;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int chunk = (int)(i >> 15);
+    const int local = (int)(i & 32767);
+    const int x = local & 31, z = (local >> 5) & 31, y = local >> 10;
+    const int chunkX = chunk % cx, chunkZ = (chunk / cx) % cz, chunkY = chunk / (cx * cz);
+    const float noiseVal = __ldg(noise + (size_t)chunk * 1024 + z * 32 + x);
+    const unsigned width = (unsigned)(32 * cy); // height scale: 32 in the reference (chunksY == 1)
+    const int gy = chunkY * 32 + y;
+    const unsigned gx = chunkX * 32 + x, gz = chunkZ * 32 + z;
+    uint8_t id = 0;
+    float terrainHeight = fmaxr_(0.1f, (noiseVal * 1.4f - 0.7f + 0.25f) * width);
+    terrainHeight = fminr_(terrainHeight, width * 0.9f);
+    if (gy < terrainHeight)
+    {
+        float verticalDepth = terrainHeight - gy;
+        if (terrainHeight < width * (0.25f + 0.05f))
+            id = (verticalDepth < 3.5f) ? 1 : 7; // Sand / Rocks
+        else if (terrainHeight < width * (0.25f + 0.6f) && terrainHeight > width * (0.25f + 0.3f))
+            id = (verticalDepth < 5.5f) ? 3 : 7; // Cliff / Rocks
+        else
+            id = (verticalDepth < 1.5f) ? 2 : (verticalDepth < 5.5f ? 3 : 7); // Soil / Cliff / Rocks
+    }
+    // the ten shader-ball mesh cells (VoxelSceneGen.cu:126-161) hold no cube: empty in the DDA world
+    if (gy == 7 && gz == 43 && gx >= 30 && gx <= 39) id = 0;
+    idsChunk[i] = id;
+}
+
+// One thread per voxel in LINEAR order (x fastest over the whole world width): the 32 lanes of a warp are
+// the 32 voxels of one occupancy word -> __ballot_sync builds the word; W is a multiple of 32.
+__global__ void repackKernel(const uint8_t *__restrict__ idsChunk, uint8_t *__restrict__ idsLinear, uint32_t *__restrict__ occ,
+                             int cx, int cy, int cz)
+{
+    const int W = cx * 32, D = cz * 32;
+    const size_t total = (size_t)cx * cy * cz * 32768;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // total is a multiple of the block size
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    const size_t r = i / W;
+    const int z = (int)(r % D), y = (int)(r / D);
+    const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
+    const uint8_t id = __ldg(idsChunk + (size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31)));
+    idsLinear[i] = id;
+    const unsigned word = __ballot_sync(0xffffffffu, id != 0);
+    if ((threadIdx.x & 31) == 0) occ[i >> 5] = word;
+}
+
+__global__ void setVoxelKernel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id)
+{
+    const int W = cx * 32, D = cz * 32;
+    const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
+    idsChunk[(size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31))] = (uint8_t)id;
+    const size_t lin = ((size_t)y * D + z) * W + x;
+    idsLinear[lin] = (uint8_t)id;
+    uint32_t w = occ[lin >> 5];
+    const uint32_t bit = 1u << (x & 31);
+    occ[lin >> 5] = id ? (w | bit) : (w & ~bit);
+}
+
+cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s)
+{
+    const size_t total = (size_t)cx * cy * cz * 32768;
+    generateTerrainKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(noise, idsChunk, cx, cy, cz);
+    return cudaGetLastError();
+}
+cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, cudaStream_t s)
+{
+    const size_t total = (size_t)cx * cy * cz * 32768;
+    repackKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz);
+    return cudaGetLastError();
+}
+cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s)
+{
+    setVoxelKernel<<<1, 1, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz, x, y, z, id);
+    return cudaGetLastError();
+}
+
+} // namespace vpt

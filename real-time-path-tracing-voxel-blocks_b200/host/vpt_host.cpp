@@ -1,0 +1,375 @@
+// Host-side mirror of the reference's host code on the hot path (no device work), exported through the
+// C ABI (include/vpt.h). Compiled by g++ with -ffp-contract=off so the camera matrices and the noise maps
+// are the same bits the CPU oracle derives.
+//
+//   Camera::init / updateMatrices / update      /root/reference/renderer/shaders/Camera.h:29-99
+//   YawPitchToDir / DirToYawPitch               /root/reference/renderer/shaders/LinearMath.h:1692-1740
+//   offline camera setup                        /root/reference/mainOffline.cpp:227-247
+//   PerlinNoiseGenerator (siv::PerlinNoise)     /root/reference/voxelengine/Noise.cpp:4-18, ext/PerlinNoise.hpp:228-243, 449-497
+//   chunk noise maps                            /root/reference/voxelengine/VoxelSceneGen.cu:358-376
+//   AliasTable::update (CPU build)              /root/reference/renderer/shaders/AliasTable.cu:66-153
+//   GlobalSettings::LoadFromYAML                /root/reference/renderer/core/GlobalSettings.cpp:69-138, 456-492
+//   SceneConfigParser::LoadFromFile             /root/reference/renderer/core/SceneConfig.cpp:6-114, 184-247
+#include "../../include/vpt.h"
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct V3 { float x, y, z; };
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline float dopf(float a, float b, float c, float d)
+{
+    float cd = c * d;
+    float err = fmaf(-c, d, cd);
+    float r = fmaf(a, b, -cd);
+    return r + err;
+}
+inline V3 cross3(V3 a, V3 b) { return {dopf(a.y, b.z, a.z, b.y), dopf(a.z, b.x, a.x, b.z), dopf(a.x, b.y, a.y, b.x)}; }
+inline V3 normalize3(V3 v)
+{
+    float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    if (n < 1e-8f || std::isnan(n)) return {0.0f, 0.0f, 1.0f};
+    return {v.x / n, v.y / n, v.z / n};
+}
+// compensated 3-term inner product (LinearMath.h:112-146)
+inline float inner3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    float p0 = a0 * b0, e0 = fmaf(a0, b0, -p0);
+    float p1 = a1 * b1, e1 = fmaf(a1, b1, -p1);
+    float p2 = a2 * b2, e2 = fmaf(a2, b2, -p2);
+    float s12 = p1 + p2, d12 = s12 - p1, se12 = (p1 - (s12 - d12)) + (p2 - d12);
+    float tpv = s12, tpe = e1 + (e2 + se12);
+    float s = p0 + tpv, d = s - p0, se = (p0 - (s - d)) + (tpv - d);
+    return s + (e0 + (tpe + se));
+}
+struct M3 { float m00, m10, m20, m01, m11, m21, m02, m12, m22; };
+inline M3 cols(V3 a, V3 b, V3 c) { return {a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z}; }
+inline M3 zero3() { M3 m; std::memset(&m, 0, sizeof m); return m; }
+inline M3 transpose3(M3 m)
+{
+    M3 r = m;
+    r.m01 = m.m10; r.m10 = m.m01; r.m02 = m.m20; r.m20 = m.m02; r.m12 = m.m21; r.m21 = m.m12;
+    return r;
+}
+inline M3 mul3(const M3 &A, const M3 &B)
+{
+    M3 C;
+    C.m00 = A.m00 * B.m00 + A.m01 * B.m10 + A.m02 * B.m20;
+    C.m01 = A.m00 * B.m01 + A.m01 * B.m11 + A.m02 * B.m21;
+    C.m02 = A.m00 * B.m02 + A.m01 * B.m12 + A.m02 * B.m22;
+    C.m10 = A.m10 * B.m00 + A.m11 * B.m10 + A.m12 * B.m20;
+    C.m11 = A.m10 * B.m01 + A.m11 * B.m11 + A.m12 * B.m21;
+    C.m12 = A.m10 * B.m02 + A.m11 * B.m12 + A.m12 * B.m22;
+    C.m20 = A.m20 * B.m00 + A.m21 * B.m10 + A.m22 * B.m20;
+    C.m21 = A.m20 * B.m01 + A.m21 * B.m11 + A.m22 * B.m21;
+    C.m22 = A.m20 * B.m02 + A.m21 * B.m12 + A.m22 * B.m22;
+    return C;
+}
+inline void store(float *dst, const M3 &m) { std::memcpy(dst, &m, sizeof m); }
+
+constexpr float kPiOver2 = 1.5707963267948966192313216916397514420985f;
+constexpr float kPiOver180 = 0.01745329251f;
+inline float clampf(float a, float lo, float hi) { return a < lo ? lo : a > hi ? hi : a; }
+
+V3 yawPitchToDir(float yaw, float pitch)
+{
+    if (std::isnan(yaw) || std::isnan(pitch)) return {0, 0, 1};
+    pitch = clampf(pitch, -kPiOver2 + 0.01f, kPiOver2 - 0.01f);
+    float sy = sinf(yaw), cy = cosf(yaw), sp = sinf(pitch), cp = cosf(pitch);
+    return normalize3({sy * cp, sp, cy * cp});
+}
+
+// ---- siv::BasicPerlinNoise<float>
+struct PerlinNoise
+{
+    std::array<uint8_t, 256> perm;
+    explicit PerlinNoise(uint32_t seed)
+    {
+        for (int i = 0; i < 256; ++i) perm[i] = (uint8_t)i;
+        std::mt19937 urbg(seed);
+        for (int i = 1; i < 256; ++i)
+        {
+            const uint64_t j = (uint64_t)urbg() % ((uint64_t)i + 1);
+            std::swap(perm[i], perm[(size_t)j]);
+        }
+    }
+    static float fade(float t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+    static float mix(float a, float b, float t) { return a + (b - a) * t; }
+    static float grad(uint8_t hash, float x, float y, float z)
+    {
+        const uint8_t h = hash & 15;
+        const float u = h < 8 ? x : y;
+        const float v = h < 4 ? y : (h == 12 || h == 14 ? x : z);
+        return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+    }
+    float noise3D(float x, float y, float z) const
+    {
+        const float fx0 = std::floor(x), fy0 = std::floor(y), fz0 = std::floor(z);
+        const int ix = (int)fx0 & 255, iy = (int)fy0 & 255, iz = (int)fz0 & 255;
+        const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+        const float u = fade(fx), v = fade(fy), w = fade(fz);
+        const uint8_t A = (perm[ix & 255] + iy) & 255, B = (perm[(ix + 1) & 255] + iy) & 255;
+        const uint8_t AA = (perm[A] + iz) & 255, AB = (perm[(A + 1) & 255] + iz) & 255;
+        const uint8_t BA = (perm[B] + iz) & 255, BB = (perm[(B + 1) & 255] + iz) & 255;
+        const float p0 = grad(perm[AA], fx, fy, fz), p1 = grad(perm[BA], fx - 1, fy, fz);
+        const float p2 = grad(perm[AB], fx, fy - 1, fz), p3 = grad(perm[BB], fx - 1, fy - 1, fz);
+        const float p4 = grad(perm[(AA + 1) & 255], fx, fy, fz - 1), p5 = grad(perm[(BA + 1) & 255], fx - 1, fy, fz - 1);
+        const float p6 = grad(perm[(AB + 1) & 255], fx, fy - 1, fz - 1), p7 = grad(perm[(BB + 1) & 255], fx - 1, fy - 1, fz - 1);
+        const float q0 = mix(p0, p1, u), q1 = mix(p2, p3, u), q2 = mix(p4, p5, u), q3 = mix(p6, p7, u);
+        return mix(mix(q0, q1, v), mix(q2, q3, v), w);
+    }
+    float octave2D_01(float x, float y, int octaves) const
+    {
+        float result = 0, amplitude = 1;
+        for (int i = 0; i < octaves; ++i)
+        {
+            result += noise3D(x, y, (float)0.34567) * amplitude;
+            x *= 2; y *= 2; amplitude *= 0.5f;
+        }
+        if (result <= -1.0f) return 0.0f;
+        if (1.0f <= result) return 1.0f;
+        return result * 0.5f + 0.5f;
+    }
+};
+
+std::string trim(const std::string &s)
+{
+    size_t b = s.find_first_not_of(" \t\r\n");
+    if (b == std::string::npos) return "";
+    size_t e = s.find_last_not_of(" \t\r\n");
+    return s.substr(b, e - b + 1);
+}
+bool parseFloat(const std::string &v, float &out)
+{
+    try { out = std::stof(trim(v)); return true; } catch (const std::exception &) { return false; }
+}
+bool parseInt(const std::string &v, int &out)
+{
+    try { out = std::stoi(trim(v)); return true; } catch (const std::exception &) { return false; }
+}
+bool parseBool(const std::string &v, int32_t &out)
+{
+    std::string t = trim(v);
+    std::transform(t.begin(), t.end(), t.begin(), ::tolower);
+    if (t == "true" || t == "1" || t == "yes" || t == "on") { out = 1; return true; }
+    if (t == "false" || t == "0" || t == "no" || t == "off") { out = 0; return true; }
+    return false;
+}
+bool parseFloat3(const std::string &value, float *out)
+{
+    std::string c = value;
+    if (!c.empty() && c.front() == '[') c = c.substr(1);
+    if (!c.empty() && c.back() == ']') c = c.substr(0, c.size() - 1);
+    std::istringstream iss(c);
+    std::string tok;
+    float vals[3];
+    int count = 0;
+    while (std::getline(iss, tok, ',') && count < 3)
+    {
+        try { vals[count++] = std::stof(trim(tok)); } catch (const std::exception &) { return false; }
+    }
+    if (count != 3) return false;
+    out[0] = vals[0]; out[1] = vals[1]; out[2] = vals[2];
+    return true;
+}
+
+} // namespace
+
+extern "C" {
+
+void vpt_camera_init(VptCamera *c, int width, int height)
+{
+    std::memset(c, 0, sizeof *c);
+    c->pos[0] = 16.0f; c->pos[1] = 25.0f; c->pos[2] = 16.0f;
+    V3 d = normalize3({1.0f, -1.0f, 1.0f});
+    c->dir[0] = d.x; c->dir[1] = d.y; c->dir[2] = d.z;
+    c->resolution[0] = (float)width; c->resolution[1] = (float)height;
+    c->inversedResolution[0] = 1.0f / c->resolution[0]; c->inversedResolution[1] = 1.0f / c->resolution[1];
+    float fovX = 90.0f * kPiOver180;
+    float fovY = fovX * (c->resolution[1] / c->resolution[0]);
+    c->tanHalfFov[0] = tanf(fovX * 0.5f); c->tanHalfFov[1] = tanf(fovY * 0.5f);
+}
+
+void vpt_camera_update(VptCamera *c)
+{
+    float *pd = c->posDelta;
+    if (std::isnan(pd[0]) || std::isnan(pd[1]) || std::isnan(pd[2]) || fabsf(pd[0]) > 1000.0f || fabsf(pd[1]) > 1000.0f || fabsf(pd[2]) > 1000.0f)
+        pd[0] = pd[1] = pd[2] = 0.0f;
+    for (int i = 0; i < 3; ++i) { c->pos[i] = c->pos[i] + pd[i]; pd[i] = 0.0f; }
+    V3 dir = yawPitchToDir(c->yaw, c->pitch);
+    c->dir[0] = dir.x; c->dir[1] = dir.y; c->dir[2] = dir.z;
+    V3 worldUp = {0.0f, 1.0f, 0.0f};
+    V3 left = normalize3(cross3(worldUp, dir));
+    V3 up = normalize3(cross3(dir, left));
+    M3 uvToNdc = cols({2, 0, 0}, {0, 2, 0}, {-1, -1, 1});
+    M3 ndcToView = zero3();
+    ndcToView.m00 = c->tanHalfFov[0]; ndcToView.m11 = c->tanHalfFov[1]; ndcToView.m22 = 1.0f;
+    M3 viewToWorld = cols(-left, up, dir);
+    store(c->uvToWorld, mul3(mul3(viewToWorld, ndcToView), uvToNdc));
+    store(c->uvToView, mul3(viewToWorld, ndcToView));
+    M3 ndcToUv = cols({0.5f, 0, 0}, {0, 0.5f, 0}, {0.5f, 0.5f, 1.0f});
+    M3 worldToView = transpose3(viewToWorld);
+    M3 viewToNdc = zero3();
+    viewToNdc.m00 = 1.0f / c->tanHalfFov[0]; viewToNdc.m11 = 1.0f / c->tanHalfFov[1]; viewToNdc.m22 = 1.0f;
+    store(c->worldToUv, mul3(mul3(ndcToUv, viewToNdc), worldToView));
+    store(c->viewToUv, mul3(viewToNdc, worldToView));
+}
+
+void vpt_camera_from_scene(VptCamera *c, int width, int height, const float *position, const float *direction, float fovDegrees)
+{
+    vpt_camera_init(c, width, height);
+    c->pos[0] = position[0]; c->pos[1] = position[1]; c->pos[2] = position[2];
+    // SceneConfigParser normalises the direction (SceneConfig.cpp:108), mainOffline normalises again (:235)
+    V3 dir = normalize3(normalize3({direction[0], direction[1], direction[2]}));
+    // DirToYawPitch: Float3::normalize() member uses the compensated length (LinearMath.h:536-548)
+    float n = sqrtf(inner3(dir.x, dir.x, dir.y, dir.y, dir.z, dir.z));
+    dir = {dir.x / n, dir.y / n, dir.z / n};
+    c->yaw = atan2f(dir.x, dir.z);
+    c->pitch = asinf(dir.y);
+    float fovX = fovDegrees * kPiOver180;
+    float fovY = fovX * (c->resolution[1] / c->resolution[0]);
+    c->tanHalfFov[0] = tanf(fovX * 0.5f); c->tanHalfFov[1] = tanf(fovY * 0.5f);
+    vpt_camera_update(c);
+}
+
+void vpt_perlin_noise_chunks(int chunksX, int chunksY, int chunksZ, unsigned seed, float *out)
+{
+    PerlinNoise gen(seed); // same seed for all chunks, 4 octaves (VoxelSceneGen.cu:358)
+    const float freq = 1.0f / (float)(chunksX * 32);
+    for (int c = 0; c < chunksX * chunksY * chunksZ; ++c)
+    {
+        const int chunkX = c % chunksX, chunkZ = (c / chunksX) % chunksZ;
+        float *noise = out + (size_t)c * 1024;
+        for (int x = 0; x < 32; ++x)
+            for (int z = 0; z < 32; ++z)
+            {
+                float gx = (float)(chunkX * 32 + x), gz = (float)(chunkZ * 32 + z);
+                noise[z * 32 + x] = gen.octave2D_01(gx * freq, gz * freq, 4);
+            }
+    }
+}
+
+void vpt_build_alias_table(const float *weights, unsigned n, VptAliasBin *bins)
+{
+    // thrust::reduce's order is unspecified in the reference; sum in double, round once
+    double acc = 0.0;
+    for (unsigned i = 0; i < n; ++i) acc += weights[i];
+    const float sum = (float)acc;
+    std::vector<float> prob(n), scaled(n);
+    std::vector<int> alias(n, -1);
+    for (unsigned i = 0; i < n; ++i) { float p = weights[i] / sum; prob[i] = p; scaled[i] = p * n; }
+    std::vector<int> smallQ, largeQ;
+    smallQ.reserve(n); largeQ.reserve(n);
+    size_t sh = 0, lh = 0;
+    for (unsigned i = 0; i < n; ++i) (scaled[i] < 1.0f ? smallQ : largeQ).push_back((int)i);
+    while (sh < smallQ.size() && lh < largeQ.size())
+    {
+        const int s = smallQ[sh++], l = largeQ[lh++];
+        alias[s] = l;
+        scaled[l] -= (1.0f - scaled[s]);
+        (scaled[l] < 1.0f ? smallQ : largeQ).push_back(l);
+    }
+    while (sh < smallQ.size()) scaled[smallQ[sh++]] = 1.0f;
+    while (lh < largeQ.size()) scaled[largeQ[lh++]] = 1.0f;
+    for (unsigned i = 0; i < n; ++i) { bins[i].p = prob[i]; bins[i].q = scaled[i]; bins[i].alias = alias[i]; }
+}
+
+void vpt_default_denoising_params(VptDenoisingParams *p)
+{
+    p->enableHitDistanceReconstruction = 0; p->enablePrePass = 0; p->enableTemporalAccumulation = 1; p->enableHistoryFix = 1;
+    p->enableHistoryClamping = 1; p->enableSpatialFiltering = 1; p->enableFireflyFilter = 1;
+    p->maxAccumulatedFrameNum = 30.0f; p->maxFastAccumulatedFrameNum = 6.0f;
+    p->phiLuminance = 2.0f; p->lobeAngleFraction = 0.5f; p->roughnessFraction = 0.15f; p->depthThreshold = 0.003f;
+    p->atrousIterationNum = 5;
+    p->disocclusionThreshold = 0.01f; p->disocclusionThresholdAlternate = 0.05f; p->denoisingRange = 500000.0f;
+}
+
+int vpt_load_denoising_settings(const char *yamlPath, VptDenoisingParams *p)
+{
+    std::ifstream file(yamlPath);
+    if (!file.is_open()) return VPT_ERR_IO;
+    std::string line, section;
+    while (std::getline(file, line))
+    {
+        line = trim(line);
+        if (line.empty() || line[0] == '#') continue;
+        if (line.back() == ':') { section = line.substr(0, line.size() - 1); continue; }
+        size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        const std::string key = trim(line.substr(0, colon)), value = trim(line.substr(colon + 1));
+        if (section != "denoising") continue;
+        if (key == "enableHitDistanceReconstruction") parseBool(value, p->enableHitDistanceReconstruction);
+        else if (key == "enablePrePass") parseBool(value, p->enablePrePass);
+        else if (key == "enableTemporalAccumulation") parseBool(value, p->enableTemporalAccumulation);
+        else if (key == "enableHistoryFix") parseBool(value, p->enableHistoryFix);
+        else if (key == "enableHistoryClamping") parseBool(value, p->enableHistoryClamping);
+        else if (key == "enableSpatialFiltering") parseBool(value, p->enableSpatialFiltering);
+        else if (key == "enableFireflyFilter") parseBool(value, p->enableFireflyFilter);
+        else if (key == "maxAccumulatedFrameNum") parseFloat(value, p->maxAccumulatedFrameNum);
+        else if (key == "maxFastAccumulatedFrameNum") parseFloat(value, p->maxFastAccumulatedFrameNum);
+        else if (key == "phiLuminance") parseFloat(value, p->phiLuminance);
+        else if (key == "lobeAngleFraction") parseFloat(value, p->lobeAngleFraction);
+        else if (key == "roughnessFraction") parseFloat(value, p->roughnessFraction);
+        else if (key == "depthThreshold") parseFloat(value, p->depthThreshold);
+        else if (key == "atrousIterationNum") { int v; if (parseInt(value, v)) p->atrousIterationNum = v; }
+        else if (key == "disocclusionThreshold") parseFloat(value, p->disocclusionThreshold);
+        else if (key == "disocclusionThresholdAlternate") parseFloat(value, p->disocclusionThresholdAlternate);
+        else if (key == "denoisingRange") parseFloat(value, p->denoisingRange);
+    }
+    return VPT_OK;
+}
+
+int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigned *chunks3)
+{
+    // CameraConfig defaults (SceneConfig.h:10-16)
+    float pos[3] = {20.0f, 15.0f, 20.0f}, dir[3] = {-1.0f, -0.3f, -1.0f}, up[3] = {0.0f, 1.0f, 0.0f};
+    *fov = 90.0f;
+    chunks3[0] = chunks3[1] = chunks3[2] = 0;
+    std::ifstream file(yamlPath);
+    const bool ok = file.is_open();
+    if (ok)
+    {
+        std::string line, section;
+        while (std::getline(file, line))
+        {
+            line = trim(line);
+            if (line.empty() || line[0] == '#') continue;
+            if (line.back() == ':') { section = line.substr(0, line.size() - 1); continue; }
+            size_t colon = line.find(':');
+            if (colon == std::string::npos) continue;
+            const std::string key = trim(line.substr(0, colon)), value = trim(line.substr(colon + 1));
+            if (section == "camera")
+            {
+                if (key == "position") parseFloat3(value, pos);
+                else if (key == "direction") parseFloat3(value, dir);
+                else if (key == "up") parseFloat3(value, up);
+                else if (key == "fov") parseFloat(value, *fov);
+            }
+            else if (section == "chunk_config")
+            {
+                try
+                {
+                    if (key == "chunksX") chunks3[0] = (unsigned)std::stoul(value);
+                    else if (key == "chunksY") chunks3[1] = (unsigned)std::stoul(value);
+                    else if (key == "chunksZ") chunks3[2] = (unsigned)std::stoul(value);
+                }
+                catch (const std::exception &) {}
+            }
+        }
+    }
+    V3 nd = normalize3({dir[0], dir[1], dir[2]});
+    out9[0] = pos[0]; out9[1] = pos[1]; out9[2] = pos[2];
+    out9[3] = nd.x; out9[4] = nd.y; out9[5] = nd.z;
+    out9[6] = up[0]; out9[7] = up[1]; out9[8] = up[2];
+    return ok ? VPT_OK : VPT_ERR_IO;
+}
+
+} // extern "C"

@@ -1,0 +1,137 @@
+"""-m gpu parity tests proper: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import common
+import vpt_scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs(oracle_lib):
+    import vpt
+    return vpt, oracle_lib
+
+
+def _pair(libs, w, h, inp, **tp):
+    vpt, O = libs
+    g = common.setup(vpt.Vpt(w, h), inp, **tp)
+    o = common.setup(O.Oracle(w, h), inp, **tp)
+    return g, o
+
+
+def test_terrain_ids_bit_exact(libs):
+    vpt, O = libs
+    for chunks in ((2, 1, 2), (4, 1, 4), (2, 2, 2)):
+        inp = common.scene_inputs(chunks)
+        g, o = _pair(libs, 64, 64, inp)
+        assert np.array_equal(g.get_grid(), o.get_grid()), chunks
+
+
+def test_cfg1_primary_hits_bit_exact_and_radiance(libs):
+    """Config 1: 256x256, 1 spp, 1 bounce, fixed seed. Primary (voxel, face) bit-exact; G-buffer exact; radiance within
+    mean relative error <= 1e-3 (north_star tolerance)."""
+    W = H = 256
+    inp = common.scene_inputs((2, 1, 2))
+    g, o = _pair(libs, W, H, inp, spp=1, total=1, diffuse=1)
+    cam = common.scene_camera(W, H)
+    g.render(cam, cam, 0)
+    o.render(cam, cam, 0)
+    hg, ho = g.read("PrimaryHits"), o.read("PrimaryHits")
+    assert np.array_equal(hg, ho), "primary hits differ at %d pixels" % int((hg != ho).any(-1).sum())
+    assert (ho[..., 3] >= 0).mean() > 0.3
+    for name in ("Depth", "Material", "NormalRoughness", "GeoNormalThinfilm", "MaterialParameter", "Albedo"):
+        assert np.array_equal(g.read(name), o.read(name)), name
+    ig, io = g.read("Illumination"), o.read("Illumination")
+    mean_rel, outliers, _ = common.rel_err_stats(ig[..., :3], io[..., :3])
+    assert mean_rel <= 1e-3, (mean_rel, outliers)
+    assert outliers <= 5e-3, (mean_rel, outliers)
+    assert g.counters()[0] == o.counters()[0] or abs(g.counters()[0] - o.counters()[0]) < 50
+
+
+def test_multiframe_restir_spp4_radiance(libs):
+    """4 spp, bounce limits 3/1, temporal ReSTIR across 3 frames with a moving camera."""
+    W, H = 320, 192
+    inp = common.scene_inputs((2, 1, 2))
+    g, o = _pair(libs, W, H, inp, spp=4, total=3, diffuse=1)
+    vpt, _ = libs
+    cam = common.scene_camera(W, H)
+    prev = cam
+    for f in range(3):
+        g.render(cam, prev, f)
+        o.render(cam, prev, f)
+        assert np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits")), f
+        mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert mean_rel <= 1e-3 and outliers <= 1e-2, (f, mean_rel, outliers)
+        rg, ro = g.read_reservoirs(f & 1), o.read_reservoirs(f & 1)
+        same = (rg["lightData"] == ro["lightData"]).mean()
+        assert same > 0.995, (f, same)
+        prev = cam
+        cam = vpt.camera_set_yaw_pitch(cam, cam[15] + np.float32(0.5 * np.pi / 180.0), cam[16])
+
+
+def test_furnace_constant_sky(libs):
+    """Oracle self-check (SURVEY 8c iii) applied to both: sky pixels of a constant sky return exactly that radiance."""
+    W = H = 128
+    inp = common.scene_inputs((2, 1, 2), constant_sky=1.0)
+    g, o = _pair(libs, W, H, inp, spp=1, total=3, diffuse=1)
+    cam = common.scene_camera(W, H)
+    g.render(cam, cam, 0)
+    o.render(cam, cam, 0)
+    ig, io = g.read("Illumination"), o.read("Illumination")
+    sky = g.read("PrimaryHits")[..., 3] < 0
+    assert sky.any()
+    assert np.allclose(ig[sky][:, :3], 1.0, atol=1e-6) and np.allclose(io[sky][:, :3], 1.0, atol=1e-6)
+    mean_rel, outliers, _ = common.rel_err_stats(ig[..., :3], io[..., :3])
+    assert mean_rel <= 1e-3
+
+
+def test_denoiser_chain_matches_oracle(libs):
+    """Full chain (firefly, temporal, history fix/clamp, a-trous x4, composite) over 4 frames, camera moving from frame 2."""
+    W, H = 256, 160
+    inp = common.scene_inputs((2, 1, 2))
+    g, o = _pair(libs, W, H, inp, spp=1, total=3, diffuse=1)
+    vpt, _ = libs
+    p = S.default_denoising_params()
+    cam = common.scene_camera(W, H)
+    prev = cam
+    for f in range(4):
+        g.render(cam, prev, f)
+        o.render(cam, prev, f)
+        # feed the oracle's noisy inputs to the GPU denoiser so this test isolates the denoiser (trace parity is tested above)
+        for name in ("Illumination",):
+            g.write(name, o.read(name))
+        g.write_reservoirs(f & 1, o.read_reservoirs(f & 1))
+        g.denoise(p, cam, prev, f, f + 1)
+        o.denoise(p, cam, prev, f, f + 1)
+        for name, tol in (("IlluminationOutput", 2e-4), ("PrevIllumination", 2e-4), ("PrevFastIllumination", 2e-4),
+                          ("HistoryLength", 2e-4), ("IlluminationPing", 2e-4), ("IlluminationPong", 2e-4)):
+            a, b = g.read(name), o.read(name)
+            mean_rel, outliers, dmax = common.rel_err_stats(a, b)
+            assert mean_rel <= tol and outliers <= 2e-3, (f, name, mean_rel, outliers, dmax)
+        prev = cam
+        if f >= 1:
+            cam = vpt.camera_set_yaw_pitch(cam, cam[15] + np.float32(0.5 * np.pi / 180.0), cam[16])
+
+
+def test_denoiser_external_cfg3_shape(libs):
+    """Config 3 input shape (synthetic G-buffer), small size: denoise_external == oracle, 3 frames."""
+    vpt, O = libs
+    W, H = 384, 216
+    g, o = vpt.Vpt(W, H), O.Oracle(W, H)
+    p = S.default_denoising_params()
+    cam = vpt.camera_init(W, H)
+    cam[6:9] = (0.0, 6.0, 0.0)
+    cam = vpt.camera_set_yaw_pitch(cam, 0.0, 0.0)
+    for f in range(3):
+        gb = S.synthetic_gbuffer(W, H, f)
+        out = g.denoise_external(p, cam, cam, f, f + 1, gb)
+        o.begin_external_frame()
+        for name in ("Illumination", "Depth", "NormalRoughness", "Material", "Albedo"):
+            o.write(name, gb[name])
+        o.denoise(p, cam, cam, f, f + 1)
+        ref = o.read("IlluminationOutput")
+        mean_rel, outliers, dmax = common.rel_err_stats(out, ref)
+        assert mean_rel <= 2e-4 and outliers <= 2e-3, (f, mean_rel, outliers, dmax)
+        assert np.isfinite(out).all()
