@@ -31,7 +31,7 @@ struct Hit { int hit, x, y, z, face, id; float t; int steps; };
 
 // ------------------------------------------------------------------------------------------------ DDA
 template <bool kSmemOcc>
-VPT_DEV Hit ddaTrace(const GridView &g, const uint32_t *__restrict__ occ, f3 o, f3 d, float tmin, float tmax)
+__device__ __noinline__ Hit ddaTrace(const GridView &g, const uint32_t *__restrict__ occ, f3 o, f3 d, float tmin, float tmax)
 {
     Hit h;
     h.hit = 0; h.x = h.y = h.z = 0; h.face = 6; h.id = 0; h.t = kRayMax; h.steps = 0;
@@ -54,13 +54,13 @@ VPT_DEV Hit ddaTrace(const GridView &g, const uint32_t *__restrict__ occ, f3 o, 
                 if (oo[a] < 0.0f || oo[a] >= dim[a]) return h;
                 continue;
             }
-            float ta = (0.0f - oo[a]) / dd[a], tb = (dim[a] - oo[a]) / dd[a];
+            float ta = ex::divf(ex::subf(0.0f, oo[a]), dd[a]), tb = ex::divf(ex::subf(dim[a], oo[a]), dd[a]);
             float tn = fminr(ta, tb), tf = fmaxr(ta, tb);
             if (tn > tEnter) { tEnter = tn; axis = a; }
             if (tf < tExit) tExit = tf;
         }
         if (axis < 0 || tEnter > tExit || tExit < 0.0f || tEnter < 0.0f) return h;
-        f3 p = o + d * tEnter;
+        f3 p = ex::pointAt(o, d, tEnter);
         x = clampi((int)floorf(p.x), 0, W - 1);
         y = clampi((int)floorf(p.y), 0, H - 1);
         z = clampi((int)floorf(p.z), 0, D - 1);
@@ -72,15 +72,15 @@ VPT_DEV Hit ddaTrace(const GridView &g, const uint32_t *__restrict__ occ, f3 o, 
     }
 
     const int stepX = (d.x > 0.0f) ? 1 : -1, stepY = (d.y > 0.0f) ? 1 : -1, stepZ = (d.z > 0.0f) ? 1 : -1;
-    const float tDeltaX = (fabsf(d.x) < 1e-8f) ? FLT_MAX : (1.0f / fabsf(d.x));
-    const float tDeltaY = (fabsf(d.y) < 1e-8f) ? FLT_MAX : (1.0f / fabsf(d.y));
-    const float tDeltaZ = (fabsf(d.z) < 1e-8f) ? FLT_MAX : (1.0f / fabsf(d.z));
+    const float tDeltaX = (fabsf(d.x) < 1e-8f) ? FLT_MAX : ex::divf(1.0f, fabsf(d.x));
+    const float tDeltaY = (fabsf(d.y) < 1e-8f) ? FLT_MAX : ex::divf(1.0f, fabsf(d.y));
+    const float tDeltaZ = (fabsf(d.z) < 1e-8f) ? FLT_MAX : ex::divf(1.0f, fabsf(d.z));
     const float nbX = (stepX > 0) ? (float)(x + 1) : (float)x;
     const float nbY = (stepY > 0) ? (float)(y + 1) : (float)y;
     const float nbZ = (stepZ > 0) ? (float)(z + 1) : (float)z;
-    float tMaxX = (fabsf(d.x) < 1e-8f) ? FLT_MAX : (nbX - o.x) / d.x;
-    float tMaxY = (fabsf(d.y) < 1e-8f) ? FLT_MAX : (nbY - o.y) / d.y;
-    float tMaxZ = (fabsf(d.z) < 1e-8f) ? FLT_MAX : (nbZ - o.z) / d.z;
+    float tMaxX = (fabsf(d.x) < 1e-8f) ? FLT_MAX : ex::divf(ex::subf(nbX, o.x), d.x);
+    float tMaxY = (fabsf(d.y) < 1e-8f) ? FLT_MAX : ex::divf(ex::subf(nbY, o.y), d.y);
+    float tMaxZ = (fabsf(d.z) < 1e-8f) ? FLT_MAX : ex::divf(ex::subf(nbZ, o.z), d.z);
 
     const int wordsX = g.wordsX;
     const int maxIter = W + H + D + 4;
@@ -105,13 +105,13 @@ VPT_DEV Hit ddaTrace(const GridView &g, const uint32_t *__restrict__ occ, f3 o, 
         ++steps;
         if (tMaxX < tMaxY)
         {
-            if (tMaxX < tMaxZ) { x += stepX; tCur = tMaxX; tMaxX += tDeltaX; hitAxis = 0; }
-            else               { z += stepZ; tCur = tMaxZ; tMaxZ += tDeltaZ; hitAxis = 2; }
+            if (tMaxX < tMaxZ) { x += stepX; tCur = tMaxX; tMaxX = ex::addf(tMaxX, tDeltaX); hitAxis = 0; }
+            else               { z += stepZ; tCur = tMaxZ; tMaxZ = ex::addf(tMaxZ, tDeltaZ); hitAxis = 2; }
         }
         else
         {
-            if (tMaxY < tMaxZ) { y += stepY; tCur = tMaxY; tMaxY += tDeltaY; hitAxis = 1; }
-            else               { z += stepZ; tCur = tMaxZ; tMaxZ += tDeltaZ; hitAxis = 2; }
+            if (tMaxY < tMaxZ) { y += stepY; tCur = tMaxY; tMaxY = ex::addf(tMaxY, tDeltaY); hitAxis = 1; }
+            else               { z += stepZ; tCur = tMaxZ; tMaxZ = ex::addf(tMaxZ, tDeltaZ); hitAxis = 2; }
         }
     }
     h.steps = steps;
@@ -139,7 +139,7 @@ VPT_DEV f3 faceNormal(int face, f3 rayDir)
 }
 VPT_DEV f3 hitPoint(const Hit &h, f3 o, f3 d)
 {
-    f3 p = o + d * h.t;
+    f3 p = ex::pointAt(o, d, h.t);
     switch (h.face)
     {
     case 0: p.y = (float)(h.y + 1); break;
@@ -266,7 +266,9 @@ __device__ __noinline__ void disneySample(f4 u, f3 n, f3 ng, f3 wo, f3 albedo, b
         cosTheta = clampf(cosTheta, kSafeCosEps, 1.0f);
         float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
         float phi = kTwoPi * u.y;
-        f3 wh = {sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta};
+        float sphi, cphi;
+        sincosFast(phi, sphi, cphi);
+        f3 wh = {sinTheta * cphi, sinTheta * sphi, cosTheta};
         alignVector(n, wh);
         wi = normalize(reflect3(-wo, wh));
         if (dot(wi, n) <= 0.0f || dot(wi, ng) <= 0.0f) { bsdfOverPdf = F3(0.0f); pdf = 0.0f; return; }
@@ -290,7 +292,9 @@ __device__ __noinline__ void disneySample(f4 u, f3 n, f3 ng, f3 wo, f3 albedo, b
         float cosTheta = sqrtf(u.x);
         float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
         float phi = kTwoPi * u.y;
-        wi = {sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta};
+        float sphi, cphi;
+        sincosFast(phi, sphi, cphi);
+        wi = {sinTheta * cphi, sinTheta * sphi, cosTheta};
         alignVector(n, wi);
         if (dot(wi, ng) <= 0.0f) { bsdfOverPdf = F3(0.0f); pdf = 0.0f; return; }
         float cosWi = fmaxf(kSafeCosEps, dot(wi, n));
@@ -401,7 +405,7 @@ struct Tracer
         pmf = __ldg(&bins[alias].p);
         return (unsigned)alias;
     }
-    VPT_DEV LightSample createSunLightSample(int idx) const
+    __device__ __noinline__ LightSample createSunLightSample(int idx) const
     {
         int ix = idx % a.sunW, iy = idx / a.sunW;
         f2 uv = {(ix + 0.5f) / float(a.sunW), (iy + 0.5f) / float(a.sunH)};
@@ -412,7 +416,7 @@ struct Tracer
         ls.lightType = LightSun;
         return ls;
     }
-    VPT_DEV LightSample createSkyLightSample(int idx) const
+    __device__ __noinline__ LightSample createSkyLightSample(int idx) const
     {
         int ix = idx % a.skyW, iy = idx / a.skyW;
         f2 uv = {(ix + 0.5f) / float(a.skyW), (iy + 0.5f) / float(a.skyH)};
@@ -423,34 +427,39 @@ struct Tracer
         ls.lightType = LightSky;
         return ls;
     }
-    VPT_DEV float surfaceBrdfPdf(const Surface &s, f3 wi) const
+    // GetLightSampleTargetPdfForSurface (Restir.h:194-211) and LightBrdfMisWeight (Restir.h:286-328, brdfCutoff == 0)
+    // evaluate the same Disney BSDF for the same direction; evalCandidate evaluates it once and returns both:
+    // the RIS target pdf and (optionally) the MIS-blended source pdf.
+    __device__ __noinline__ float evalCandidate(const Surface &s, const LightSample &ls, float lightSelectionPdf, float lightMisWeight,
+                                                float brdfMisWeight, float *blendedSourcePdf) const
     {
+        const bool invalid = ls.solidAnglePdf <= 0 || ls.lightType == LightInvalid;
+        const float lpdf = ls.solidAnglePdf;
+        const bool plainMis = (brdfMisWeight == 0.0f || lpdf <= 0.0f || isinf(lpdf) || isnan(lpdf));
+        if (invalid && (plainMis || !blendedSourcePdf))
+        {
+            if (blendedSourcePdf) *blendedSourcePdf = lightMisWeight * lightSelectionPdf;
+            return 0.0f;
+        }
+        const f3 wi = (ls.lightType == LightLocalTriangle) ? normalize(ls.position - s.pos) : ls.position;
         f3 f; float pdf;
         disneyEvaluate(s.normal, s.geoNormal, wi, s.wo, s.albedo, s.metallic, s.roughness, f, pdf);
-        return pdf;
-    }
-    VPT_DEV float targetPdfForSurface(const LightSample &ls, const Surface &s) const
-    {
-        if (ls.solidAnglePdf <= 0 || ls.lightType == LightInvalid) return 0.0f;
-        f3 wi = (ls.lightType == LightLocalTriangle) ? normalize(ls.position - s.pos) : ls.position;
-        f3 f; float pdf;
-        disneyEvaluate(s.normal, s.geoNormal, wi, s.wo, s.albedo, s.metallic, s.roughness, f, pdf);
-        f3 refl = ls.radiance * f * fabsf(dot(wi, s.normal)) / ls.solidAnglePdf;
+        if (blendedSourcePdf)
+        {
+            if (plainMis) *blendedSourcePdf = lightMisWeight * lightSelectionPdf;
+            else
+            {
+                const float sourcePdfWrtSolidAngle = lightSelectionPdf * lpdf;
+                const float blended = lightMisWeight * sourcePdfWrtSolidAngle + brdfMisWeight * pdf;
+                *blendedSourcePdf = blended / lpdf;
+            }
+        }
+        if (invalid) return 0.0f;
+        const f3 refl = ls.radiance * f * fabsf(dot(wi, s.normal)) / ls.solidAnglePdf;
         return luminance(refl);
     }
-    VPT_DEV float lightBrdfMisWeight(const Surface &s, const LightSample &ls, float lightSelectionPdf, float lightMisWeight, float brdfMisWeight) const
-    {
-        float lpdf = ls.solidAnglePdf;
-        if (brdfMisWeight == 0.0f || lpdf <= 0.0f || isinf(lpdf) || isnan(lpdf)) return lightMisWeight * lightSelectionPdf;
-        f3 lightDir;
-        if (ls.lightType == LightSky || ls.lightType == LightSun) lightDir = ls.position;
-        else { f3 toLight = ls.position - s.pos; float dist = length(toLight); lightDir = toLight / dist; }
-        float brdfPdf = surfaceBrdfPdf(s, lightDir);
-        float sourcePdfWrtSolidAngle = lightSelectionPdf * lpdf;
-        float blended = lightMisWeight * sourcePdfWrtSolidAngle + brdfMisWeight * brdfPdf;
-        return blended / lpdf;
-    }
-    VPT_DEV bool lightSampleFromReservoir(LightSample &ls, const VptReservoir &r) const
+    VPT_DEV float targetPdfForSurface(const LightSample &ls, const Surface &s) const { return evalCandidate(s, ls, 0.0f, 0.0f, 0.0f, nullptr); }
+    __device__ __noinline__ bool lightSampleFromReservoir(LightSample &ls, const VptReservoir &r) const
     {
         uint32_t li = r.lightData & kLightIndexMask;
         f2 uv = {float(r.uvData & 0xffff) / float(0xffff), float(r.uvData >> 16) / float(0xffff)};
@@ -466,7 +475,7 @@ struct Tracer
         }
         return li < kInvalidLight;
     }
-    VPT_DEV bool getPrevSurface(Surface &s, int x, int y) const
+    __device__ __noinline__ bool getPrevSurface(Surface &s, int x, int y) const
     {
         const VptCamera &pc = a.prevCam;
         if (x < 0 || y < 0 || x >= pc.resolution[0] || y >= pc.resolution[1]) return false;
@@ -540,7 +549,7 @@ VPT_DEV VptReservoir loadReservoir(const VptReservoir *src)
 
 // ------------------------------------------------------------------------------------------------ miss
 template <bool kSmemOcc>
-VPT_DEV void missRadiance(Tracer<kSmemOcc> &c, RayData &rd, bool ownsGBuffer)
+__device__ __noinline__ void missRadiance(Tracer<kSmemOcc> &c, RayData &rd, bool ownsGBuffer)
 {
     const TraceArgs &a = c.a;
     const size_t pix = (size_t)c.py * a.width + c.px;
@@ -699,8 +708,8 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
         LightSample cand = c.createSunLightSample(idx);
         int ix = idx % a.sunW, iy = idx / a.sunW;
         f2 uv = {(ix + 0.5f) / float(a.sunW), (iy + 0.5f) / float(a.sunH)};
-        float blended = c.lightBrdfMisWeight(s, cand, sourcePdf, sunMisW, brdfMisW);
-        float targetPdf = c.targetPdfForSurface(cand, s);
+        float blended;
+        float targetPdf = c.evalCandidate(s, cand, sourcePdf, sunMisW, brdfMisW, &blended);
         float risRnd = c.rnd();
         if (streamSample(sunRes, kSunLight, uv, risRnd, targetPdf, 1.0f / blended)) sunSample = cand;
     }
@@ -716,8 +725,8 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
         LightSample cand = c.createSkyLightSample(idx);
         int ix = idx % a.skyW, iy = idx / a.skyW;
         f2 uv = {(ix + 0.5f) / float(a.skyW), (iy + 0.5f) / float(a.skyH)};
-        float blended = c.lightBrdfMisWeight(s, cand, sourcePdf, skyMisW, brdfMisW);
-        float targetPdf = c.targetPdfForSurface(cand, s);
+        float blended;
+        float targetPdf = c.evalCandidate(s, cand, sourcePdf, skyMisW, brdfMisW, &blended);
         float risRnd = c.rnd();
         if (streamSample(skyRes, kSkyLight, uv, risRnd, targetPdf, 1.0f / blended)) skySample = cand;
     }
@@ -766,9 +775,9 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
             }
         }
         if (lightSourcePdf == 0.0f) continue;
-        float targetPdf = c.targetPdfForSurface(cand, s);
         float misW = (lightIndex == kSkyLight) ? skyMisW : ((lightIndex == kSunLight) ? sunMisW : localMisW);
-        float blended = c.lightBrdfMisWeight(s, cand, lightSourcePdf, misW, brdfMisW);
+        float blended;
+        float targetPdf = c.evalCandidate(s, cand, lightSourcePdf, misW, brdfMisW, &blended);
         float risRnd = c.rnd();
         if (streamSample(brdfRes, lightIndex, uv, risRnd, targetPdf, 1.0f / blended)) brdfSample = cand;
     }
@@ -900,9 +909,10 @@ VPT_DEV f3 tracePath(Tracer<kSmemOcc> &c, bool ownsGBuffer, float &primaryDist)
     RayData rd;
     c.randIdx = 0;
     f2 jitter = c.rnd2();
-    f2 sampleUv = {(float(c.px) + jitter.x) * a.cam.inversedResolution[0], (float(c.py) + jitter.y) * a.cam.inversedResolution[1]};
+    // exact arithmetic up to the primary hit (bit-exact voxel/face vs the oracle)
+    f2 sampleUv = {ex::mulf(ex::addf(float(c.px), jitter.x), a.cam.inversedResolution[0]), ex::mulf(ex::addf(float(c.py), jitter.y), a.cam.inversedResolution[1])};
     rd.pos = F3(a.cam.pos[0], a.cam.pos[1], a.cam.pos[2]);
-    rd.wi = c.uvToWorldDirection(a.cam, sampleUv);
+    rd.wi = ex::normalize(ex::mulMat3(a.cam.uvToWorld, F3(sampleUv.x, sampleUv.y, 1.0f)));
     f3 radiance = F3(0.0f), throughput = F3(1.0f);
     rd.depth = 0;
     rd.isCurrentBounceDiffuse = false;
