@@ -171,7 +171,7 @@ int vpt_set_tables(vpt_ctx *c, const uint8_t *sobol, const uint8_t *scrambling, 
 static int allocGrid(vpt_ctx *c, int cx, int cy, int cz)
 {
     if (cx <= 0 || cy <= 0 || cz <= 0) return fail(VPT_ERR_ARG, "grid: chunk counts must be positive");
-    if ((size_t)cx * cy * cz * 32768 > ((size_t)1 << 31)) return fail(VPT_ERR_ARG, "grid: more than 2^31 voxels");
+    if (cx > 32 || cz > 32 || cy > 16) return fail(VPT_ERR_ARG, "grid: at most 32 x 16 x 32 chunks (1024 x 512 x 1024 voxels)");
     if (c->cx != cx || c->cy != cy || c->cz != cz)
     {
         if (c->idsChunk) cudaFree(c->idsChunk);
@@ -293,7 +293,7 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     a.grid.wordsX = c->cx; a.grid.occWords = c->cx * (c->cy * 32) * (c->cz * 32);
     a.grid.occ = c->occ; a.grid.idsLinear = c->idsLinear;
     // two CTAs per SM must fit next to each other (plus 1 KiB/CTA reserved by the runtime)
-    a.occInSmem = ((size_t)a.grid.occWords * 4 * 2 + 2048 <= (size_t)c->smemOptIn + 1024) && ((size_t)a.grid.occWords * 4 <= 100 * 1024) ? 1 : 0;
+    a.occInSmem = ((size_t)a.grid.occWords * 4 <= 72 * 1024) ? 1 : 0; // up to 3 CTAs/SM x (mask + 1 KiB reserved) within 228 KiB
     a.sobol = c->sobol; a.scrambling = c->scrambling; a.ranking = c->ranking;
     a.materials = c->materials; a.blockToMaterial = c->blockToMaterial;
     a.sky = c->sky; a.sun = c->sun; a.skyAlias = c->skyAlias; a.sunAlias = c->sunAlias;

@@ -9,7 +9,7 @@
 //  * Grid residency: the 1-bit/voxel occupancy mask (64 KiB for the 16-chunk world) is staged whole in
 //    shared memory once per CTA; a DDA step is one LDS + bit test, the 1-byte block id is fetched from
 //    L2 only on a hit. Worlds whose mask exceeds shared memory walk the mask through L1/L2 instead.
-//  * Scheduling: persistent CTAs (2 per SM), each warp claims 8x4-pixel tiles from a global atomic
+//  * Scheduling: persistent CTAs (2 x 512 threads per SM = 32 warps at 64 registers), each warp claims 8x4-pixel tiles from a global atomic
 //    counter (warp-granular dynamic load balance, no CTA barrier in the loop). A warp's lanes are an
 //    8x4 pixel block so primary rays stay coherent and every G-buffer float4 row store is a full 128-byte line.
 //  * Shading: Disney BSDF (Bsdf.h:371-617), RIS over sun / sky / BSDF candidates and temporal ReSTIR with
@@ -82,39 +82,61 @@ __device__ __noinline__ Hit ddaTrace(const GridView &g, const uint32_t *__restri
     float tMaxY = (fabsf(d.y) < 1e-8f) ? FLT_MAX : ex::divf(ex::subf(nbY, o.y), d.y);
     float tMaxZ = (fabsf(d.z) < 1e-8f) ? FLT_MAX : ex::divf(ex::subf(nbZ, o.z), d.z);
 
-    const int wordsX = g.wordsX;
-    const int maxIter = W + H + D + 4;
-    int steps = 0;
-    for (int it = 0; it < maxIter; ++it)
+    // Walk. Same decisions as the reference loop (bounds test, solid test, tMaxX<tMaxY / <tMaxZ selection with its
+    // tie order, tMax += tDelta) in a branch-light form:
+    //  * the cell is a linear voxel index: word = lin>>5, bit = lin&31 (W is a multiple of 32);
+    //  * "if X<Y then (X<Z ? X : Z) else (Y<Z ? Y : Z)" == "A = X<Y ? X : Y; A<Z ? A : Z" (two compares);
+    //  * the bounds test is a packed count of steps left inside the grid per axis (11-bit fields + guard bits:
+    //    a borrow out of a field clears its guard), so leaving the grid costs one subtract and one test;
+    //  * only the selected axis' tMax is advanced, by an exact __fadd_rn.
+    int lin = (y * D + z) * W + x;
+    const int dLinX = stepX, dLinY = stepY * W * D, dLinZ = stepZ * W;
+    const uint32_t remX = (uint32_t)(stepX > 0 ? W - 1 - x : x), remY = (uint32_t)(stepY > 0 ? H - 1 - y : y),
+                   remZ = (uint32_t)(stepZ > 0 ? D - 1 - z : z);
+    // fields: X bits 0-9 (guard 10), Z bits 11-20 (guard 21), Y bits 22-30 (guard 31): W,D <= 1024, H <= 512 (checked by vpt_set_grid)
+    constexpr uint32_t kGuards = (1u << 10) | (1u << 21) | (1u << 31);
+    constexpr uint32_t kDecX = 1u, kDecZ = 1u << 11, kDecY = 1u << 22;
+    const uint32_t rem0 = kGuards | remX | (remZ << 11) | (remY << 22);
+    uint32_t rem = rem0, lastDec = 0;
+    uint32_t occShared = 0;
+    if (kSmemOcc) occShared = (uint32_t)__cvta_generic_to_shared(occ);
+    bool found = false, left = false;
+    for (;;)
     {
-        if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H || (unsigned)z >= (unsigned)D) break;
         if (tCur >= tmax) break;
-        const int wi = (y * D + z) * wordsX + (x >> 5);
-        const uint32_t word = kSmemOcc ? occ[wi] : __ldg(occ + wi);
-        if (((word >> (x & 31)) & 1u) && tCur >= tmin)
-        {
-            h.hit = 1; h.x = x; h.y = y; h.z = z; h.t = tCur;
-            h.id = __ldg(g.idsLinear + ((size_t)(y * D + z) * W + x));
-            if (hitAxis == 0) h.face = stepX > 0 ? 2 : 3;
-            else if (hitAxis == 1) h.face = stepY > 0 ? 1 : 0;
-            else if (hitAxis == 2) h.face = stepZ > 0 ? 5 : 4;
-            else h.face = 6;
-            h.steps = steps;
-            return h;
-        }
-        ++steps;
-        if (tMaxX < tMaxY)
-        {
-            if (tMaxX < tMaxZ) { x += stepX; tCur = tMaxX; tMaxX = ex::addf(tMaxX, tDeltaX); hitAxis = 0; }
-            else               { z += stepZ; tCur = tMaxZ; tMaxZ = ex::addf(tMaxZ, tDeltaZ); hitAxis = 2; }
-        }
-        else
-        {
-            if (tMaxY < tMaxZ) { y += stepY; tCur = tMaxY; tMaxY = ex::addf(tMaxY, tDeltaY); hitAxis = 1; }
-            else               { z += stepZ; tCur = tMaxZ; tMaxZ = ex::addf(tMaxZ, tDeltaZ); hitAxis = 2; }
-        }
+        uint32_t word;
+        if (kSmemOcc) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(occShared + (((uint32_t)lin >> 3) & ~3u)));
+        else word = __ldg(occ + (lin >> 5));
+        if (((word >> (lin & 31)) & 1u) && tCur >= tmin) { found = true; break; }
+        const bool xy = tMaxX < tMaxY;
+        const float tA = xy ? tMaxX : tMaxY;
+        const bool az = tA < tMaxZ;
+        const uint32_t dec = az ? (xy ? kDecX : kDecY) : kDecZ;
+        rem -= dec;
+        lastDec = dec;
+        if ((rem & kGuards) != kGuards) { left = true; break; } // this step leaves the grid
+        tCur = az ? tA : tMaxZ;
+        if (az && xy) tMaxX = ex::addf(tMaxX, tDeltaX);
+        if (az && !xy) tMaxY = ex::addf(tMaxY, tDeltaY);
+        if (!az) tMaxZ = ex::addf(tMaxZ, tDeltaZ);
+        lin += az ? (xy ? dLinX : dLinY) : dLinZ;
     }
-    h.steps = steps;
+    if (lastDec == kDecX) hitAxis = 0; else if (lastDec == kDecY) hitAxis = 1; else if (lastDec == kDecZ) hitAxis = 2;
+    {
+        // steps walked (statistics): initial minus remaining counts; the step that left the grid counts too
+        const uint32_t r = left ? rem + lastDec : rem;
+        h.steps = (int)((remX - (r & 1023u)) + (remZ - ((r >> 11) & 1023u)) + (remY - ((r >> 22) & 511u))) + (left ? 1 : 0);
+    }
+    if (found)
+    {
+        h.hit = 1; h.t = tCur;
+        h.x = lin % W; const int yz = lin / W; h.z = yz % D; h.y = yz / D;
+        h.id = __ldg(g.idsLinear + lin);
+        if (hitAxis == 0) h.face = stepX > 0 ? 2 : 3;
+        else if (hitAxis == 1) h.face = stepY > 0 ? 1 : 0;
+        else if (hitAxis == 2) h.face = stepZ > 0 ? 5 : 4;
+        else h.face = 6;
+    }
     return h;
 }
 
@@ -733,6 +755,14 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
     finalizeResampling(skyRes, 1.0f, (float)nMis);
     skyRes.M = 1;
 
+    // Shadow rays from frontPos over an unbounded range depend only on the direction: the reference re-traces the
+    // BSDF-sampled direction when RIS selects it (closesthit.cu:616) and re-traces the initial sample for the final
+    // visibility when temporal resampling keeps it (:801). Identical (origin, direction) -> identical result, so the
+    // result is reused instead of walking the grid again (rays are counted only when actually traced).
+    f3 visDir0 = F3(0.0f), visDir1 = F3(0.0f);
+    bool visRes0 = false, visRes1 = false, visHave0 = false, visHave1 = false;
+    auto sameDir = [](f3 a, f3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; };
+
     VptReservoir brdfRes = emptyReservoir();
     LightSample brdfSample = noLight();
     for (int i = 0; i < nBrdf; ++i)
@@ -747,6 +777,7 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
         if (brdfPdf > 0.0f)
         {
             Hit sh = c.trace(frontPos, sampleDir, 0.0f, FLT_MAX);
+            visDir0 = sampleDir; visRes0 = !sh.hit; visHave0 = true;
             if (!sh.hit)
             {
                 if (equalAreaMapConeInv(uv, sunD, sampleDir, a.sunCosThetaMax))
@@ -798,8 +829,13 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
     bool isLightVisible = false;
     if (lightSample.lightType != LightInvalid && isValidReservoir(ris))
     {
-        Hit vh = c.trace(frontPos, lightSample.position, 0.0f, kRayMax);
-        isLightVisible = !vh.hit;
+        if (visHave0 && sameDir(visDir0, lightSample.position)) isLightVisible = visRes0;
+        else
+        {
+            Hit vh = c.trace(frontPos, lightSample.position, 0.0f, kRayMax);
+            isLightVisible = !vh.hit;
+        }
+        visDir1 = lightSample.position; visRes1 = isLightVisible; visHave1 = true;
         if (!isLightVisible) { ris.lightData = 0; ris.weightSum = 0; }
     }
 
@@ -881,8 +917,13 @@ __device__ __noinline__ void closestHit(Tracer<kSmemOcc> &c, RayData &rd, const 
         }
         if (lightSample.lightType != LightInvalid)
         {
-            Hit vh = c.trace(frontPos, lightSample.position, 0.0f, kRayMax);
-            isLightVisible = !vh.hit;
+            if (visHave1 && sameDir(visDir1, lightSample.position)) isLightVisible = visRes1;
+            else if (visHave0 && sameDir(visDir0, lightSample.position)) isLightVisible = visRes0;
+            else
+            {
+                Hit vh = c.trace(frontPos, lightSample.position, 0.0f, kRayMax);
+                isLightVisible = !vh.hit;
+            }
             if (!isLightVisible) { restir.lightData = 0; restir.weightSum = 0; }
         }
     }
@@ -945,10 +986,16 @@ VPT_DEV f3 tracePath(Tracer<kSmemOcc> &c, bool ownsGBuffer, float &primaryDist)
     return radiance;
 }
 
-constexpr int kTraceThreads = 256;
+#ifndef VPT_TRACE_THREADS
+#define VPT_TRACE_THREADS 512
+#endif
+constexpr int kTraceThreads = VPT_TRACE_THREADS;
+#ifndef VPT_TRACE_CTAS_PER_SM
+#define VPT_TRACE_CTAS_PER_SM 2
+#endif
 
 template <bool kSmemOcc>
-__global__ void __launch_bounds__(kTraceThreads, 2) traceKernel(const __grid_constant__ TraceArgs a)
+__global__ void __launch_bounds__(kTraceThreads, VPT_TRACE_CTAS_PER_SM) traceKernel(const __grid_constant__ TraceArgs a)
 {
     extern __shared__ uint32_t occS[];
     const uint32_t *occ = a.grid.occ;
@@ -1021,7 +1068,7 @@ cudaError_t launchTrace(const TraceArgs &a, cudaStream_t s, int smCount, size_t 
 {
     const size_t occBytes = (size_t)a.grid.occWords * 4;
     const bool smem = a.occInSmem != 0;
-    const int grid = smCount * 2;
+    const int grid = smCount * VPT_TRACE_CTAS_PER_SM;
     if (smem)
     {
         if (occBytes > smemOptIn) return cudaErrorInvalidValue;

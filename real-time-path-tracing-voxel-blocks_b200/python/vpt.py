@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvpt.so")
+LIB_PATH = os.environ.get("VPT_LIB") or os.path.join(os.path.dirname(_HERE), "libvpt.so")  # VPT_LIB: A/B builds while tuning
 _LIB = None
 
 BUF = dict(
