@@ -142,6 +142,7 @@ def main():
     import common
     import vpt
     import vpt_scenes as S
+    import vpt_shard
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,9 +175,7 @@ def main():
             g.render(cam, cam, f)
             g.denoise(p, cam, cam, f, f + 1)
         else:
-            g.render_shard(cam, cam, f, rank, world)
-            g.comm_allreduce_illumination()
-            g.resolve()
+            vpt_shard.render_sharded(g, cam, cam, f, rank, world, lambda c: c.comm_allreduce_illumination())
             if rank == 0:
                 g.denoise(p, cam, cam, f, f + 1)
         if read_back and rank == 0:

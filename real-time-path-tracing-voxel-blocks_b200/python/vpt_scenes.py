@@ -150,8 +150,9 @@ def synthetic_gbuffer(width, height, frame, cam_pos=(0.0, 6.0, 0.0)):
     hit = tg < t_best
     t_best = np.where(hit, tg, t_best)
     normal[hit] = (0.0, 1.0, 0.0)
-    px = ox + dx * tg
-    pz = oz + dz * tg
+    tgf = np.where(np.isfinite(tg), tg, 0.0)
+    px = ox + dx * tgf
+    pz = oz + dz * tgf
     checker = ((np.floor(px / 4.0) + np.floor(pz / 4.0)) % 2 == 0)
     mat = np.where(hit, np.where(checker, 1.0, 2.0), mat)
     # two axis-aligned boxes

@@ -1,0 +1,35 @@
+"""Host-side sharding logic of the multi-GPU paths. Pure Python so the CPU test-suite can exercise it
+with gloo and the oracle as the compute stand-in; the GPU path uses the same functions with libvpt + NCCL.
+
+  * spp sharding: rank r of n renders sample indices {k : k mod n == r} of all pixels (vpt_render_shard(begin=r, step=n)),
+    the un-normalised fp32 sums are all-reduced (sum) and every rank divides by the total spp (vpt_resolve).
+    The G-buffer, depth and the ReSTIR reservoir belong to sample 0, i.e. to rank 0.
+  * row bands: rank r owns rows [b[r], b[r+1]) with every boundary a multiple of 4 (FireflyBoilingFilter's 8x4 tile
+    statistics must not straddle ranks, FireflyFilter.h:51-65)."""
+
+
+def sample_shard(rank, nranks):
+    """(sample_begin, sample_step) for vpt_render_shard."""
+    if not (0 <= rank < nranks):
+        raise ValueError("rank out of range")
+    return rank, nranks
+
+
+def samples_of(rank, nranks, spp):
+    return list(range(rank, spp, nranks))
+
+
+def row_bands(height, nranks):
+    """nranks+1 row boundaries, multiples of 4 (the last one is `height`)."""
+    if nranks < 1 or height < 4 * nranks:
+        raise ValueError("need at least 4 rows per rank")
+    b = [(height * r // nranks) // 4 * 4 for r in range(nranks)] + [height]
+    return b
+
+
+def render_sharded(ctx, cam, prev_cam, iteration_index, rank, nranks, allreduce_sum):
+    """One spp-sharded frame: ctx is a vpt.Vpt or an oracle.Oracle; allreduce_sum(ctx) sums Illumination over ranks."""
+    begin, step = sample_shard(rank, nranks)
+    ctx.render_shard(cam, prev_cam, iteration_index, begin, step)
+    allreduce_sum(ctx)
+    ctx.resolve()

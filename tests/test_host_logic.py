@@ -1,0 +1,167 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/vpt.h declares (no compute calls
+without a GPU), the loaders mirror the reference parsers, host helpers agree with the oracle, failure is loud without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import vpt_scenes as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SETTINGS_YAML = """# Global Settings Configuration File
+# Generated automatically
+
+denoising:
+  enableHitDistanceReconstruction: false
+  enablePrePass: false
+  enableTemporalAccumulation: true
+  enableHistoryFix: yes
+  enableHistoryClamping: on
+  enableSpatialFiltering: 1
+  enableFireflyFilter: TRUE
+  maxAccumulatedFrameNum: 30
+  maxFastAccumulatedFrameNum: 6
+  phiLuminance: 2
+  lobeAngleFraction: 0.5
+  roughnessFraction: 0.15
+  depthThreshold: 0.003
+  atrousIterationNum: 1
+  disocclusionThreshold: 0.01
+  disocclusionThresholdAlternate: 0.05
+  denoisingRange: 500000
+
+postprocess:
+  manualExposure: 0.8
+  enableBloom: true
+sky:
+  timeOfDay: 0.25
+"""
+
+SCENE_YAML = """# Scene Configuration File
+camera:
+  position: [35.6184, 11.8733, 42.0387]
+  direction: [-0.321564, -0.0129988, -0.946799]
+  up: [0, 1, 0]
+  fov: 90
+
+character:
+  position: [32.0, 10.0, 38.0]
+
+chunk_config:
+  chunksX: 4
+  chunksY: 1
+  chunksZ: 4
+"""
+
+
+def test_library_exports_every_declared_symbol():
+    import vpt
+    L = vpt.lib()
+    header = open(os.path.join(ROOT, "include", "vpt.h")).read()
+    declared = set(re.findall(r"\b(vpt_[a-z0-9_]+)\s*\(", header))
+    declared.discard("vpt_ctx")
+    assert declared == set(vpt.EXPORTS), declared ^ set(vpt.EXPORTS)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+
+
+def test_pod_layouts_match_the_header():
+    import oracle
+    header = open(os.path.join(ROOT, "include", "vpt.h")).read()
+    assert oracle.CAMERA_FLOATS * 4 == 212                       # Camera.h POD
+    assert oracle.RESERVOIR_DTYPE.itemsize == 20 and oracle.ALIAS_DTYPE.itemsize == 12
+    assert S.MATERIAL_DTYPE.itemsize == 48 and S.DENOISE_DTYPE.itemsize == 68
+    fields = re.findall(r"^\s+(?:int32_t|float) (\w+);", header[header.index("typedef struct VptDenoisingParams"):header.index("} VptDenoisingParams")], re.M)
+    assert tuple(fields) == S.DENOISE_DTYPE.names                 # same order as GlobalSettings.h:124-140 grouping in the C ABI
+    for name, val in re.findall(r"VPT_BUF_(\w+) = (\d+)", header):
+        assert oracle.BUF[name] == int(val)
+
+
+def test_no_gpu_fails_loudly():
+    """No CPU fallback: without a usable sm_100 device vpt_create returns VPT_ERR_CUDA and says why."""
+    import torch
+    import vpt
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(vpt.VptError) as e:
+        vpt.Vpt(64, 64)
+    assert "vpt_create" in str(e.value) and "(2)" in str(e.value)
+
+
+def test_settings_loader(tmp_path):
+    import vpt
+    f = tmp_path / "global_settings.yaml"
+    f.write_text(SETTINGS_YAML)
+    p, ok = vpt.load_denoising_settings(str(f))
+    assert ok
+    d = vpt.default_denoising_params()
+    assert d["atrousIterationNum"][0] == 5 and p["atrousIterationNum"][0] == 1      # C++ default vs shipped YAML
+    for k in ("enableTemporalAccumulation", "enableHistoryFix", "enableHistoryClamping", "enableSpatialFiltering", "enableFireflyFilter"):
+        assert p[k][0] == 1                                                           # parseBool: true/1/yes/on, any case
+    assert p["enableHitDistanceReconstruction"][0] == 0 and p["enablePrePass"][0] == 0
+    assert np.isclose(p["depthThreshold"][0], 0.003) and p["denoisingRange"][0] == 500000.0 and p["maxAccumulatedFrameNum"][0] == 30.0
+    assert p.tobytes() == S.default_denoising_params().tobytes()                      # == the params the benchmarks use
+    q, ok2 = vpt.load_denoising_settings(str(tmp_path / "missing.yaml"))
+    assert not ok2 and q.tobytes() == d.tobytes()                                     # returns false, values stay default
+    ref_yaml = "/root/reference/data/settings/global_settings.yaml"
+    if os.path.exists(ref_yaml):
+        r, ok3 = vpt.load_denoising_settings(ref_yaml)
+        assert ok3 and r.tobytes() == p.tobytes()
+
+
+def test_scene_loader(tmp_path):
+    import vpt
+    f = tmp_path / "scene.yaml"
+    f.write_text(SCENE_YAML)
+    sc = vpt.load_scene_config(str(f))
+    assert sc["loaded"] and np.allclose(sc["position"], [35.6184, 11.8733, 42.0387]) and sc["fov"] == 90.0
+    assert abs(np.linalg.norm(sc["direction"]) - 1.0) < 1e-6 and sc["chunks"] == (4, 1, 4)       # direction normalised (SceneConfig.cpp:108)
+    miss = vpt.load_scene_config(str(tmp_path / "nope.yaml"))
+    assert not miss["loaded"] and np.allclose(miss["position"], [20, 15, 20])                    # CameraConfig defaults (SceneConfig.h:10-16)
+    assert np.allclose(miss["direction"], np.array([-1, -0.3, -1]) / np.linalg.norm([-1, -0.3, -1]), atol=1e-6)
+    cam = vpt.camera_from_scene(256, 256, sc["position"], sc["direction"], sc["fov"])
+    assert np.allclose(cam[6:9], sc["position"]) and abs(cam[4] - 1.0) < 1e-6                    # tan(45 deg)
+
+
+def test_alias_table_matches_oracle_and_is_a_distribution(oracle_lib):
+    import vpt
+    rng = np.random.default_rng(4)
+    w = rng.random(4097).astype(np.float32) ** 4
+    a, b = vpt.build_alias_table(w), oracle_lib.build_alias_table(w)
+    assert a.tobytes() == b.tobytes()
+    assert abs(a["p"].sum() - 1.0) < 1e-4 and (a["q"] <= 1.0 + 1e-6).all() and (a["q"] >= 0).all()
+    # reconstruct the distribution from (q, alias): P(i) = (q_i + sum_{j: alias_j = i} (1 - q_j)) / n
+    n = w.size
+    rec = a["q"].astype(np.float64).copy()
+    has = a["alias"] >= 0
+    np.add.at(rec, a["alias"][has], 1.0 - a["q"][has].astype(np.float64))
+    assert np.allclose(rec / n, w / w.sum(), atol=2e-6)
+
+
+def test_sharding_helpers():
+    import vpt_shard
+    for n in (1, 2, 4, 8):
+        got = sorted(k for r in range(n) for k in vpt_shard.samples_of(r, n, 4 * n))
+        assert got == list(range(4 * n))
+        for h in (1080, 2160, 544, 36):
+            if h < 4 * n:
+                continue
+            b = vpt_shard.row_bands(h, n)
+            assert b[0] == 0 and b[-1] == h and all(x % 4 == 0 for x in b[:-1]) and all(b[i] < b[i + 1] for i in range(n))
+    with pytest.raises(ValueError):
+        vpt_shard.row_bands(8, 4)
+
+
+def test_vpt_offline_cli_help():
+    import subprocess
+    exe = os.path.join(ROOT, "real-time-path-tracing-voxel-blocks_b200", "vpt_offline")
+    if not os.path.exists(exe):
+        pytest.skip("vpt_offline not built")
+    out = subprocess.run([exe, "--help"], capture_output=True, text=True, timeout=30)
+    assert out.returncode == 0
+    for flag in ("--width", "--height", "--output", "--scene", "--frames", "--test-canonical", "--update-canonical", "--canonical-image",
+                 "--comment", "--test-sequence", "--test-remove20", "--test-remove-circle"):   # mainOffline.cpp:57-133
+        assert flag in out.stdout, flag

@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import common  # noqa: E402
 import vpt  # noqa: E402
 import vpt_scenes as S  # noqa: E402
+import vpt_shard  # noqa: E402
 
 
 def main():
@@ -40,9 +41,7 @@ def main():
     g.comm_init(rank, world, uid)
     cam = common.scene_camera(W, H, (4, 1, 4))
     for f in range(2):
-        g.render_shard(cam, cam, f, rank, world)
-        g.comm_allreduce_illumination()
-        g.resolve()
+        vpt_shard.render_sharded(g, cam, cam, f, rank, world, lambda c: c.comm_allreduce_illumination())
     sharded = g.read("Illumination")
     if rank == 0:
         ref = common.setup(vpt.Vpt(W, H, local), inp, spp=spp, total=3, diffuse=1)
@@ -62,7 +61,7 @@ def main():
     cam = vpt.camera_init(W, H)
     cam[6:9] = (0.0, 6.0, 0.0)
     cam = vpt.camera_set_yaw_pitch(cam, 0.0, 0.0)
-    rows = [(H * r // world) // 4 * 4 for r in range(world)] + [H]
+    rows = vpt_shard.row_bands(H, world)
     r0, r1 = rows[rank], rows[rank + 1]
     b = vpt.Vpt(W, H, local)
     b.comm_init(rank, world, fresh_uid())
