@@ -141,6 +141,10 @@ typedef struct VptTimings
     float denoise_total_ms; /* whole chain, first launch to last */
     int32_t atrous_passes;
     int32_t kernel_launches; /* kernels launched by the last render + denoise calls */
+    float trace_dda_ms;     /* sum over the DDA (traversal) kernels of the last render */
+    float trace_shade_ms;   /* sum over the raygen / shading-stage / accumulate kernels of the last render */
+    int32_t trace_dda_launches;
+    int32_t trace_shade_launches;
 } VptTimings;
 
 /* ---- lifetime. Replaces OfflineBackend::init + BufferManager::init + OptixRenderer::init
@@ -207,7 +211,8 @@ void *vpt_device_ptr(vpt_ctx *ctx, VptBufferName name);
 /* Device-side counters of the last render: traversal calls (rays) and voxel steps. */
 int vpt_get_counters(vpt_ctx *ctx, uint64_t *rays, uint64_t *steps);
 int vpt_get_timings(vpt_ctx *ctx, VptTimings *out);
-/* Toggle CUDA-event stage timing (default on; adds event records between kernels). */
+/* Toggle CUDA-event stage timing and the DDA step counter (default on; adds event records between kernels and one
+ * add per DDA step). Throughput runs switch it off. */
 int vpt_set_profiling(vpt_ctx *ctx, int enabled);
 
 /* ---- multi-GPU: one context per rank, NCCL communicator owned by the library. */

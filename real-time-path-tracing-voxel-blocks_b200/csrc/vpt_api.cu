@@ -62,6 +62,11 @@ struct vpt_ctx
     int4 *primaryHits = nullptr;
     unsigned long long *counters = nullptr;
     FireflyPatch *patches = nullptr; int *patchCount = nullptr; int maxPatches = 0;
+    // wavefront workspace (vpt_wave.cu), sized at the first render for (pixel slots, samples per wave)
+    WaveWorkspace wave;
+    TraceProfile traceProf;
+    bool anySpecular = false; // a non-diffuse, non-emissive material exists: paths may continue past their first hit
+    int countSteps = 1;
     // staging for vpt_denoise_external
     void *pinned = nullptr; size_t pinnedBytes = 0;
     // profiling
@@ -121,6 +126,7 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     CU(alloc((void **)&c->sobol, 65536)); CU(alloc((void **)&c->scrambling, 131072)); CU(alloc((void **)&c->ranking, 131072 + 256));
     CU(alloc((void **)&c->blockToMaterial, 256 * sizeof(uint16_t)));
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i <= TraceProfile::kMax; ++i) CU(cudaEventCreate(&c->traceProf.ev[i]));
     CU(cudaStreamSynchronize(c->stream));
     *out = c;
     return VPT_OK;
@@ -133,7 +139,7 @@ void vpt_destroy(vpt_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
                     c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
-                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount};
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
     {
@@ -155,7 +161,7 @@ int vpt_sync(vpt_ctx *c)
     return VPT_OK;
 }
 void *vpt_stream(vpt_ctx *c) { return c ? (void *)c->stream : nullptr; }
-int vpt_set_profiling(vpt_ctx *c, int enabled) { if (!c) return VPT_ERR_ARG; c->profiling = enabled != 0; return VPT_OK; }
+int vpt_set_profiling(vpt_ctx *c, int enabled) { if (!c) return VPT_ERR_ARG; c->profiling = enabled != 0; c->countSteps = enabled != 0; return VPT_OK; }
 
 int vpt_set_tables(vpt_ctx *c, const uint8_t *sobol, const uint8_t *scrambling, const uint8_t *ranking)
 {
@@ -181,7 +187,7 @@ static int allocGrid(vpt_ctx *c, int cx, int cy, int cz)
         const size_t vox = (size_t)cx * cy * cz * 32768;
         CU(cudaMalloc((void **)&c->idsChunk, vox));
         CU(cudaMalloc((void **)&c->idsLinear, vox));
-        CU(cudaMalloc((void **)&c->occ, vox / 8));
+        CU(cudaMalloc((void **)&c->occ, paddedOccWords(cx * 32, cy * 32, cz * 32) * 4));
         c->cx = cx; c->cy = cy; c->cz = cz;
     }
     return VPT_OK;
@@ -241,6 +247,9 @@ int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_
     if (c->materials) cudaFree(c->materials);
     CU(cudaMalloc((void **)&c->materials, (size_t)count * sizeof(VptMaterial)));
     c->nMaterials = count;
+    c->anySpecular = false;
+    for (int i = 0; i < count; ++i)
+        if (!m[i].isEmissive && !(m[i].roughness > 0.00001f)) c->anySpecular = true; // isDiffuse = roughness > 1e-5 (Bsdf.h:5)
     CU(cudaMemcpyAsync(c->materials, m, (size_t)count * sizeof(VptMaterial), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->blockToMaterial, b2m, 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -289,11 +298,28 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     a.width = c->width; a.height = c->height;
     a.iterationIndex = iterationIndex; a.spp = c->spp; a.totalBounceLimit = c->totalBounceLimit; a.diffuseBounceLimit = c->diffuseBounceLimit;
     a.enableRestir = c->enableRestir; a.sampleBegin = sampleBegin; a.sampleStep = sampleStep;
-    a.grid.W = c->cx * 32; a.grid.H = c->cy * 32; a.grid.D = c->cz * 32; a.grid.cx = c->cx; a.grid.cy = c->cy; a.grid.cz = c->cz;
-    a.grid.wordsX = c->cx; a.grid.occWords = c->cx * (c->cy * 32) * (c->cz * 32);
+    a.grid.W = c->cx * 32; a.grid.H = c->cy * 32; a.grid.D = c->cz * 32;
+    a.grid.Wp = paddedW(a.grid.W); a.grid.Hp = a.grid.H + 2; a.grid.Dp = a.grid.D + 2;
+    a.grid.occWords = (int)paddedOccWords(a.grid.W, a.grid.H, a.grid.D); a.grid.parkLin = (a.grid.occWords - 4) * 32;
     a.grid.occ = c->occ; a.grid.idsLinear = c->idsLinear;
-    // two CTAs per SM must fit next to each other (plus 1 KiB/CTA reserved by the runtime)
-    a.occInSmem = ((size_t)a.grid.occWords * 4 <= 72 * 1024) ? 1 : 0; // up to 3 CTAs/SM x (mask + 1 KiB reserved) within 228 KiB
+    a.tilesX = (c->width + 7) / 8;
+    a.nSlots = a.tilesX * ((c->height + 3) / 4) * 32;
+    // a path continues past its first hit only through a specular surface or with a diffuse limit above 1
+    a.depthRounds = (c->anySpecular || c->diffuseBounceLimit > 1) ? c->totalBounceLimit : 1;
+    a.countSteps = c->countSteps;
+    // wave size: as many samples per wave as fit a 16 M-path budget
+    const int shardSamples = sampleBegin < c->spp ? (c->spp - sampleBegin + sampleStep - 1) / sampleStep : 0;
+    int samplesPerWave = (int)((size_t)(16u << 20) / (size_t)a.nSlots);
+    if (samplesPerWave < 1) samplesPerWave = 1;
+    if (samplesPerWave > shardSamples) samplesPerWave = shardSamples > 0 ? shardSamples : 1;
+    if (c->wave.nSlots != a.nSlots || c->wave.maxSamplesInWave < samplesPerWave)
+    {
+        if (c->wave.arena) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->wave.arena)); c->wave.arena = nullptr; }
+        c->wave.arenaBytes = waveWorkspaceBytes(a.nSlots, samplesPerWave);
+        CU(cudaMalloc(&c->wave.arena, c->wave.arenaBytes));
+        waveCarve(c->wave, a.nSlots, samplesPerWave);
+    }
+    a.wb = c->wave.wb;
     a.sobol = c->sobol; a.scrambling = c->scrambling; a.ranking = c->ranking;
     a.materials = c->materials; a.blockToMaterial = c->blockToMaterial;
     a.sky = c->sky; a.sun = c->sun; a.skyAlias = c->skyAlias; a.sunAlias = c->sunAlias;
@@ -308,9 +334,11 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     a.counters = c->counters;
     CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
     if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE0], c->stream));
-    CU(launchTrace(a, c->stream, c->smCount, c->smemOptIn));
+    int launches = 0;
+    c->traceProf.enabled = c->profiling;
+    CU(launchTrace(a, c->wave.maxSamplesInWave, c->stream, c->smCount, c->smemOptIn, &launches, &c->traceProf));
     if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE1], c->stream));
-    c->haveTrace = c->profiling; c->ranResolve = false; c->launchesRender = 1;
+    c->haveTrace = c->profiling; c->ranResolve = false; c->launchesRender = launches;
     return VPT_OK;
 }
 int vpt_resolve(vpt_ctx *c)
@@ -537,6 +565,16 @@ int vpt_get_timings(vpt_ctx *c, VptTimings *t)
         t->atrous_ms = el(EV_ASMEM, EV_ATROUS);
         t->denoise_total_ms = el(EV_DN0, EV_COMP);
         t->atrous_passes = c->atrousPasses;
+    }
+    if (c->haveTrace)
+    {
+        for (int i = 0; i < c->traceProf.n; ++i)
+        {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, c->traceProf.ev[i], c->traceProf.ev[i + 1]);
+            if (c->traceProf.kind[i] == 0) { t->trace_dda_ms += ms; t->trace_dda_launches++; }
+            else { t->trace_shade_ms += ms; t->trace_shade_launches++; }
+        }
     }
     t->kernel_launches = c->launchesRender + c->launchesDenoise;
     return VPT_OK;

@@ -1,0 +1,215 @@
+// Ray–voxel DDA engine for sm_100a: replaces optixTraverse over the triangle BVH
+// (/root/reference/renderer/shaders/RayGen.cu:49-54, closesthit.cu:458,616,745,801) — B200 has no RT cores.
+//
+// Algorithm: Amanatides–Woo with the comparison order and the tMax += tDelta accumulation of
+// VoxelEngine::performRayTraversal (/root/reference/voxelengine/VoxelEngine.cu:1133-1162), bit-exact vs the oracle.
+//
+// B200 shape:
+//  * one persistent 1024-thread CTA per SM; the padded 1-bit occupancy mask (86 KiB for the 16-chunk world) is staged
+//    whole in shared memory, so a step is one LDS + bit test; worlds whose mask exceeds shared memory walk it
+//    through L1/L2 (kSmem = false).
+//  * the mask has a solid one-voxel shell: leaving the grid is "hitting" the shell — the step loop has NO bounds
+//    arithmetic. 20-odd SASS instructions per step.
+//  * warp-level ray compaction: a warp reserves chunks of the prepared-ray queue (one atomic per 128 rays); whenever
+//    at most kRefillBelow lanes still hold a live ray, the idle lanes are re-armed from the queue
+//    (__ballot_sync/__popc slot assignment), so the step loop runs with most lanes active regardless of how
+//    different the trip counts are. Lanes without a ray are parked on a spare all-zero mask word with zero
+//    strides: they execute the same instructions harmlessly — no per-step predicate.
+#include "vpt_dda.cuh"
+
+namespace vpt {
+
+constexpr int kDdaThreads = 1024;
+constexpr int kChunk = 128;       // rays reserved per warp per atomic
+constexpr int kRefillBelow = 20;  // re-arm idle lanes when <= this many lanes are live
+constexpr unsigned kFull = 0xffffffffu;
+
+template <bool kSmem, bool kClosest, bool kStats>
+__global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constant__ DdaArgs a)
+{
+    extern __shared__ uint32_t occS[];
+    if (kSmem)
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.grid.occ);
+        uint4 *dst = reinterpret_cast<uint4 *>(occS);
+        const int n4 = a.grid.occWords >> 2; // occWords is a multiple of 4
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const uint32_t *__restrict__ occG = a.grid.occ;
+    const unsigned count = __ldg(a.count);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int Wp = a.grid.Wp, Dp = a.grid.Dp, W = a.grid.W, H = a.grid.H, D = a.grid.D;
+    const int strideY = Wp * Dp;
+    const int parkLin = a.grid.parkLin;
+
+    // per-lane DDA state
+    float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f;
+    int lin = parkLin, dX = 0, dY = 0, dZ = 0, lastD = 0;
+    uint32_t meta = 0, result = 0;
+    bool live = false;
+    // a finished ray's result is written later, together with the other idle lanes (convergent), not inside the step loop
+    bool pending = false;
+    int finLin = 0, finD = 0;
+    float finT = 0.0f;
+    // warp-uniform queue chunk
+    unsigned chunkPos = 0, chunkEnd = 0;
+    bool exhausted = (count == 0);
+    unsigned raysAcc = 0, stepsAcc = 0;
+
+    for (;;)
+    {
+        // ---- retire finished rays
+        if (pending)
+        {
+            const int xp = finLin % Wp, r = finLin / Wp;
+            const int zp = r % Dp, yp = r / Dp;
+            const int x = xp - 1, y = yp - 1, z = zp - 1;
+            const bool shell = (unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H || (unsigned)z >= (unsigned)D;
+            if (kClosest)
+            {
+                uint32_t packed = kHitMiss;
+                if (!shell)
+                {
+                    uint32_t face = (meta >> 4) & 7u;
+                    if (finD != 0)
+                    {
+                        const int ax = finD < 0 ? -finD : finD;
+                        if (ax == 1) face = (meta & 1u) ? 2u : 3u;
+                        else if (ax == strideY) face = (meta & 2u) ? 1u : 0u;
+                        else face = (meta & 4u) ? 5u : 4u;
+                    }
+                    packed = ((uint32_t)((y * D + z) * W + x) << 3) | face;
+                }
+                a.hitT[result] = shell ? kRayMax : finT;
+                a.hitPacked[result] = packed;
+            }
+            else
+                a.vis[result] = shell ? (uint8_t)0 : (uint8_t)1;
+            pending = false;
+        }
+        // ---- re-arm idle lanes
+        unsigned idle = __ballot_sync(kFull, !live);
+        while (idle != 0 && !exhausted)
+        {
+            if (chunkPos >= chunkEnd)
+            {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(a.cursor, (unsigned)kChunk);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= count) { exhausted = true; break; }
+                chunkPos = base;
+                chunkEnd = min(base + (unsigned)kChunk, count);
+            }
+            const unsigned avail = chunkEnd - chunkPos;
+            const unsigned rank = __popc(idle & ltMask);
+            const bool take = !live && rank < avail;
+            if (take)
+            {
+                const uint4 *q = a.queue + (size_t)(chunkPos + rank) * 3;
+                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                tX = __uint_as_float(q0.x); tY = __uint_as_float(q0.y); tZ = __uint_as_float(q0.z); tCur = __uint_as_float(q0.w);
+                dtX = __uint_as_float(q1.x); dtY = __uint_as_float(q1.y); dtZ = __uint_as_float(q1.z); tmin = __uint_as_float(q1.w);
+                lin = (int)q2.x; meta = q2.y; result = q2.z;
+                dX = (meta & 1u) ? 1 : -1;
+                dY = (meta & 2u) ? strideY : -strideY;
+                dZ = (meta & 4u) ? Wp : -Wp;
+                lastD = 0;
+                live = true;
+                ++raysAcc;
+            }
+            chunkPos += min((unsigned)__popc(idle), avail);
+            idle = __ballot_sync(kFull, !live);
+        }
+        if (idle == kFull) break; // nothing live and nothing left to take
+
+        // ---- step loop
+        for (;;)
+        {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                uint32_t word;
+                if (kSmem) word = occS[(unsigned)lin >> 5];
+                else word = __ldg(occG + ((unsigned)lin >> 5));
+                if ((word >> (lin & 31)) & 1u)
+                {
+                    // solid voxel or shell: once per ray (twice for a ray whose origin voxel lies before tmin)
+                    bool fin = tCur >= tmin;
+                    if (!fin)
+                    {
+                        const int xp = lin % Wp, r = lin / Wp;
+                        const int zp = r % Dp, yp = r / Dp;
+                        fin = (unsigned)(xp - 1) >= (unsigned)W || (unsigned)(yp - 1) >= (unsigned)H || (unsigned)(zp - 1) >= (unsigned)D;
+                    }
+                    if (fin)
+                    {
+                        finLin = lin; finT = tCur; finD = lastD;
+                        pending = true;
+                        live = false;
+                        lin = parkLin; dX = 0; dY = 0; dZ = 0; // parked: steps in place on an empty spare word
+                    }
+                }
+                // advance the axis with the smallest tMax: X<Y ? (X<Z ? X : Z) : (Y<Z ? Y : Z)  ==  A = min(X,Y); A<Z ? A : Z
+                const bool xy = tX < tY;
+                const float tA = xy ? tX : tY;
+                const bool az = tA < tZ;
+                tCur = az ? tA : tZ;
+                const int dd = az ? (xy ? dX : dY) : dZ;
+                const float dt = az ? (xy ? dtX : dtY) : dtZ;
+                const float tN = __fadd_rn(tCur, dt);
+                if (az && xy) tX = tN;
+                if (az && !xy) tY = tN;
+                if (!az) tZ = tN;
+                lin += dd;
+                lastD = dd;
+                if (kStats) stepsAcc += live ? 1u : 0u;
+            }
+            const unsigned act = __ballot_sync(kFull, live);
+            if (act == 0u) break;
+            if (!exhausted && __popc(act) <= kRefillBelow) break;
+        }
+    }
+    // statistics: one atomic pair per warp
+    unsigned long long r64 = raysAcc, s64 = stepsAcc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        r64 += __shfl_down_sync(kFull, r64, off);
+        s64 += __shfl_down_sync(kFull, s64, off);
+    }
+    if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); if (kStats) atomicAdd(a.counters + 1, s64); }
+}
+
+template <bool kSmem, bool kClosest, bool kStats>
+static cudaError_t launchDdaT(const DdaArgs &a, cudaStream_t s, int smCount)
+{
+    size_t smem = 0;
+    if (kSmem)
+    {
+        smem = (size_t)a.grid.occWords * 4;
+        cudaError_t e = cudaFuncSetAttribute(ddaKernel<kSmem, kClosest, kStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    ddaKernel<kSmem, kClosest, kStats><<<smCount, kDdaThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, cudaStream_t s, int smCount)
+{
+    const int sel = (occInSmem ? 4 : 0) | (closest ? 2 : 0) | (countSteps ? 1 : 0);
+    switch (sel)
+    {
+    case 0: return launchDdaT<false, false, false>(a, s, smCount);
+    case 1: return launchDdaT<false, false, true>(a, s, smCount);
+    case 2: return launchDdaT<false, true, false>(a, s, smCount);
+    case 3: return launchDdaT<false, true, true>(a, s, smCount);
+    case 4: return launchDdaT<true, false, false>(a, s, smCount);
+    case 5: return launchDdaT<true, false, true>(a, s, smCount);
+    case 6: return launchDdaT<true, true, false>(a, s, smCount);
+    default: return launchDdaT<true, true, true>(a, s, smCount);
+    }
+}
+
+} // namespace vpt

@@ -4,8 +4,9 @@
 //    height-field terrain from a per-chunk 32x32 noise map, written in the reference's chunk-major
 //    GetLinearId order (voxelengine/VoxelMath.h:120-127). Compiled -fmad=false: the float height tests
 //    must agree with the CPU restatement for every voxel (bit-exact ids).
-//  * repackKernel builds the traversal layouts from the chunk-major bytes: a linear id volume
-//    x + W*(z + D*y) and the 1-bit occupancy mask (one warp ballot per 32 x-consecutive voxels).
+//  * repackIdsKernel / repackMaskKernel build the traversal layouts from the chunk-major bytes: a linear id
+//    volume x + W*(z + D*y) and the padded 1-bit occupancy mask with a solid one-voxel shell (GridView,
+//    vpt_kernels.h; one warp ballot per 32 x-consecutive bits).
 #include "vpt_kernels.h"
 
 namespace vpt {
@@ -45,35 +46,59 @@ __global__ void generateTerrainKernel(const float *__restrict__ noise, uint8_t *
     idsChunk[i] = id;
 }
 
-// One thread per voxel in LINEAR order (x fastest over the whole world width): the 32 lanes of a warp are
-// the 32 voxels of one occupancy word -> __ballot_sync builds the word; W is a multiple of 32.
-__global__ void repackKernel(const uint8_t *__restrict__ idsChunk, uint8_t *__restrict__ idsLinear, uint32_t *__restrict__ occ,
-                             int cx, int cy, int cz)
+// idsLinear: one thread per voxel in LINEAR order (x fastest over the whole world width).
+__global__ void repackIdsKernel(const uint8_t *__restrict__ idsChunk, uint8_t *__restrict__ idsLinear, int cx, int cy, int cz)
 {
     const int W = cx * 32, D = cz * 32;
     const size_t total = (size_t)cx * cy * cz * 32768;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // total is a multiple of the block size
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int x = (int)(i % W);
     const size_t r = i / W;
     const int z = (int)(r % D), y = (int)(r / D);
     const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
-    const uint8_t id = __ldg(idsChunk + (size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31)));
-    idsLinear[i] = id;
-    const unsigned word = __ballot_sync(0xffffffffu, id != 0);
-    if ((threadIdx.x & 31) == 0) occ[i >> 5] = word;
+    idsLinear[i] = __ldg(idsChunk + (size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31)));
 }
 
-__global__ void setVoxelKernel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id)
+// Padded traversal mask (GridView): one thread per bit of the padded volume, x fastest, so the 32 lanes of a warp
+// are the 32 bits of one word -> __ballot_sync builds it. The one-voxel shell (and the row padding beyond it) is solid.
+__global__ void repackMaskKernel(const uint8_t *__restrict__ idsChunk, uint32_t *__restrict__ occ, int cx, int cy, int cz, int Wp)
 {
-    const int W = cx * 32, D = cz * 32;
+    const int W = cx * 32, H = cy * 32, D = cz * 32, Dp = D + 2, Hp = H + 2;
+    const size_t total = (size_t)Wp * Hp * Dp; // a multiple of 32; the block size is a multiple of 32
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool solid = false;
+    if (i < total)
+    {
+        const int xp = (int)(i % Wp);
+        const size_t r = i / Wp;
+        const int zp = (int)(r % Dp), yp = (int)(r / Dp);
+        const int x = xp - 1, y = yp - 1, z = zp - 1;
+        if (x < 0 || y < 0 || z < 0 || x >= W || y >= H || z >= D) solid = true;
+        else
+        {
+            const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
+            solid = __ldg(idsChunk + (size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31))) != 0;
+        }
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, solid);
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (i < total) occ[i >> 5] = word;
+        else if (i < total + 128) occ[i >> 5] = 0u; // the four spare (parking) words
+    }
+}
+
+__global__ void setVoxelKernel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int Wp, int x, int y, int z, int id)
+{
+    const int W = cx * 32, D = cz * 32, Dp = D + 2;
     const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
     idsChunk[(size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31))] = (uint8_t)id;
-    const size_t lin = ((size_t)y * D + z) * W + x;
-    idsLinear[lin] = (uint8_t)id;
-    uint32_t w = occ[lin >> 5];
-    const uint32_t bit = 1u << (x & 31);
-    occ[lin >> 5] = id ? (w | bit) : (w & ~bit);
+    idsLinear[((size_t)y * D + z) * W + x] = (uint8_t)id;
+    const size_t linP = ((size_t)(y + 1) * Dp + (z + 1)) * Wp + (x + 1);
+    uint32_t w = occ[linP >> 5];
+    const uint32_t bit = 1u << (linP & 31);
+    occ[linP >> 5] = id ? (w | bit) : (w & ~bit);
 }
 
 cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s)
@@ -85,12 +110,15 @@ cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx,
 cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, cudaStream_t s)
 {
     const size_t total = (size_t)cx * cy * cz * 32768;
-    repackKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz);
+    repackIdsKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(idsChunk, idsLinear, cx, cy, cz);
+    const int Wp = paddedW(cx * 32);
+    const size_t bits = (size_t)Wp * (cy * 32 + 2) * (cz * 32 + 2) + 128;
+    repackMaskKernel<<<(unsigned)((bits + 255) / 256), 256, 0, s>>>(idsChunk, occ, cx, cy, cz, Wp);
     return cudaGetLastError();
 }
 cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s)
 {
-    setVoxelKernel<<<1, 1, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz, x, y, z, id);
+    setVoxelKernel<<<1, 1, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz, paddedW(cx * 32), x, y, z, id);
     return cudaGetLastError();
 }
 

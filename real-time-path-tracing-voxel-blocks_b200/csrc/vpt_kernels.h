@@ -8,23 +8,64 @@ namespace vpt {
 
 // Device-side voxel grid (repacked):
 //   idsChunk  chunk-major bytes exactly as the reference's VoxelChunk::data (the API layout)
-//   idsLinear x + W*(z + D*y): the traversal layout (1 byte, fetched once per hit)
-//   occ       1 bit per voxel, 32 x-consecutive voxels per word, word = (y*D + z)*(W/32) + x/32.
-//             128x32x128 (16 chunks) = 64 KiB -> staged whole in shared memory by the trace kernel.
+//   idsLinear x + W*(z + D*y): 1 byte per voxel, fetched once per hit by the shading stage
+//   occ       traversal mask, 1 bit per voxel of the PADDED volume (W+2) x (H+2) x (D+2) whose one-voxel shell is
+//             all ones: a ray that leaves the grid "hits" the shell, so the DDA step loop carries no bounds test.
+//             Rows are padded to Wp = roundup32(W+2) bits; voxel (x,y,z) is bit linP = ((y+1)*Dp + (z+1))*Wp + (x+1).
+//             Four all-zero spare words follow the volume: lanes without a ray are parked on bit parkLin there.
+//             128x32x128 (16 chunks): 160 x 34 x 130 bits = 86.3 KiB -> staged whole in shared memory by the DDA kernel.
 struct GridView
 {
     int W, H, D;        // voxels
-    int cx, cy, cz;     // chunks
-    int wordsX;         // W/32
-    int occWords;       // wordsX*H*D
+    int Wp, Hp, Dp;     // padded mask dimensions
+    int occWords;       // Wp/32 * Hp * Dp + 4
+    int parkLin;        // (occWords - 4) * 32
     const uint32_t *occ;
     const uint8_t *idsLinear;
 };
+inline int paddedW(int W) { return ((W + 2) + 31) & ~31; }
+inline size_t paddedOccWords(int W, int H, int D) { return (size_t)(paddedW(W) / 32) * (H + 2) * (D + 2) + 4; }
 
 struct GBufferPtrs
 {
     float *depth, *material;
     float4 *normalRoughness, *geoNormalThinfilm, *materialParameter, *albedo;
+};
+
+// ---- wavefront path-tracing state (csrc/vpt_wave.cu). One "wave" = nSlots pixel slots x samplesInWave samples;
+// path p = sampleInWave * nSlots + slot, slot = tile * 32 + lane of an 8x4 pixel tile.
+struct WaveBuffers
+{
+    // per path
+    float4 *dirT;       // ray direction of the current segment (xyz)
+    float4 *org;        // ray origin of the current segment (depth > 0; depth 0 starts at the camera)
+    float *hitT;        // closest-hit distance
+    uint32_t *hitPacked; // (linear voxel index << 3) | face, 0xFFFFFFFF = miss
+    float4 *surfA;      // spawn position xyz, hit distance
+    float4 *surfB;      // wo xyz, bits: face | material index << 3
+    uint32_t *pflag;    // path flags (vpt_wave.cu: F_*)
+    float4 *candA;      // sun idx, sun weightSum, sun targetPdf, sky idx
+    float4 *candB;      // sky weightSum, sky targetPdf
+    float4 *dir1;       // direction of the BSDF-candidate ray
+    uint4 *ris;         // lightData, uvData, weightSum, targetPdf (M == 1)
+    float4 *lightA;     // selected light sample: direction xyz, solidAnglePdf
+    float4 *lightB;     // radiance rgb, light type
+    uint8_t *vis1, *vis2, *vis4; // occlusion results of ray #1 (BSDF candidate), #2 (RIS visibility), #5 (final visibility)
+    float4 *rad;        // accumulated radiance rgb, primary hit distance
+    float4 *thr;        // throughput rgb
+    float4 *nextD;      // continuation direction
+    float4 *bop;        // continuation bsdfOverPdf
+    // per pixel slot (temporal ReSTIR, sample 0)
+    uint4 *rstA;        // lightData, uvData, weightSum, targetPdf
+    uint4 *rstB;        // M, meta (cached mask | selected idx | ray mask | valid), -, -
+    float4 *light2A, *light2B;
+    float4 *psA;        // ps[0..2], -
+    float4 *psB;        // M[0..2], -
+    uint8_t *vis3;      // 3 per slot: bias-correction rays
+    // queues
+    uint4 *queue;       // prepared rays, 48 bytes each
+    int *listA, *listB; // active path lists for depth > 0 (ping-pong)
+    unsigned *cnt;      // device counters: see vpt_wave.cu (CNT_*)
 };
 
 struct TraceArgs
@@ -48,8 +89,26 @@ struct TraceArgs
     VptReservoir *resCur;
     const VptReservoir *resPrev;
     int4 *primaryHits;
-    unsigned long long *counters; // [0] rays, [1] steps, [2] tile scheduler
+    unsigned long long *counters; // [0] rays, [1] steps
+    // wavefront
+    WaveBuffers wb;
+    int tilesX, nSlots;          // 8x4 tiles per row, slots = tiles * 32
+    int samplesInWave, waveFirst; // this wave renders local samples waveFirst .. waveFirst+samplesInWave-1 of the shard
+    int nPaths;                  // nSlots * samplesInWave
+    int depthRounds;             // 1 when no path can continue past its first hit (all-diffuse materials, diffuse limit 1)
+    int countSteps;              // DDA step statistics on/off
 };
+
+struct WaveWorkspace
+{
+    void *arena = nullptr;
+    size_t arenaBytes = 0;
+    int nSlots = 0, maxSamplesInWave = 0;
+    WaveBuffers wb = {};
+};
+// bytes of workspace for nSlots pixel slots and samplesInWave samples per wave; carve() lays the arena out
+size_t waveWorkspaceBytes(int nSlots, int samplesInWave);
+void waveCarve(WaveWorkspace &ws, int nSlots, int samplesInWave);
 
 struct DenoiseBuffers
 {
@@ -66,8 +125,32 @@ struct FireflyPatch
     VptReservoir reservoir;
 };
 
-cudaError_t launchTrace(const TraceArgs &a, cudaStream_t s, int smCount, size_t smemOptIn);
+// Optional per-launch timing: an event is recorded after every kernel of launchTrace (kind 0 = DDA, 1 = shading stage).
+struct TraceProfile
+{
+    static constexpr int kMax = 96;
+    cudaEvent_t ev[kMax + 1]; // ev[0] = start, ev[i+1] = after launch i
+    int kind[kMax];
+    int n = 0;
+    bool enabled = false;
+};
+// Renders every sample of the shard (a.sampleBegin/a.sampleStep) wave by wave; returns the number of kernels launched.
+cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, int smCount, size_t smemOptIn, int *launches, TraceProfile *prof);
 cudaError_t launchResolve(float4 *illum, int npix, float spp, cudaStream_t s);
+
+// DDA over a queue of prepared rays (csrc/vpt_dda.cu)
+struct DdaArgs
+{
+    const uint4 *queue;
+    const unsigned *count; // entries in the queue (device)
+    unsigned *cursor;      // chunk cursor (device, zero at launch)
+    float *hitT;           // closest mode outputs, indexed by the ray's result slot
+    uint32_t *hitPacked;
+    uint8_t *vis;          // visibility mode output
+    GridView grid;
+    unsigned long long *counters;
+};
+cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, cudaStream_t s, int smCount);
 
 cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, cudaStream_t s);
 cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s);

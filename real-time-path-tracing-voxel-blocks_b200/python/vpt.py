@@ -27,7 +27,8 @@ RESERVOIR_DTYPE = np.dtype([("lightData", "<u4"), ("uvData", "<u4"), ("weightSum
 ALIAS_DTYPE = np.dtype([("q", "<f4"), ("p", "<f4"), ("alias", "<i4")])
 TIMINGS_DTYPE = np.dtype([("trace_ms", "<f4"), ("resolve_ms", "<f4"), ("firefly_ms", "<f4"), ("temporal_ms", "<f4"),
                           ("history_fix_ms", "<f4"), ("history_clamp_ms", "<f4"), ("atrous_smem_ms", "<f4"), ("atrous_ms", "<f4"),
-                          ("composite_ms", "<f4"), ("denoise_total_ms", "<f4"), ("atrous_passes", "<i4"), ("kernel_launches", "<i4")])
+                          ("composite_ms", "<f4"), ("denoise_total_ms", "<f4"), ("atrous_passes", "<i4"), ("kernel_launches", "<i4"),
+                          ("trace_dda_ms", "<f4"), ("trace_shade_ms", "<f4"), ("trace_dda_launches", "<i4"), ("trace_shade_launches", "<i4")])
 CAMERA_FLOATS = 53
 
 # every symbol include/vpt.h declares (checked by the CPU test-suite against the built library)
