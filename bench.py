@@ -212,12 +212,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), wall, sampler.summary()
 
+    # throughput runs: per-stage event records and the DDA step counter off
+    g.set_profiling(False)
     for _ in range(args.warmup):
         step(False)
     # per-step ray counts are deterministic for a static camera after warm-up; read them once per timed loop end
     ms_dev, wall, clocks = timed(False, args.steps)
     rays_step = g.counters()[0]
-    tim = g.timings() if rank == 0 else None
     rays_t = torch.tensor([float(rays_step)], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(rays_t)
@@ -228,6 +229,19 @@ def main():
     ms_e2e, wall_e2e, _ = timed(True, args.steps)
     e2e_value = rays_all * args.steps / (wall_e2e) / 1e9
 
+    # per-kernel breakdown: a few extra frames with CUDA-event stage timing + step counting on (not part of the timed runs)
+    g.set_profiling(True)
+    tim = None
+    steps_frame = 0
+    for _ in range(3):
+        step(False)
+        if rank == 0:
+            t_ = g.timings()
+            if tim is None or t_["trace_ms"] + t_["denoise_total_ms"] < tim["trace_ms"] + tim["denoise_total_ms"]:
+                tim = t_
+            steps_frame = g.counters()[1]
+    g.set_profiling(False)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -235,7 +249,8 @@ def main():
 
     peak, peak_src = load_peaks()
     npix = WIDTH * HEIGHT
-    stages = [("trace", tim["trace_ms"] + tim["resolve_ms"], None), ("firefly", tim["firefly_ms"], "firefly"), ("temporal", tim["temporal_ms"], "temporal"),
+    stages = [("trace_dda_x%d" % tim["trace_dda_launches"], tim["trace_dda_ms"], None),
+              ("trace_shade_x%d" % tim["trace_shade_launches"], tim["trace_shade_ms"] + tim["resolve_ms"], None), ("firefly", tim["firefly_ms"], "firefly"), ("temporal", tim["temporal_ms"], "temporal"),
               ("history_fix", tim["history_fix_ms"], "history_fix"), ("history_clamp", tim["history_clamp_ms"], "history_clamp"),
               ("atrous_smem", tim["atrous_smem_ms"], "atrous_smem"), ("atrous_x%d" % tim["atrous_passes"], tim["atrous_ms"], "atrous"),
               ("composite", tim["composite_ms"], "composite")]
@@ -264,7 +279,7 @@ def main():
             traffic = None
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
-                "note": "dominant DENOISER kernel (the metric's HBM figure); the trace kernel is L2/latency bound (see kernels[])",
+                "note": "dominant DENOISER kernel (the metric's HBM figure); traversal is shared-memory/issue bound (see trace{} and kernels[])",
                 "denoiser_chain": {"algorithmic_bytes": chain_bytes, "ms": round(chain_ms, 4), "gbs": round(chain_bytes / (chain_ms * 1e-3) / 1e9, 1),
                                    "frac": round(chain_bytes / (chain_ms * 1e-3) / 1e9 / peak, 4)}}
 
@@ -291,6 +306,10 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
             "gpixel_samples_per_s": npix * total_spp * args.steps / (ms_dev * 1e-3) / 1e9, "rays_per_frame": rays_all,
+            "dda_steps_per_ray": (steps_frame / rays_step) if rays_step else None,
+            "trace": {"ms": round(tim["trace_ms"] + tim["resolve_ms"], 4), "dda_ms": round(tim["trace_dda_ms"], 4),
+                      "shade_ms": round(tim["trace_shade_ms"], 4), "dda_grays_per_s": round(rays_step / (tim["trace_dda_ms"] * 1e-3) / 1e9, 3) if tim["trace_dda_ms"] > 0 else None,
+                      "note": "traversal is shared-memory/issue bound, not HBM bound: figures of merit are Grays/s and the ncu warp-execution efficiency / issue utilisation in profiles/"},
             "clocks": clocks, "gpu_launches": tim["kernel_launches"] * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": wall_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": 2 * 212 + 68 + 64, "d2h_bytes_per_step": npix * 16,

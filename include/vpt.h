@@ -246,6 +246,9 @@ void vpt_default_denoising_params(VptDenoisingParams *params);
  * and chunk_config. out9 = pos[3], dir[3], up[3]. */
 int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigned *chunks3);
 
+/* Test hook (no device work): the launch-invariant division the kernels use for index decoding. */
+void vpt_debug_fastdiv(uint32_t n, uint32_t d, uint32_t *q, uint32_t *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,7 @@ struct vpt_ctx
     int cx = 0, cy = 0, cz = 0;
     uint8_t *idsChunk = nullptr, *idsLinear = nullptr;
     uint32_t *occ = nullptr;
+    int *upHDev = nullptr; int upH = 0; // highest solid y + 1 (GridView::upH)
     // materials / sky
     VptMaterial *materials = nullptr; int nMaterials = 0;
     uint16_t *blockToMaterial = nullptr;
@@ -139,7 +140,7 @@ void vpt_destroy(vpt_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
                     c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
-                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena};
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
     {
@@ -188,6 +189,7 @@ static int allocGrid(vpt_ctx *c, int cx, int cy, int cz)
         CU(cudaMalloc((void **)&c->idsChunk, vox));
         CU(cudaMalloc((void **)&c->idsLinear, vox));
         CU(cudaMalloc((void **)&c->occ, paddedOccWords(cx * 32, cy * 32, cz * 32) * 4));
+        if (!c->upHDev) CU(cudaMalloc((void **)&c->upHDev, sizeof(int)));
         c->cx = cx; c->cy = cy; c->cz = cz;
     }
     return VPT_OK;
@@ -200,7 +202,7 @@ int vpt_set_grid(vpt_ctx *c, int cx, int cy, int cz, const uint8_t *ids)
     int rc = allocGrid(c, cx, cy, cz);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->idsChunk, ids, (size_t)cx * cy * cz * 32768, cudaMemcpyHostToDevice, c->stream));
-    CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, cx, cy, cz, c->stream));
+    CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, c->upHDev, &c->upH, cx, cy, cz, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return VPT_OK;
 }
@@ -215,7 +217,7 @@ int vpt_generate_terrain(vpt_ctx *c, int cx, int cy, int cz, const float *noise)
     CU(cudaMalloc((void **)&dNoise, nb));
     CU(cudaMemcpyAsync(dNoise, noise, nb, cudaMemcpyHostToDevice, c->stream));
     CU(launchGenerateTerrain(dNoise, c->idsChunk, cx, cy, cz, c->stream));
-    CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, cx, cy, cz, c->stream));
+    CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, c->upHDev, &c->upH, cx, cy, cz, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFree(dNoise));
     return VPT_OK;
@@ -235,7 +237,7 @@ int vpt_set_voxel(vpt_ctx *c, int x, int y, int z, int blockId)
     if (!c || !c->idsChunk) return fail(VPT_ERR_STATE, "vpt_set_voxel: no grid set");
     if (x < 0 || y < 0 || z < 0 || x >= c->cx * 32 || y >= c->cy * 32 || z >= c->cz * 32) return VPT_OK; // reference ignores out-of-range edits
     CU(cudaSetDevice(c->device));
-    CU(launchSetVoxel(c->idsChunk, c->idsLinear, c->occ, c->cx, c->cy, c->cz, x, y, z, blockId, c->stream));
+    CU(launchSetVoxel(c->idsChunk, c->idsLinear, c->occ, &c->upH, c->cx, c->cy, c->cz, x, y, z, blockId, c->stream));
     return VPT_OK;
 }
 
@@ -300,10 +302,16 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     a.enableRestir = c->enableRestir; a.sampleBegin = sampleBegin; a.sampleStep = sampleStep;
     a.grid.W = c->cx * 32; a.grid.H = c->cy * 32; a.grid.D = c->cz * 32;
     a.grid.Wp = paddedW(a.grid.W); a.grid.Hp = a.grid.H + 2; a.grid.Dp = a.grid.D + 2;
-    a.grid.occWords = (int)paddedOccWords(a.grid.W, a.grid.H, a.grid.D); a.grid.parkLin = (a.grid.occWords - 4) * 32;
+    a.grid.maskWords = (int)paddedMaskWords(a.grid.W, a.grid.H, a.grid.D);
+    a.grid.occWords = 2 * a.grid.maskWords + 4; a.grid.parkLin = 2 * a.grid.maskWords * 32;
+    a.grid.upH = c->upH;
     a.grid.occ = c->occ; a.grid.idsLinear = c->idsLinear;
+    a.grid.divW = makeFastDiv(a.grid.W); a.grid.divD = makeFastDiv(a.grid.D);
+    a.grid.divWp = makeFastDiv(a.grid.Wp); a.grid.divDp = makeFastDiv(a.grid.Dp);
     a.tilesX = (c->width + 7) / 8;
     a.nSlots = a.tilesX * ((c->height + 3) / 4) * 32;
+    a.divSlots = makeFastDiv(a.nSlots); a.divTilesX = makeFastDiv(a.tilesX);
+    a.divSkyW = makeFastDiv(c->skyW); a.divSunW = makeFastDiv(c->sunW);
     // a path continues past its first hit only through a specular surface or with a diffuse limit above 1
     a.depthRounds = (c->anySpecular || c->diffuseBounceLimit > 1) ? c->totalBounceLimit : 1;
     a.countSteps = c->countSteps;

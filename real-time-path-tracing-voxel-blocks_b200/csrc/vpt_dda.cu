@@ -9,7 +9,8 @@
 //    whole in shared memory, so a step is one LDS + bit test; worlds whose mask exceeds shared memory walk it
 //    through L1/L2 (kSmem = false).
 //  * the mask has a solid one-voxel shell: leaving the grid is "hitting" the shell — the step loop has NO bounds
-//    arithmetic. 20-odd SASS instructions per step.
+//    arithmetic. 22 SASS instructions per step. Rays with dir.y > 0 walk a second copy of the mask that is solid
+//    from the highest solid voxel up (GridView::upH): they retire as soon as nothing can be above them.
 //  * warp-level ray compaction: a warp reserves chunks of the prepared-ray queue (one atomic per 128 rays); whenever
 //    at most kRefillBelow lanes still hold a live ray, the idle lanes are re-armed from the queue
 //    (__ballot_sync/__popc slot assignment), so the step loop runs with most lanes active regardless of how
@@ -42,7 +43,17 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
     const unsigned ltMask = (1u << lane) - 1u;
     const int Wp = a.grid.Wp, Dp = a.grid.Dp, W = a.grid.W, H = a.grid.H, D = a.grid.D;
     const int strideY = Wp * Dp;
-    const int parkLin = a.grid.parkLin;
+    const int parkLin = a.grid.parkLin, maskBits = a.grid.maskWords * 32, upH = a.grid.upH;
+    // padded bit index -> voxel; shell = outside the grid, or at/above upH in the upward mask
+    auto decode = [&](int l, int &x, int &y, int &z) -> bool {
+        const bool up = l >= maskBits;
+        if (up) l -= maskBits;
+        uint32_t r, xp, yp, zp;
+        a.grid.divWp.div((uint32_t)l, r, xp);
+        a.grid.divDp.div(r, yp, zp);
+        x = (int)xp - 1; y = (int)yp - 1; z = (int)zp - 1;
+        return (unsigned)x >= (unsigned)W || (unsigned)z >= (unsigned)D || (unsigned)y >= (unsigned)(up ? upH : H);
+    };
 
     // per-lane DDA state
     float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f;
@@ -63,10 +74,8 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         // ---- retire finished rays
         if (pending)
         {
-            const int xp = finLin % Wp, r = finLin / Wp;
-            const int zp = r % Dp, yp = r / Dp;
-            const int x = xp - 1, y = yp - 1, z = zp - 1;
-            const bool shell = (unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H || (unsigned)z >= (unsigned)D;
+            int x, y, z;
+            const bool shell = decode(finLin, x, y, z);
             if (kClosest)
             {
                 uint32_t packed = kHitMiss;
@@ -137,12 +146,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                 {
                     // solid voxel or shell: once per ray (twice for a ray whose origin voxel lies before tmin)
                     bool fin = tCur >= tmin;
-                    if (!fin)
-                    {
-                        const int xp = lin % Wp, r = lin / Wp;
-                        const int zp = r % Dp, yp = r / Dp;
-                        fin = (unsigned)(xp - 1) >= (unsigned)W || (unsigned)(yp - 1) >= (unsigned)H || (unsigned)(zp - 1) >= (unsigned)D;
-                    }
+                    if (!fin) { int x, y, z; fin = decode(lin, x, y, z); }
                     if (fin)
                     {
                         finLin = lin; finT = tCur; finD = lastD;

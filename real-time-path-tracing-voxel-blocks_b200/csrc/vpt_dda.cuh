@@ -70,7 +70,8 @@ VPT_DEV bool prepareRay(const GridView &g, f3 o, f3 d, float tmin, uint32_t resu
     r.tMaxZ = zz ? FLT_MAX : ex::divf(ex::subf(nbZ, o.z), d.z);
     r.tCur = tCur;
     r.tmin = tmin;
-    r.lin = ((y + 1) * g.Dp + (z + 1)) * g.Wp + (x + 1);
+    // rays that climb (dir.y > 0) walk the upward mask (solid from GridView::upH up): same hits, earlier exits
+    r.lin = ((y + 1) * g.Dp + (z + 1)) * g.Wp + (x + 1) + (py ? g.maskWords * 32 : 0);
     uint32_t face0 = 6u;
     if (hitAxis == 0) face0 = px ? 2u : 3u;
     else if (hitAxis == 1) face0 = py ? 1u : 0u;

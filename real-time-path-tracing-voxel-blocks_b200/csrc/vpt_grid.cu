@@ -4,7 +4,7 @@
 //    height-field terrain from a per-chunk 32x32 noise map, written in the reference's chunk-major
 //    GetLinearId order (voxelengine/VoxelMath.h:120-127). Compiled -fmad=false: the float height tests
 //    must agree with the CPU restatement for every voxel (bit-exact ids).
-//  * repackIdsKernel / repackMaskKernel build the traversal layouts from the chunk-major bytes: a linear id
+//  * repackIdsKernel / maxSolidYKernel / repackMaskKernel build the traversal layouts from the chunk-major bytes: a linear id
 //    volume x + W*(z + D*y) and the padded 1-bit occupancy mask with a solid one-voxel shell (GridView,
 //    vpt_kernels.h; one warp ballot per 32 x-consecutive bits).
 #include "vpt_kernels.h"
@@ -60,45 +60,61 @@ __global__ void repackIdsKernel(const uint8_t *__restrict__ idsChunk, uint8_t *_
     idsLinear[i] = __ldg(idsChunk + (size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31)));
 }
 
-// Padded traversal mask (GridView): one thread per bit of the padded volume, x fastest, so the 32 lanes of a warp
-// are the 32 bits of one word -> __ballot_sync builds it. The one-voxel shell (and the row padding beyond it) is solid.
-__global__ void repackMaskKernel(const uint8_t *__restrict__ idsChunk, uint32_t *__restrict__ occ, int cx, int cy, int cz, int Wp)
+// Highest solid voxel: upH = max(y + 1) over solid voxels (0 for an empty world).
+__global__ void maxSolidYKernel(const uint8_t *__restrict__ idsLinear, int *upH, int W, int D, size_t total)
 {
-    const int W = cx * 32, H = cy * 32, D = cz * 32, Dp = D + 2, Hp = H + 2;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int y1 = 0;
+    if (i < total && __ldg(idsLinear + i) != 0) y1 = (int)(i / ((size_t)W * D)) + 1;
+    y1 = __reduce_max_sync(0xffffffffu, y1);
+    if ((threadIdx.x & 31) == 0 && y1 > 0) atomicMax(upH, y1);
+}
+
+// Padded traversal masks (GridView): one thread per bit of the padded volume, x fastest, so the 32 lanes of a warp
+// are the 32 bits of one word -> __ballot_sync builds it. The one-voxel shell (and the row padding beyond it) is solid.
+// Mask 0 is the grid; mask 1 (the upward mask, for rays with dir.y > 0) is additionally solid from y = upH up.
+__global__ void repackMaskKernel(const uint8_t *__restrict__ idsLinear, uint32_t *__restrict__ occ, int W, int H, int D, int Wp, int upH)
+{
+    const int Dp = D + 2, Hp = H + 2;
     const size_t total = (size_t)Wp * Hp * Dp; // a multiple of 32; the block size is a multiple of 32
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool solid = false;
+    bool solid = false, shell = false;
+    int y = 0;
     if (i < total)
     {
         const int xp = (int)(i % Wp);
         const size_t r = i / Wp;
         const int zp = (int)(r % Dp), yp = (int)(r / Dp);
-        const int x = xp - 1, y = yp - 1, z = zp - 1;
-        if (x < 0 || y < 0 || z < 0 || x >= W || y >= H || z >= D) solid = true;
-        else
-        {
-            const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
-            solid = __ldg(idsChunk + (size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31))) != 0;
-        }
+        const int x = xp - 1, z = zp - 1;
+        y = yp - 1;
+        if (x < 0 || y < 0 || z < 0 || x >= W || y >= H || z >= D) shell = true;
+        else solid = __ldg(idsLinear + ((size_t)y * D + z) * W + x) != 0;
     }
-    const unsigned word = __ballot_sync(0xffffffffu, solid);
+    const unsigned word0 = __ballot_sync(0xffffffffu, solid || shell);
+    const unsigned word1 = __ballot_sync(0xffffffffu, solid || shell || y >= upH);
     if ((threadIdx.x & 31) == 0)
     {
-        if (i < total) occ[i >> 5] = word;
-        else if (i < total + 128) occ[i >> 5] = 0u; // the four spare (parking) words
+        if (i < total) { occ[i >> 5] = word0; occ[(total >> 5) + (i >> 5)] = word1; }
+        else if (i < total + 128) occ[2 * (total >> 5) + ((i - total) >> 5)] = 0u; // the four spare (parking) words
     }
 }
 
-__global__ void setVoxelKernel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int Wp, int x, int y, int z, int id)
+__global__ void setVoxelKernel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int Wp, int upH, int x, int y, int z, int id)
 {
-    const int W = cx * 32, D = cz * 32, Dp = D + 2;
+    const int W = cx * 32, H = cy * 32, D = cz * 32, Dp = D + 2;
     const int chunk = (x >> 5) + cx * ((z >> 5) + cz * (y >> 5));
     idsChunk[(size_t)chunk * 32768 + (x & 31) + 32 * ((z & 31) + 32 * (y & 31))] = (uint8_t)id;
     idsLinear[((size_t)y * D + z) * W + x] = (uint8_t)id;
     const size_t linP = ((size_t)(y + 1) * Dp + (z + 1)) * Wp + (x + 1);
-    uint32_t w = occ[linP >> 5];
+    const size_t maskWords = (size_t)(Wp / 32) * (H + 2) * Dp;
     const uint32_t bit = 1u << (linP & 31);
+    uint32_t w = occ[linP >> 5];
     occ[linP >> 5] = id ? (w | bit) : (w & ~bit);
+    if (y < upH) // above upH the upward mask stays solid
+    {
+        w = occ[maskWords + (linP >> 5)];
+        occ[maskWords + (linP >> 5)] = id ? (w | bit) : (w & ~bit);
+    }
 }
 
 cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s)
@@ -107,18 +123,37 @@ cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx,
     generateTerrainKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(noise, idsChunk, cx, cy, cz);
     return cudaGetLastError();
 }
-cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, cudaStream_t s)
+static cudaError_t launchMask(const uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int upH, cudaStream_t s)
+{
+    const int Wp = paddedW(cx * 32);
+    const size_t bits = (size_t)Wp * (cy * 32 + 2) * (cz * 32 + 2) + 128;
+    repackMaskKernel<<<(unsigned)((bits + 255) / 256), 256, 0, s>>>(idsLinear, occ, cx * 32, cy * 32, cz * 32, Wp, upH);
+    return cudaGetLastError();
+}
+// Builds idsLinear, finds upH (synchronises the stream to read it back: grid uploads are not on the frame path) and
+// builds both masks.
+cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHDev, int *upHHost, int cx, int cy, int cz, cudaStream_t s)
 {
     const size_t total = (size_t)cx * cy * cz * 32768;
     repackIdsKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(idsChunk, idsLinear, cx, cy, cz);
-    const int Wp = paddedW(cx * 32);
-    const size_t bits = (size_t)Wp * (cy * 32 + 2) * (cz * 32 + 2) + 128;
-    repackMaskKernel<<<(unsigned)((bits + 255) / 256), 256, 0, s>>>(idsChunk, occ, cx, cy, cz, Wp);
-    return cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(upHDev, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    maxSolidYKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(idsLinear, upHDev, cx * 32, cz * 32, total);
+    e = cudaMemcpyAsync(upHHost, upHDev, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    return launchMask(idsLinear, occ, cx, cy, cz, *upHHost, s);
 }
-cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s)
+// upH is the host's copy; a solid block above it raises it and rebuilds the masks (rare: an edit above the skyline).
+cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHHost, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s)
 {
-    setVoxelKernel<<<1, 1, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz, paddedW(cx * 32), x, y, z, id);
+    setVoxelKernel<<<1, 1, 0, s>>>(idsChunk, idsLinear, occ, cx, cy, cz, paddedW(cx * 32), *upHHost, x, y, z, id);
+    if (id != 0 && y + 1 > *upHHost)
+    {
+        *upHHost = y + 1;
+        return launchMask(idsLinear, occ, cx, cy, cz, *upHHost, s);
+    }
     return cudaGetLastError();
 }
 

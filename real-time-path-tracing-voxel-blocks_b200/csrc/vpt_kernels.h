@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/vpt.h"
+#include "vpt_fastdiv.h"
 
 namespace vpt {
 
@@ -12,19 +13,26 @@ namespace vpt {
 //   occ       traversal mask, 1 bit per voxel of the PADDED volume (W+2) x (H+2) x (D+2) whose one-voxel shell is
 //             all ones: a ray that leaves the grid "hits" the shell, so the DDA step loop carries no bounds test.
 //             Rows are padded to Wp = roundup32(W+2) bits; voxel (x,y,z) is bit linP = ((y+1)*Dp + (z+1))*Wp + (x+1).
-//             Four all-zero spare words follow the volume: lanes without a ray are parked on bit parkLin there.
-//             128x32x128 (16 chunks): 160 x 34 x 130 bits = 86.3 KiB -> staged whole in shared memory by the DDA kernel.
+//             A second copy — the UPWARD mask — follows it: identical below y = upH (highest solid voxel + 1) and solid
+//             from there up; rays with dir.y > 0 walk it and retire as soon as they rise above everything solid
+//             (same results, fewer steps). Four all-zero spare words follow: lanes without a ray are parked on bit
+//             parkLin there. 128x32x128 (16 chunks): 2 x 160 x 34 x 130 bits = 172.7 KiB -> staged whole in shared
+//             memory by the DDA kernel (one 1024-thread CTA per SM).
 struct GridView
 {
     int W, H, D;        // voxels
     int Wp, Hp, Dp;     // padded mask dimensions
-    int occWords;       // Wp/32 * Hp * Dp + 4
-    int parkLin;        // (occWords - 4) * 32
+    int maskWords;      // Wp/32 * Hp * Dp: one padded mask
+    int occWords;       // 2 * maskWords + 4: full mask, "upward" mask, spare words
+    int parkLin;        // 2 * maskWords * 32
+    int upH;            // the upward mask is solid from y = upH (highest solid voxel + 1): nothing to hit above it
     const uint32_t *occ;
     const uint8_t *idsLinear;
+    FastDiv divW, divD, divWp, divDp;
 };
 inline int paddedW(int W) { return ((W + 2) + 31) & ~31; }
-inline size_t paddedOccWords(int W, int H, int D) { return (size_t)(paddedW(W) / 32) * (H + 2) * (D + 2) + 4; }
+inline size_t paddedMaskWords(int W, int H, int D) { return (size_t)(paddedW(W) / 32) * (H + 2) * (D + 2); }
+inline size_t paddedOccWords(int W, int H, int D) { return 2 * paddedMaskWords(W, H, D) + 4; }
 
 struct GBufferPtrs
 {
@@ -93,6 +101,7 @@ struct TraceArgs
     // wavefront
     WaveBuffers wb;
     int tilesX, nSlots;          // 8x4 tiles per row, slots = tiles * 32
+    FastDiv divSlots, divTilesX, divSkyW, divSunW;
     int samplesInWave, waveFirst; // this wave renders local samples waveFirst .. waveFirst+samplesInWave-1 of the shard
     int nPaths;                  // nSlots * samplesInWave
     int depthRounds;             // 1 when no path can continue past its first hit (all-diffuse materials, diffuse limit 1)
@@ -152,8 +161,9 @@ struct DdaArgs
 };
 cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, cudaStream_t s, int smCount);
 
-cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, cudaStream_t s);
-cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s);
+// upH (device int): highest solid y + 1, maintained by the repack / set-voxel kernels; the upward mask is rebuilt from it
+cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHDev, int *upHHost, int cx, int cy, int cz, cudaStream_t s);
+cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHHost, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s);
 cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s);
 
 // Denoiser passes; rows [rowBegin,rowEnd) are processed (whole image: 0,H).

@@ -21,6 +21,10 @@
 // (vpt_math.cuh). RNG dimensions are consumed in exactly the reference's order (randIdx travels in the path flags).
 #include "vpt_dda.cuh"
 
+#ifndef VPT_FN
+#define VPT_FN __device__ __forceinline__
+#endif
+
 namespace vpt {
 
 constexpr float kSpawnEps = 0.0009765625f; // 2^-10
@@ -130,7 +134,7 @@ VPT_DEV float disneySpecularProb(float avgF, float metalness, bool &valid, float
     return specularProb;
 }
 
-__device__ __noinline__ void disneySample(f4 u, f3 n, f3 ng, f3 wo, f3 albedo, bool metallic, float translucency, float roughness,
+VPT_FN void disneySample(f4 u, f3 n, f3 ng, f3 wo, f3 albedo, bool metallic, float translucency, float roughness,
                                           f3 &wi, f3 &bsdfOverPdf, float &pdf, bool &transmissive)
 {
     if (roughness < kRoughnessThreshold)
@@ -221,7 +225,7 @@ __device__ __noinline__ void disneySample(f4 u, f3 n, f3 ng, f3 wo, f3 albedo, b
     }
 }
 
-__device__ __noinline__ void disneyEvaluate(f3 n, f3 ng, f3 wi, f3 wo, f3 albedo, bool metallic, float roughness, f3 &bsdf, float &pdf)
+VPT_FN void disneyEvaluate(f3 n, f3 ng, f3 wi, f3 wo, f3 albedo, bool metallic, float roughness, f3 &bsdf, float &pdf)
 {
     bsdf = F3(0.0f);
     if (roughness < kRoughnessThreshold) { pdf = 0.0f; return; }
@@ -274,16 +278,29 @@ struct Ctx
 {
     const TraceArgs &a;
     int px, py, sampleIndex, prevSampleIndex, randIdx;
-
+    // ranking keys of dims 0..15 (16 contiguous bytes from this pixel's slot: the reference indexes the ranking tile with
+    // the un-wrapped dimension) and the 8 scrambling keys, fetched once per thread with three 8-byte loads
+    unsigned long long rkLo, rkHi, sc;
+    VPT_DEV void loadKeys()
+    {
+        const int base = ((px & 127) + (py & 127) * 128) * 8;
+        const uint2 a0 = __ldg(reinterpret_cast<const uint2 *>(a.ranking + base));
+        const uint2 a1 = __ldg(reinterpret_cast<const uint2 *>(a.ranking + base + 8));
+        const uint2 s0 = __ldg(reinterpret_cast<const uint2 *>(a.scrambling + base));
+        rkLo = ((unsigned long long)a0.y << 32) | a0.x;
+        rkHi = ((unsigned long long)a1.y << 32) | a1.x;
+        sc = ((unsigned long long)s0.y << 32) | s0.x;
+    }
     VPT_DEV float blueNoise(int sIdx, int dim) const
     {
         // BlueNoiseRandGenerator::rand (RandGen.h:21-45); ranking table is padded with 256 zero bytes
-        const int pi = px & 127, pj = py & 127;
         sIdx &= 255;
-        const int base = (pi + pj * 128) * 8;
-        const int ranked = sIdx ^ __ldg(a.ranking + dim + base);
+        int rank;
+        if (dim < 16) rank = (int)((unsigned)((dim < 8 ? rkLo : rkHi) >> ((dim & 7) * 8)) & 0xffu);
+        else rank = __ldg(a.ranking + dim + ((px & 127) + (py & 127) * 128) * 8);
+        const int ranked = sIdx ^ rank;
         int value = __ldg(a.sobol + dim + ranked * 256);
-        value ^= __ldg(a.scrambling + (dim % 8) + base);
+        value ^= (int)((unsigned)(sc >> ((dim & 7) * 8)) & 0xffu);
         return value / 256.0f;
     }
     VPT_DEV float rnd() { return blueNoise(sampleIndex, randIdx++); }
@@ -305,9 +322,11 @@ struct Ctx
         pmf = __ldg(&bins[alias].p);
         return (unsigned)alias;
     }
-    __device__ __noinline__ LightSample createSunLightSample(int idx) const
+    VPT_FN LightSample createSunLightSample(int idx) const
     {
-        int ix = idx % a.sunW, iy = idx / a.sunW;
+        uint32_t ixu, iyu;
+        a.divSunW.div((uint32_t)idx, iyu, ixu);
+        const int ix = (int)ixu, iy = (int)iyu;
         f2 uv = {(ix + 0.5f) / float(a.sunW), (iy + 0.5f) / float(a.sunH)};
         LightSample ls;
         ls.solidAnglePdf = (a.sunW * a.sunH) / (kTwoPi * (1.0f - a.sunCosThetaMax));
@@ -316,9 +335,11 @@ struct Ctx
         ls.lightType = LightSun;
         return ls;
     }
-    __device__ __noinline__ LightSample createSkyLightSample(int idx) const
+    VPT_FN LightSample createSkyLightSample(int idx) const
     {
-        int ix = idx % a.skyW, iy = idx / a.skyW;
+        uint32_t ixu, iyu;
+        a.divSkyW.div((uint32_t)idx, iyu, ixu);
+        const int ix = (int)ixu, iy = (int)iyu;
         f2 uv = {(ix + 0.5f) / float(a.skyW), (iy + 0.5f) / float(a.skyH)};
         LightSample ls;
         ls.solidAnglePdf = (a.skyW * a.skyH) / (4.0f * kPi);
@@ -330,7 +351,7 @@ struct Ctx
     // GetLightSampleTargetPdfForSurface (Restir.h:194-211) and LightBrdfMisWeight (Restir.h:286-328, brdfCutoff == 0)
     // evaluate the same Disney BSDF for the same direction; evalCandidate evaluates it once and returns both:
     // the RIS target pdf and (optionally) the MIS-blended source pdf.
-    __device__ __noinline__ float evalCandidate(const Surface &s, const LightSample &ls, float lightSelectionPdf, float lightMisWeight,
+    VPT_FN float evalCandidate(const Surface &s, const LightSample &ls, float lightSelectionPdf, float lightMisWeight,
                                                 float brdfMisWeight, float *blendedSourcePdf) const
     {
         const bool invalid = ls.solidAnglePdf <= 0 || ls.lightType == LightInvalid;
@@ -359,7 +380,7 @@ struct Ctx
         return luminance(refl);
     }
     VPT_DEV float targetPdfForSurface(const LightSample &ls, const Surface &s) const { return evalCandidate(s, ls, 0.0f, 0.0f, 0.0f, nullptr); }
-    __device__ __noinline__ bool lightSampleFromReservoir(LightSample &ls, const VptReservoir &r) const
+    VPT_FN bool lightSampleFromReservoir(LightSample &ls, const VptReservoir &r) const
     {
         uint32_t li = r.lightData & kLightIndexMask;
         f2 uv = {float(r.uvData & 0xffff) / float(0xffff), float(r.uvData >> 16) / float(0xffff)};
@@ -375,7 +396,7 @@ struct Ctx
         }
         return li < kInvalidLight;
     }
-    __device__ __noinline__ bool getPrevSurface(Surface &s, int x, int y) const
+    VPT_FN bool getPrevSurface(Surface &s, int x, int y) const
     {
         const VptCamera &pc = a.prevCam;
         if (x < 0 || y < 0 || x >= pc.resolution[0] || y >= pc.resolution[1]) return false;
@@ -499,18 +520,22 @@ VPT_DEV PathId pathId(const TraceArgs &a, int p)
 {
     PathId id;
     id.p = p;
-    id.sl = p / a.nSlots;
-    id.slot = p - id.sl * a.nSlots;
-    const int tile = id.slot >> 5, lane = id.slot & 31;
-    id.px = (tile % a.tilesX) * 8 + (lane & 7);
-    id.py = (tile / a.tilesX) * 4 + (lane >> 3);
+    uint32_t sl, slot, ty, tx;
+    a.divSlots.div((uint32_t)p, sl, slot);
+    id.sl = (int)sl; id.slot = (int)slot;
+    const int lane = id.slot & 31;
+    a.divTilesX.div(slot >> 5, ty, tx);
+    id.px = (int)tx * 8 + (lane & 7);
+    id.py = (int)ty * 4 + (lane >> 3);
     id.k = a.sampleBegin + (a.waveFirst + id.sl) * a.sampleStep;
     id.inImage = id.px < a.width && id.py < a.height;
     return id;
 }
 VPT_DEV Ctx makeCtx(const TraceArgs &a, const PathId &id, int randIdx)
 {
-    return Ctx{a, id.px, id.py, a.iterationIndex * a.spp + id.k, (a.iterationIndex - 1) * a.spp, randIdx};
+    Ctx c{a, id.px, id.py, a.iterationIndex * a.spp + id.k, (a.iterationIndex - 1) * a.spp, randIdx, 0ull, 0ull, 0ull};
+    c.loadKeys();
+    return c;
 }
 VPT_DEV f3 camPos(const TraceArgs &a) { return F3(a.cam.pos[0], a.cam.pos[1], a.cam.pos[2]); }
 
@@ -667,8 +692,10 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
         else
         {
             const int lin = (int)(hp >> 3), face = (int)(hp & 7u);
-            const int hx = lin % a.grid.W, yz = lin / a.grid.W;
-            const int hz = yz % a.grid.D, hy = yz / a.grid.D;
+            uint32_t hxu, yzu, hzu, hyu;
+            a.grid.divW.div((uint32_t)lin, yzu, hxu);
+            a.grid.divD.div(yzu, hyu, hzu);
+            const int hx = (int)hxu, hy = (int)hyu, hz = (int)hzu;
             if (gbufferPass) a.primaryHits[pix] = make_int4(hx, hy, hz, face);
             const int blockId = __ldg(a.grid.idsLinear + lin);
             distance = t;
@@ -706,8 +733,14 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
                     a.cur.materialParameter[pix] = make_float4(s.metallic ? 1.0f : 0.0f, s.translucency, 0.0f, 0.0f);
                     a.cur.albedo[pix] = make_float4(s.albedo.x, s.albedo.y, s.albedo.z, 1.0f);
                 }
-                f3 bsdfWi, bsdfOverPdf; float bsdfPdf; bool transmission = false;
-                disneySample(c.rnd4(), s.normal, s.geoNormal, s.wo, s.albedo, s.metallic, s.translucency, s.roughness, bsdfWi, bsdfOverPdf, bsdfPdf, transmission);
+                // The bounce sample (closesthit.cu:282-293) is only looked at when the path may continue; when the bounce limits
+                // end it here anyway, its four RNG dimensions are consumed without evaluating the BSDF.
+                const bool mayContinue = !(depth + 1 == a.totalBounceLimit || diffuseBounce + (isDiffuse ? 1 : 0) == a.diffuseBounceLimit);
+                f3 bsdfWi = F3(0.0f), bsdfOverPdf = F3(0.0f); float bsdfPdf = 0.0f; bool transmission = false;
+                if (mayContinue)
+                    disneySample(c.rnd4(), s.normal, s.geoNormal, s.wo, s.albedo, s.metallic, s.translucency, s.roughness, bsdfWi, bsdfOverPdf, bsdfPdf, transmission);
+                else
+                    c.randIdx += 4;
                 s.pos = frontPos;
                 s.depth = distance;
                 bool needSurf = false;
@@ -733,7 +766,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
                         float sourcePdf;
                         const int cidx = (int)c.aliasSample(a.sunAlias, a.sunW * a.sunH, c.rnd(), sourcePdf);
                         const LightSample cand = c.createSunLightSample(cidx);
-                        const int ix = cidx % a.sunW, iy = cidx / a.sunW;
+                        uint32_t ixu, iyu;
+                        a.divSunW.div((uint32_t)cidx, iyu, ixu);
+                        const int ix = (int)ixu, iy = (int)iyu;
                         const f2 uv = {(ix + 0.5f) / float(a.sunW), (iy + 0.5f) / float(a.sunH)};
                         float blended;
                         const float targetPdf = c.evalCandidate(s, cand, sourcePdf, sunMisW, brdfMisW, &blended);
@@ -748,7 +783,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
                         float sourcePdf;
                         const int cidx = (int)c.aliasSample(a.skyAlias, a.skyW * a.skyH, c.rnd16(), sourcePdf);
                         const LightSample cand = c.createSkyLightSample(cidx);
-                        const int ix = cidx % a.skyW, iy = cidx / a.skyW;
+                        uint32_t ixu, iyu;
+                        a.divSkyW.div((uint32_t)cidx, iyu, ixu);
+                        const int ix = (int)ixu, iy = (int)iyu;
                         const f2 uv = {(ix + 0.5f) / float(a.skyW), (iy + 0.5f) / float(a.skyH)};
                         float blended;
                         const float targetPdf = c.evalCandidate(s, cand, sourcePdf, skyMisW, brdfMisW, &blended);
@@ -772,8 +809,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
                     if (a.enableRestir && gbufferPass) nf |= F_RESTIR;
                 }
                 // continuation (RayGen.cu:79-84, 146-165)
-                bool cont = !(bsdfPdf <= 0.0f || isNull(bsdfOverPdf));
-                if (depth + 1 == a.totalBounceLimit || newDiffuse == a.diffuseBounceLimit) cont = false;
+                const bool cont = mayContinue && !(bsdfPdf <= 0.0f || isNull(bsdfOverPdf));
                 if (cont)
                 {
                     nf |= F_CONT;
@@ -839,7 +875,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade2Kernel(const __grid_const
         sunRes.weightSum = ca.y; sunRes.targetPdf = ca.z; sunRes.M = 1;
         if (sunIdx >= 0)
         {
-            const int ix = sunIdx % a.sunW, iy = sunIdx / a.sunW;
+            uint32_t ixu, iyu;
+            a.divSunW.div((uint32_t)sunIdx, iyu, ixu);
+            const int ix = (int)ixu, iy = (int)iyu;
             const f2 uv = {(ix + 0.5f) / float(a.sunW), (iy + 0.5f) / float(a.sunH)};
             sunRes.lightData = kSunLight | kLightValidBit;
             sunRes.uvData = (uint32_t)(saturate(uv.x) * 0xffff) | ((uint32_t)(saturate(uv.y) * 0xffff) << 16);
@@ -848,7 +886,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade2Kernel(const __grid_const
         skyRes.weightSum = cb.x; skyRes.targetPdf = cb.y; skyRes.M = 1;
         if (skyIdx >= 0)
         {
-            const int ix = skyIdx % a.skyW, iy = skyIdx / a.skyW;
+            uint32_t ixu, iyu;
+            a.divSkyW.div((uint32_t)skyIdx, iyu, ixu);
+            const int ix = (int)ixu, iy = (int)iyu;
             const f2 uv = {(ix + 0.5f) / float(a.skyW), (iy + 0.5f) / float(a.skyH)};
             skyRes.lightData = kSkyLight | kLightValidBit;
             skyRes.uvData = (uint32_t)(saturate(uv.x) * 0xffff) | ((uint32_t)(saturate(uv.y) * 0xffff) << 16);

@@ -11,6 +11,7 @@
 //   GlobalSettings::LoadFromYAML                /root/reference/renderer/core/GlobalSettings.cpp:69-138, 456-492
 //   SceneConfigParser::LoadFromFile             /root/reference/renderer/core/SceneConfig.cpp:6-114, 184-247
 #include "../../include/vpt.h"
+#include "../csrc/vpt_fastdiv.h"
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -373,3 +374,10 @@ int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigne
 }
 
 } // extern "C"
+
+// Test hook: the magic-number division used by the kernels (csrc/vpt_fastdiv.h), evaluated on the host.
+extern "C" void vpt_debug_fastdiv(uint32_t n, uint32_t d, uint32_t *q, uint32_t *r)
+{
+    const vpt::FastDiv f = vpt::makeFastDiv(d);
+    f.div(n, *q, *r);
+}

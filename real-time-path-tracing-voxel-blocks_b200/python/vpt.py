@@ -39,7 +39,8 @@ EXPORTS = [
     "vpt_write_buffer", "vpt_read_reservoirs", "vpt_write_reservoirs", "vpt_device_ptr", "vpt_get_counters", "vpt_get_timings",
     "vpt_set_profiling", "vpt_comm_unique_id", "vpt_comm_init", "vpt_comm_allreduce_illumination", "vpt_comm_broadcast_gbuffer",
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
-    "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config"]
+    "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
+    "vpt_debug_fastdiv"]
 
 
 class VptError(RuntimeError):

@@ -165,3 +165,22 @@ def test_vpt_offline_cli_help():
     for flag in ("--width", "--height", "--output", "--scene", "--frames", "--test-canonical", "--update-canonical", "--canonical-image",
                  "--comment", "--test-sequence", "--test-remove20", "--test-remove-circle"):   # mainOffline.cpp:57-133
         assert flag in out.stdout, flag
+
+
+def test_fastdiv_matches_integer_division():
+    """csrc/vpt_fastdiv.h (index decoding in the kernels: path -> slot/sample, slot -> tile, voxel index -> x,y,z, light
+    texel index -> x,y): the magic-number quotient/remainder equals // and % for every divisor the kernels can meet."""
+    import ctypes as C
+    import vpt
+    L = vpt.lib()
+    L.vpt_debug_fastdiv.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.vpt_debug_fastdiv.restype = None
+    q, r = C.c_uint32(), C.c_uint32()
+    rng = np.random.default_rng(7)
+    divisors = [1, 2, 3, 5, 7, 30, 32, 34, 66, 128, 130, 160, 240, 258, 480, 960, 1024, 1026, 1056, 2073600, 8294400, 33177600, 2**31 - 1]
+    for d in divisors:
+        ns = np.concatenate([np.arange(0, 300), np.array([d - 1, d, d + 1, 2 * d - 1, 2 * d, 2**31 - 1, 2**32 - 1], np.uint64) % 2**32,
+                             rng.integers(0, 2**32, 300)]).astype(np.uint64)
+        for n in ns:
+            L.vpt_debug_fastdiv(int(n), d, C.byref(q), C.byref(r))
+            assert (q.value, r.value) == (int(n) // d, int(n) % d), (int(n), d, q.value, r.value)
