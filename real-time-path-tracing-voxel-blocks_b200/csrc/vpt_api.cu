@@ -66,6 +66,8 @@ struct vpt_ctx
     // wavefront workspace (vpt_wave.cu), sized at the first render for (pixel slots, samples per wave)
     WaveWorkspace wave;
     TraceProfile traceProf;
+    TraceStreams traceStreams;
+    bool overlapParts = false; // two-stream part overlap: measured, no gain (see vpt_wave.cu launchTrace)
     bool anySpecular = false; // a non-diffuse, non-emissive material exists: paths may continue past their first hit
     int countSteps = 1;
     // staging for vpt_denoise_external
@@ -128,6 +130,12 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     CU(alloc((void **)&c->blockToMaterial, 256 * sizeof(uint16_t)));
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i <= TraceProfile::kMax; ++i) CU(cudaEventCreate(&c->traceProf.ev[i]));
+    for (int i = 0; i < 2; ++i)
+    {
+        CU(cudaStreamCreateWithFlags(&c->traceStreams.part[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->traceStreams.join[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->traceStreams.fork, cudaEventDisableTiming));
     CU(cudaStreamSynchronize(c->stream));
     *out = c;
     return VPT_OK;
@@ -344,7 +352,7 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE0], c->stream));
     int launches = 0;
     c->traceProf.enabled = c->profiling;
-    CU(launchTrace(a, c->wave.maxSamplesInWave, c->stream, c->smCount, c->smemOptIn, &launches, &c->traceProf));
+    CU(launchTrace(a, c->wave.maxSamplesInWave, c->stream, c->overlapParts ? &c->traceStreams : nullptr, c->smCount, c->smemOptIn, &launches, &c->traceProf));
     if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE1], c->stream));
     c->haveTrace = c->profiling; c->ranResolve = false; c->launchesRender = launches;
     return VPT_OK;

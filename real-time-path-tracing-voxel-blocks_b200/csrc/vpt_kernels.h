@@ -104,6 +104,10 @@ struct TraceArgs
     FastDiv divSlots, divTilesX, divSkyW, divSunW;
     int samplesInWave, waveFirst; // this wave renders local samples waveFirst .. waveFirst+samplesInWave-1 of the shard
     int nPaths;                  // nSlots * samplesInWave
+    // a wave is cut into PARTS of whole tiles, each with its own queue / counters, run on its own stream so the
+    // issue-bound DDA kernel of one part overlaps the latency-bound shading stage of the other
+    int slotBase, partSlots, partPaths; // this launch covers slots [slotBase, slotBase + partSlots) of every sample in the wave
+    FastDiv divPartSlots;
     int depthRounds;             // 1 when no path can continue past its first hit (all-diffuse materials, diffuse limit 1)
     int countSteps;              // DDA step statistics on/off
 };
@@ -144,7 +148,13 @@ struct TraceProfile
     bool enabled = false;
 };
 // Renders every sample of the shard (a.sampleBegin/a.sampleStep) wave by wave; returns the number of kernels launched.
-cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, int smCount, size_t smemOptIn, int *launches, TraceProfile *prof);
+struct TraceStreams
+{
+    cudaStream_t part[2] = {nullptr, nullptr}; // side streams, one per part
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, const TraceStreams *ts, int smCount, size_t smemOptIn, int *launches,
+                        TraceProfile *prof);
 cudaError_t launchResolve(float4 *illum, int npix, float spp, cudaStream_t s);
 
 // DDA over a queue of prepared rays (csrc/vpt_dda.cu)

@@ -531,6 +531,13 @@ VPT_DEV PathId pathId(const TraceArgs &a, int p)
     id.inImage = id.px < a.width && id.py < a.height;
     return id;
 }
+// index within this part's launch -> path
+VPT_DEV int partPath(const TraceArgs &a, int idx)
+{
+    uint32_t sl, ls;
+    a.divPartSlots.div((uint32_t)idx, sl, ls);
+    return (int)sl * a.nSlots + a.slotBase + (int)ls;
+}
 VPT_DEV Ctx makeCtx(const TraceArgs &a, const PathId &id, int randIdx)
 {
     Ctx c{a, id.px, id.py, a.iterationIndex * a.spp + id.k, (a.iterationIndex - 1) * a.spp, randIdx, 0ull, 0ull, 0ull};
@@ -624,11 +631,12 @@ VPT_DEV f3 missEmission(const Ctx &c, f3 rayDir)
 // RayGen.cu:102-135: jittered primary ray, exact arithmetic up to the prepared DDA state.
 __global__ void __launch_bounds__(kShadeThreads) genKernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
-    const int p = blockIdx.x * kShadeThreads + threadIdx.x;
+    const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     bool want = false;
     PreparedRay r;
-    if (p < a.nPaths)
+    if (idx < a.partPaths)
     {
+        const int p = partPath(a, idx);
         const PathId id = pathId(a, p);
         uint32_t fl = 0;
         if (id.inImage)
@@ -655,9 +663,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
-    const int n = list ? (int)__ldg(listCount) : a.nPaths;
+    const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
-    const int p = act ? (list ? __ldg(list + idx) : idx) : 0;
+    const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
     const uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_LIVE);
     bool want = false;
@@ -848,9 +856,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade2Kernel(const __grid_const
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
-    const int n = list ? (int)__ldg(listCount) : a.nPaths;
+    const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
-    const int p = act ? (list ? __ldg(list + idx) : idx) : 0;
+    const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS);
     bool want = false;
@@ -1004,8 +1012,9 @@ VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float
 // Temporal ReSTIR: candidates from the previous frame + the bias-correction rays (closesthit.cu:636-760).
 __global__ void __launch_bounds__(kShadeThreads) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
-    const int p = blockIdx.x * kShadeThreads + threadIdx.x; // sample 0 of the wave: path == slot
-    bool act = p < a.nSlots;
+    const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
+    const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
+    bool act = idx < a.partSlots;
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS) && (fl & F_RESTIR);
     unsigned nWant = 0;
@@ -1113,8 +1122,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade3Kernel(const __grid_const
 // Bias-corrected normalisation and the final visibility ray (closesthit.cu:760-820).
 __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
-    const int p = blockIdx.x * kShadeThreads + threadIdx.x;
-    bool act = p < a.nSlots;
+    const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
+    const int p = a.slotBase + idx;
+    bool act = idx < a.partSlots;
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS) && (fl & F_RESTIR);
     bool want = false;
@@ -1181,9 +1191,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade5Kernel(const __grid_const
                                                               unsigned *nextCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
-    const int n = list ? (int)__ldg(listCount) : a.nPaths;
+    const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
-    const int p = act ? (list ? __ldg(list + idx) : idx) : 0;
+    const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & (F_RIS | F_CONT));
     bool cont = false, want = false;
@@ -1269,8 +1279,9 @@ __global__ void __launch_bounds__(kShadeThreads) shade5Kernel(const __grid_const
 // Per pixel: sum of the wave's samples in sample order (RayGen.cu:175-181 NaN guard per sample), depth from sample 0.
 __global__ void __launch_bounds__(kShadeThreads) accumulateKernel(const __grid_constant__ TraceArgs a)
 {
-    const int slot = blockIdx.x * kShadeThreads + threadIdx.x;
-    if (slot >= a.nSlots) return;
+    const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
+    if (idx >= a.partSlots) return;
+    const int slot = a.slotBase + idx;
     const PathId id = pathId(a, slot);
     if (!id.inImage) return;
     const size_t pix = (size_t)id.py * a.width + id.px;
@@ -1315,16 +1326,16 @@ static void carveAll(char *base, WaveBuffers &wb, int nSlots, int samples)
     carve(cur, wb.rad, N); carve(cur, wb.thr, N); carve(cur, wb.nextD, N); carve(cur, wb.bop, N);
     carve(cur, wb.rstA, S); carve(cur, wb.rstB, S); carve(cur, wb.light2A, S); carve(cur, wb.light2B, S);
     carve(cur, wb.psA, S); carve(cur, wb.psB, S); carve(cur, wb.vis3, S * 3);
-    const size_t q = N > S * 3 ? N : S * 3;
+    const size_t q = (N > S * 3 ? N : S * 3) + 64; // parts use disjoint sub-ranges
     carve(cur, wb.queue, q * 3);
     carve(cur, wb.listA, N); carve(cur, wb.listB, N);
-    carve(cur, wb.cnt, (size_t)kCntWords);
+    carve(cur, wb.cnt, (size_t)kCntWords * 2);
 }
 size_t waveWorkspaceBytes(int nSlots, int samplesInWave)
 {
     WaveBuffers wb;
     carveAll(nullptr, wb, nSlots, samplesInWave);
-    return (size_t)(reinterpret_cast<char *>(wb.cnt) - (char *)nullptr) + alignUp(kCntWords * sizeof(unsigned));
+    return (size_t)(reinterpret_cast<char *>(wb.cnt) - (char *)nullptr) + alignUp(2 * kCntWords * sizeof(unsigned));
 }
 void waveCarve(WaveWorkspace &ws, int nSlots, int samplesInWave)
 {
@@ -1332,60 +1343,91 @@ void waveCarve(WaveWorkspace &ws, int nSlots, int samplesInWave)
     ws.nSlots = nSlots; ws.maxSamplesInWave = samplesInWave;
 }
 
-cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, int smCount, size_t smemOptIn, int *launches, TraceProfile *prof)
+cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, const TraceStreams *ts, int smCount, size_t smemOptIn, int *launches,
+                        TraceProfile *prof)
 {
     int nl = 0;
     const bool timing = prof && prof->enabled;
+    // two parts on two side streams (overlap), or one part after the other on the caller's stream when every launch is timed
+    const bool overlap = ts && ts->part[0] && !timing;
     if (timing) { prof->n = 0; cudaEventRecord(prof->ev[0], s); }
-    auto mark = [&](int kind) {
-        if (timing && prof->n < TraceProfile::kMax) { prof->kind[prof->n] = kind; cudaEventRecord(prof->ev[prof->n + 1], s); ++prof->n; }
+    auto mark = [&](int kind, cudaStream_t st) {
+        if (timing && prof->n < TraceProfile::kMax) { prof->kind[prof->n] = kind; cudaEventRecord(prof->ev[prof->n + 1], st); ++prof->n; }
     };
     const int shardSamples = a.sampleBegin < a.spp ? (a.spp - a.sampleBegin + a.sampleStep - 1) / a.sampleStep : 0;
     a.occInSmem = ((size_t)a.grid.occWords * 4 + 1024 <= smemOptIn) ? 1 : 0;
     const bool smem = a.occInSmem != 0, stats = a.countSteps != 0;
-    unsigned *cnt = a.wb.cnt;
-    auto dda = [&](int pair, bool closest, uint8_t *vis) -> cudaError_t {
-        DdaArgs d;
-        d.queue = a.wb.queue; d.count = cnt + 2 * pair; d.cursor = cnt + 2 * pair + 1;
-        d.hitT = a.wb.hitT; d.hitPacked = a.wb.hitPacked; d.vis = vis; d.grid = a.grid; d.counters = a.counters;
-        ++nl;
-        cudaError_t e = launchDda(d, closest, smem, stats, s, smCount);
-        mark(0);
-        return e;
-    };
+    const WaveBuffers wb0 = a.wb;
+    const int nTiles = a.nSlots / 32;
+    // Parts exist so two streams can overlap one part's DDA with the other's shading. Measured on B200 (r1 w5): no
+    // gain — a shading kernel's thousands of pending CTAs keep back-filling the SMs, so the other part's 1024-thread
+    // DDA CTA (173 KiB of shared memory) only gets in at the tail. One part unless the caller passes side streams.
+    const int nParts = (overlap && nTiles >= 2) ? 2 : 1;
 #define VPT_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
     for (int first = 0; first < shardSamples; first += maxSamplesInWave)
     {
         a.waveFirst = first;
         a.samplesInWave = shardSamples - first < maxSamplesInWave ? shardSamples - first : maxSamplesInWave;
         a.nPaths = a.nSlots * a.samplesInWave;
-        const unsigned gridPaths = (unsigned)((a.nPaths + kShadeThreads - 1) / kShadeThreads);
-        const unsigned gridSlots = (unsigned)((a.nSlots + kShadeThreads - 1) / kShadeThreads);
         const bool restirWave = a.enableRestir && a.sampleBegin == 0 && first == 0;
-        VPT_TRY(cudaMemsetAsync(cnt, 0, kCntWords * sizeof(unsigned), s));
-        int pair = 0;
-        genKernel<<<gridPaths, kShadeThreads, 0, s>>>(a, cnt + 2 * pair); ++nl; mark(1);
-        for (int depth = 0; depth < a.depthRounds; ++depth)
+        VPT_TRY(cudaMemsetAsync(wb0.cnt, 0, 2 * kCntWords * sizeof(unsigned), s));
+        if (overlap) VPT_TRY(cudaEventRecord(ts->fork, s));
+        size_t queueBase = 0, listBase = 0;
+        for (int part = 0; part < nParts; ++part)
         {
-            const int *list = depth == 0 ? nullptr : (depth & 1 ? a.wb.listA : a.wb.listB);
-            int *nextList = (depth + 1 < a.depthRounds) ? ((depth + 1) & 1 ? a.wb.listA : a.wb.listB) : nullptr;
-            const unsigned *listCount = cnt + kCntList + depth;
-            VPT_TRY(dda(pair, true, nullptr)); ++pair;
-            shade1Kernel<<<gridPaths, kShadeThreads, 0, s>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1);
-            VPT_TRY(dda(pair, false, a.wb.vis1)); ++pair;
-            shade2Kernel<<<gridPaths, kShadeThreads, 0, s>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1);
-            VPT_TRY(dda(pair, false, a.wb.vis2)); ++pair;
-            if (depth == 0 && restirWave)
+            cudaStream_t st = overlap ? ts->part[part] : s;
+            if (overlap) VPT_TRY(cudaStreamWaitEvent(st, ts->fork, 0));
+            const int tile0 = part == 0 ? 0 : (nTiles + 1) / 2, tile1 = (part == 0 && nParts == 2) ? (nTiles + 1) / 2 : nTiles;
+            a.slotBase = tile0 * 32; a.partSlots = (tile1 - tile0) * 32; a.partPaths = a.partSlots * a.samplesInWave;
+            a.divPartSlots = makeFastDiv((uint32_t)a.partSlots);
+            a.wb = wb0;
+            a.wb.queue = wb0.queue + queueBase * 3;
+            a.wb.listA = wb0.listA + listBase; a.wb.listB = wb0.listB + listBase;
+            a.wb.cnt = wb0.cnt + part * kCntWords;
+            queueBase += (size_t)(a.partPaths > a.partSlots * 3 ? a.partPaths : a.partSlots * 3);
+            listBase += (size_t)a.partPaths;
+            unsigned *cnt = a.wb.cnt;
+            auto dda = [&](int pair, bool closest, uint8_t *vis) -> cudaError_t {
+                DdaArgs d;
+                d.queue = a.wb.queue; d.count = cnt + 2 * pair; d.cursor = cnt + 2 * pair + 1;
+                d.hitT = a.wb.hitT; d.hitPacked = a.wb.hitPacked; d.vis = vis; d.grid = a.grid; d.counters = a.counters;
+                ++nl;
+                cudaError_t e = launchDda(d, closest, smem, stats, st, smCount);
+                mark(0, st);
+                return e;
+            };
+            const unsigned gridPaths = (unsigned)((a.partPaths + kShadeThreads - 1) / kShadeThreads);
+            const unsigned gridSlots = (unsigned)((a.partSlots + kShadeThreads - 1) / kShadeThreads);
+            int pair = 0;
+            genKernel<<<gridPaths, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
+            for (int depth = 0; depth < a.depthRounds; ++depth)
             {
-                shade3Kernel<<<gridSlots, kShadeThreads, 0, s>>>(a, cnt + 2 * pair); ++nl; mark(1);
-                VPT_TRY(dda(pair, false, a.wb.vis3)); ++pair;
-                shade4Kernel<<<gridSlots, kShadeThreads, 0, s>>>(a, cnt + 2 * pair); ++nl; mark(1);
-                VPT_TRY(dda(pair, false, a.wb.vis4)); ++pair;
+                const int *list = depth == 0 ? nullptr : (depth & 1 ? a.wb.listA : a.wb.listB);
+                int *nextList = (depth + 1 < a.depthRounds) ? ((depth + 1) & 1 ? a.wb.listA : a.wb.listB) : nullptr;
+                const unsigned *listCount = cnt + kCntList + depth;
+                VPT_TRY(dda(pair, true, nullptr)); ++pair;
+                shade1Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
+                VPT_TRY(dda(pair, false, a.wb.vis1)); ++pair;
+                shade2Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
+                VPT_TRY(dda(pair, false, a.wb.vis2)); ++pair;
+                if (depth == 0 && restirWave)
+                {
+                    shade3Kernel<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
+                    VPT_TRY(dda(pair, false, a.wb.vis3)); ++pair;
+                    shade4Kernel<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
+                    VPT_TRY(dda(pair, false, a.wb.vis4)); ++pair;
+                }
+                shade5Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, nextList, cnt + kCntList + depth + 1, cnt + 2 * pair); ++nl; mark(1, st);
             }
-            shade5Kernel<<<gridPaths, kShadeThreads, 0, s>>>(a, depth, list, listCount, nextList, cnt + kCntList + depth + 1, cnt + 2 * pair); ++nl; mark(1);
+            accumulateKernel<<<gridSlots, kShadeThreads, 0, st>>>(a); ++nl; mark(1, st);
+            VPT_TRY(cudaGetLastError());
+            if (overlap)
+            {
+                VPT_TRY(cudaEventRecord(ts->join[part], st));
+                VPT_TRY(cudaStreamWaitEvent(s, ts->join[part], 0));
+            }
         }
-        accumulateKernel<<<gridSlots, kShadeThreads, 0, s>>>(a); ++nl; mark(1);
-        VPT_TRY(cudaGetLastError());
+        a.wb = wb0;
     }
 #undef VPT_TRY
     if (launches) *launches = nl;
