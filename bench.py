@@ -31,8 +31,11 @@ METRIC, UNIT = "Grays/s (1080p trace+denoise, 4 spp/GPU, 3 bounces; ms/frame in 
 # Algorithmic bytes per pixel of each denoiser kernel in THIS build's layout: every distinct
 # plane read once + every plane written once. The reference-layout figures are alongside.
 PASS_BYTES = {  # name: (this build B/px, reference layout B/px)
-    "firefly": (24, 24), "temporal": (132, 148), "history_fix": (8, 8), "history_clamp": (92, 92),
-    "atrous_smem": (60, 60), "atrous": (60, 60), "composite": (52, 52)}
+    "firefly": (64, 60),        # prep: packed denoiser G-buffer + BufferCopySky + firefly detect (D1 + D9a)
+    "temporal": (132, 148), "history_fix": (8, 8), "history_clamp": (92, 92),
+    "atrous_smem": (56, 60),
+    "atrous": (56, 60),         # per plain pass; the LAST pass also reads albedo and writes the output: +16 (this) / +52 (reference: + BufferCopyNonSky)
+    "composite": (0, 0)}        # fused into the last a-trous pass
 
 
 def load_peaks():
@@ -250,7 +253,7 @@ def main():
     peak, peak_src = load_peaks()
     npix = WIDTH * HEIGHT
     stages = [("trace_dda_x%d" % tim["trace_dda_launches"], tim["trace_dda_ms"], None),
-              ("trace_shade_x%d" % tim["trace_shade_launches"], tim["trace_shade_ms"] + tim["resolve_ms"], None), ("firefly", tim["firefly_ms"], "firefly"), ("temporal", tim["temporal_ms"], "temporal"),
+              ("trace_shade_x%d" % tim["trace_shade_launches"], tim["trace_shade_ms"] + tim["resolve_ms"], None), ("prep_firefly_sky", tim["firefly_ms"], "firefly"), ("temporal", tim["temporal_ms"], "temporal"),
               ("history_fix", tim["history_fix_ms"], "history_fix"), ("history_clamp", tim["history_clamp_ms"], "history_clamp"),
               ("atrous_smem", tim["atrous_smem_ms"], "atrous_smem"), ("atrous_x%d" % tim["atrous_passes"], tim["atrous_ms"], "atrous"),
               ("composite", tim["composite_ms"], "composite")]
@@ -260,11 +263,12 @@ def main():
         k = {"name": name, "ms": round(ms, 4), "share": round(ms / total_stage, 4) if total_stage > 0 else None}
         if key:
             mult = tim["atrous_passes"] if key == "atrous" else 1
-            k["algorithmic_bytes"] = PASS_BYTES[key][0] * npix * mult
+            extra = (16, 52) if key == "atrous" else (0, 0)   # the last pass carries the composite
+            k["algorithmic_bytes"] = (PASS_BYTES[key][0] * mult + extra[0]) * npix
             k["gbs"] = round(k["algorithmic_bytes"] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
-            k["gbs_ref_layout"] = round(PASS_BYTES[key][1] * npix * mult / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
+            k["gbs_ref_layout"] = round((PASS_BYTES[key][1] * mult + extra[1]) * npix / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
         kernels.append(k)
-    den = [k for k in kernels if "gbs" in k and k["ms"] > 0]
+    den = [k for k in kernels if "gbs" in k and k["ms"] > 0.01 and k["algorithmic_bytes"] > 0 and not k["name"].startswith("history_fix")]
     top = max(den, key=lambda k: k["ms"] / (tim["atrous_passes"] if k["name"].startswith("atrous_x") else 1))
     launches = tim["atrous_passes"] if top["name"].startswith("atrous_x") else 1
     achieved = top["algorithmic_bytes"] / launches / (top["ms"] / launches * 1e-3) / 1e9

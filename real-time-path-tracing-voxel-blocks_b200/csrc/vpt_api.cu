@@ -8,6 +8,7 @@
 // resident in 180 GB HBM3e. The Prev* G-buffer copies of the reference (Denoiser.cu:394-407, OptixRenderer.cpp:476-478)
 // are pointer ping-pong here: the "current" set flips at every render.
 #include "vpt_kernels.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -63,6 +64,8 @@ struct vpt_ctx
     int4 *primaryHits = nullptr;
     unsigned long long *counters = nullptr;
     FireflyPatch *patches = nullptr; int *patchCount = nullptr; int maxPatches = 0;
+    float4 *dnG = nullptr; uint32_t *dnMQ = nullptr; // packed denoiser G-buffer (vpt_denoise.cu)
+    unsigned *dnCounters = nullptr; int4 *fireflyList = nullptr; int *fixList = nullptr;
     // wavefront workspace (vpt_wave.cu), sized at the first render for (pixel slots, samples per wave)
     WaveWorkspace wave;
     TraceProfile traceProf;
@@ -126,6 +129,8 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     c->maxPatches = (int)(n / 4 + 64);
     CU(alloc((void **)&c->patches, (size_t)c->maxPatches * sizeof(FireflyPatch)));
     CU(alloc((void **)&c->patchCount, sizeof(int)));
+    CU(alloc((void **)&c->dnG, n * 16)); CU(alloc((void **)&c->dnMQ, n * 4)); CU(alloc((void **)&c->dnCounters, 4 * sizeof(unsigned)));
+    CU(alloc((void **)&c->fireflyList, (size_t)c->maxPatches * sizeof(int4))); CU(alloc((void **)&c->fixList, n * sizeof(int)));
     CU(alloc((void **)&c->sobol, 65536)); CU(alloc((void **)&c->scrambling, 131072)); CU(alloc((void **)&c->ranking, 131072 + 256));
     CU(alloc((void **)&c->blockToMaterial, 256 * sizeof(uint16_t)));
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
@@ -148,7 +153,7 @@ void vpt_destroy(vpt_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
                     c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
-                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev};
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
     {
@@ -377,8 +382,12 @@ int vpt_render(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int i
 }
 int vpt_begin_external_frame(vpt_ctx *c) { if (!c) return VPT_ERR_ARG; c->cur ^= 1; return VPT_OK; }
 
-static int denoiseRows(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
-                       int rowBegin, int rowEnd, bool timing)
+static int haloExchange(vpt_ctx *c, void *plane, int elemFloats, int rowBegin, int rowEnd, int rows);
+
+// Denoiser::run (renderer/denoising/Denoiser.cu:24-408) over rows [rowBegin,rowEnd). band: this rank owns only those rows
+//  and exchanges halo rows with its neighbours between passes; inputs are valid on the band plus a guard.
+static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
+                        int rowBegin, int rowEnd, bool timing, bool band)
 {
     DenoiseLaunch d;
     d.width = c->width; d.height = c->height; d.rowBegin = rowBegin; d.rowEnd = rowEnd;
@@ -386,53 +395,93 @@ static int denoiseRows(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera 
     d.b.cur = c->gb[c->cur].ptrs(); d.b.prev = c->gb[c->cur ^ 1].ptrs();
     d.b.illumination = c->illumination; d.b.illumOutput = c->illumOutput; d.b.ping = c->ping; d.b.pong = c->pong;
     d.b.prevIllum = c->prevIllum; d.b.prevFastIllum = c->prevFastIllum; d.b.historyLength = c->historyLength; d.b.prevHistoryLength = c->prevHistoryLength;
+    d.view = makeDnView(*cam); d.G = c->dnG; d.MQ = c->dnMQ; d.counters = c->dnCounters; d.fireflyList = c->fireflyList; d.fixList = c->fixList;
     const int usedIter = iterationIndex > 0 ? iterationIndex - 1 : 0;
     d.b.reservoirs = c->reservoirs + (size_t)(usedIter & 1) * c->npix();
     auto rec = [&](int e) -> cudaError_t { return timing ? cudaEventRecord(c->ev[e], c->stream) : cudaSuccess; };
-    int launches = 0;
+    auto halo = [&](void *plane, int elemFloats, int rows) -> int { return band ? haloExchange(c, plane, elemFloats, rowBegin, rowEnd, rows) : VPT_OK; };
+    int launches = 0, rc;
     c->ranFirefly = c->ranTemporal = c->ranFix = c->ranClamp = c->ranSpatial = false;
     c->atrousPasses = 0;
     CU(rec(EV_DN0));
-    if (p->enableFireflyFilter) { CU(launchFirefly(d, c->patches, c->patchCount, c->maxPatches)); launches += 2; c->ranFirefly = true; }
+    // packed G-buffer + sky copy (+ firefly): the stencil passes read G/MQ up to 18 rows outside the band
+    const int guard = 32;
+    const int prep0 = band ? std::max(0, rowBegin - guard) : rowBegin, prep1 = band ? std::min(c->height, rowEnd + guard) : rowEnd;
+    CU(launchPrep(d, prep0, prep1, p->enableFireflyFilter != 0, c->patches, c->maxPatches));
+    launches += p->enableFireflyFilter ? 3 : 1; c->ranFirefly = true;
+    if (p->enableFireflyFilter && (rc = halo(c->illumination, 4, 2))) return rc; // 5x5 noisy moments in HistoryClamping
     CU(rec(EV_FIREFLY));
-    CU(launchCopySky(d)); launches++;
-    if (frameNum == 0) { CU(launchFrame0Init(d)); launches++; }
+    if (frameNum == 0)
+    {
+        CU(launchFrame0Init(d)); launches++;
+        if ((rc = halo(c->prevIllum, 4, 2))) return rc;
+    }
     CU(rec(EV_SKY));
     int finalBuf = 0;
     if (p->enableTemporalAccumulation && frameNum > 0)
     {
+        // band mode: static camera or small motion — history taps stay within the guard band exchanged at the end of the last frame
         CU(launchTemporal(d)); launches++; finalBuf = 1; c->ranTemporal = true;
+        if ((rc = halo(c->historyLength, 1, 18))) return rc;
+        if ((rc = halo(c->ping, 4, 18))) return rc; // HistoryFix stride <= 9, 2 taps
+        if ((rc = halo(c->pong, 4, 2))) return rc;
         CU(rec(EV_TEMPORAL));
-        if (p->enableHistoryFix) { CU(launchHistoryFix(d)); launches++; finalBuf = 2; c->ranFix = true; }
+        if (p->enableHistoryFix)
+        {
+            CU(launchHistoryFix(d, c->smCount)); launches++; finalBuf = 2; c->ranFix = true;
+            if ((rc = halo(c->pong, 4, 2))) return rc;
+        }
         CU(rec(EV_HFIX));
         if (p->enableHistoryClamping) { CU(launchHistoryClamping(d)); launches++; finalBuf = 3; c->ranClamp = true; }
         CU(rec(EV_HCLAMP));
     }
     else { CU(rec(EV_TEMPORAL)); CU(rec(EV_HFIX)); CU(rec(EV_HCLAMP)); }
+    bool composited = false;
     if (p->enableSpatialFiltering)
     {
+        if ((rc = halo(c->prevIllum, 4, 2))) return rc;
         CU(launchAtrousSmem(d, c->prevIllum, c->ping)); launches++; finalBuf = 1; c->ranSpatial = true;
         CU(rec(EV_ASMEM));
         if (p->atrousIterationNum > 0)
         {
             int idx = 1, step = 1 << idx;
             const int maxIt = p->atrousIterationNum * 2;
+            auto pass = [&](float4 *in, float4 *out, bool last) -> int {
+                const int hrows = step + (step > 4 ? step / 4 + 1 : 0);
+                int r2 = halo(in, 4, hrows);
+                if (r2) return r2;
+                // the last pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky fused)
+                cudaError_t e = launchAtrous(d, in, last ? c->illumOutput : out, (unsigned)iterationIndex, (unsigned)step, last);
+                if (e != cudaSuccess) return fail(VPT_ERR_CUDA, cudaGetErrorString(e));
+                launches++; c->atrousPasses++;
+                return VPT_OK;
+            };
             while (idx < maxIt)
             {
-                CU(launchAtrous(d, c->ping, c->pong, (unsigned)iterationIndex, (unsigned)step)); launches++; c->atrousPasses++;
+                if ((rc = pass(c->ping, c->pong, false))) return rc;
                 ++idx; step = 1 << idx;
-                CU(launchAtrous(d, c->pong, c->ping, (unsigned)iterationIndex, (unsigned)step)); launches++; c->atrousPasses++;
+                if ((rc = pass(c->pong, c->ping, false))) return rc;
                 ++idx; step = 1 << idx;
             }
-            CU(launchAtrous(d, c->ping, c->pong, (unsigned)iterationIndex, (unsigned)step)); launches++; c->atrousPasses++;
-            finalBuf = 2;
+            if ((rc = pass(c->ping, c->pong, true))) return rc;
+            finalBuf = 2; composited = true;
         }
         CU(rec(EV_ATROUS));
     }
     else { CU(rec(EV_ASMEM)); CU(rec(EV_ATROUS)); }
-    const float4 *fin = finalBuf == 1 ? c->ping : finalBuf == 2 ? c->pong : finalBuf == 3 ? c->prevIllum : c->illumination;
-    CU(launchCompositeNonSky(d, fin)); launches++;
+    if (!composited)
+    {
+        const float4 *fin = finalBuf == 1 ? c->ping : finalBuf == 2 ? c->pong : finalBuf == 3 ? c->prevIllum : c->illumination;
+        CU(launchCompositeNonSky(d, fin)); launches++;
+    }
     CU(rec(EV_COMP));
+    if (band)
+    {
+        // history for the next frame's temporal pass: guard band of 32 rows (bicubic footprint + small camera motion)
+        if ((rc = halo(c->prevIllum, 4, 32))) return rc;
+        if ((rc = halo(c->prevFastIllum, 4, 32))) return rc;
+        if ((rc = halo(c->prevHistoryLength, 1, 32))) return rc;
+    }
     c->launchesDenoise = launches;
     c->haveDenoise = timing;
     return VPT_OK;
@@ -444,7 +493,7 @@ int vpt_denoise(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, c
     if (p->enableHitDistanceReconstruction || p->enablePrePass)
         return fail(VPT_ERR_ARG, "vpt_denoise: HitDistReconstruction / PrePass are off in the shipped settings and not built (SURVEY 8a D2/D3)");
     CU(cudaSetDevice(c->device));
-    return denoiseRows(c, p, cam, prevCam, frameNum, iterationIndex, 0, c->height, c->profiling);
+    return denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, 0, c->height, c->profiling, false);
 }
 
 static int planeInfo(vpt_ctx *c, VptBufferName name, void **ptr, size_t *bytes)
@@ -716,7 +765,7 @@ static int haloExchange(vpt_ctx *c, void *plane, int elemFloats, int rowBegin, i
 
 // Row-band sharded Denoiser::run: every rank holds full-size planes but only its band
 // [rowBegin,rowEnd) (+ halos) is valid. Inputs (Illumination + current G-buffer) must be valid on the band plus
-// kGuard rows either side (the caller uploads them that way); history planes are exchanged as they are produced.
+// 32 guard rows either side (the caller uploads them that way); history planes are exchanged as they are produced.
 int vpt_denoise_band(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
                      int rowBegin, int rowEnd)
 {
@@ -725,75 +774,7 @@ int vpt_denoise_band(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *c
     if (c->nranks > 1 && !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_denoise_band: communicator not initialised");
     if (p->enableHitDistanceReconstruction || p->enablePrePass) return fail(VPT_ERR_ARG, "vpt_denoise_band: unsupported pass enabled");
     CU(cudaSetDevice(c->device));
-    DenoiseLaunch d;
-    d.width = c->width; d.height = c->height; d.rowBegin = rowBegin; d.rowEnd = rowEnd;
-    d.cam = *cam; d.prevCam = *prevCam; d.p = *p; d.stream = c->stream;
-    d.b.cur = c->gb[c->cur].ptrs(); d.b.prev = c->gb[c->cur ^ 1].ptrs();
-    d.b.illumination = c->illumination; d.b.illumOutput = c->illumOutput; d.b.ping = c->ping; d.b.pong = c->pong;
-    d.b.prevIllum = c->prevIllum; d.b.prevFastIllum = c->prevFastIllum; d.b.historyLength = c->historyLength; d.b.prevHistoryLength = c->prevHistoryLength;
-    const int usedIter = iterationIndex > 0 ? iterationIndex - 1 : 0;
-    d.b.reservoirs = c->reservoirs + (size_t)(usedIter & 1) * c->npix();
-    int rc;
-    if (p->enableFireflyFilter)
-    {
-        CU(launchFirefly(d, c->patches, c->patchCount, c->maxPatches));
-        if ((rc = haloExchange(c, c->illumination, 4, rowBegin, rowEnd, 2))) return rc; // 5x5 noisy moments in HistoryClamping
-    }
-    CU(launchCopySky(d));
-    if (frameNum == 0)
-    {
-        CU(launchFrame0Init(d));
-        if ((rc = haloExchange(c, c->prevIllum, 4, rowBegin, rowEnd, 2))) return rc;
-    }
-    int finalBuf = 0;
-    if (p->enableTemporalAccumulation && frameNum > 0)
-    {
-        // static camera or small motion: history taps stay within the guard band exchanged at the end of the last frame
-        CU(launchTemporal(d)); finalBuf = 1;
-        if ((rc = haloExchange(c, c->historyLength, 1, rowBegin, rowEnd, 18))) return rc;
-        if ((rc = haloExchange(c, c->ping, 4, rowBegin, rowEnd, 18))) return rc; // HistoryFix stride <= 9, 2 taps
-        if ((rc = haloExchange(c, c->pong, 4, rowBegin, rowEnd, 2))) return rc;
-        if (p->enableHistoryFix)
-        {
-            CU(launchHistoryFix(d)); finalBuf = 2;
-            if ((rc = haloExchange(c, c->pong, 4, rowBegin, rowEnd, 2))) return rc;
-        }
-        if (p->enableHistoryClamping) { CU(launchHistoryClamping(d)); finalBuf = 3; }
-    }
-    if (p->enableSpatialFiltering)
-    {
-        if ((rc = haloExchange(c, c->prevIllum, 4, rowBegin, rowEnd, 2))) return rc;
-        CU(launchAtrousSmem(d, c->prevIllum, c->ping)); finalBuf = 1;
-        if (p->atrousIterationNum > 0)
-        {
-            int idx = 1, step = 1 << idx;
-            const int maxIt = p->atrousIterationNum * 2;
-            auto pass = [&](float4 *in, float4 *out) -> int {
-                const int halo = step + (step > 4 ? step / 4 + 1 : 0);
-                int r2 = haloExchange(c, in, 4, rowBegin, rowEnd, halo);
-                if (r2) return r2;
-                cudaError_t e = launchAtrous(d, in, out, (unsigned)iterationIndex, (unsigned)step);
-                if (e != cudaSuccess) return fail(VPT_ERR_CUDA, cudaGetErrorString(e));
-                return VPT_OK;
-            };
-            while (idx < maxIt)
-            {
-                if ((rc = pass(c->ping, c->pong))) return rc;
-                ++idx; step = 1 << idx;
-                if ((rc = pass(c->pong, c->ping))) return rc;
-                ++idx; step = 1 << idx;
-            }
-            if ((rc = pass(c->ping, c->pong))) return rc;
-            finalBuf = 2;
-        }
-    }
-    const float4 *fin = finalBuf == 1 ? c->ping : finalBuf == 2 ? c->pong : finalBuf == 3 ? c->prevIllum : c->illumination;
-    CU(launchCompositeNonSky(d, fin));
-    // history for the next frame's temporal pass: guard band of 32 rows (bicubic footprint + small camera motion)
-    if ((rc = haloExchange(c, c->prevIllum, 4, rowBegin, rowEnd, 32))) return rc;
-    if ((rc = haloExchange(c, c->prevFastIllum, 4, rowBegin, rowEnd, 32))) return rc;
-    if ((rc = haloExchange(c, c->prevHistoryLength, 1, rowBegin, rowEnd, 32))) return rc;
-    return VPT_OK;
+    return denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, rowBegin, rowEnd, false, c->nranks > 1);
 }
 
 } // extern "C"

@@ -1,95 +1,36 @@
-// Denoiser pass chain for sm_100a — bandwidth-bound stencil kernels over linear fp32 planes.
+// Denoiser pass chain for sm_100a — bandwidth-bound stencil kernels over dense fp32 planes.
 // Replaces /root/reference/renderer/denoising/*.h (cudaArray surface kernels, 8x8 blocks):
-//   FireflyBoilingFilter  FireflyFilter.h:9-251      -> fireflyDetectKernel + fireflyApplyKernel
-//   BufferCopySky/NonSky  BufferCopy.h:6-34, 36-116  -> copySkyKernel, compositeKernel
+//   FireflyBoilingFilter  FireflyFilter.h:9-251      -> prepKernel (detect) + fireflyApplyKernel
+//   BufferCopySky         BufferCopy.h:6-34          -> prepKernel
 //   TemporalAccumulation  TemporalAccumulation.h     -> temporalKernel
 //   HistoryFix            HistoryFix.h:20-120        -> historyFixKernel
 //   HistoryClamping       HistoryClamping.h:27-219   -> historyClampKernel
 //   AtrousSmem            AtrousSmem.h:66-303        -> atrousFirstKernel
-//   Atrous                Atrous.h:6-158             -> atrousKernel
-// Layout: every plane is a dense row-major array (float4 or float per pixel); a warp covers 32
-// x-consecutive pixels, so each float4 row access is four full 128-byte lines. Stencil taps are served
-// from L1/L2 (read-only path); each plane crosses HBM once per pass. Clamp addressing everywhere, as the
-// reference's cudaBoundaryModeClamp surface reads. Rows [rowBegin,rowEnd) are processed so the same kernels
-// serve the row-band sharded multi-GPU path. Compiled -fmad=false (oracle-exact + - * / sqrt).
-#include "vpt_kernels.h"
-#include "vpt_math.cuh"
+//   Atrous                Atrous.h:6-158             -> atrousKernel<kComposite>
+//   BufferCopyNonSky      BufferCopy.h:36-116        -> fused into the last atrousKernel (compositeKernel when spatial filtering is off)
+//
+// B200 shape. The reference rebuilds, PER TAP, the tap's world position (normalize(M*uv)*depth: a 3x3 product, an
+// rsqrt, three multiplies) and re-reads three separate G-buffer planes; its 5x5 passes recompute per-pixel colour
+// transforms 25 times. Measured on B200 those kernels are ALU-bound at 25 % of HBM peak. Here:
+//  * prepKernel writes, once per frame, the packed DENOISER G-BUFFER the stencil passes read:
+//      G  float4 = (normal.xyz, zs)   zs = depth / |M*(u,v,1)| (view-scaled depth): world position = cam + v(x,y)*zs
+//                                      with v(x,y) = M0 + x*Mx + y*My affine in the pixel -> a tap's plane distance
+//                                      to the centre's tangent plane is zs_tap*(A0 + x*Ax + y*Ay) - c0: 3 FMAs
+//      MQ uint32 = material id (exact, hi 16) | the "Load2DUshort1" 16-bit value (lo 16; the reference reads the
+//                  float material surface as ushorts: Sampler.h:102-107 at HistoryFix.h:61,87 and Atrous.h:47,110)
+//    fused with BufferCopySky and the firefly detection (all three are one pass over depth/normal/material/reservoir).
+//  * the 5x5 moment pass (HistoryClamping) stages colour transforms once per pixel in shared memory and sums them
+//    separably (5 + 5 taps instead of 25).
+//  * the last a-trous pass multiplies by albedo and writes IlluminationOutput directly (no Pong round trip).
+// Every plane is a dense row-major array; a warp covers 32 x-consecutive pixels (full 128-byte lines per float4 row).
+// Clamp addressing as the reference's cudaBoundaryModeClamp. Rows [rowBegin,rowEnd) are processed so the same kernels
+// serve the row-band sharded multi-GPU path. Fast arithmetic class (vpt_math.cuh); differences of squares that cancel
+// (variance estimates) use explicit non-contracted multiplies so they round like the oracle.
+#include "vpt_denoise_common.cuh"
 
 namespace vpt {
 
-constexpr float kDenoisingRange = 500000.0f;
-constexpr int kBX = 32, kBY = 8;
-
-struct Cam
-{
-    f3 pos, dir; float invResX, invResY, tanHalfFovX, resX;
-    mat3 uvToWorld, worldToUv;
-};
-VPT_DEV Cam loadCam(const VptCamera &c)
-{
-    Cam k;
-    k.pos = F3(c.pos[0], c.pos[1], c.pos[2]); k.dir = F3(c.dir[0], c.dir[1], c.dir[2]);
-    k.invResX = c.inversedResolution[0]; k.invResY = c.inversedResolution[1];
-    k.tanHalfFovX = c.tanHalfFov[0]; k.resX = c.resolution[0];
-    k.uvToWorld = mat3From(c.uvToWorld); k.worldToUv = mat3From(c.worldToUv);
-    return k;
-}
-VPT_DEV f3 uvToWorldDirection(const Cam &c, f2 uv) { return normalize(mul(c.uvToWorld, F3(uv.x, uv.y, 1.0f))); }
-VPT_DEV f2 worldDirectionToUV(const Cam &c, f3 d) { f3 h = mul(c.worldToUv, d); return {h.x / h.z, h.y / h.z}; }
-VPT_DEV f3 worldPosFromPixel(const Cam &c, int x, int y, float depth)
-{
-    f2 uv = {(float(x) + 0.5f) * c.invResX, (float(y) + 0.5f) * c.invResY};
-    return c.pos + uvToWorldDirection(c, uv) * depth;
-}
-VPT_DEV f4 ld4(const float4 *b, int W, int H, int x, int y)
-{
-    x = clampi(x, 0, W - 1); y = clampi(y, 0, H - 1);
-    return F4(__ldg(b + (size_t)y * W + x));
-}
-VPT_DEV float ld1(const float *b, int W, int H, int x, int y)
-{
-    x = clampi(x, 0, W - 1); y = clampi(y, 0, H - 1);
-    return __ldg(b + (size_t)y * W + x);
-}
-// Load2DUshort1 on the float material surface (Sampler.h:102-107 used at HistoryFix.h:61,87; Atrous.h:47,110)
-VPT_DEV float matU16(const float *mat, int W, int H, int x, int y)
-{
-    y = clampi(y, 0, H - 1);
-    x = clampi(x, 0, 2 * W - 1);
-    const unsigned short *row = reinterpret_cast<const unsigned short *>(mat + (size_t)y * W);
-    return (float)__ldg(row + x);
-}
-VPT_DEV float linearStep(float a, float b, float x) { return saturate((x - a) / (b - a)); }
-VPT_DEV float smoothStep(float a, float b, float x) { float t = linearStep(a, b, x); return t * t * (3.0f - 2.0f * t); }
-VPT_DEV float acosApprox(float x) { return sqrtf(2.0f) * sqrtf(saturate(1.0f - x)); }
-VPT_DEV float nonExpWeight(float x, float px, float py) { return smoothStep(1.0f, 0.0f, fabsf(x * px + py)); }
-VPT_DEV float specLobeTanHalfAngle(float roughness, float percentOfVolume)
-{
-    roughness = saturate(roughness); percentOfVolume = saturate(percentOfVolume);
-    return roughness * roughness * percentOfVolume / (1.0f - percentOfVolume + 1e-6f);
-}
-VPT_DEV float normalWeightParam2(float roughness, float angleFraction)
-{
-    float angle = atanf(specLobeTanHalfAngle(roughness, angleFraction));
-    return 1.0f / fmaxr(angle, 1e-6f);
-}
-VPT_DEV float planeDistWeightAtrous(f3 cpos, f3 cn, f3 spos, float thr) { return fabsf(dot(spos - cpos, cn)) < thr ? 1.0f : 0.0f; }
-VPT_DEV f3 rgbToYCoCg(f3 c) { return {0.25f * (c.x + 2.0f * c.y + c.z), c.x - c.z, c.y - 0.5f * (c.x + c.z)}; }
-VPT_DEV f3 yCoCgToRgb(f3 c) { return {c.x + 0.5f * (c.y - c.z), c.x + 0.5f * c.z, c.x - 0.5f * (c.y + c.z)}; }
-VPT_DEV uint32_t seqHash(uint32_t x) { x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16; return x; }
-VPT_DEV uint32_t seqExplode(uint32_t x)
-{
-    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
-    return x;
-}
-
-#define PIXEL_GUARD(W_, rowBegin_, rowEnd_)                       \
-    const int x = blockIdx.x * kBX + threadIdx.x;                 \
-    const int y = (rowBegin_) + blockIdx.y * kBY + threadIdx.y;   \
-    if (x >= (W_) || y >= (rowEnd_)) return;                      \
-    const size_t pix = (size_t)y * (W_) + x;
-
-// ------------------------------------------------------------------------------------------------ firefly
+// ------------------------------------------------------------------------------------------------ prep + firefly detect + sky copy
 VPT_DEV bool reservoirValid(const VptReservoir &r) { return r.lightData != 0 && isfinite(r.weightSum) && r.weightSum > 0.0f; }
 VPT_DEV VptReservoir ldRes(const VptReservoir *p)
 {
@@ -100,34 +41,62 @@ VPT_DEV VptReservoir ldRes(const VptReservoir *p)
     return r;
 }
 
-// Detect + filter, reading only pre-pass values; results go to a patch list that fireflyApplyKernel commits
-// (the reference's in-place read-modify-write is a race, FireflyFilter.h:151,236). 256 threads = 8 warps,
-// each warp is one 8x4 tile exactly as the reference's 8x4 block, so the tile statistics partition matches.
-__global__ void __launch_bounds__(256) fireflyDetectKernel(int W, int H, int rowBegin, int rowEnd, const float4 *__restrict__ illum,
-                                                           const float4 *__restrict__ normalRough, const float *__restrict__ depth,
-                                                           const float *__restrict__ material, const VptReservoir *__restrict__ res,
-                                                           float weightThreshold, float minWeight, float normalThreshold, float depthSigma,
-                                                           float phiLuminance, VptCamera camIn, FireflyPatch *patches, int *patchCount, int maxPatches)
+struct PrepArgs
 {
+    int W, H, prepRow0, prepRow1, ffRow0, ffRow1, enableFirefly;
+    DnView view;
+    const float *depth, *material;
+    const float4 *normalRough, *illum;
+    const VptReservoir *res;
+    float4 *G; uint32_t *MQ; float4 *out;
+    unsigned *counters; // [0] firefly candidates, [1] HistoryFix list length (zeroed here for the temporal pass)
+    float weightThreshold, minWeight;
+    int4 *fireflyList;  // pixel, neighbourValidCount, neighbourWeightSum bits, -
+    int maxList;
+};
+
+// One warp = one 8x4 pixel tile (256 threads = 8 tiles), exactly the reference's 8x4 firefly block, so the tile
+// statistics partition matches (FireflyFilter.h:51-65). Per pixel: the packed denoiser G-buffer, the sky copy
+// (BufferCopySky) and the firefly TEST on the reservoir weights; the rare positives go to a list that
+// fireflyFilterKernel turns into patches and fireflyApplyKernel commits (the reference's in-place read-modify-write
+// is a race, FireflyFilter.h:151,236).
+__global__ void __launch_bounds__(256) prepKernel(const __grid_constant__ PrepArgs a)
+{
+    const int W = a.W, H = a.H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tilesX = (W + 7) >> 3;
     const int tile = blockIdx.x * 8 + warp;
-    const int tilesY = (rowEnd - rowBegin + 3) >> 2;
+    const int tilesY = (a.prepRow1 - a.prepRow0 + 3) >> 2;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[1] = 0u;
     if (tile >= tilesX * tilesY) return;
     const int x = (tile % tilesX) * 8 + (lane & 7);
-    const int y = rowBegin + (tile / tilesX) * 4 + (lane >> 3);
-    const bool inb = x < W && y < rowEnd;
+    const int y = a.prepRow0 + (tile / tilesX) * 4 + (lane >> 3);
+    const bool inb = x < W && y < a.prepRow1;
     const size_t pix = (size_t)y * W + x;
     float centerDepth = 0.0f;
-    VptReservoir reservoir; reservoir.lightData = 0; reservoir.uvData = 0; reservoir.weightSum = 0; reservoir.targetPdf = 0; reservoir.M = 0;
-    bool participates = false;
     if (inb)
     {
-        centerDepth = __ldg(depth + pix);
-        if (!(centerDepth > kDenoisingRange)) { reservoir = ldRes(res + pix); participates = true; }
+        centerDepth = __ldg(a.depth + pix);
+        const float4 nr = __ldg(a.normalRough + pix);
+        const float m = __ldg(a.material + pix);
+        const uint32_t quirk = (uint32_t)matU16(a.material, W, H, x, y);
+        const f3 v = viewVec(a.view, (float)x, (float)y);
+        const float zs = centerDepth * rsqrtf(dot(v, v));
+        a.G[pix] = make_float4(nr.x, nr.y, nr.z, zs);
+        a.MQ[pix] = (quirk & 0xffffu) | ((uint32_t)m << 16);
+        if (centerDepth > kDenoisingRange) a.out[pix] = __ldg(a.illum + pix);
     }
-    const bool valid = participates && reservoirValid(reservoir);
-    float wsum = valid ? reservoir.weightSum : 0.0f;
+    if (!a.enableFirefly) return;
+    // ---- firefly test (FireflyFilter.h:9-110): only lightData / weightSum of the reservoir are needed here
+    const bool participates = inb && y >= a.ffRow0 && y < a.ffRow1 && !(centerDepth > kDenoisingRange);
+    uint32_t lightData = 0; float weight = 0.0f;
+    if (participates)
+    {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(a.res + pix);
+        lightData = __ldg(q); weight = __uint_as_float(__ldg(q + 2));
+    }
+    const bool valid = participates && lightData != 0 && isfinite(weight) && weight > 0.0f;
+    float wsum = valid ? weight : 0.0f;
     unsigned wcnt = valid ? 1u : 0u;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
@@ -138,100 +107,129 @@ __global__ void __launch_bounds__(256) fireflyDetectKernel(int W, int H, int row
     wsum = __shfl_sync(0xffffffffu, wsum, 0);
     wcnt = __shfl_sync(0xffffffffu, wcnt, 0);
     if (!valid) return;
-
-    const float currentWeight = reservoir.weightSum;
-    const float neighborWeightSum = wsum - currentWeight;
+    const float neighborWeightSum = wsum - weight;
     const int neighborValidCount = (int)wcnt - 1;
     bool isFirefly = false;
-    if (currentWeight >= minWeight)
+    if (weight >= a.minWeight)
     {
         if (neighborValidCount <= 0) isFirefly = true;
         else
         {
             const float avg = neighborWeightSum / float(neighborValidCount);
-            if (avg > 0.0f && currentWeight > avg * weightThreshold) isFirefly = true;
+            if (avg > 0.0f && weight > avg * a.weightThreshold) isFirefly = true;
         }
     }
     if (!isFirefly) return;
+    const unsigned slot = atomicAdd(a.counters, 1u);
+    if (slot < (unsigned)a.maxList) a.fireflyList[slot] = make_int4((int)pix, neighborValidCount, __float_as_int(neighborWeightSum), 0);
+}
 
-    const Cam cam = loadCam(camIn);
-    const f4 centerColor4 = F4(__ldg(illum + pix));
-    const float centerLum = luminance(xyz(centerColor4));
-    f3 centerNormal = xyz(__ldg(normalRough + pix));
-    const float cnLen = length(centerNormal);
-    if (cnLen > 0.0f) centerNormal /= cnLen; else centerNormal = F3(0.0f, 1.0f, 0.0f);
-    const float centerMaterial = __ldg(material + pix);
-    const f3 centerWorldPos = worldPosFromPixel(cam, x, y, centerDepth);
-    const float gaussian[3] = {1.0f, 2.0f, 1.0f};
-    f4 filteredColor = centerColor4; float filteredWeight = 1.0f;
-    f4 fallbackColor = centerColor4 * (gaussian[0] * gaussian[0]); float fallbackWeight = gaussian[0] * gaussian[0];
-    const float depthScale = fmaxf(fabsf(centerDepth), 1.0f);
-    const float normalWeightParam = normalWeightParam2(1.0f, 0.25f);
-    VptReservoir best = reservoir; float bestScore = FLT_MAX; bool hasReplacement = false;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx)
-        {
-            if (dx == 0 && dy == 0) continue;
-            const int sx = x + dx, sy = y + dy;
-            if (sx < 0 || sy < 0 || sx >= W || sy >= H) continue;
-            const size_t sp = (size_t)sy * W + sx;
-            const float gw = gaussian[abs(dx)] * gaussian[abs(dy)];
-            const f4 sc4 = F4(__ldg(illum + sp));
-            fallbackColor += sc4 * gw; fallbackWeight += gw;
-            const float sd = __ldg(depth + sp);
-            if (sd > kDenoisingRange) continue;
-            f3 sn = xyz(__ldg(normalRough + sp));
-            const float snLen = length(sn);
-            if (snLen <= 0.0f) continue;
-            sn /= snLen;
-            const float nd = dot(centerNormal, sn);
-            if (nd < normalThreshold) continue;
-            if (fabsf(__ldg(material + sp) - centerMaterial) > 0.5f) continue;
-            const f3 swp = worldPosFromPixel(cam, sx, sy, sd);
-            const float geomW = planeDistWeightAtrous(centerWorldPos, centerNormal, swp, depthSigma * depthScale);
-            if (geomW <= 0.0f) continue;
-            const float normalW = nonExpWeight(acosApprox(clampf(nd, -1.0f, 1.0f)), normalWeightParam, 0.0f);
-            const float depthW = expf(-fabsf(sd - centerDepth) / (depthScale * depthSigma + 1e-6f));
-            const float lumW = expf(-fabsf(luminance(xyz(sc4)) - centerLum) * phiLuminance);
-            const float total = gw * geomW * normalW * depthW * lumW;
-            if (total > 1e-5f) { filteredColor += sc4 * total; filteredWeight += total; }
-            const VptReservoir nr = ldRes(res + sp);
-            const bool nValid = nr.lightData != 0 && isfinite(nr.weightSum) && nr.weightSum > 0.0f && nr.weightSum < currentWeight;
-            if (nValid)
+struct FireflyArgs
+{
+    int W, H;
+    VptCamera cam;
+    const float *depth, *material;
+    const float4 *normalRough, *illum;
+    const VptReservoir *res;
+    const unsigned *counters;
+    const int4 *fireflyList; int maxList;
+    float weightThreshold, minWeight, normalThreshold, depthSigma, phiLuminance;
+    FireflyPatch *patches;
+};
+// 3x3 bilateral replacement of a firefly's colour and reservoir (FireflyFilter.h:112-251), one thread per list entry,
+// reading only pre-pass values.
+__global__ void __launch_bounds__(128) fireflyFilterKernel(const __grid_constant__ FireflyArgs a)
+{
+    const int W = a.W, H = a.H;
+    const int n = (int)min(__ldg(a.counters), (unsigned)a.maxList);
+    const float weightThreshold = a.weightThreshold, minWeight = a.minWeight, normalThreshold = a.normalThreshold, depthSigma = a.depthSigma;
+    const float4 *illum = a.illum; const float4 *normalRough = a.normalRough; const float *depth = a.depth, *material = a.material;
+    const VptReservoir *res = a.res;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    {
+        const int4 ent = __ldg(a.fireflyList + e);
+        const size_t pix = (size_t)ent.x;
+        const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
+        const int neighborValidCount = ent.y;
+        const float neighborWeightSum = __int_as_float(ent.z);
+        const VptReservoir reservoir = ldRes(res + pix);
+        const float currentWeight = reservoir.weightSum;
+        const float centerDepth = __ldg(depth + pix);
+        const Cam cam = loadCam(a.cam);
+        const f4 centerColor4 = F4(__ldg(illum + pix));
+        const float centerLum = luminance(xyz(centerColor4));
+        f3 centerNormal = xyz(__ldg(normalRough + pix));
+        const float cnLen = length(centerNormal);
+        if (cnLen > 0.0f) centerNormal /= cnLen; else centerNormal = F3(0.0f, 1.0f, 0.0f);
+        const float centerMaterial = __ldg(material + pix);
+        const f3 centerWorldPos = worldPosFromPixel(cam, x, y, centerDepth);
+        const float gaussian[3] = {1.0f, 2.0f, 1.0f};
+        f4 filteredColor = centerColor4; float filteredWeight = 1.0f;
+        f4 fallbackColor = centerColor4 * (gaussian[0] * gaussian[0]); float fallbackWeight = gaussian[0] * gaussian[0];
+        const float depthScale = fmaxf(fabsf(centerDepth), 1.0f);
+        const float normalWeightParam = normalWeightParam2(1.0f, 0.25f);
+        VptReservoir best = reservoir; float bestScore = FLT_MAX; bool hasReplacement = false;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
             {
-                const float depthTerm = fabsf(sd - centerDepth) / (depthScale + 1e-6f);
-                const float normalTerm = 1.0f - clampf(nd, 0.0f, 1.0f);
-                const float weightDiff = fabsf(nr.weightSum - currentWeight);
-                const float score = depthTerm + normalTerm + 0.25f * weightDiff;
-                if (score < bestScore) { bestScore = score; best = nr; hasReplacement = true; }
+                if (dx == 0 && dy == 0) continue;
+                const int sx = x + dx, sy = y + dy;
+                if (sx < 0 || sy < 0 || sx >= W || sy >= H) continue;
+                const size_t sp = (size_t)sy * W + sx;
+                const float gw = gaussian[abs(dx)] * gaussian[abs(dy)];
+                const f4 sc4 = F4(__ldg(illum + sp));
+                fallbackColor += sc4 * gw; fallbackWeight += gw;
+                const float sd = __ldg(depth + sp);
+                if (sd > kDenoisingRange) continue;
+                f3 sn = xyz(__ldg(normalRough + sp));
+                const float snLen = length(sn);
+                if (snLen <= 0.0f) continue;
+                sn /= snLen;
+                const float nd = dot(centerNormal, sn);
+                if (nd < normalThreshold) continue;
+                if (fabsf(__ldg(material + sp) - centerMaterial) > 0.5f) continue;
+                const f3 swp = worldPosFromPixel(cam, sx, sy, sd);
+                const float geomW = planeDistWeightAtrous(centerWorldPos, centerNormal, swp, depthSigma * depthScale);
+                if (geomW <= 0.0f) continue;
+                const float normalW = nonExpWeight(acosApprox(clampf(nd, -1.0f, 1.0f)), normalWeightParam, 0.0f);
+                const float depthW = expf(-fabsf(sd - centerDepth) / (depthScale * depthSigma + 1e-6f));
+                const float lumW = expf(-fabsf(luminance(xyz(sc4)) - centerLum) * a.phiLuminance);
+                const float total = gw * geomW * normalW * depthW * lumW;
+                if (total > 1e-5f) { filteredColor += sc4 * total; filteredWeight += total; }
+                const VptReservoir nr = ldRes(res + sp);
+                const bool nValid = nr.lightData != 0 && isfinite(nr.weightSum) && nr.weightSum > 0.0f && nr.weightSum < currentWeight;
+                if (nValid)
+                {
+                    const float depthTerm = fabsf(sd - centerDepth) / (depthScale + 1e-6f);
+                    const float normalTerm = 1.0f - clampf(nd, 0.0f, 1.0f);
+                    const float weightDiff = fabsf(nr.weightSum - currentWeight);
+                    const float score = depthTerm + normalTerm + 0.25f * weightDiff;
+                    if (score < bestScore) { bestScore = score; best = nr; hasReplacement = true; }
+                }
             }
+        f4 outColor;
+        if (filteredWeight > 0.0f) outColor = filteredColor / filteredWeight;
+        else if (fallbackWeight > 0.0f) outColor = fallbackColor / fallbackWeight;
+        else outColor = centerColor4;
+        VptReservoir outRes;
+        if (hasReplacement) outRes = best;
+        else
+        {
+            outRes = reservoir;
+            float avg = (neighborValidCount > 0) ? (neighborWeightSum / float(neighborValidCount)) : minWeight;
+            float target = (neighborValidCount > 0) ? (avg * weightThreshold) : minWeight;
+            target = fmaxf(target, minWeight);
+            outRes.weightSum = fminf(outRes.weightSum, target);
         }
-    f4 outColor;
-    if (filteredWeight > 0.0f) outColor = filteredColor / filteredWeight;
-    else if (fallbackWeight > 0.0f) outColor = fallbackColor / fallbackWeight;
-    else outColor = centerColor4;
-    VptReservoir outRes;
-    if (hasReplacement) outRes = best;
-    else
-    {
-        outRes = reservoir;
-        float avg = (neighborValidCount > 0) ? (neighborWeightSum / float(neighborValidCount)) : minWeight;
-        float target = (neighborValidCount > 0) ? (avg * weightThreshold) : minWeight;
-        target = fmaxf(target, minWeight);
-        outRes.weightSum = fminf(outRes.weightSum, target);
-    }
-    const int slot = atomicAdd(patchCount, 1);
-    if (slot < maxPatches)
-    {
-        patches[slot].pixel = (int)pix;
-        patches[slot].color = toFloat4(outColor);
-        patches[slot].reservoir = outRes;
+        a.patches[e].pixel = (int)pix;
+        a.patches[e].color = toFloat4(outColor);
+        a.patches[e].reservoir = outRes;
     }
 }
-__global__ void fireflyApplyKernel(const FireflyPatch *__restrict__ patches, const int *__restrict__ patchCount, int maxPatches,
+__global__ void fireflyApplyKernel(const FireflyPatch *__restrict__ patches, const unsigned *__restrict__ patchCount, int maxPatches,
                                    float4 *illum, VptReservoir *res)
 {
-    const int n = min(*patchCount, maxPatches);
+    const int n = (int)min(*patchCount, (unsigned)maxPatches);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const FireflyPatch p = patches[i];
@@ -241,13 +239,7 @@ __global__ void fireflyApplyKernel(const FireflyPatch *__restrict__ patches, con
 }
 
 // ------------------------------------------------------------------------------------------------ copies
-__global__ void __launch_bounds__(kBX *kBY) copySkyKernel(int W, int rowBegin, int rowEnd, const float4 *__restrict__ illum,
-                                                           const float *__restrict__ depth, float4 *__restrict__ out)
-{
-    PIXEL_GUARD(W, rowBegin, rowEnd)
-    if (__ldg(depth + pix) <= kDenoisingRange) return;
-    out[pix] = __ldg(illum + pix);
-}
+// BufferCopyNonSky when spatial filtering is off (otherwise fused into the last a-trous pass)
 __global__ void __launch_bounds__(kBX *kBY) compositeKernel(int W, int rowBegin, int rowEnd, const float4 *__restrict__ fin,
                                                              const float *__restrict__ depth, const float4 *__restrict__ albedo,
                                                              float4 *__restrict__ out)
@@ -267,280 +259,140 @@ __global__ void __launch_bounds__(kBX *kBY) frame0Kernel(int W, int rowBegin, in
     prevIllum[pix] = v; prevFast[pix] = v; histLen[pix] = 0.0f; prevHistLen[pix] = 0.0f;
 }
 
-// ------------------------------------------------------------------------------------------------ samplers
-VPT_DEV void bilinearSetup(f2 uv, int W, int H, f2 &f, int &tx0, int &ty0)
+// ------------------------------------------------------------------------------------------------ history fix
+// Only pixels with historyLength <= 4 do work (HistoryFix.h:20-120): ~1 % of the frame in steady state (disocclusion
+// edges). temporalKernel appends them to a list; here ONE WARP handles one pixel: lanes 0..24 are the 5x5 sparse
+// taps (stride 2^(4-hl)+1), reduced with shuffles — no thread scans the other 99 %.
+struct HistoryFixArgs
 {
-    f2 UV = {uv.x * W, uv.y * H};
-    f2 tc = {floorf(UV.x - 0.5f) + 0.5f, floorf(UV.y - 0.5f) + 0.5f};
-    f = UV - tc;
-    tx0 = (int)floorf(UV.x - 0.5f); ty0 = (int)floorf(UV.y - 0.5f);
-}
-VPT_DEV f4 bilinearWeight(f2 uv, int W, int H)
-{
-    f2 f; int a, b; bilinearSetup(uv, W, H, f, a, b);
-    f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
-    return {w0.x * w0.y, w1.x * w0.y, w0.x * w1.y, w1.x * w1.y};
-}
-VPT_DEV f4 sampleBilinearCustom4(const float4 *tex, f2 uv, int W, int H, f4 cw)
-{
-    f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
-    f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
-    const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
-    const float ws[4] = {w0.x * w0.y * cw.x, w1.x * w0.y * cw.y, w0.x * w1.y * cw.z, w1.x * w1.y * cw.w};
-    f4 out = F4(0.0f); float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-        f4 v = ld4(tex, W, H, xs[i], ys[i]);
-        float w = max1f(ws[i], 1e-6f);
-        sum += w; out += v * w;
-    }
-    return out / sum;
-}
-VPT_DEV float sampleBilinearCustom1(const float *tex, f2 uv, int W, int H, f4 cw)
-{
-    f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
-    f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
-    const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
-    const float ws[4] = {w0.x * w0.y * cw.x, w1.x * w0.y * cw.y, w0.x * w1.y * cw.z, w1.x * w1.y * cw.w};
-    float out = 0.0f, sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-        float v = ld1(tex, W, H, xs[i], ys[i]);
-        float w = max1f(ws[i], 1e-6f);
-        sum += w; out += v * w;
-    }
-    return out / sum;
-}
-VPT_DEV f4 sampleBicubic12(const float4 *tex, f2 uv, int W, int H)
-{
-    f2 f; int x1, y1; bilinearSetup(uv, W, H, f, x1, y1);
-    f2 f2_ = f * f, f3_ = f2_ * f;
-    f2 w0 = {f2_.x - 0.5f * (f3_.x + f.x), f2_.y - 0.5f * (f3_.y + f.y)};
-    f2 w1 = {1.5f * f3_.x - 2.5f * f2_.x + 1.0f, 1.5f * f3_.y - 2.5f * f2_.y + 1.0f};
-    f2 w3 = {0.5f * (f3_.x - f2_.x), 0.5f * (f3_.y - f2_.y)};
-    f2 w2 = {1.0f - w0.x - w1.x - w3.x, 1.0f - w0.y - w1.y - w3.y};
-    const int x0 = x1 - 1, x2 = x1 + 1, x3 = x1 + 2, y0 = y1 - 1, y2 = y1 + 1, y3 = y1 + 2;
-    const int xs[12] = {x1, x2, x0, x1, x2, x3, x0, x1, x2, x3, x1, x2};
-    const int ys[12] = {y0, y0, y1, y1, y1, y1, y2, y2, y2, y2, y3, y3};
-    const float ws[12] = {w1.x * w0.y, w2.x * w0.y, w0.x * w1.y, w1.x * w1.y, w2.x * w1.y, w3.x * w1.y,
-                          w0.x * w2.y, w1.x * w2.y, w2.x * w2.y, w3.x * w2.y, w1.x * w3.y, w2.x * w3.y};
-    f4 out = F4(0.0f); float sum = 0;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) { sum += ws[i]; out += ld4(tex, W, H, xs[i], ys[i]) * ws[i]; }
-    return out / sum;
-}
-VPT_DEV f3 sampleSmoothStep3(const float4 *tex, f2 uv, int W, int H)
-{
-    f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
-    f2 f2_ = f * f, f3_ = f2_ * f;
-    f2 w1 = {-2.0f * f3_.x + 3.0f * f2_.x, -2.0f * f3_.y + 3.0f * f2_.y};
-    f2 w0 = {1.0f - w1.x, 1.0f - w1.y};
-    const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
-    const float ws[4] = {w0.x * w0.y, w1.x * w0.y, w0.x * w1.y, w1.x * w1.y};
-    f3 out = F3(0.0f); float sum = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { sum += ws[i]; out += xyz(ld4(tex, W, H, xs[i], ys[i])) * ws[i]; }
-    return out / sum;
-}
-VPT_DEV float parallaxInPixels(f3 X, f2 uvZero, const Cam &cam, f2 rectSize)
-{
-    f2 uv = worldDirectionToUV(cam, normalize(X - cam.pos));
-    f2 d = (uv - uvZero) * rectSize;
-    return sqrtf(d.x * d.x + d.y * d.y);
-}
-
-// ------------------------------------------------------------------------------------------------ temporal
-struct TemporalArgs
-{
-    int W, H, rowBegin, rowEnd;
-    VptCamera cam, prevCam;
-    float denoisingRange, disocclusionThreshold, disocclusionThresholdAlternate, maxAccum, maxFastAccum;
-    const float *depth, *prevDepth, *prevHistLen;
-    const float4 *normalRough, *prevNormalRough, *illum, *prevIllum, *prevFast;
-    float4 *ping, *pong;
-    float *histLen;
+    int W, H;
+    DnView view;
+    const float4 *G; const uint32_t *MQ; const float *histLen; const float4 *ping;
+    float4 *pong;
+    const unsigned *fixCount; const int *fixList;
 };
-__global__ void __launch_bounds__(kBX *kBY) temporalKernel(const __grid_constant__ TemporalArgs a)
+__global__ void __launch_bounds__(256) historyFixKernel(const __grid_constant__ HistoryFixArgs a)
 {
     const int W = a.W, H = a.H;
-    PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
-    const float z = __ldg(a.depth + pix);
-    if (z > a.denoisingRange) return;
-    const Cam cam = loadCam(a.cam), prevCam = loadCam(a.prevCam);
-    const quat prevToCur = rotationBetween(prevCam.dir, cam.dir);
-    const f2 pixelUv = {(float(x) + 0.5f) * (1.0f / (float)W), (float(y) + 0.5f) * (1.0f / (float)H)};
-    const f3 n = xyz(__ldg(a.normalRough + pix));
-    const f2 curUV = {(float(x) + 0.5f) * cam.invResX, (float(y) + 0.5f) * cam.invResY};
-    const f3 viewVec = uvToWorldDirection(cam, curUV);
-    const f3 worldPos = worldPosFromPixel(cam, x, y, z);
-    const f3 V = -normalize(viewVec);
-    const float NoV = fabsf(dot(n, V));
-    const f3 prevWorldPos = worldPos;
-    const f2 prevUV = worldDirectionToUV(prevCam, normalize(prevWorldPos - prevCam.pos));
-    const f3 illum = xyz(__ldg(a.illum + pix));
-    f3 nAvg = n;
-#pragma unroll
-    for (int i = -1; i <= 1; ++i)
-#pragma unroll
-        for (int j = -1; j <= 1; ++j)
+    const unsigned n = __ldg(a.fixCount);
+    const int lane = threadIdx.x & 31;
+    const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
+    const f3 M0 = F3(a.view.M0[0], a.view.M0[1], a.view.M0[2]), Mx = F3(a.view.Mx[0], a.view.Mx[1], a.view.Mx[2]), My = F3(a.view.My[0], a.view.My[1], a.view.My[2]);
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warpsTotal)
+    {
+        const size_t pix = (size_t)__ldg(a.fixList + e);
+        const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
+        const float4 g = __ldg(a.G + pix);
+        if (g.w > kSkyZs) continue; // (never listed: the temporal pass skips sky pixels)
+        const float hl = __ldg(a.histLen + pix);
+        const uint32_t cMat = __ldg(a.MQ + pix) & 0xffffu;
+        const f3 cn = {g.x, g.y, g.z};
+        const f3 vc = viewVec(a.view, (float)x, (float)y);
+        const float c0 = g.w * dot(vc, cn);
+        const float depthThr = 0.003f * (g.w * sqrtf(dot(vc, vc)));
+        const float A0 = dot(M0, cn), Ax = dot(Mx, cn), Ay = dot(My, cn);
+        const float r = exp2f(4.0f - hl) + 1.0f;
+        f4 sum = F4(0.0f);
+        float wsum = 0.0f;
+        if (lane < 25)
         {
-            if (i == 0 && j == 0) continue;
-            nAvg += xyz(ld4(a.normalRough, W, H, x + i, y + j));
+            const int j = lane / 5 - 2, k = lane % 5 - 2;
+            if (j == 0 && k == 0) { sum = F4(__ldg(a.ping + pix)); wsum = 1.0f; }
+            else
+            {
+                const int sx = x + (int)(k * r), sy = y + (int)(j * r);
+                const bool inside = sx >= 0 && sy >= 0 && sx < W && sy < H;
+                const int qx = clampi(sx, 0, W - 1), qy = clampi(sy, 0, H - 1);
+                const size_t sp = (size_t)qy * W + qx;
+                const float4 sg = __ldg(a.G + sp);
+                const uint32_t sMat = __ldg(a.MQ + sp) & 0xffffu;
+                const float dist = fabsf(fmaf(sg.w, fmaf((float)qy, Ay, fmaf((float)qx, Ax, A0)), -c0));
+                float w = dist < depthThr ? 1.0f : 0.0f;
+                w *= powf(fmaxr(0.01f, dot(cn, F3(sg.x, sg.y, sg.z))), 8.0f);
+                w = (inside && sMat == cMat) ? w : 0.0f;
+                if (w > 1e-4f) { sum = F4(__ldg(a.ping + sp)) * w; wsum = w; }
+            }
         }
-    nAvg /= 9.0f;
-    const float m1 = luminance(illum), m2 = m1 * m1;
-    const f3 camDelta = prevCam.pos - cam.pos;
-    const f2 rect = {(float)W, (float)H};
-    const float par1 = parallaxInPixels(prevWorldPos + camDelta, pixelUv, prevCam, rect);
-    const float par2 = parallaxInPixels(prevWorldPos - camDelta, prevUV, cam, rect);
-    const float parMax = fmaxr(par1, par2);
-    const float thrBonus = a.disocclusionThreshold + (1.5f / H);
-    const float thrAltBonus = a.disocclusionThresholdAlternate + (1.5f / H);
-    const float disThr = lerpf(thrBonus, thrAltBonus, 0.0f);
-
-    const f3 curNormalAvg = normalize(nAvg);
-    const float estPrevDepth = length(prevWorldPos - prevCam.pos);
-    const f2 prevPixF = {prevUV.x * W, prevUV.y * H};
-    const int bx = (int)floorf(prevPixF.x - 0.5f), by = (int)floorf(prevPixF.y - 0.5f);
-    const float pixelSize = (cam.tanHalfFovX / (cam.resX / 2)) * z;
-    const float frustumSize = pixelSize * (float)min(W, H);
-    const float slopeScale = 1.0f / lerpf(lerpf(0.05f, 1.0f, NoV), 1.0f, saturate(parMax / 30.0f));
-    float thr[4];
-    {
-        const float base = saturate(disThr * slopeScale) * frustumSize;
-        const int px0 = bx, py0 = by, px1 = bx + 1, py1 = by + 1;
-        float rx0 = (px0 >= 0) ? 1.0f : 0.0f, ry0 = (py0 >= 0) ? 1.0f : 0.0f, rx1 = (px1 >= 0) ? 1.0f : 0.0f, ry1 = (py1 >= 0) ? 1.0f : 0.0f;
-        rx0 *= (px0 < W) ? 1.0f : 0.0f; ry0 *= (py0 < H) ? 1.0f : 0.0f; rx1 *= (px1 < W) ? 1.0f : 0.0f; ry1 *= (py1 < H) ? 1.0f : 0.0f;
-        const float inScreen[4] = {rx0 * ry0, rx1 * ry0, rx0 * ry1, rx1 * ry1};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { thr[i] = base * inScreen[i]; thr[i] -= 1e-6f; }
-    }
-    const int bic[4][2][2] = {{{0, -1}, {-1, 0}}, {{1, -1}, {2, 0}}, {{-1, 1}, {0, 2}}, {{2, 1}, {1, 2}}};
-    const int bil[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
-    float bicubicValid = 1.0f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int off = 16; off > 0; off >>= 1)
         {
-            float pz = ld1(a.prevDepth, W, H, bx + bic[i][j][0], by + bic[i][j][1]);
-            bicubicValid *= fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
+            sum.x += __shfl_down_sync(0xffffffffu, sum.x, off); sum.y += __shfl_down_sync(0xffffffffu, sum.y, off);
+            sum.z += __shfl_down_sync(0xffffffffu, sum.z, off); sum.w += __shfl_down_sync(0xffffffffu, sum.w, off);
+            wsum += __shfl_down_sync(0xffffffffu, wsum, off);
         }
-    float tv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-        float pz = ld1(a.prevDepth, W, H, bx + bil[i][0], by + bil[i][1]);
-        float v = fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
-        bicubicValid *= v; tv[i] = v;
+        if (lane == 0) a.pong[pix] = toFloat4(sum / wsum);
     }
-    f4 tapsValid = {tv[0], tv[1], tv[2], tv[3]};
-    const f3 prevNFlat = normalize(sampleSmoothStep3(a.prevNormalRough, prevUV, W, H));
-    const f3 prevNRot = normalize(qrotate(prevToCur, prevNFlat));
-    if (dot(curNormalAvg, prevNRot) < 0.0f) { tapsValid = F4(0.0f); bicubicValid = 0.0f; }
-    const bool useBicubic = bicubicValid > 0;
-    f4 prevIllum; f3 prevFast;
-    if (useBicubic)
-    {
-        prevIllum = sampleBicubic12(a.prevIllum, prevUV, W, H);
-        prevFast = xyz(sampleBicubic12(a.prevFast, prevUV, W, H));
-    }
-    else
-    {
-        prevIllum = sampleBilinearCustom4(a.prevIllum, prevUV, W, H, tapsValid);
-        prevFast = xyz(sampleBilinearCustom4(a.prevFast, prevUV, W, H, tapsValid));
-    }
-    prevIllum = max4f(prevIllum, F4(0.0f));
-    prevFast = max3f(prevFast, F3(0.0f));
-    float reprojFound = (bicubicValid > 0.0f) ? 2.0f : 1.0f;
-    const f4 bw = bilinearWeight(prevUV, W, H);
-    float footprintQuality = (bicubicValid > 0) ? 1.0f : dot4(bw, F4(1.0f));
-    float historyLength;
-    if (dot4(tapsValid, F4(1.0f)) == 0.0f) { reprojFound = 0.0f; footprintQuality = 0.0f; historyLength = 0.0f; }
-    else historyLength = sampleBilinearCustom1(a.prevHistLen, prevUV, W, H, tapsValid);
-
-    historyLength = historyLength + 1.0f;
-    const f3 Vprev = normalize(prevWorldPos - prevCam.pos);
-    const float NoVprev = fabsf(dot(n, Vprev));
-    float sizeQuality = (NoVprev + 1e-3f) / (NoV + 1e-3f);
-    sizeQuality *= sizeQuality; sizeQuality *= sizeQuality;
-    footprintQuality *= lerpf(0.1f, 1.0f, saturate(sizeQuality));
-    if (footprintQuality < 1.0f) { historyLength *= sqrtf(footprintQuality); historyLength = fmaxr(historyLength, 1.0f); }
-    historyLength = fminr(historyLength, a.maxAccum);
-    const float alpha = (reprojFound > 0) ? fmaxr(1.0f / (a.maxAccum + 1.0f), 1.0f / historyLength) : 1.0f;
-    const float alphaFast = (reprojFound > 0) ? fmaxr(1.0f / (a.maxFastAccum + 1.0f), 1.0f / historyLength) : 1.0f;
-    a.ping[pix] = toFloat4(lerp4(prevIllum, F4(illum, m2), alpha));
-    a.pong[pix] = toFloat4(F4(lerp3(prevFast, illum, alphaFast), 0.0f));
-    a.histLen[pix] = historyLength;
-}
-
-// ------------------------------------------------------------------------------------------------ history fix
-__global__ void __launch_bounds__(kBX *kBY) historyFixKernel(int W, int H, int rowBegin, int rowEnd, VptCamera camIn,
-                                                              const float *__restrict__ depth, const float *__restrict__ material,
-                                                              const float4 *__restrict__ normalRough, const float *__restrict__ histLen,
-                                                              const float4 *__restrict__ ping, float4 *__restrict__ pong)
-{
-    PIXEL_GUARD(W, rowBegin, rowEnd)
-    const float z = __ldg(depth + pix);
-    const float hl = __ldg(histLen + pix);
-    if (z > kDenoisingRange || hl > 4.0f) return;
-    const Cam cam = loadCam(camIn);
-    const float cMat = matU16(material, W, H, x, y);
-    const f3 cn = xyz(__ldg(normalRough + pix));
-    const f3 cpos = worldPosFromPixel(cam, x, y, z);
-    const float depthThr = 0.003f * z;
-    f4 sum = F4(__ldg(ping + pix));
-    float wsum = 1.0f;
-    const float r = exp2f(4.0f - hl) + 1.0f;
-    for (int j = -2; j <= 2; ++j)
-        for (int i = -2; i <= 2; ++i)
-        {
-            const int dx = (int)(i * r), dy = (int)(j * r);
-            const int sx = x + dx, sy = y + dy;
-            const bool inside = sx >= 0 && sy >= 0 && sx < W && sy < H;
-            if (i == 0 && j == 0) continue;
-            const float sMat = matU16(material, W, H, sx, sy);
-            const f3 sn = xyz(ld4(normalRough, W, H, sx, sy));
-            const float sz = ld1(depth, W, H, sx, sy);
-            const f3 spos = worldPosFromPixel(cam, sx, sy, sz);
-            float w = planeDistWeightAtrous(cpos, cn, spos, depthThr);
-            w *= powf(fmaxr(0.01f, dot(cn, sn)), fmaxr(8.0f, 0.01f));
-            w = inside ? w : 0;
-            w *= (sMat == cMat) ? 1.0f : 0.0f;
-            if (w > 1e-4f) { sum += ld4(ping, W, H, sx, sy) * w; wsum += w; }
-        }
-    pong[pix] = toFloat4(sum / wsum);
 }
 
 // ------------------------------------------------------------------------------------------------ history clamping
-__global__ void __launch_bounds__(kBX *kBY) historyClampKernel(int W, int H, int rowBegin, int rowEnd, const float *__restrict__ depth,
-                                                                const float4 *__restrict__ illum, const float4 *__restrict__ ping,
-                                                                const float4 *__restrict__ pong, const float *__restrict__ histLen,
-                                                                float4 *__restrict__ prevIllum, float4 *__restrict__ prevFast,
-                                                                float *__restrict__ prevHistLen)
+// 5x5 mean / sigma of the responsive history (YCoCg) and of the noisy input, colour-box clamp, anti-lag, history write
+// (HistoryClamping.h:27-219). The per-pixel transforms are staged once in shared memory for the 36x12 tile and summed
+// separably (5 horizontal + 5 vertical taps per channel instead of 25 taps each redoing the transform).
+struct ClampArgs
 {
-    PIXEL_GUARD(W, rowBegin, rowEnd)
-    if (__ldg(depth + pix) > kDenoisingRange) return;
-    const float hl = __ldg(histLen + pix);
-    f3 rM1 = F3(0.0f), rM2 = F3(0.0f), nM1 = F3(0.0f); float nM2 = 0.0f;
-    for (int dx = -2; dx <= 2; ++dx)
-        for (int dy = -2; dy <= 2; ++dy)
+    int W, H, rowBegin, rowEnd;
+    const float4 *illum, *ping, *pong;
+    const float *depth, *histLen;
+    float4 *prevIllum, *prevFast;
+    float *prevHistLen;
+};
+constexpr int kClampTW = kBX + 4, kClampTH = kBY + 4;
+__global__ void __launch_bounds__(kBX *kBY) historyClampKernel(const __grid_constant__ ClampArgs a)
+{
+    // 12 channels per pixel: responsive YCoCg (3), its squares (3), noisy rgb (3), noisy luminance^2 (1), pad (2)
+    __shared__ float4 tA[3][kClampTH][kClampTW];
+    __shared__ float4 tB[3][kClampTH][kBX];
+    const int W = a.W, H = a.H;
+    const int x0 = blockIdx.x * kBX, y0 = a.rowBegin + blockIdx.y * kBY;
+    const int tid = threadIdx.y * kBX + threadIdx.x;
+    for (int i = tid; i < kClampTW * kClampTH; i += kBX * kBY)
+    {
+        const int ty = i / kClampTW, tx = i - ty * kClampTW;
+        const f3 s = rgbToYCoCg(xyz(ld4(a.pong, W, H, x0 + tx - 2, y0 + ty - 2)));
+        const f3 nz = xyz(ld4(a.illum, W, H, x0 + tx - 2, y0 + ty - 2));
+        const float nl = luminance(nz);
+        tA[0][ty][tx] = make_float4(s.x, s.y, s.z, s.x * s.x);
+        tA[1][ty][tx] = make_float4(s.y * s.y, s.z * s.z, nz.x, nz.y);
+        tA[2][ty][tx] = make_float4(nz.z, nl * nl, 0.0f, 0.0f);
+    }
+    __syncthreads();
+    for (int i = tid; i < kBX * kClampTH; i += kBX * kBY)
+    {
+        const int ty = i / kBX, tx = i - ty * kBX;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
         {
-            const f3 s = rgbToYCoCg(xyz(ld4(pong, W, H, x + dx, y + dy)));
-            rM1 += s; rM2 += s * s;
-            const f3 nz = xyz(ld4(illum, W, H, x + dx, y + dy));
-            const float nl = luminance(nz);
-            nM1 += nz; nM2 += nl * nl;
+            float4 acc = tA[c][ty][tx];
+#pragma unroll
+            for (int d = 1; d < 5; ++d) { const float4 v = tA[c][ty][tx + d]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            tB[c][ty][tx] = acc;
         }
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= a.rowEnd) return;
+    const size_t pix = (size_t)y * W + x;
+    if (__ldg(a.depth + pix) > kDenoisingRange) return;
+    float4 m[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+    {
+        float4 acc = tB[c][threadIdx.y][threadIdx.x];
+#pragma unroll
+        for (int d = 1; d < 5; ++d) { const float4 v = tB[c][threadIdx.y + d][threadIdx.x]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        m[c] = acc;
+    }
+    const float hl = __ldg(a.histLen + pix);
+    f3 rM1 = {m[0].x, m[0].y, m[0].z}, rM2 = {m[0].w, m[1].x, m[1].y}, nM1 = {m[1].z, m[1].w, m[2].x};
+    float nM2 = m[2].y;
     rM1 /= 25.0f; rM2 /= 25.0f; nM1 /= 25.0f; nM2 /= 25.0f;
-    const f3 sigma = sqrt3(max3f(F3(0.0f), rM2 - rM1 * rM1));
+    const f3 sigma = sqrt3(max3f(F3(0.0f), F3(subSq(rM2.x, rM1.x), subSq(rM2.y, rM1.y), subSq(rM2.z, rM1.z))));
     f3 cmin = rM1 - 2.0f * sigma, cmax = rM1 + 2.0f * sigma;
-    const f3 centerY = rgbToYCoCg(xyz(__ldg(pong + pix)));
+    const float4 ctr = tA[0][threadIdx.y + 2][threadIdx.x + 2];
+    const f3 centerY = {ctr.x, ctr.y, ctr.z};
     cmin = (cmin.x < centerY.x) ? cmin : centerY;
     cmax = (cmax.x > centerY.x) ? cmax : centerY;
-    const f4 acc = F4(__ldg(ping + pix));
+    const f4 acc = F4(__ldg(a.ping + pix));
     const f3 accY = rgbToYCoCg(xyz(acc));
     const f3 clampedY = clamp3(accY, cmin, cmax);
     const f3 clamped = yCoCgToRgb(clampedY);
@@ -564,61 +416,88 @@ __global__ void __launch_bounds__(kBX *kBY) historyClampKernel(int W, int H, int
     outR.x += accel.x; outR.y += accel.y; outR.z += accel.z;
     const float diffL = luminance(xyz(acc));
     const float noisyL = luminance(nM1);
-    const float tSigma = 0.5f * sqrtf(fmaxr(0.0f, nM2 - noisyL * noisyL));
+    const float tSigma = 0.5f * sqrtf(fmaxr(0.0f, subSq(nM2, noisyL)));
     const float sSigma = 4.5f * sigma.x;
     float reset = 0.5f * fmaxr(0.0f, fabsf(diffL - noisyL) - sSigma - tSigma) / (1.0e-6f + fmaxr(diffL, noisyL) + sSigma + tSigma);
     reset = saturate(reset);
-    const f3 noisyC = xyz(__ldg(illum + pix));
+    const float4 tn0 = tA[1][threadIdx.y + 2][threadIdx.x + 2], tn1 = tA[2][threadIdx.y + 2][threadIdx.x + 2];
+    const f3 noisyC = {tn0.z, tn0.w, tn1.x};
     f3 d3 = lerp3(xyz(outD), noisyC, reset), r3 = lerp3(xyz(outR), noisyC, reset);
     outD = F4(d3, outD.w); outR = F4(r3, outR.w);
     const float outL = luminance(xyz(outD));
-    outD.w += (outL * outL - diffL * diffL);
+    outD.w += diffSq(outL, diffL);
     outD.w = fmaxr(0.0f, outD.w);
-    prevIllum[pix] = toFloat4(outD);
-    prevFast[pix] = toFloat4(outR);
-    prevHistLen[pix] = hl;
+    a.prevIllum[pix] = toFloat4(outD);
+    a.prevFast[pix] = toFloat4(outR);
+    a.prevHistLen[pix] = hl;
 }
 
 // ------------------------------------------------------------------------------------------------ à-trous
 struct AtrousArgs
 {
     int W, H, rowBegin, rowEnd;
-    VptCamera cam;
+    DnView view;
     float phiLuminance, depthThreshold, lobeAngleFraction;
     unsigned frameIndex, step;
-    const float4 *in, *normalRough;
-    const float *material, *depth, *histLen;
+    const float4 *in, *G;
+    const uint32_t *MQ;
+    const float *histLen;
+    const float4 *albedo; // composite variant
     float4 *out;
 };
+// per-centre constants of the tangent-plane test: dist(tap) = | zs_tap * (A0 + x*Ax + y*Ay) - c0 |
+struct PlaneTest { float A0, Ax, Ay, c0, thr; };
+VPT_DEV PlaneTest planeTest(const DnView &v, int x, int y, f3 cn, float zs, float depthThreshold)
+{
+    const f3 vc = viewVec(v, (float)x, (float)y);
+    PlaneTest p;
+    p.A0 = dot(F3(v.M0[0], v.M0[1], v.M0[2]), cn); p.Ax = dot(F3(v.Mx[0], v.Mx[1], v.Mx[2]), cn); p.Ay = dot(F3(v.My[0], v.My[1], v.My[2]), cn);
+    p.c0 = zs * dot(vc, cn);
+    p.thr = depthThreshold * (zs * sqrtf(dot(vc, vc))); // depthThreshold * z
+    return p;
+}
+VPT_DEV bool planeNear(const PlaneTest &p, float zsTap, float x, float y)
+{
+    return fabsf(fmaf(zsTap, fmaf(y, p.Ay, fmaf(x, p.Ax, p.A0)), -p.c0)) < p.thr;
+}
+
+// AtrousSmem (AtrousSmem.h:66-303): first spatial pass on the freshly written history.
 __global__ void __launch_bounds__(kBX *kBY) atrousFirstKernel(const __grid_constant__ AtrousArgs a)
 {
     const int W = a.W, H = a.H;
     PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
-    const float z = __ldg(a.depth + pix);
-    if (z > 500000.0f) return;
-    const Cam cam = loadCam(a.cam);
-    const f3 cn = xyz(__ldg(a.normalRough + pix));
-    const f3 cpos = worldPosFromPixel(cam, x, y, z);
-    const float cMat = __ldg(a.material + pix);
+    const float4 g = __ldg(a.G + pix);
+    if (g.w > kSkyZs) return;
+    const f3 cn = {g.x, g.y, g.z};
+    const uint32_t cMat = __ldg(a.MQ + pix) >> 16;
     const float hl = __ldg(a.histLen + pix);
+    const float nParam = normalWeightParam2(1.0f, a.lobeAngleFraction);
     if (hl >= 3.0f)
     {
+        // the 3x3 neighbourhood is read once: gaussian variance prefilter, then the edge-stopping filter
+        float4 sv[9];
+#pragma unroll
+        for (int cx = -1; cx <= 1; cx++)
+#pragma unroll
+            for (int cy = -1; cy <= 1; cy++)
+                sv[(cx + 1) * 3 + (cy + 1)] = __ldg(a.in + (size_t)clampi(y + cy, 0, H - 1) * W + clampi(x + cx, 0, W - 1));
         f4 vsum = F4(0.0f);
         const float kern[4] = {1.0f / 4.0f, 1.0f / 8.0f, 1.0f / 8.0f, 1.0f / 16.0f};
 #pragma unroll
         for (int dx = -1; dx <= 1; dx++)
 #pragma unroll
             for (int dy = -1; dy <= 1; dy++)
-                vsum += ld4(a.in, W, H, x + dx, y + dy) * kern[abs(dx) * 2 + abs(dy)];
+                vsum += F4(sv[(dx + 1) * 3 + (dy + 1)]) * kern[abs(dx) * 2 + abs(dy)];
         const float v1 = luminance(xyz(vsum));
-        const float cVar = fmaxr(0.0f, vsum.w - v1 * v1);
-        const float cLum = luminance(xyz(__ldg(a.in + pix)));
+        const float cVar = fmaxr(0.0f, subSq(vsum.w, v1));
+        const float cLum = luminance(xyz(sv[4]));
         const float phiInv = 1.0f / fmaxr(1.0e-4f, a.phiLuminance * sqrtf(cVar));
-        const float nParam = normalWeightParam2(1.0f, a.lobeAngleFraction);
+        const PlaneTest pt = planeTest(a.view, x, y, cn, g.w, a.depthThreshold);
         float sumW = 0.0f; f4 sum = F4(0.0f);
         const float k3[2] = {0.44198f, 0.27901f};
-        const float depthThr = a.depthThreshold * z;
+#pragma unroll
         for (int cx = -1; cx <= 1; cx++)
+#pragma unroll
             for (int cy = -1; cy <= 1; cy++)
             {
                 const int sx = x + cx, sy = y + cy;
@@ -627,75 +506,74 @@ __global__ void __launch_bounds__(kBX *kBY) atrousFirstKernel(const __grid_const
                 const float kernel = inside ? k3[abs(cx)] * k3[abs(cy)] : 0.0f;
                 const int qx = clampi(sx, 0, W - 1), qy = clampi(sy, 0, H - 1);
                 const size_t sp = (size_t)qy * W + qx;
-                const f3 sn = xyz(__ldg(a.normalRough + sp));
-                const f3 spos = worldPosFromPixel(cam, qx, qy, __ldg(a.depth + sp));
-                const float sMat = __ldg(a.material + sp);
-                float geomW = planeDistWeightAtrous(cpos, cn, spos, depthThr);
-                geomW *= kernel;
-                const float normalW = nonExpWeight(acosApprox(dot(cn, sn)), nParam, 0.0f);
-                const f4 sv = F4(__ldg(a.in + sp));
-                const float sLum = luminance(xyz(sv));
-                const float lumW = fabsf(cLum - sLum) * phiInv;
-                float w = geomW * normalW * expf(-lumW);
+                const float4 sg = __ldg(a.G + sp);
+                const uint32_t sMat = __ldg(a.MQ + sp) >> 16;
+                const float geomW = planeNear(pt, sg.w, (float)qx, (float)qy) ? kernel : 0.0f;
+                const float normalW = normalWeight(dot(cn, F3(sg.x, sg.y, sg.z)), nParam);
+                const f4 v = F4(sv[(cx + 1) * 3 + (cy + 1)]);
+                const float lumW = fabsf(cLum - luminance(xyz(v))) * phiInv;
+                float w = geomW * normalW * __expf(-lumW);
                 w = center ? kernel : w;
-                w *= (sMat == cMat) ? 1.0f : 0.0f;
+                w = (sMat == cMat) ? w : 0.0f;
                 sumW += w;
-                sum += w * sv;
+                sum += w * v;
             }
         sumW = fmaxr(sumW, 1e-6f);
         sum = sum / sumW;
         const float m1 = luminance(xyz(sum));
-        a.out[pix] = make_float4(sum.x, sum.y, sum.z, fmaxr(0.0f, sum.w - m1 * m1));
+        a.out[pix] = make_float4(sum.x, sum.y, sum.z, fmaxr(0.0f, subSq(sum.w, m1)));
     }
     else
     {
         float sumW = 0.0f; f3 sumI = F3(0.0f); float s1 = 0.0f, s2 = 0.0f;
-        const float nParam = normalWeightParam2(1.0f, a.lobeAngleFraction);
         for (int cx = -2; cx <= 2; cx++)
             for (int cy = -2; cy <= 2; cy++)
             {
                 const int qx = clampi(x + cx, 0, W - 1), qy = clampi(y + cy, 0, H - 1);
                 const size_t sp = (size_t)qy * W + qx;
-                const f3 sn = xyz(__ldg(a.normalRough + sp));
-                const float sMat = __ldg(a.material + sp);
-                const float normalW = nonExpWeight(acosApprox(dot(cn, sn)), nParam, 0.0f);
-                const f4 sv = F4(__ldg(a.in + sp));
-                const float l1 = luminance(xyz(sv));
-                float w = normalW * 1.0f;
-                w *= (sMat == cMat) ? 1.0f : 0.0f;
-                sumW += w; sumI += xyz(sv) * w; s1 += l1 * w; s2 += sv.w * w;
+                const float4 sg = __ldg(a.G + sp);
+                const uint32_t sMat = __ldg(a.MQ + sp) >> 16;
+                const float normalW = normalWeight(dot(cn, F3(sg.x, sg.y, sg.z)), nParam);
+                const f4 v = F4(__ldg(a.in + sp));
+                const float l1 = luminance(xyz(v));
+                const float w = (sMat == cMat) ? normalW : 0.0f;
+                sumW += w; sumI += xyz(v) * w; s1 += l1 * w; s2 += v.w * w;
             }
         const float boost = fmaxr(1.0f, 4.0f / (hl + 1.0f));
         sumW = fmaxr(sumW, 1e-6f);
         sumI /= sumW; s1 /= sumW; s2 /= sumW;
-        float var = fmaxr(0.0f, s2 - s1 * s1);
+        float var = fmaxr(0.0f, subSq(s2, s1));
         var *= boost;
         a.out[pix] = make_float4(sumI.x, sumI.y, sumI.z, var);
     }
 }
 
-__global__ void __launch_bounds__(kBX *kBY) atrousKernel(const __grid_constant__ AtrousArgs a)
+// Atrous (Atrous.h:6-158): 3x3 taps at stride `step`, hashed sub-stride jitter for step > 4. kComposite: the last
+// pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky, BufferCopy.h:36-116).
+template <bool kComposite>
+__global__ void __launch_bounds__(kBX *kAtrousBY) atrousKernel(const __grid_constant__ AtrousArgs a)
 {
     const int W = a.W, H = a.H;
-    PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
-    const float z = __ldg(a.depth + pix);
-    if (z > 500000.0f) return;
-    const Cam cam = loadCam(a.cam);
-    const float cMat = matU16(a.material, W, H, x, y);
-    const f3 cn = xyz(__ldg(a.normalRough + pix));
-    const f3 cpos = worldPosFromPixel(cam, x, y, z);
+    const int x = blockIdx.x * kBX + threadIdx.x;
+    const int y = a.rowBegin + blockIdx.y * kAtrousBY + threadIdx.y;
+    if (x >= W || y >= a.rowEnd) return;
+    const size_t pix = (size_t)y * W + x;
+    const float4 g = __ldg(a.G + pix);
+    if (g.w > kSkyZs) return;
+    const uint32_t cMat = __ldg(a.MQ + pix) & 0xffffu;
+    const f3 cn = {g.x, g.y, g.z};
     const float hl = __ldg(a.histLen + pix);
-    const unsigned stepSize = a.step;
+    const int stepSize = (int)a.step;
     float lobeFrac = a.lobeAngleFraction / sqrtf((float)stepSize);
     lobeFrac = lerpf(0.99f, lobeFrac, saturate(hl / 5.0f));
     const f4 cv = F4(__ldg(a.in + pix));
     const float cLum = luminance(xyz(cv));
     const float phiInv = 1.0f / fmaxr(1.0e-4f, a.phiLuminance * sqrtf(cv.w));
     const float nParam = normalWeightParam2(1.0f, lobeFrac);
+    const PlaneTest pt = planeTest(a.view, x, y, cn, g.w, a.depthThreshold);
     float sumW = 0.44198f * 0.44198f;
     f4 sum = cv * f4{sumW, sumW, sumW, sumW * sumW};
     const float k3[2] = {0.44198f, 0.27901f};
-    const float depthThr = a.depthThreshold * z;
     int offx = 0, offy = 0;
     if (stepSize > 4)
     {
@@ -707,57 +585,88 @@ __global__ void __launch_bounds__(kBX *kBY) atrousKernel(const __grid_constant__
         offx = (int)((float)stepSize * 0.5f * (u0 - 0.5f));
         offy = (int)((float)stepSize * 0.5f * (u1 - 0.5f));
     }
+#pragma unroll
     for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
         for (int xx = -1; xx <= 1; xx++)
         {
             if (xx == 0 && yy == 0) continue;
-            const int sx = x + offx + xx * (int)stepSize, sy = y + offy + yy * (int)stepSize;
+            const int sx = x + offx + xx * stepSize, sy = y + offy + yy * stepSize;
             const bool inside = sx >= 0 && sy >= 0 && sx < W && sy < H;
-            const float kernel = k3[abs(xx)] * k3[abs(yy)];
-            const float sMat = matU16(a.material, W, H, sx, sy);
-            const f3 sn = xyz(ld4(a.normalRough, W, H, sx, sy));
-            const float sz = ld1(a.depth, W, H, sx, sy);
-            const f3 spos = worldPosFromPixel(cam, sx, sy, sz);
-            float geomW = planeDistWeightAtrous(cpos, cn, spos, depthThr);
-            geomW *= kernel;
-            geomW *= (inside && sz < 500000.0f) ? 1.0f : 0.0f;
-            const float normalW = nonExpWeight(acosApprox(dot(cn, sn)), nParam, 0.0f);
-            float w = geomW * normalW;
-            w *= (sMat == cMat) ? 1.0f : 0.0f;
+            const int qx = clampi(sx, 0, W - 1), qy = clampi(sy, 0, H - 1);
+            const size_t sp = (size_t)qy * W + qx;
+            const float4 sg = __ldg(a.G + sp);
+            const uint32_t sMat = __ldg(a.MQ + sp) & 0xffffu;
+            float w = k3[abs(xx)] * k3[abs(yy)];
+            w = (inside && sg.w < kSkyZs && sMat == cMat && planeNear(pt, sg.w, (float)qx, (float)qy)) ? w : 0.0f;
+            w *= normalWeight(dot(cn, F3(sg.x, sg.y, sg.z)), nParam);
             if (w > 1e-4f)
             {
-                const f4 sv = ld4(a.in, W, H, sx, sy);
-                const float sLum = luminance(xyz(sv));
-                const float lumW = fabsf(cLum - sLum) * phiInv;
-                w *= expf(-lumW);
+                const f4 sv = F4(__ldg(a.in + sp));
+                const float lumW = fabsf(cLum - luminance(xyz(sv))) * phiInv;
+                w *= __expf(-lumW);
                 sumW += w;
                 sum += f4{w, w, w, w * w} * sv;
             }
         }
-    a.out[pix] = toFloat4(sum / f4{sumW, sumW, sumW, sumW * sumW});
+    const f4 res = sum / f4{sumW, sumW, sumW, sumW * sumW};
+    if (kComposite)
+    {
+        const float4 al = __ldg(a.albedo + pix);
+        a.out[pix] = make_float4(res.x * al.x, res.y * al.y, res.z * al.z, 0.0f);
+    }
+    else
+        a.out[pix] = toFloat4(res);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+DnView makeDnView(const VptCamera &c)
+{
+    // uvToWorld columns (storage m00,m10,m20 | m01,m11,m21 | m02,m12,m22); u = (x+0.5)/W, v = (y+0.5)/H
+    DnView v;
+    for (int i = 0; i < 3; ++i)
+    {
+        v.pos[i] = c.pos[i];
+        v.Mx[i] = c.uvToWorld[i] * c.inversedResolution[0];
+        v.My[i] = c.uvToWorld[3 + i] * c.inversedResolution[1];
+        v.M0[i] = c.uvToWorld[6 + i] + 0.5f * v.Mx[i] + 0.5f * v.My[i];
+    }
+    return v;
+}
 static dim3 gridFor(const DenoiseLaunch &d)
 {
     return dim3((d.width + kBX - 1) / kBX, (d.rowEnd - d.rowBegin + kBY - 1) / kBY);
 }
 static const dim3 kBlock(kBX, kBY);
 
-cudaError_t launchFirefly(const DenoiseLaunch &d, FireflyPatch *patches, int *patchCount, int maxPatches)
+cudaError_t launchPrep(const DenoiseLaunch &d, int prepRow0, int prepRow1, bool firefly, FireflyPatch *patches, int maxPatches)
 {
-    cudaError_t e = cudaMemsetAsync(patchCount, 0, sizeof(int), d.stream);
-    if (e != cudaSuccess) return e;
-    const int tiles = ((d.width + 7) / 8) * ((d.rowEnd - d.rowBegin + 3) / 4);
-    fireflyDetectKernel<<<(tiles + 7) / 8, 256, 0, d.stream>>>(d.width, d.height, d.rowBegin, d.rowEnd, d.b.illumination, d.b.cur.normalRoughness,
-                                                               d.b.cur.depth, d.b.cur.material, d.b.reservoirs, 80.0f, 5.0f, 0.8f, 0.02f,
-                                                               d.p.phiLuminance, d.cam, patches, patchCount, maxPatches);
-    fireflyApplyKernel<<<64, 256, 0, d.stream>>>(patches, patchCount, maxPatches, d.b.illumination, d.b.reservoirs);
-    return cudaGetLastError();
-}
-cudaError_t launchCopySky(const DenoiseLaunch &d)
-{
-    copySkyKernel<<<gridFor(d), kBlock, 0, d.stream>>>(d.width, d.rowBegin, d.rowEnd, d.b.illumination, d.b.cur.depth, d.b.illumOutput);
+    if (firefly)
+    {
+        cudaError_t e = cudaMemsetAsync(d.counters, 0, sizeof(unsigned), d.stream);
+        if (e != cudaSuccess) return e;
+    }
+    PrepArgs a;
+    a.W = d.width; a.H = d.height; a.prepRow0 = prepRow0; a.prepRow1 = prepRow1; a.ffRow0 = d.rowBegin; a.ffRow1 = d.rowEnd;
+    a.enableFirefly = firefly ? 1 : 0;
+    a.view = d.view;
+    a.depth = d.b.cur.depth; a.material = d.b.cur.material; a.normalRough = d.b.cur.normalRoughness; a.illum = d.b.illumination;
+    a.res = d.b.reservoirs; a.G = d.G; a.MQ = d.MQ; a.out = d.b.illumOutput; a.counters = d.counters;
+    a.weightThreshold = 80.0f; a.minWeight = 5.0f;
+    a.fireflyList = d.fireflyList; a.maxList = maxPatches;
+    const int tiles = ((d.width + 7) / 8) * ((prepRow1 - prepRow0 + 3) / 4);
+    prepKernel<<<(tiles + 7) / 8, 256, 0, d.stream>>>(a);
+    if (firefly)
+    {
+        FireflyArgs f;
+        f.W = d.width; f.H = d.height; f.cam = d.cam;
+        f.depth = d.b.cur.depth; f.material = d.b.cur.material; f.normalRough = d.b.cur.normalRoughness; f.illum = d.b.illumination;
+        f.res = d.b.reservoirs; f.counters = d.counters; f.fireflyList = d.fireflyList; f.maxList = maxPatches;
+        f.weightThreshold = 80.0f; f.minWeight = 5.0f; f.normalThreshold = 0.8f; f.depthSigma = 0.02f; f.phiLuminance = d.p.phiLuminance;
+        f.patches = patches;
+        fireflyFilterKernel<<<64, 128, 0, d.stream>>>(f);
+        fireflyApplyKernel<<<64, 256, 0, d.stream>>>(patches, d.counters, maxPatches, d.b.illumination, d.b.reservoirs);
+    }
     return cudaGetLastError();
 }
 cudaError_t launchFrame0Init(const DenoiseLaunch &d)
@@ -766,42 +675,31 @@ cudaError_t launchFrame0Init(const DenoiseLaunch &d)
                                                       d.b.historyLength, d.b.prevHistoryLength);
     return cudaGetLastError();
 }
-cudaError_t launchTemporal(const DenoiseLaunch &d)
+cudaError_t launchHistoryFix(const DenoiseLaunch &d, int smCount)
 {
-    TemporalArgs a;
-    a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd;
-    a.cam = d.cam; a.prevCam = d.prevCam;
-    a.denoisingRange = d.p.denoisingRange; a.disocclusionThreshold = d.p.disocclusionThreshold;
-    a.disocclusionThresholdAlternate = d.p.disocclusionThresholdAlternate;
-    a.maxAccum = d.p.maxAccumulatedFrameNum; a.maxFastAccum = d.p.maxFastAccumulatedFrameNum;
-    a.depth = d.b.cur.depth; a.prevDepth = d.b.prev.depth; a.prevHistLen = d.b.prevHistoryLength;
-    a.normalRough = d.b.cur.normalRoughness; a.prevNormalRough = d.b.prev.normalRoughness;
-    a.illum = d.b.illumination; a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum;
-    a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength;
-    temporalKernel<<<gridFor(d), kBlock, 0, d.stream>>>(a);
-    return cudaGetLastError();
-}
-cudaError_t launchHistoryFix(const DenoiseLaunch &d)
-{
-    historyFixKernel<<<gridFor(d), kBlock, 0, d.stream>>>(d.width, d.height, d.rowBegin, d.rowEnd, d.cam, d.b.cur.depth, d.b.cur.material,
-                                                          d.b.cur.normalRoughness, d.b.historyLength, d.b.ping, d.b.pong);
+    HistoryFixArgs a;
+    a.W = d.width; a.H = d.height; a.view = d.view;
+    a.G = d.G; a.MQ = d.MQ; a.histLen = d.b.historyLength; a.ping = d.b.ping; a.pong = d.b.pong;
+    a.fixCount = d.counters + 1; a.fixList = d.fixList;
+    historyFixKernel<<<smCount * 8, 256, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launchHistoryClamping(const DenoiseLaunch &d)
 {
-    historyClampKernel<<<gridFor(d), kBlock, 0, d.stream>>>(d.width, d.height, d.rowBegin, d.rowEnd, d.b.cur.depth, d.b.illumination, d.b.ping,
-                                                            d.b.pong, d.b.historyLength, d.b.prevIllum, d.b.prevFastIllum, d.b.prevHistoryLength);
+    ClampArgs a;
+    a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd;
+    a.depth = d.b.cur.depth; a.illum = d.b.illumination; a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength;
+    a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum; a.prevHistLen = d.b.prevHistoryLength;
+    historyClampKernel<<<gridFor(d), kBlock, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
 static AtrousArgs atrousArgs(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step)
 {
     AtrousArgs a;
-    a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd;
-    a.cam = d.cam;
+    a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd; a.view = d.view;
     a.phiLuminance = d.p.phiLuminance; a.depthThreshold = d.p.depthThreshold; a.lobeAngleFraction = d.p.lobeAngleFraction;
     a.frameIndex = frameIndex; a.step = step;
-    a.in = in; a.normalRough = d.b.cur.normalRoughness; a.material = d.b.cur.material; a.depth = d.b.cur.depth;
-    a.histLen = d.b.historyLength; a.out = out;
+    a.in = in; a.G = d.G; a.MQ = d.MQ; a.histLen = d.b.historyLength; a.albedo = d.b.cur.albedo; a.out = out;
     return a;
 }
 cudaError_t launchAtrousSmem(const DenoiseLaunch &d, const float4 *in, float4 *out)
@@ -809,9 +707,11 @@ cudaError_t launchAtrousSmem(const DenoiseLaunch &d, const float4 *in, float4 *o
     atrousFirstKernel<<<gridFor(d), kBlock, 0, d.stream>>>(atrousArgs(d, in, out, 0, 1));
     return cudaGetLastError();
 }
-cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step)
+cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step, bool composite)
 {
-    atrousKernel<<<gridFor(d), kBlock, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
+    const dim3 grid((d.width + kBX - 1) / kBX, (d.rowEnd - d.rowBegin + kAtrousBY - 1) / kAtrousBY), block(kBX, kAtrousBY);
+    if (composite) atrousKernel<true><<<grid, block, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
+    else atrousKernel<false><<<grid, block, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
     return cudaGetLastError();
 }
 cudaError_t launchCompositeNonSky(const DenoiseLaunch &d, const float4 *finalBuf)

@@ -176,6 +176,10 @@ cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32
 cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHHost, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s);
 cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s);
 
+// Pixel-space view-vector basis of the current camera: M*(u,v,1) = M0 + x*Mx + y*My (vpt_denoise.cu)
+struct DnView { float pos[3], M0[3], Mx[3], My[3]; };
+DnView makeDnView(const VptCamera &c);
+
 // Denoiser passes; rows [rowBegin,rowEnd) are processed (whole image: 0,H).
 struct DenoiseLaunch
 {
@@ -183,15 +187,21 @@ struct DenoiseLaunch
     VptCamera cam, prevCam;
     VptDenoisingParams p;
     DenoiseBuffers b;
+    DnView view;
+    float4 *G;        // packed denoiser G-buffer: normal.xyz, view-scaled depth
+    uint32_t *MQ;     // material id << 16 | Load2DUshort1 value
+    unsigned *counters; // [0] firefly candidates, [1] HistoryFix list length
+    int4 *fireflyList;  // firefly candidates found by the prep pass
+    int *fixList;       // pixels with historyLength <= 4 (HistoryFix work list, filled by the temporal pass)
     cudaStream_t stream;
 };
-cudaError_t launchFirefly(const DenoiseLaunch &d, FireflyPatch *patches, int *patchCount, int maxPatches);
-cudaError_t launchCopySky(const DenoiseLaunch &d);
+// packed G-buffer over rows [prepRow0,prepRow1) + sky copy; firefly detection/apply over the launch rows
+cudaError_t launchPrep(const DenoiseLaunch &d, int prepRow0, int prepRow1, bool firefly, FireflyPatch *patches, int maxPatches);
 cudaError_t launchTemporal(const DenoiseLaunch &d);
-cudaError_t launchHistoryFix(const DenoiseLaunch &d);
+cudaError_t launchHistoryFix(const DenoiseLaunch &d, int smCount);
 cudaError_t launchHistoryClamping(const DenoiseLaunch &d);
 cudaError_t launchAtrousSmem(const DenoiseLaunch &d, const float4 *in, float4 *out);
-cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step);
+cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step, bool composite);
 cudaError_t launchCompositeNonSky(const DenoiseLaunch &d, const float4 *finalBuf);
 cudaError_t launchFrame0Init(const DenoiseLaunch &d);
 

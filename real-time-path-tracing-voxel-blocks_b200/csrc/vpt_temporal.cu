@@ -1,0 +1,256 @@
+// TemporalAccumulation (/root/reference/renderer/denoising/TemporalAccumulation.h:228-449, 29-215; samplers
+// shaders/Sampler.h:396-498, 576-698) — compiled as the EXACT arithmetic class (-fmad=false -prec-div=true
+// -prec-sqrt=true -DVPT_FAST_MATH=0: compensated dot / Mat3*v like the reference's LinearMath, IEEE divide / sqrt).
+//
+// Why this pass alone: it produces historyLength, which is a CONTROL variable of the rest of the chain — HistoryFix and
+// HistoryClamping branch on hl <= 4, AtrousSmem on hl >= 3 — and in the first frames hl sits exactly on those integers
+// (n frames of history -> n +- an ulp from the bilinear weight normalisation). One ulp of difference flips the branch
+// for half the image. Computing the reprojection and hl with the oracle's arithmetic makes the plane bit-identical, so
+// every implementation takes the same branches (the same reasoning as the exact class for primary hits).
+#include "vpt_denoise_common.cuh"
+
+namespace vpt {
+
+// ------------------------------------------------------------------------------------------------ samplers
+VPT_DEV void bilinearSetup(f2 uv, int W, int H, f2 &f, int &tx0, int &ty0)
+{
+    f2 UV = {uv.x * W, uv.y * H};
+    f2 tc = {floorf(UV.x - 0.5f) + 0.5f, floorf(UV.y - 0.5f) + 0.5f};
+    f = UV - tc;
+    tx0 = (int)floorf(UV.x - 0.5f); ty0 = (int)floorf(UV.y - 0.5f);
+}
+VPT_DEV f4 bilinearWeight(f2 uv, int W, int H)
+{
+    f2 f; int a, b; bilinearSetup(uv, W, H, f, a, b);
+    f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
+    return {w0.x * w0.y, w1.x * w0.y, w0.x * w1.y, w1.x * w1.y};
+}
+VPT_DEV f4 sampleBilinearCustom4(const float4 *tex, f2 uv, int W, int H, f4 cw)
+{
+    f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
+    f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
+    const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+    const float ws[4] = {w0.x * w0.y * cw.x, w1.x * w0.y * cw.y, w0.x * w1.y * cw.z, w1.x * w1.y * cw.w};
+    f4 out = F4(0.0f); float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        f4 v = ld4(tex, W, H, xs[i], ys[i]);
+        float w = max1f(ws[i], 1e-6f);
+        sum += w; out += v * w;
+    }
+    return out / sum;
+}
+VPT_DEV float sampleBilinearCustom1(const float *tex, f2 uv, int W, int H, f4 cw)
+{
+    f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
+    f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
+    const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+    const float ws[4] = {w0.x * w0.y * cw.x, w1.x * w0.y * cw.y, w0.x * w1.y * cw.z, w1.x * w1.y * cw.w};
+    float out = 0.0f, sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        float v = ld1(tex, W, H, xs[i], ys[i]);
+        float w = max1f(ws[i], 1e-6f);
+        sum += w; out += v * w;
+    }
+    return out / sum;
+}
+VPT_DEV f4 sampleBicubic12(const float4 *tex, f2 uv, int W, int H)
+{
+    f2 f; int x1, y1; bilinearSetup(uv, W, H, f, x1, y1);
+    f2 f2_ = f * f, f3_ = f2_ * f;
+    f2 w0 = {f2_.x - 0.5f * (f3_.x + f.x), f2_.y - 0.5f * (f3_.y + f.y)};
+    f2 w1 = {1.5f * f3_.x - 2.5f * f2_.x + 1.0f, 1.5f * f3_.y - 2.5f * f2_.y + 1.0f};
+    f2 w3 = {0.5f * (f3_.x - f2_.x), 0.5f * (f3_.y - f2_.y)};
+    f2 w2 = {1.0f - w0.x - w1.x - w3.x, 1.0f - w0.y - w1.y - w3.y};
+    const int x0 = x1 - 1, x2 = x1 + 1, x3 = x1 + 2, y0 = y1 - 1, y2 = y1 + 1, y3 = y1 + 2;
+    const int xs[12] = {x1, x2, x0, x1, x2, x3, x0, x1, x2, x3, x1, x2};
+    const int ys[12] = {y0, y0, y1, y1, y1, y1, y2, y2, y2, y2, y3, y3};
+    const float ws[12] = {w1.x * w0.y, w2.x * w0.y, w0.x * w1.y, w1.x * w1.y, w2.x * w1.y, w3.x * w1.y,
+                          w0.x * w2.y, w1.x * w2.y, w2.x * w2.y, w3.x * w2.y, w1.x * w3.y, w2.x * w3.y};
+    f4 out = F4(0.0f); float sum = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { sum += ws[i]; out += ld4(tex, W, H, xs[i], ys[i]) * ws[i]; }
+    return out / sum;
+}
+VPT_DEV f3 sampleSmoothStep3(const float4 *tex, f2 uv, int W, int H)
+{
+    f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
+    f2 f2_ = f * f, f3_ = f2_ * f;
+    f2 w1 = {-2.0f * f3_.x + 3.0f * f2_.x, -2.0f * f3_.y + 3.0f * f2_.y};
+    f2 w0 = {1.0f - w1.x, 1.0f - w1.y};
+    const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+    const float ws[4] = {w0.x * w0.y, w1.x * w0.y, w0.x * w1.y, w1.x * w1.y};
+    f3 out = F3(0.0f); float sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sum += ws[i]; out += xyz(ld4(tex, W, H, xs[i], ys[i])) * ws[i]; }
+    return out / sum;
+}
+VPT_DEV float parallaxInPixels(f3 X, f2 uvZero, const Cam &cam, f2 rectSize)
+{
+    f2 uv = worldDirectionToUV(cam, normalize(X - cam.pos));
+    f2 d = (uv - uvZero) * rectSize;
+    return sqrtf(d.x * d.x + d.y * d.y);
+}
+
+// ------------------------------------------------------------------------------------------------ temporal
+struct TemporalArgs
+{
+    int W, H, rowBegin, rowEnd;
+    VptCamera cam, prevCam;
+    float denoisingRange, disocclusionThreshold, disocclusionThresholdAlternate, maxAccum, maxFastAccum;
+    const float *depth, *prevDepth, *prevHistLen;
+    const float4 *normalRough, *prevNormalRough, *illum, *prevIllum, *prevFast;
+    float4 *ping, *pong;
+    float *histLen;
+    unsigned *fixCount; int *fixList; // pixels that end with historyLength <= 4: HistoryFix's work list
+};
+__global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_constant__ TemporalArgs a)
+{
+    const int W = a.W, H = a.H;
+    // launch-uniform: rotation between the previous and current view directions, once per CTA
+    __shared__ quat prevToCurS;
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+        prevToCurS = rotationBetween(F3(a.prevCam.dir[0], a.prevCam.dir[1], a.prevCam.dir[2]), F3(a.cam.dir[0], a.cam.dir[1], a.cam.dir[2]));
+    __syncthreads();
+    PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
+    const float z = __ldg(a.depth + pix);
+    if (z > a.denoisingRange) return;
+    const Cam cam = loadCam(a.cam), prevCam = loadCam(a.prevCam);
+    const quat prevToCur = prevToCurS;
+    const f2 pixelUv = {(float(x) + 0.5f) * (1.0f / (float)W), (float(y) + 0.5f) * (1.0f / (float)H)};
+    const f3 n = xyz(__ldg(a.normalRough + pix));
+    const f2 curUV = {(float(x) + 0.5f) * cam.invResX, (float(y) + 0.5f) * cam.invResY};
+    const f3 viewVec = uvToWorldDirection(cam, curUV);
+    const f3 worldPos = worldPosFromPixel(cam, x, y, z);
+    const f3 V = -normalize(viewVec);
+    const float NoV = fabsf(dot(n, V));
+    const f3 prevWorldPos = worldPos;
+    const f2 prevUV = worldDirectionToUV(prevCam, normalize(prevWorldPos - prevCam.pos));
+    const f3 illum = xyz(__ldg(a.illum + pix));
+    f3 nAvg = n;
+#pragma unroll
+    for (int i = -1; i <= 1; ++i)
+#pragma unroll
+        for (int j = -1; j <= 1; ++j)
+        {
+            if (i == 0 && j == 0) continue;
+            nAvg += xyz(ld4(a.normalRough, W, H, x + i, y + j));
+        }
+    nAvg /= 9.0f;
+    const float m1 = luminance(illum), m2 = m1 * m1;
+    const f3 camDelta = prevCam.pos - cam.pos;
+    const f2 rect = {(float)W, (float)H};
+    const float par1 = parallaxInPixels(prevWorldPos + camDelta, pixelUv, prevCam, rect);
+    const float par2 = parallaxInPixels(prevWorldPos - camDelta, prevUV, cam, rect);
+    const float parMax = fmaxr(par1, par2);
+    const float thrBonus = a.disocclusionThreshold + (1.5f / H);
+    const float thrAltBonus = a.disocclusionThresholdAlternate + (1.5f / H);
+    const float disThr = lerpf(thrBonus, thrAltBonus, 0.0f);
+
+    const f3 curNormalAvg = normalize(nAvg);
+    const float estPrevDepth = length(prevWorldPos - prevCam.pos);
+    const f2 prevPixF = {prevUV.x * W, prevUV.y * H};
+    const int bx = (int)floorf(prevPixF.x - 0.5f), by = (int)floorf(prevPixF.y - 0.5f);
+    const float pixelSize = (cam.tanHalfFovX / (cam.resX / 2)) * z;
+    const float frustumSize = pixelSize * (float)min(W, H);
+    const float slopeScale = 1.0f / lerpf(lerpf(0.05f, 1.0f, NoV), 1.0f, saturate(parMax / 30.0f));
+    float thr[4];
+    {
+        const float base = saturate(disThr * slopeScale) * frustumSize;
+        const int px0 = bx, py0 = by, px1 = bx + 1, py1 = by + 1;
+        float rx0 = (px0 >= 0) ? 1.0f : 0.0f, ry0 = (py0 >= 0) ? 1.0f : 0.0f, rx1 = (px1 >= 0) ? 1.0f : 0.0f, ry1 = (py1 >= 0) ? 1.0f : 0.0f;
+        rx0 *= (px0 < W) ? 1.0f : 0.0f; ry0 *= (py0 < H) ? 1.0f : 0.0f; rx1 *= (px1 < W) ? 1.0f : 0.0f; ry1 *= (py1 < H) ? 1.0f : 0.0f;
+        const float inScreen[4] = {rx0 * ry0, rx1 * ry0, rx0 * ry1, rx1 * ry1};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { thr[i] = base * inScreen[i]; thr[i] -= 1e-6f; }
+    }
+    const int bic[4][2][2] = {{{0, -1}, {-1, 0}}, {{1, -1}, {2, 0}}, {{-1, 1}, {0, 2}}, {{2, 1}, {1, 2}}};
+    const int bil[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
+    float bicubicValid = 1.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+        {
+            float pz = ld1(a.prevDepth, W, H, bx + bic[i][j][0], by + bic[i][j][1]);
+            bicubicValid *= fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
+        }
+    float tv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        float pz = ld1(a.prevDepth, W, H, bx + bil[i][0], by + bil[i][1]);
+        float v = fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
+        bicubicValid *= v; tv[i] = v;
+    }
+    f4 tapsValid = {tv[0], tv[1], tv[2], tv[3]};
+    const f3 prevNFlat = normalize(sampleSmoothStep3(a.prevNormalRough, prevUV, W, H));
+    const f3 prevNRot = normalize(qrotate(prevToCur, prevNFlat));
+    if (dot(curNormalAvg, prevNRot) < 0.0f) { tapsValid = F4(0.0f); bicubicValid = 0.0f; }
+    const bool useBicubic = bicubicValid > 0;
+    f4 prevIllum; f3 prevFast;
+    if (useBicubic)
+    {
+        prevIllum = sampleBicubic12(a.prevIllum, prevUV, W, H);
+        prevFast = xyz(sampleBicubic12(a.prevFast, prevUV, W, H));
+    }
+    else
+    {
+        prevIllum = sampleBilinearCustom4(a.prevIllum, prevUV, W, H, tapsValid);
+        prevFast = xyz(sampleBilinearCustom4(a.prevFast, prevUV, W, H, tapsValid));
+    }
+    prevIllum = max4f(prevIllum, F4(0.0f));
+    prevFast = max3f(prevFast, F3(0.0f));
+    float reprojFound = (bicubicValid > 0.0f) ? 2.0f : 1.0f;
+    const f4 bw = bilinearWeight(prevUV, W, H);
+    float footprintQuality = (bicubicValid > 0) ? 1.0f : dot4(bw, F4(1.0f));
+    float historyLength;
+    if (dot4(tapsValid, F4(1.0f)) == 0.0f) { reprojFound = 0.0f; footprintQuality = 0.0f; historyLength = 0.0f; }
+    else historyLength = sampleBilinearCustom1(a.prevHistLen, prevUV, W, H, tapsValid);
+
+    historyLength = historyLength + 1.0f;
+    const f3 Vprev = normalize(prevWorldPos - prevCam.pos);
+    const float NoVprev = fabsf(dot(n, Vprev));
+    float sizeQuality = (NoVprev + 1e-3f) / (NoV + 1e-3f);
+    sizeQuality *= sizeQuality; sizeQuality *= sizeQuality;
+    footprintQuality *= lerpf(0.1f, 1.0f, saturate(sizeQuality));
+    if (footprintQuality < 1.0f) { historyLength *= sqrtf(footprintQuality); historyLength = fmaxr(historyLength, 1.0f); }
+    historyLength = fminr(historyLength, a.maxAccum);
+    const float alpha = (reprojFound > 0) ? fmaxr(1.0f / (a.maxAccum + 1.0f), 1.0f / historyLength) : 1.0f;
+    const float alphaFast = (reprojFound > 0) ? fmaxr(1.0f / (a.maxFastAccum + 1.0f), 1.0f / historyLength) : 1.0f;
+    a.ping[pix] = toFloat4(lerp4(prevIllum, F4(illum, m2), alpha));
+    a.pong[pix] = toFloat4(F4(lerp3(prevFast, illum, alphaFast), 0.0f));
+    a.histLen[pix] = historyLength;
+    if (historyLength <= 4.0f)
+    {
+        // warp-aggregated append (one atomic per warp)
+        const unsigned m = __activemask();
+        const int lane = (threadIdx.y * kBX + threadIdx.x) & 31, leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(a.fixCount, (unsigned)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        a.fixList[base + __popc(m & ((1u << lane) - 1u))] = (int)pix;
+    }
+}
+
+cudaError_t launchTemporal(const DenoiseLaunch &d)
+{
+    const dim3 grid((d.width + kBX - 1) / kBX, (d.rowEnd - d.rowBegin + kBY - 1) / kBY), block(kBX, kBY);
+    TemporalArgs a;
+    a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd;
+    a.cam = d.cam; a.prevCam = d.prevCam;
+    a.denoisingRange = d.p.denoisingRange; a.disocclusionThreshold = d.p.disocclusionThreshold;
+    a.disocclusionThresholdAlternate = d.p.disocclusionThresholdAlternate;
+    a.maxAccum = d.p.maxAccumulatedFrameNum; a.maxFastAccum = d.p.maxFastAccumulatedFrameNum;
+    a.depth = d.b.cur.depth; a.prevDepth = d.b.prev.depth; a.prevHistLen = d.b.prevHistoryLength;
+    a.normalRough = d.b.cur.normalRoughness; a.prevNormalRough = d.b.prev.normalRoughness;
+    a.illum = d.b.illumination; a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum;
+    a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength; a.fixCount = d.counters + 1; a.fixList = d.fixList;
+    temporalKernel<<<grid, block, 0, d.stream>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace vpt

@@ -89,7 +89,7 @@ def test_furnace_constant_sky(libs):
 
 
 def test_denoiser_chain_matches_oracle(libs):
-    """Full chain (firefly, temporal, history fix/clamp, a-trous x4, composite) over 4 frames, camera moving from frame 2."""
+    """Full chain (firefly, temporal, history fix/clamp, a-trous x4, composite) over 6 frames, camera moving from frame 2."""
     W, H = 256, 160
     inp = common.scene_inputs((2, 1, 2))
     g, o = _pair(libs, W, H, inp, spp=1, total=3, diffuse=1)
@@ -97,7 +97,7 @@ def test_denoiser_chain_matches_oracle(libs):
     p = S.default_denoising_params()
     cam = common.scene_camera(W, H)
     prev = cam
-    for f in range(4):
+    for f in range(6):
         g.render(cam, prev, f)
         o.render(cam, prev, f)
         # feed the oracle's noisy inputs to the GPU denoiser so this test isolates the denoiser (trace parity is tested above)
@@ -106,13 +106,18 @@ def test_denoiser_chain_matches_oracle(libs):
         g.write_reservoirs(f & 1, o.read_reservoirs(f & 1))
         g.denoise(p, cam, prev, f, f + 1)
         o.denoise(p, cam, prev, f, f + 1)
-        # tolerances: the CUDA denoiser is the fast arithmetic class (FMA, MUFU rcp/rsqrt — like the reference's own
-        # --use_fast_math build); a few threshold tests (plane distance, history reset) flip on borderline pixels.
-        for name, tol in (("IlluminationOutput", 5e-4), ("PrevIllumination", 2e-3), ("PrevFastIllumination", 2e-3),
-                          ("HistoryLength", 5e-4), ("IlluminationPing", 2e-3), ("IlluminationPong", 2e-3)):
+        # The temporal pass is the exact arithmetic class (csrc/vpt_temporal.cu): historyLength — the control variable the later
+        # passes branch on (hl <= 4, hl >= 3) — must be BIT-IDENTICAL, or an ulp flips those branches for half the image in
+        # the first frames. The other passes are the fast class (FMA, MUFU rcp/rsqrt, like the reference's --use_fast_math
+        # build): measured mean relative error ~3e-6; a few threshold tests flip on borderline pixels (the > 1e-3 tail).
+        assert np.array_equal(g.read("HistoryLength"), o.read("HistoryLength")), f
+        # (IlluminationPong is not compared: the last a-trous pass is fused with the albedo composite and writes
+        # IlluminationOutput directly, so Pong keeps the step-2 result while the oracle's holds the final one.)
+        for name, tol, tail in (("IlluminationOutput", 5e-5, 5e-3), ("PrevIllumination", 1e-4, 5e-3), ("PrevFastIllumination", 1e-4, 5e-3),
+                                ("IlluminationPing", 1e-4, 5e-3)):
             a, b = g.read(name), o.read(name)
             mean_rel, outliers, dmax = common.rel_err_stats(a, b)
-            assert mean_rel <= tol and outliers <= 1e-2, (f, name, mean_rel, outliers, dmax)
+            assert mean_rel <= tol and outliers <= tail, (f, name, mean_rel, outliers, dmax)
         prev = cam
         if f >= 1:
             cam = vpt.camera_set_yaw_pitch(cam, cam[15] + np.float32(0.5 * np.pi / 180.0), cam[16])
