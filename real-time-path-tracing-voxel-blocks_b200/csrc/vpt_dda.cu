@@ -21,8 +21,14 @@
 namespace vpt {
 
 constexpr int kDdaThreads = 1024;
-constexpr int kChunk = 128;       // rays reserved per warp per atomic
-constexpr int kRefillBelow = 20;  // re-arm idle lanes when <= this many lanes are live
+#ifndef VPT_DDA_CHUNK
+#define VPT_DDA_CHUNK 128
+#endif
+#ifndef VPT_DDA_REFILL
+#define VPT_DDA_REFILL 20
+#endif
+constexpr int kChunk = VPT_DDA_CHUNK;        // rays reserved per warp per atomic
+constexpr int kRefillBelow = VPT_DDA_REFILL; // re-arm idle lanes when <= this many lanes are live
 constexpr unsigned kFull = 0xffffffffu;
 
 template <bool kSmem, bool kClosest, bool kStats>

@@ -485,6 +485,9 @@ enum : uint32_t
 };
 constexpr int kRandShift = 16, kDepthShift = 24, kDiffuseShift = 28;
 constexpr int kShadeThreads = 256;
+#ifndef VPT_SHADE_MINB
+#define VPT_SHADE_MINB 4 // measured on B200 (r1 variants): 4 resident CTAs/SM (<= 64 regs) is the optimum for S1-S3: shade 1.94 -> 1.61 ms
+#endif
 constexpr int kCntWords = 256, kCntList = 128; // cnt[2k], cnt[2k+1] = count / cursor of the k-th DDA launch; cnt[128+d] = active paths at depth d
 
 // Queue reservation with ONE atomic per CTA. Every thread of the CTA calls it (convergent); n = entries wanted.
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(kShadeThreads) genKernel(const __grid_constant
 
 // ------------------------------------------------------------------------------------------------ S1
 // __miss__radiance, and __closesthit__radiance up to the BSDF-candidate ray (closesthit.cu:96-468).
-__global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+__global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
@@ -852,7 +855,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade1Kernel(const __grid_const
 
 // ------------------------------------------------------------------------------------------------ S2
 // RIS: classify the BSDF candidate, merge the three reservoirs, cast the winner's visibility ray (closesthit.cu:470-634).
-__global__ void __launch_bounds__(kShadeThreads) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+__global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
@@ -1010,7 +1013,7 @@ VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float
 
 // ------------------------------------------------------------------------------------------------ S3
 // Temporal ReSTIR: candidates from the previous frame + the bias-correction rays (closesthit.cu:636-760).
-__global__ void __launch_bounds__(kShadeThreads) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
+__global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
