@@ -174,6 +174,24 @@ int vpt_set_materials(vpt_ctx *ctx, const VptMaterial *materials, int count, con
  * their alias tables (shaders/AliasTable.cu:66-153) and the sun direction. */
 int vpt_set_sky(vpt_ctx *ctx, const float *skyRGBA, int skyW, int skyH, const float *sunRGBA, int sunW, int sunH,
                 const VptAliasBin *skyAlias, const VptAliasBin *sunAlias, const float *sunDir /*[3]*/);
+/* SkyParams (renderer/core/GlobalSettings.h:188-204) */
+typedef struct VptSkyParams
+{
+    float timeOfDay;     /* 0.25 */
+    float sunAxisAngle;  /* 45 */
+    float sunAxisRotate; /* 0 */
+    float skyBrightness; /* 1 */
+} VptSkyParams;
+/* SkyModel::update (renderer/sky/Sky.cu:355-396): evaluates the Hosek-Wilkie sky (1024 x 512 equal-area sphere map) and the
+ * solar disc (32 x 32 cone map) ON THE DEVICE from the parameters, builds both alias tables (CPU build path like the
+ * reference, shaders/AliasTable.cu:66-153) and installs them like vpt_set_sky. tables = the 2460 floats of
+ * data/sky_tables.bin (the coefficient datasets of renderer/sky/SkyData.h). */
+int vpt_generate_sky(vpt_ctx *ctx, const VptSkyParams *params, const float *tables);
+/* Current sky state: RGBA32F maps, sun direction (any pointer may be NULL); sizes via vpt_sky_size. */
+int vpt_read_sky(vpt_ctx *ctx, float *skyRGBA, float *sunRGBA, float *sunDir3);
+int vpt_sky_size(vpt_ctx *ctx, int *skyW, int *skyH, int *sunW, int *sunH);
+/* Host part of SkyModel::update: sun direction (Sky.cu:362-367) and updateSkyState (Sky.cu:52-79). */
+void vpt_sky_state(const VptSkyParams *params, const float *tables, float *configs90, float *radiances10, float *sunDir3);
 /* New parameters of this build (SURVEY "five facts" #2); the reference is spp=1, limits 3/1, ReSTIR on
  * (renderer/shaders/RayGen.cu:146-147). */
 int vpt_set_trace_params(vpt_ctx *ctx, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir);

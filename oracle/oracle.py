@@ -127,6 +127,26 @@ def build_alias_table(weights):
     return bins
 
 
+def generate_sky(params, tables, sky_w=1024, sky_h=512, sun_w=32, sun_h=32):
+    """SkyModel::update restatement: params = (timeOfDay, sunAxisAngle, sunAxisRotate, skyBrightness), tables = the 2460
+    floats of data/sky_tables.bin. Returns sky[h,w,4], sun[h,w,4], skyPdf, sunPdf, sunDir."""
+    pr = np.asarray(params, np.float32)
+    tb = np.ascontiguousarray(tables, np.float32)
+    sky = np.zeros((sky_h, sky_w, 4), np.float32); sun = np.zeros((sun_h, sun_w, 4), np.float32)
+    sky_pdf = np.zeros(sky_h * sky_w, np.float32); sun_pdf = np.zeros(sun_h * sun_w, np.float32)
+    sd = np.zeros(3, np.float32)
+    lib().orc_generate_sky(_p(pr), _p(tb), sky_w, sky_h, sun_w, sun_h, _p(sky), _p(sun), _p(sky_pdf), _p(sun_pdf), _p(sd))
+    return sky, sun, sky_pdf, sun_pdf, sd
+
+
+def sky_state(params, tables):
+    pr = np.asarray(params, np.float32)
+    tb = np.ascontiguousarray(tables, np.float32)
+    cfg = np.zeros(90, np.float32); rad = np.zeros(10, np.float32); sd = np.zeros(3, np.float32)
+    lib().orc_sky_state(_p(pr), _p(tb), _p(cfg), _p(rad), _p(sd))
+    return cfg, rad, sd
+
+
 def set_threads(n):
     lib().orc_set_threads(int(n))
 

@@ -2,6 +2,7 @@
 // (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.
 // Mirrors the shape of include/vpt.h so parity tests drive both sides with the same bytes.
 #include "orc_denoise.h"
+#include "orc_sky.h"
 #include <omp.h>
 #include <cstdio>
 
@@ -250,6 +251,21 @@ float orc_perlin_noise(unsigned seed, int octaves, float x, float y)
 {
     Perlin p(seed);
     return p.octave2D_01(x, y, octaves);
+}
+// SkyModel::update restatement (orc_sky.h). params: timeOfDay, sunAxisAngle, sunAxisRotate, skyBrightness.
+void orc_generate_sky(const float *params, const float *tables, int skyW, int skyH, int sunW, int sunH, float *sky, float *sun, float *skyPdf,
+                      float *sunPdf, float *sunDir)
+{
+    f3 sd;
+    generateSky(params, tables, skyW, skyH, sunW, sunH, (f4 *)sky, (f4 *)sun, skyPdf, sunPdf, &sd);
+    sunDir[0] = sd.x; sunDir[1] = sd.y; sunDir[2] = sd.z;
+}
+void orc_sky_state(const float *params, const float *tables, float *configs90, float *radiances10, float *sunDir)
+{
+    const f3 sd = skySunDir(params[0], params[1], params[2]);
+    const SkyState st = skyUpdateState(skyTablesFrom(tables), sd);
+    std::memcpy(configs90, st.configs, sizeof st.configs); std::memcpy(radiances10, st.radiances, sizeof st.radiances);
+    sunDir[0] = sd.x; sunDir[1] = sd.y; sunDir[2] = sd.z;
 }
 void orc_build_alias_table(const float *weights, unsigned n, AliasBin *bins) { buildAliasTable(weights, n, bins); }
 float orc_rand(orc_ctx *c, int px, int py, int sampleIndex, int dim) { return blueNoiseRand(c->sc.tables, px, py, sampleIndex, dim); }

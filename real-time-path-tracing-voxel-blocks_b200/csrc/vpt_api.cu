@@ -291,6 +291,61 @@ int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *s
     return VPT_OK;
 }
 
+int vpt_generate_sky(vpt_ctx *c, const VptSkyParams *params, const float *tables)
+{
+    if (!c || !params || !tables) return fail(VPT_ERR_ARG, "vpt_generate_sky: null argument");
+    CU(cudaSetDevice(c->device));
+    const int skyW = 1024, skyH = 512, sunW = 32, sunH = 32; // SkyModel::skyRes / sunRes (renderer/sky/Sky.h:51-52)
+    const size_t ns = (size_t)skyW * skyH, nu = (size_t)sunW * sunH;
+    float configs[90], radiances[10], sunDir[3];
+    vpt_sky_state(params, tables, configs, radiances, sunDir);
+    for (void *p : {(void *)c->sky, (void *)c->sun, (void *)c->skyAlias, (void *)c->sunAlias}) if (p) cudaFree(p);
+    c->sky = c->sun = nullptr; c->skyAlias = c->sunAlias = nullptr;
+    CU(cudaMalloc((void **)&c->sky, ns * 16)); CU(cudaMalloc((void **)&c->sun, nu * 16));
+    CU(cudaMalloc((void **)&c->skyAlias, ns * sizeof(VptAliasBin))); CU(cudaMalloc((void **)&c->sunAlias, nu * sizeof(VptAliasBin)));
+    float *dPdf = nullptr, *dTab = nullptr;
+    CU(cudaMalloc((void **)&dPdf, (ns + nu) * sizeof(float)));
+    CU(cudaMalloc((void **)&dTab, 1860 * sizeof(float)));
+    CU(cudaMemcpyAsync(dTab, tables + 600, 1860 * sizeof(float), cudaMemcpyHostToDevice, c->stream)); // solar[1800], limb[60]
+    std::vector<float> pdf(ns + nu);
+    CU(launchSkyUpper(configs, radiances, sunDir, params->skyBrightness, c->sky, dPdf, skyW, skyH, c->stream));
+    // thrust::reduce over the upper hemisphere (Sky.cu:378): summed on the host in double, rounded once
+    CU(cudaMemcpyAsync(pdf.data() + ns / 2, dPdf + ns / 2, (ns / 2) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double sum = 0.0;
+    for (size_t i = ns / 2; i < ns; ++i) sum += (double)pdf[i];
+    CU(launchSkyLower(c->sky, dPdf, skyW, skyH, (float)sum, c->stream));
+    CU(launchSkySun(sunDir, params->skyBrightness, dTab, dTab + 1800, c->sun, dPdf + ns, sunW, sunH, c->stream));
+    CU(cudaMemcpyAsync(pdf.data(), dPdf, (ns + nu) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<VptAliasBin> skyBins(ns), sunBins(nu);
+    vpt_build_alias_table(pdf.data(), (unsigned)ns, skyBins.data());
+    vpt_build_alias_table(pdf.data() + ns, (unsigned)nu, sunBins.data());
+    CU(cudaMemcpyAsync(c->skyAlias, skyBins.data(), ns * sizeof(VptAliasBin), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->sunAlias, sunBins.data(), nu * sizeof(VptAliasBin), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(dPdf)); CU(cudaFree(dTab));
+    c->skyW = skyW; c->skyH = skyH; c->sunW = sunW; c->sunH = sunH;
+    c->sunDir[0] = sunDir[0]; c->sunDir[1] = sunDir[1]; c->sunDir[2] = sunDir[2];
+    return VPT_OK;
+}
+int vpt_sky_size(vpt_ctx *c, int *skyW, int *skyH, int *sunW, int *sunH)
+{
+    if (!c || !c->sky) return fail(VPT_ERR_STATE, "vpt_sky_size: no sky set");
+    if (skyW) *skyW = c->skyW; if (skyH) *skyH = c->skyH; if (sunW) *sunW = c->sunW; if (sunH) *sunH = c->sunH;
+    return VPT_OK;
+}
+int vpt_read_sky(vpt_ctx *c, float *skyRGBA, float *sunRGBA, float *sunDir3)
+{
+    if (!c || !c->sky) return fail(VPT_ERR_STATE, "vpt_read_sky: no sky set");
+    CU(cudaSetDevice(c->device));
+    if (skyRGBA) CU(cudaMemcpyAsync(skyRGBA, c->sky, (size_t)c->skyW * c->skyH * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (sunRGBA) CU(cudaMemcpyAsync(sunRGBA, c->sun, (size_t)c->sunW * c->sunH * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (sunDir3) { sunDir3[0] = c->sunDir[0]; sunDir3[1] = c->sunDir[1]; sunDir3[2] = c->sunDir[2]; }
+    return VPT_OK;
+}
+
 int vpt_set_trace_params(vpt_ctx *c, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir)
 {
     if (!c || spp < 1 || totalBounceLimit < 1 || diffuseBounceLimit < 1) return fail(VPT_ERR_ARG, "vpt_set_trace_params: bad argument");

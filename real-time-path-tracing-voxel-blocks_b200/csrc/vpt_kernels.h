@@ -172,6 +172,12 @@ struct DdaArgs
 cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, cudaStream_t s, int smCount);
 
 // upH (device int): highest solid y + 1, maintained by the repack / set-voxel kernels; the upward mask is rebuilt from it
+// sky generator (vpt_sky.cu)
+cudaError_t launchSkyUpper(const float *configs, const float *radiances, const float *sunDir, float brightness, float4 *sky, float *pdf, int W, int H,
+                           cudaStream_t s);
+cudaError_t launchSkyLower(float4 *sky, float *pdf, int W, int H, float sumSkyPdf, cudaStream_t s);
+cudaError_t launchSkySun(const float *sunDir, float brightness, const float *solar, const float *limb, float4 *sun, float *pdf, int W, int H, cudaStream_t s);
+
 cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHDev, int *upHHost, int cx, int cy, int cz, cudaStream_t s);
 cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHHost, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s);
 cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s);

@@ -375,6 +375,47 @@ int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigne
 
 } // extern "C"
 
+// ---- sky state on the host: SkyModel::update's sun direction (renderer/sky/Sky.cu:362-367) and updateSkyState
+// (Sky.cu:52-79; getFittingData/2 :18-50). tables = data/sky_tables.bin (skyDataSets[540], skyDataSetsRad[60], ...).
+namespace {
+inline float dot3c(V3 a, V3 b) { return inner3(a.x, b.x, a.y, b.y, a.z, b.z); }
+struct Q4 { V3 v; float w; };
+inline V3 scale3(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 add3(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Q4 qmul(Q4 p, Q4 q) { return {add3(add3(scale3(q.v, p.w), scale3(p.v, q.w)), cross3(p.v, q.v)), p.w * q.w - dot3c(p.v, q.v)}; }
+inline float skyFit(const float *m, float s, int i)
+{
+    return (powf(1.0f - s, 5.0f) * m[i] + 5.0f * powf(1.0f - s, 4.0f) * s * m[i + 9] + 10.0f * powf(1.0f - s, 3.0f) * powf(s, 2.0f) * m[i + 18] +
+            10.0f * powf(1.0f - s, 2.0f) * powf(s, 3.0f) * m[i + 27] + 5.0f * (1.0f - s) * powf(s, 4.0f) * m[i + 36] + powf(s, 5.0f) * m[i + 45]);
+}
+inline float skyFit2(const float *m, float s)
+{
+    return (powf(1.0f - s, 5.0f) * m[0] + 5.0f * powf(1.0f - s, 4.0f) * s * m[1] + 10.0f * powf(1.0f - s, 3.0f) * powf(s, 2.0f) * m[2] +
+            10.0f * powf(1.0f - s, 2.0f) * powf(s, 3.0f) * m[3] + 5.0f * (1.0f - s) * powf(s, 4.0f) * m[4] + powf(s, 5.0f) * m[5]);
+}
+} // namespace
+extern "C" void vpt_sky_state(const VptSkyParams *p, const float *tables, float *configs90, float *radiances10, float *sunDir3)
+{
+    const float kPi = 3.1415926535897932384626422832795028841971f, kTwoPi = 6.2831853071795864769252867665590057683943f;
+    const float d2r = kPi / 180.0f;
+    V3 axis = {1.0f, cosf(p->sunAxisAngle * d2r), sinf(p->sunAxisAngle * d2r)};
+    axis = {axis.x * sinf(p->sunAxisRotate * d2r), axis.y * 1.0f, axis.z * cosf(p->sunAxisRotate * d2r)};
+    axis = normalize3(axis);
+    const float angle = fmodf(p->timeOfDay * kPi, kTwoPi);
+    const V3 v = cross3({0.0f, 1.0f, 0.0f}, axis);
+    const Q4 q = {scale3(normalize3(axis), sinf(angle / 2)), cosf(angle / 2)};
+    const Q4 r = qmul(qmul(q, Q4{v, 0.0f}), Q4{-q.v, q.w});
+    const V3 sd = normalize3(r.v);
+    sunDir3[0] = sd.x; sunDir3[1] = sd.y; sunDir3[2] = sd.z;
+    const float elevation = (kPi / 2.0f) - (float)acos((double)sd.y);
+    const float solarElevation = powf(elevation / (kPi / 2.0f), (1.0f / 3.0f));
+    for (int c = 0; c < 10; ++c)
+    {
+        for (int i = 0; i < 9; ++i) configs90[c * 9 + i] = skyFit(tables + c * 54, solarElevation, i);
+        radiances10[c] = skyFit2(tables + 540 + c * 6, solarElevation);
+    }
+}
+
 // Test hook: the magic-number division used by the kernels (csrc/vpt_fastdiv.h), evaluated on the host.
 extern "C" void vpt_debug_fastdiv(uint32_t n, uint32_t d, uint32_t *q, uint32_t *r)
 {

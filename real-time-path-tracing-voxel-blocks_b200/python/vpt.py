@@ -40,7 +40,7 @@ EXPORTS = [
     "vpt_set_profiling", "vpt_comm_unique_id", "vpt_comm_init", "vpt_comm_allreduce_illumination", "vpt_comm_broadcast_gbuffer",
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
-    "vpt_debug_fastdiv"]
+    "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state"]
 
 
 class VptError(RuntimeError):
@@ -126,6 +126,16 @@ def build_alias_table(weights):
     bins = np.zeros(w.size, ALIAS_DTYPE)
     lib().vpt_build_alias_table(_p(w), w.size, _p(bins))
     return bins
+
+
+def sky_state(params, tables):
+    """Host part of SkyModel::update: (configs[90], radiances[10], sunDir[3]) for params = (timeOfDay, sunAxisAngle,
+    sunAxisRotate, skyBrightness)."""
+    pr = np.asarray(params, np.float32)
+    tb = np.ascontiguousarray(tables, np.float32)
+    cfg = np.zeros(90, np.float32); rad = np.zeros(10, np.float32); sd = np.zeros(3, np.float32)
+    lib().vpt_sky_state(_p(pr), _p(tb), _p(cfg), _p(rad), _p(sd))
+    return cfg, rad, sd
 
 
 def default_denoising_params():
@@ -226,6 +236,19 @@ class Vpt:
         sd = np.asarray(sun_dir, np.float32)
         _check(self.L.vpt_set_sky(self.ctx, _p(sky), sky.shape[1], sky.shape[0], _p(sun), sun.shape[1], sun.shape[0], _p(sa), _p(su), _p(sd)),
                "vpt_set_sky")
+
+    def generate_sky(self, params, tables):
+        pr = np.asarray(params, np.float32)
+        tb = np.ascontiguousarray(tables, np.float32)
+        assert pr.size == 4 and tb.size == 2460
+        _check(self.L.vpt_generate_sky(self.ctx, _p(pr), _p(tb)), "vpt_generate_sky")
+
+    def read_sky(self):
+        w, h, sw, sh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(self.L.vpt_sky_size(self.ctx, C.byref(w), C.byref(h), C.byref(sw), C.byref(sh)), "vpt_sky_size")
+        sky = np.zeros((h.value, w.value, 4), np.float32); sun = np.zeros((sh.value, sw.value, 4), np.float32); sd = np.zeros(3, np.float32)
+        _check(self.L.vpt_read_sky(self.ctx, _p(sky), _p(sun), _p(sd)), "vpt_read_sky")
+        return sky, sun, sd
 
     def set_trace_params(self, spp=1, total_bounce_limit=3, diffuse_bounce_limit=1, enable_restir=1):
         _check(self.L.vpt_set_trace_params(self.ctx, spp, total_bounce_limit, diffuse_bounce_limit, enable_restir), "vpt_set_trace_params")

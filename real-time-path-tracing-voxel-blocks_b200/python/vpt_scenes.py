@@ -36,6 +36,16 @@ def load_tables():
     return t
 
 
+def load_sky_tables():
+    """Hosek-Wilkie coefficient datasets (data/sky_tables.bin, exported from the reference's SkyData.h by tools/export_sky_tables.py)."""
+    t = np.fromfile(os.path.join(DATA_DIR, "sky_tables.bin"), dtype="<f4")
+    assert t.size == 2460, "sky_tables.bin is corrupt"
+    return t
+
+
+DEFAULT_SKY_PARAMS = (0.25, 45.0, 0.0, 1.0)  # SkyParams defaults: timeOfDay, sunAxisAngle, sunAxisRotate, skyBrightness (GlobalSettings.h:200-203)
+
+
 def default_materials():
     """12 terrain materials (ids 0..11 = materials.yaml order) and the block id -> material index map
     (block id i -> material i-1, blocks.yaml ids 1..12)."""
