@@ -264,6 +264,29 @@ void vpt_default_denoising_params(VptDenoisingParams *params);
  * and chunk_config. out9 = pos[3], dir[3], up[3]. */
 int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigned *chunks3);
 
+/* ---- output stage (SURVEY 8f "next" row 2): the deterministic part of PostProcessor::run.
+ * ToneMappingParams (renderer/core/GlobalSettings.h:145-172); curve: 0 Narkowicz ACES, 1 Uncharted 2, 2 Reinhard. */
+typedef struct VptToneMappingParams
+{
+    float manualExposure; /* 10 (C++ default); the shipped yaml sets 0.8 */
+    int32_t curve;
+    float highlightDesaturation;
+    float whitePoint;
+    float contrast;
+    float saturation;
+    float lift;
+    float gain;
+} VptToneMappingParams;
+void vpt_default_tonemapping_params(VptToneMappingParams *params);
+/* GlobalSettings::LoadFromYAML, "postprocess" section (GlobalSettings.cpp:275-296) and "sky" section. */
+int vpt_load_tonemapping_settings(const char *yamlPath, VptToneMappingParams *params);
+int vpt_load_sky_settings(const char *yamlPath, VptSkyParams *params);
+/* FilmicToneMapping (renderer/postprocessing/FilmicToneMapping.h:58-117) with the MANUAL exposure (auto-exposure, bloom,
+ * lens flare and vignette are wall-clock / history dependent and stay out of scope) on IlluminationOutput, then the PNG
+ * conversion of OfflineBackend::writeFrameBufferToPNG (renderer/core/OfflineBackend.cpp:191-221: y flip, clamp, *255).
+ * rgb8: W*H*3 bytes, top row first (may be NULL); rgbaLDR: W*H float4 sRGB-encoded, bottom row first (may be NULL). */
+int vpt_tonemap(vpt_ctx *ctx, const VptToneMappingParams *params, uint8_t *rgb8, float *rgbaLDR);
+
 /* Test hook (no device work): the launch-invariant division the kernels use for index decoding. */
 void vpt_debug_fastdiv(uint32_t n, uint32_t d, uint32_t *q, uint32_t *r);
 

@@ -147,6 +147,20 @@ def sky_state(params, tables):
     return cfg, rad, sd
 
 
+TONEMAP_DTYPE = np.dtype([("manualExposure", "<f4"), ("curve", "<i4"), ("highlightDesaturation", "<f4"), ("whitePoint", "<f4"),
+                          ("contrast", "<f4"), ("saturation", "<f4"), ("lift", "<f4"), ("gain", "<f4")])
+
+
+def tonemap(hdr_rgba, params):
+    """FilmicToneMapping (manual exposure) + PNG conversion restatement: returns (rgb8[h,w,3] top row first, ldr[h,w,4])."""
+    hdr = np.ascontiguousarray(hdr_rgba, np.float32)
+    h, w = hdr.shape[:2]
+    pr = np.ascontiguousarray(params, TONEMAP_DTYPE)
+    rgb8 = np.zeros((h, w, 3), np.uint8); ldr = np.zeros((h, w, 4), np.float32)
+    lib().orc_tonemap(_p(hdr), w, h, _p(pr), _p(rgb8), _p(ldr))
+    return rgb8, ldr
+
+
 def set_threads(n):
     lib().orc_set_threads(int(n))
 

@@ -267,6 +267,10 @@ void orc_sky_state(const float *params, const float *tables, float *configs90, f
     std::memcpy(configs90, st.configs, sizeof st.configs); std::memcpy(radiances10, st.radiances, sizeof st.radiances);
     sunDir[0] = sd.x; sunDir[1] = sd.y; sunDir[2] = sd.z;
 }
+void orc_tonemap(const float *hdrRGBA, int W, int H, const ToneMappingParams *p, uint8_t *rgb8, float *ldrRGBA)
+{
+    tonemap((const f4 *)hdrRGBA, W, H, *p, rgb8, (f4 *)ldrRGBA);
+}
 void orc_build_alias_table(const float *weights, unsigned n, AliasBin *bins) { buildAliasTable(weights, n, bins); }
 float orc_rand(orc_ctx *c, int px, int py, int sampleIndex, int dim) { return blueNoiseRand(c->sc.tables, px, py, sampleIndex, dim); }
 

@@ -651,6 +651,22 @@ int vpt_denoise_external(vpt_ctx *c, const VptDenoisingParams *p, const VptCamer
     return VPT_OK;
 }
 
+int vpt_tonemap(vpt_ctx *c, const VptToneMappingParams *p, uint8_t *rgb8, float *rgbaLDR)
+{
+    if (!c || !p) return fail(VPT_ERR_ARG, "vpt_tonemap: null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->npix();
+    // ping is free between frames (it is rewritten by the next denoise): LDR float plane; the bytes go after it
+    uint8_t *d8 = nullptr;
+    if (rgb8) CU(cudaMalloc((void **)&d8, n * 3));
+    CU(launchTonemap(c->illumOutput, c->width, c->height, *p, d8, rgbaLDR ? c->ping : nullptr, c->stream));
+    if (rgb8) CU(cudaMemcpyAsync(rgb8, d8, n * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (rgbaLDR) CU(cudaMemcpyAsync(rgbaLDR, c->ping, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (d8) CU(cudaFree(d8));
+    return VPT_OK;
+}
+
 int vpt_get_counters(vpt_ctx *c, uint64_t *rays, uint64_t *steps)
 {
     if (!c || !rays || !steps) return fail(VPT_ERR_ARG, "vpt_get_counters: null argument");

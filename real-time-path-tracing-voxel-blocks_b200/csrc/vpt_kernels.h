@@ -176,6 +176,7 @@ cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool count
 cudaError_t launchSkyUpper(const float *configs, const float *radiances, const float *sunDir, float brightness, float4 *sky, float *pdf, int W, int H,
                            cudaStream_t s);
 cudaError_t launchSkyLower(float4 *sky, float *pdf, int W, int H, float sumSkyPdf, cudaStream_t s);
+cudaError_t launchTonemap(const float4 *hdr, int W, int H, const VptToneMappingParams &p, uint8_t *rgb8, float4 *ldr, cudaStream_t s);
 cudaError_t launchSkySun(const float *sunDir, float brightness, const float *solar, const float *limb, float4 *sun, float *pdf, int W, int H, cudaStream_t s);
 
 cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHDev, int *upHHost, int cx, int cy, int cz, cudaStream_t s);

@@ -159,4 +159,59 @@ cudaError_t launchSkySun(const float *sunDir, float brightness, const float *sol
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- output stage
+// FilmicToneMapping (renderer/postprocessing/FilmicToneMapping.h:12-117) with the manual exposure, then
+// OfflineBackend::writeFrameBufferToPNG's conversion (renderer/core/OfflineBackend.cpp:191-221).
+__device__ __forceinline__ f3 clamp01(f3 v) { return {clampf(v.x, 0.0f, 1.0f), clampf(v.y, 0.0f, 1.0f), clampf(v.z, 0.0f, 1.0f)}; }
+__device__ __forceinline__ f3 acesFilm(f3 x)
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    return clamp01(x * (a * x + F3(b)) / (x * (c * x + F3(d)) + F3(e)));
+}
+__device__ __forceinline__ f3 uncharted2(f3 x)
+{
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, Fc = 0.30f;
+    return ((x * (A * x + F3(C * B)) + F3(D * E)) / (x * (A * x + F3(B)) + F3(D * Fc))) - F3(E / Fc);
+}
+__device__ __forceinline__ float linearToSrgb(float c) { return (c <= 0.0031308f) ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
+__global__ void tonemapKernel(const float4 *__restrict__ hdr, int W, int H, VptToneMappingParams p, uint8_t *__restrict__ rgb8, float4 *__restrict__ ldr)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 in = __ldg(hdr + (size_t)y * W + x);
+    f3 color = F3(in.x, in.y, in.z) * p.manualExposure;
+    f3 tm;
+    if (p.curve == 1)
+    {
+        const f3 whiteScale = F3(1.0f) / uncharted2(F3(p.whitePoint));
+        tm = uncharted2(color * 2.0f) * whiteScale;
+    }
+    else if (p.curve == 2)
+    {
+        const f3 numerator = color * (F3(1.0f) + (color / (p.whitePoint * p.whitePoint)));
+        tm = numerator / (F3(1.0f) + color);
+    }
+    else tm = acesFilm(color);
+    tm = clamp01(tm);
+    tm = {powf(tm.x, p.contrast), powf(tm.y, p.contrast), powf(tm.z, p.contrast)};
+    const float lum = dot(tm, F3(0.2126f, 0.7152f, 0.0722f));
+    tm = lerp3(F3(lum), tm, p.saturation);
+    tm = clamp01(tm * p.gain + F3(p.lift));
+    tm = {linearToSrgb(tm.x), linearToSrgb(tm.y), linearToSrgb(tm.z)};
+    if (ldr) ldr[(size_t)y * W + x] = make_float4(tm.x, tm.y, tm.z, 1.0f);
+    if (rgb8)
+    {
+        uint8_t *q = rgb8 + ((size_t)(H - 1 - y) * W + x) * 3;
+        q[0] = (uint8_t)(fminf(1.0f, fmaxf(0.0f, tm.x)) * 255.0f);
+        q[1] = (uint8_t)(fminf(1.0f, fmaxf(0.0f, tm.y)) * 255.0f);
+        q[2] = (uint8_t)(fminf(1.0f, fmaxf(0.0f, tm.z)) * 255.0f);
+    }
+}
+cudaError_t launchTonemap(const float4 *hdr, int W, int H, const VptToneMappingParams &p, uint8_t *rgb8, float4 *ldr, cudaStream_t s)
+{
+    const dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    tonemapKernel<<<g, b, 0, s>>>(hdr, W, H, p, rgb8, ldr);
+    return cudaGetLastError();
+}
+
 } // namespace vpt

@@ -328,6 +328,52 @@ int vpt_load_denoising_settings(const char *yamlPath, VptDenoisingParams *p)
     return VPT_OK;
 }
 
+void vpt_default_tonemapping_params(VptToneMappingParams *p)
+{
+    p->manualExposure = 10.0f; p->curve = 0; p->highlightDesaturation = 0.8f; p->whitePoint = 10.0f;
+    p->contrast = 1.0f; p->saturation = 1.0f; p->lift = 0.0f; p->gain = 1.0f;
+}
+// one pass of the reference's line parser over a section: calls f(key, value) for its "key: value" lines
+extern "C++" template <typename F> int parseSection(const char *yamlPath, const char *wanted, F f)
+{
+    std::ifstream file(yamlPath);
+    if (!file.is_open()) return VPT_ERR_IO;
+    std::string line, section;
+    while (std::getline(file, line))
+    {
+        line = trim(line);
+        if (line.empty() || line[0] == '#') continue;
+        if (line.back() == ':') { section = line.substr(0, line.size() - 1); continue; }
+        size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        if (section != wanted) continue;
+        f(trim(line.substr(0, colon)), trim(line.substr(colon + 1)));
+    }
+    return VPT_OK;
+}
+int vpt_load_tonemapping_settings(const char *yamlPath, VptToneMappingParams *p)
+{
+    return parseSection(yamlPath, "postprocess", [&](const std::string &key, const std::string &value) {
+        if (key == "manualExposure") parseFloat(value, p->manualExposure);
+        else if (key == "toneMappingCurve") { int v; if (parseInt(value, v) && v >= 0 && v <= 2) p->curve = v; }
+        else if (key == "highlightDesaturation") parseFloat(value, p->highlightDesaturation);
+        else if (key == "whitePoint") parseFloat(value, p->whitePoint);
+        else if (key == "contrast") parseFloat(value, p->contrast);
+        else if (key == "saturation") parseFloat(value, p->saturation);
+        else if (key == "gain") parseFloat(value, p->gain);
+        else if (key == "lift") parseFloat(value, p->lift);
+    });
+}
+int vpt_load_sky_settings(const char *yamlPath, VptSkyParams *p)
+{
+    return parseSection(yamlPath, "sky", [&](const std::string &key, const std::string &value) {
+        if (key == "timeOfDay") parseFloat(value, p->timeOfDay);
+        else if (key == "sunAxisAngle") parseFloat(value, p->sunAxisAngle);
+        else if (key == "sunAxisRotate") parseFloat(value, p->sunAxisRotate);
+        else if (key == "skyBrightness") parseFloat(value, p->skyBrightness);
+    });
+}
+
 int vpt_load_scene_config(const char *yamlPath, float *out9, float *fov, unsigned *chunks3)
 {
     // CameraConfig defaults (SceneConfig.h:10-16)

@@ -5,10 +5,11 @@
 // SceneConfigParser::LoadFromFile), the same frame loop (historyCamera = camera; camera.update(); renderFrame;
 // frames 1,4,16,64 saved as <prefix>_<frame:04>.png) and the PNG writer of OfflineBackend::writeFrameBufferToPNG
 // (renderer/core/OfflineBackend.cpp:191-221: y-flip, clamp to [0,1], *255). Out of scope here, as in SURVEY §2:
-// post-processing (auto-exposure/bloom/tone-map: the linear denoised HDR image is written with a fixed exposure),
+// the wall-clock / history dependent post effects (auto-exposure, bloom, lens flare, vignette); the deterministic part —
+// FilmicToneMapping with the manual exposure of the settings file, sRGB, the PNG conversion — runs on the device (vpt_tonemap),
 // scripted edit tests (--test-sequence / --test-remove20 / --test-remove-circle are accepted and ignored with a
 // notice), canonical comparison (the golden PNG is absent from the reference tree).
-// New flags of this build: --spp N, --bounces T D, --chunks X Y Z, --exposure E, --tables PATH.
+// New flags of this build: --spp N, --bounces T D, --chunks X Y Z, --exposure E, --tables PATH, --sky-tables PATH.
 #include "../../include/vpt.h"
 #include <algorithm>
 #include <chrono>
@@ -97,13 +98,13 @@ int main(int argc, char *argv[])
 {
     int width = 3840, height = 2160;
     std::string outputPrefix = "offline_render", sceneFile = "data/scene/scene_export.yaml";
-    std::string settingsFile = "data/settings/global_settings.yaml", tablesFile = "data/bluenoise_tables.bin";
+    std::string settingsFile = "data/settings/global_settings.yaml", tablesFile = "data/bluenoise_tables.bin", skyTablesFile = "data/sky_tables.bin";
     int totalFrames = 64;
     std::vector<int> savedFrames = {1, 4, 16, 64};
     int spp = 1, totalBounce = 3, diffuseBounce = 1;
     int chunks[3] = {2, 1, 2}; // ChunkConfiguration default (voxelengine/VoxelSceneGen.h:10-20)
     bool chunksFromCli = false;
-    float exposure = 0.8f; // postprocess.manualExposure of the shipped settings
+    float exposure = -1.0f; // --exposure overrides postprocess.manualExposure of the settings file
     for (int i = 1; i < argc; i++)
     {
         std::string arg = argv[i];
@@ -113,6 +114,7 @@ int main(int argc, char *argv[])
         else if (arg == "--scene" && i + 1 < argc) sceneFile = argv[++i];
         else if (arg == "--settings" && i + 1 < argc) settingsFile = argv[++i];
         else if (arg == "--tables" && i + 1 < argc) tablesFile = argv[++i];
+        else if (arg == "--sky-tables" && i + 1 < argc) skyTablesFile = argv[++i];
         else if (arg == "--test-canonical" || arg == "--test" || arg == "--update-canonical")
             std::printf("note: %s ignored (data/canonical/canonical_render.png is not part of the reference tree)\n", arg.c_str());
         else if (arg == "--canonical-image" && i + 1 < argc) ++i;
@@ -134,7 +136,7 @@ int main(int argc, char *argv[])
                         "  --width <int> --height <int> --output <prefix> --scene <file> --frames <int>\n"
                         "  --test-canonical --update-canonical --canonical-image <path> --comment <text>\n"
                         "  --test-sequence --test-remove20 --test-remove-circle   (accepted, ignored)\n"
-                        "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file>\n", argv[0]);
+                        "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file> --sky-tables <file>\n", argv[0]);
             return 0;
         }
     }
@@ -144,6 +146,10 @@ int main(int argc, char *argv[])
     vpt_default_denoising_params(&dn);
     if (vpt_load_denoising_settings(settingsFile.c_str(), &dn) != VPT_OK)
         std::fprintf(stderr, "Failed to open global settings file: %s (defaults kept)\n", settingsFile.c_str());
+    VptToneMappingParams tone;
+    vpt_default_tonemapping_params(&tone);
+    vpt_load_tonemapping_settings(settingsFile.c_str(), &tone);
+    if (exposure > 0.0f) tone.manualExposure = exposure;
     float cam9[9], fov; unsigned sceneChunks[3];
     if (vpt_load_scene_config(sceneFile.c_str(), cam9, &fov, sceneChunks) != VPT_OK)
         std::printf("Scene file not found: %s, using defaults\n", sceneFile.c_str());
@@ -175,38 +181,16 @@ int main(int argc, char *argv[])
     uint16_t b2m[256] = {0};
     for (int b = 1; b <= 12; ++b) b2m[b] = (uint16_t)(b - 1);
     CHECK(vpt_set_materials(ctx, mats, 12, b2m));
-    // stand-in sky until the Hosek-Wilkie model lands: zenith/horizon gradient + sun disk
-    const int skyW = 1024, skyH = 512, sunW = 32, sunH = 32;
-    std::vector<float> sky((size_t)skyW * skyH * 4), sun((size_t)sunW * sunH * 4), skyWt((size_t)skyW * skyH), sunWt((size_t)sunW * sunH);
-    const float sunDir[3] = {0.70710678f, 0.5f, -0.5f};
-    for (int y = 0; y < skyH; ++y)
-        for (int x = 0; x < skyW; ++x)
-        {
-            const float v = (y + 0.5f) / skyH, u = (x + 0.5f) / skyW;
-            const float dy = 2.0f * v - 1.0f, r = std::sqrt(std::max(0.0f, 1.0f - dy * dy));
-            const float dx = r * std::cos(6.2831853f * u), dz = r * std::sin(6.2831853f * u);
-            const float t = std::pow(std::min(std::max(dy, 0.0f), 1.0f), 0.45f);
-            const float cosg = dx * sunDir[0] + dy * sunDir[1] + dz * sunDir[2];
-            const float glow = 0.9f * std::exp((cosg - 1.0f) * 24.0f);
-            float c[3];
-            if (dy >= 0.0f) { c[0] = 0.75f * (1 - t) + 0.20f * t + glow; c[1] = 0.82f * (1 - t) + 0.38f * t + glow * 0.85f; c[2] = 0.95f * (1 - t) + 0.90f * t + glow * 0.6f; }
-            else { const float k = 1.0f + 0.5f * std::min(std::max(dy + 0.2f, 0.0f), 1.0f); c[0] = 0.22f * k; c[1] = 0.21f * k; c[2] = 0.20f * k; }
-            float *p = &sky[((size_t)y * skyW + x) * 4];
-            p[0] = c[0]; p[1] = c[1]; p[2] = c[2]; p[3] = 0.0f;
-            skyWt[(size_t)y * skyW + x] = 0.2126f * c[0] + 0.7152f * c[1] + 0.0722f * c[2];
-        }
-    for (int y = 0; y < sunH; ++y)
-        for (int x = 0; x < sunW; ++x)
-        {
-            const float limb = 1.0f - 0.4f * (x + 0.5f) / sunW;
-            float *p = &sun[((size_t)y * sunW + x) * 4];
-            p[0] = 52000.0f * limb; p[1] = 47000.0f * limb; p[2] = 40000.0f * limb; p[3] = 0.0f;
-            sunWt[(size_t)y * sunW + x] = 0.2126f * p[0] + 0.7152f * p[1] + 0.0722f * p[2];
-        }
-    std::vector<VptAliasBin> skyAlias(skyWt.size()), sunAlias(sunWt.size());
-    vpt_build_alias_table(skyWt.data(), (unsigned)skyWt.size(), skyAlias.data());
-    vpt_build_alias_table(sunWt.data(), (unsigned)sunWt.size(), sunAlias.data());
-    CHECK(vpt_set_sky(ctx, sky.data(), skyW, skyH, sun.data(), sunW, sunH, skyAlias.data(), sunAlias.data(), sunDir));
+    // SkyModel::init/update (mainOffline.cpp:191 -> OfflineBackend::init -> SkyModel; Sky.cu:355-396): Hosek-Wilkie sky + solar
+    // disc evaluated on the device from the "sky" section of the settings file
+    {
+        std::vector<float> skyTables(2460);
+        std::ifstream f(skyTablesFile, std::ios::binary);
+        if (!f.read((char *)skyTables.data(), skyTables.size() * sizeof(float))) { std::fprintf(stderr, "Error: cannot read sky tables %s\n", skyTablesFile.c_str()); return 1; }
+        VptSkyParams sky = {0.25f, 45.0f, 0.0f, 1.0f};
+        vpt_load_sky_settings(settingsFile.c_str(), &sky);
+        CHECK(vpt_generate_sky(ctx, &sky, skyTables.data()));
+    }
     CHECK(vpt_set_trace_params(ctx, spp, totalBounce, diffuseBounce, 1));
 
     // camera from the scene (mainOffline.cpp:227-247)
@@ -217,7 +201,6 @@ int main(int argc, char *argv[])
                 camera.pos[0], camera.pos[1], camera.pos[2], camera.dir[0], camera.dir[1], camera.dir[2], fov);
 
     int iterationIndex = 0; // GlobalSettings::iterationIndex, reset for a fresh offline run (mainOffline.cpp:252)
-    std::vector<float> frame((size_t)width * height * 4);
     double traceMs = 0, denoiseMs = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (int f = 0; f < totalFrames; ++f)
@@ -233,22 +216,10 @@ int main(int argc, char *argv[])
         traceMs += tm.trace_ms + tm.resolve_ms; denoiseMs += tm.denoise_total_ms;
         if (std::find(savedFrames.begin(), savedFrames.end(), frameNumber) != savedFrames.end())
         {
-            CHECK(vpt_read_buffer(ctx, VPT_BUF_IlluminationOutput, frame.data(), frame.size() * sizeof(float)));
+            // PostProcessor::run's deterministic part (FilmicToneMapping with the manual exposure) + the PNG conversion of
+            // OfflineBackend::writeFrameBufferToPNG, on the device
             std::vector<uint8_t> rgb((size_t)width * height * 3);
-            for (int y = 0; y < height; ++y)
-                for (int x = 0; x < width; ++x)
-                {
-                    const float *p = &frame[((size_t)y * width + x) * 4];
-                    uint8_t *q = &rgb[((size_t)(height - 1 - y) * width + x) * 3];
-                    for (int k = 0; k < 3; ++k)
-                    {
-                        float v = p[k] * exposure;
-                        v = v / (1.0f + v);                      // fixed Reinhard curve in place of the out-of-scope post chain
-                        v = std::pow(std::max(v, 0.0f), 1.0f / 2.2f);
-                        v = std::min(1.0f, std::max(0.0f, v));
-                        q[k] = (unsigned char)(v * 255.0f);
-                    }
-                }
+            CHECK(vpt_tonemap(ctx, &tone, rgb.data(), nullptr));
             char name[512];
             std::snprintf(name, sizeof name, "%s_%04d.png", outputPrefix.c_str(), f);
             if (!writePng(name, width, height, rgb)) std::fprintf(stderr, "Failed to save image to: %s\n", name);

@@ -40,7 +40,8 @@ EXPORTS = [
     "vpt_set_profiling", "vpt_comm_unique_id", "vpt_comm_init", "vpt_comm_allreduce_illumination", "vpt_comm_broadcast_gbuffer",
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
-    "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state"]
+    "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
+    "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
 
 
 class VptError(RuntimeError):
@@ -126,6 +127,30 @@ def build_alias_table(weights):
     bins = np.zeros(w.size, ALIAS_DTYPE)
     lib().vpt_build_alias_table(_p(w), w.size, _p(bins))
     return bins
+
+
+TONEMAP_DTYPE = np.dtype([("manualExposure", "<f4"), ("curve", "<i4"), ("highlightDesaturation", "<f4"), ("whitePoint", "<f4"),
+                          ("contrast", "<f4"), ("saturation", "<f4"), ("lift", "<f4"), ("gain", "<f4")])
+SKYPARAMS_DTYPE = np.dtype([("timeOfDay", "<f4"), ("sunAxisAngle", "<f4"), ("sunAxisRotate", "<f4"), ("skyBrightness", "<f4")])
+
+
+def default_tonemapping_params():
+    p = np.zeros(1, TONEMAP_DTYPE)
+    lib().vpt_default_tonemapping_params(_p(p))
+    return p
+
+
+def load_tonemapping_settings(path, params=None):
+    p = default_tonemapping_params() if params is None else params
+    rc = lib().vpt_load_tonemapping_settings(path.encode(), _p(p))
+    return p, rc
+
+
+def load_sky_settings(path):
+    p = np.zeros(1, SKYPARAMS_DTYPE)
+    p["timeOfDay"], p["sunAxisAngle"], p["sunAxisRotate"], p["skyBrightness"] = 0.25, 45.0, 0.0, 1.0
+    rc = lib().vpt_load_sky_settings(path.encode(), _p(p))
+    return p, rc
 
 
 def sky_state(params, tables):
@@ -249,6 +274,13 @@ class Vpt:
         sky = np.zeros((h.value, w.value, 4), np.float32); sun = np.zeros((sh.value, sw.value, 4), np.float32); sd = np.zeros(3, np.float32)
         _check(self.L.vpt_read_sky(self.ctx, _p(sky), _p(sun), _p(sd)), "vpt_read_sky")
         return sky, sun, sd
+
+    def tonemap(self, params):
+        """vpt_tonemap on IlluminationOutput: (rgb8[h,w,3] top row first, ldr[h,w,4])."""
+        pr = np.ascontiguousarray(params, TONEMAP_DTYPE)
+        rgb8 = np.zeros((self.h, self.w, 3), np.uint8); ldr = np.zeros((self.h, self.w, 4), np.float32)
+        _check(self.L.vpt_tonemap(self.ctx, _p(pr), _p(rgb8), _p(ldr)), "vpt_tonemap")
+        return rgb8, ldr
 
     def set_trace_params(self, spp=1, total_bounce_limit=3, diffuse_bounce_limit=1, enable_restir=1):
         _check(self.L.vpt_set_trace_params(self.ctx, spp, total_bounce_limit, diffuse_bounce_limit, enable_restir), "vpt_set_trace_params")
