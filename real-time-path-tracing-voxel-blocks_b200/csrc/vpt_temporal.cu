@@ -1,12 +1,15 @@
 // TemporalAccumulation (/root/reference/renderer/denoising/TemporalAccumulation.h:228-449, 29-215; samplers
-// shaders/Sampler.h:396-498, 576-698) — compiled as the EXACT arithmetic class (-fmad=false -prec-div=true
-// -prec-sqrt=true -DVPT_FAST_MATH=0: compensated dot / Mat3*v like the reference's LinearMath, IEEE divide / sqrt).
+// shaders/Sampler.h:396-498, 576-698).
 //
-// Why this pass alone: it produces historyLength, which is a CONTROL variable of the rest of the chain — HistoryFix and
-// HistoryClamping branch on hl <= 4, AtrousSmem on hl >= 3 — and in the first frames hl sits exactly on those integers
-// (n frames of history -> n +- an ulp from the bilinear weight normalisation). One ulp of difference flips the branch
-// for half the image. Computing the reprojection and hl with the oracle's arithmetic makes the plane bit-identical, so
-// every implementation takes the same branches (the same reasoning as the exact class for primary hits).
+// Mixed arithmetic classes. This pass produces historyLength, which is a CONTROL variable of the rest of the chain —
+// HistoryFix and HistoryClamping branch on hl <= 4, AtrousSmem on hl >= 3 — and in the first frames hl sits exactly on
+// those integers (n frames of history -> n +- an ulp from the bilinear weight normalisation and the footprint quality).
+// One ulp of difference flips the branch for half the image. So the chain that decides hl — view vector, world position,
+// reprojected uv, N.V of both frames, the bilinear weights, the custom-weight history-length fetch and the footprint
+// arithmetic — is the EXACT class (vpt::ex::, explicit round-to-nearest intrinsics, compensated dot / Mat3*v like the
+// reference's LinearMath): historyLength is bit-identical to the oracle, every implementation takes the same branches
+// (the same reasoning as the exact class for primary hits). Everything else (parallax, disocclusion thresholds, normal
+// tests, the 12-tap history fetches, the blends) is the fast class.
 #include "vpt_denoise_common.cuh"
 
 namespace vpt {
@@ -95,6 +98,39 @@ VPT_DEV float parallaxInPixels(f3 X, f2 uvZero, const Cam &cam, f2 rectSize)
     return sqrtf(d.x * d.x + d.y * d.y);
 }
 
+// ------------------------------------------------------------------------------------------------ exact-class pieces
+VPT_DEV f3 exSub3(f3 a, f3 b) { return {ex::subf(a.x, b.x), ex::subf(a.y, b.y), ex::subf(a.z, b.z)}; }
+VPT_DEV float exLerp(float a, float b, float w) { return ex::addf(a, ex::mulf(w, ex::subf(b, a))); }
+struct ExBilinear { float fx, fy; int x0, y0; };
+VPT_DEV ExBilinear exBilinearSetup(f2 uv, int W, int H)
+{
+    const float U = ex::mulf(uv.x, (float)W), V = ex::mulf(uv.y, (float)H);
+    const float flx = floorf(ex::subf(U, 0.5f)), fly = floorf(ex::subf(V, 0.5f));
+    return {ex::subf(U, ex::addf(flx, 0.5f)), ex::subf(V, ex::addf(fly, 0.5f)), (int)flx, (int)fly};
+}
+// bilinearWeight (Sampler.h:328-348)
+VPT_DEV f4 exBilinearWeight(const ExBilinear &b)
+{
+    const float w1x = b.fx, w1y = b.fy, w0x = ex::subf(1.0f, b.fx), w0y = ex::subf(1.0f, b.fy);
+    return {ex::mulf(w0x, w0y), ex::mulf(w1x, w0y), ex::mulf(w0x, w1y), ex::mulf(w1x, w1y)};
+}
+// sampleBilinearCustom1 (Sampler.h:452-498): custom tap weights floored at 1e-6, normalised
+VPT_DEV float exSampleBilinearCustom1(const float *tex, const ExBilinear &b, int W, int H, f4 cw)
+{
+    const f4 bw = exBilinearWeight(b);
+    const int xs[4] = {b.x0, b.x0 + 1, b.x0, b.x0 + 1}, ys[4] = {b.y0, b.y0, b.y0 + 1, b.y0 + 1};
+    const float ws[4] = {ex::mulf(bw.x, cw.x), ex::mulf(bw.y, cw.y), ex::mulf(bw.z, cw.z), ex::mulf(bw.w, cw.w)};
+    float out = 0.0f, sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const float v = ld1(tex, W, H, xs[i], ys[i]);
+        const float w = max1f(ws[i], 1e-6f);
+        sum = ex::addf(sum, w); out = ex::addf(out, ex::mulf(v, w));
+    }
+    return ex::divf(out, sum);
+}
+
 // ------------------------------------------------------------------------------------------------ temporal
 struct TemporalArgs
 {
@@ -122,13 +158,18 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
     const quat prevToCur = prevToCurS;
     const f2 pixelUv = {(float(x) + 0.5f) * (1.0f / (float)W), (float(y) + 0.5f) * (1.0f / (float)H)};
     const f3 n = xyz(__ldg(a.normalRough + pix));
-    const f2 curUV = {(float(x) + 0.5f) * cam.invResX, (float(y) + 0.5f) * cam.invResY};
-    const f3 viewVec = uvToWorldDirection(cam, curUV);
-    const f3 worldPos = worldPosFromPixel(cam, x, y, z);
-    const f3 V = -normalize(viewVec);
-    const float NoV = fabsf(dot(n, V));
+    // ---- exact class: the chain that decides historyLength
+    const f2 curUV = {ex::mulf(ex::addf(float(x), 0.5f), cam.invResX), ex::mulf(ex::addf(float(y), 0.5f), cam.invResY)};
+    const f3 viewVec = ex::normalize(ex::mulMat3(a.cam.uvToWorld, F3(curUV.x, curUV.y, 1.0f)));
+    const f3 worldPos = ex::pointAt(cam.pos, viewVec, z);
+    const f3 V = -ex::normalize(viewVec);
+    const float NoV = fabsf(ex::dot(n, V));
     const f3 prevWorldPos = worldPos;
-    const f2 prevUV = worldDirectionToUV(prevCam, normalize(prevWorldPos - prevCam.pos));
+    const f3 Vprev = ex::normalize(exSub3(prevWorldPos, prevCam.pos));
+    const f3 hUv = ex::mulMat3(a.prevCam.worldToUv, Vprev);
+    const f2 prevUV = {ex::divf(hUv.x, hUv.z), ex::divf(hUv.y, hUv.z)};
+    const ExBilinear bil = exBilinearSetup(prevUV, W, H);
+    // ---- fast class from here on, except where noted
     const f3 illum = xyz(__ldg(a.illum + pix));
     f3 nAvg = n;
 #pragma unroll
@@ -152,8 +193,7 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
 
     const f3 curNormalAvg = normalize(nAvg);
     const float estPrevDepth = length(prevWorldPos - prevCam.pos);
-    const f2 prevPixF = {prevUV.x * W, prevUV.y * H};
-    const int bx = (int)floorf(prevPixF.x - 0.5f), by = (int)floorf(prevPixF.y - 0.5f);
+    const int bx = bil.x0, by = bil.y0;
     const float pixelSize = (cam.tanHalfFovX / (cam.resX / 2)) * z;
     const float frustumSize = pixelSize * (float)min(W, H);
     const float slopeScale = 1.0f / lerpf(lerpf(0.05f, 1.0f, NoV), 1.0f, saturate(parMax / 30.0f));
@@ -168,7 +208,7 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
         for (int i = 0; i < 4; ++i) { thr[i] = base * inScreen[i]; thr[i] -= 1e-6f; }
     }
     const int bic[4][2][2] = {{{0, -1}, {-1, 0}}, {{1, -1}, {2, 0}}, {{-1, 1}, {0, 2}}, {{2, 1}, {1, 2}}};
-    const int bil[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
+    const int bilTap[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
     float bicubicValid = 1.0f;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -182,7 +222,7 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
-        float pz = ld1(a.prevDepth, W, H, bx + bil[i][0], by + bil[i][1]);
+        float pz = ld1(a.prevDepth, W, H, bx + bilTap[i][0], by + bilTap[i][1]);
         float v = fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
         bicubicValid *= v; tv[i] = v;
     }
@@ -205,20 +245,20 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
     prevIllum = max4f(prevIllum, F4(0.0f));
     prevFast = max3f(prevFast, F3(0.0f));
     float reprojFound = (bicubicValid > 0.0f) ? 2.0f : 1.0f;
-    const f4 bw = bilinearWeight(prevUV, W, H);
-    float footprintQuality = (bicubicValid > 0) ? 1.0f : dot4(bw, F4(1.0f));
+    // ---- exact class: historyLength
+    const f4 bw = exBilinearWeight(bil);
+    float footprintQuality = (bicubicValid > 0) ? 1.0f : ex::addf(ex::addf(ex::addf(bw.x, bw.y), bw.z), bw.w);
     float historyLength;
     if (dot4(tapsValid, F4(1.0f)) == 0.0f) { reprojFound = 0.0f; footprintQuality = 0.0f; historyLength = 0.0f; }
-    else historyLength = sampleBilinearCustom1(a.prevHistLen, prevUV, W, H, tapsValid);
-
-    historyLength = historyLength + 1.0f;
-    const f3 Vprev = normalize(prevWorldPos - prevCam.pos);
-    const float NoVprev = fabsf(dot(n, Vprev));
-    float sizeQuality = (NoVprev + 1e-3f) / (NoV + 1e-3f);
-    sizeQuality *= sizeQuality; sizeQuality *= sizeQuality;
-    footprintQuality *= lerpf(0.1f, 1.0f, saturate(sizeQuality));
-    if (footprintQuality < 1.0f) { historyLength *= sqrtf(footprintQuality); historyLength = fmaxr(historyLength, 1.0f); }
+    else historyLength = exSampleBilinearCustom1(a.prevHistLen, bil, W, H, tapsValid);
+    historyLength = ex::addf(historyLength, 1.0f);
+    const float NoVprev = fabsf(ex::dot(n, Vprev));
+    float sizeQuality = ex::divf(ex::addf(NoVprev, 1e-3f), ex::addf(NoV, 1e-3f));
+    sizeQuality = ex::mulf(sizeQuality, sizeQuality); sizeQuality = ex::mulf(sizeQuality, sizeQuality);
+    footprintQuality = ex::mulf(footprintQuality, exLerp(0.1f, 1.0f, saturate(sizeQuality)));
+    if (footprintQuality < 1.0f) { historyLength = ex::mulf(historyLength, __fsqrt_rn(footprintQuality)); historyLength = fmaxr(historyLength, 1.0f); }
     historyLength = fminr(historyLength, a.maxAccum);
+    // ---- fast class
     const float alpha = (reprojFound > 0) ? fmaxr(1.0f / (a.maxAccum + 1.0f), 1.0f / historyLength) : 1.0f;
     const float alphaFast = (reprojFound > 0) ? fmaxr(1.0f / (a.maxFastAccum + 1.0f), 1.0f / historyLength) : 1.0f;
     a.ping[pix] = toFloat4(lerp4(prevIllum, F4(illum, m2), alpha));
