@@ -196,6 +196,10 @@ void vpt_sky_state(const VptSkyParams *params, const float *tables, float *confi
  * (renderer/shaders/RayGen.cu:146-147). */
 int vpt_set_trace_params(vpt_ctx *ctx, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir);
 
+/* Wavefront sizing: the renderer processes at most `maxPaths` (pixel slots x samples) per wave; more samples run wave by
+ * wave (default 16 Mi paths ~ 4.9 GB of path state). A tuning / test knob: results do not depend on it. */
+int vpt_set_wave_budget(vpt_ctx *ctx, size_t maxPaths);
+
 /* ---- the hot path */
 /* OptixRenderer::render (renderer/core/OptixRenderer.cpp:411-485) == __raygen__pathtracer over W x H
  * (renderer/shaders/RayGen.cu:102-181). iterationIndex is the pre-increment value the reference stores in

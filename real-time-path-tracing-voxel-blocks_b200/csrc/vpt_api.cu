@@ -73,6 +73,7 @@ struct vpt_ctx
     bool overlapParts = false; // two-stream part overlap: measured, no gain (see vpt_wave.cu launchTrace)
     bool anySpecular = false; // a non-diffuse, non-emissive material exists: paths may continue past their first hit
     int countSteps = 1;
+    size_t waveBudget = (size_t)16u << 20;
     // staging for vpt_denoise_external
     void *pinned = nullptr; size_t pinnedBytes = 0;
     // profiling
@@ -291,6 +292,12 @@ int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *s
     return VPT_OK;
 }
 
+int vpt_set_wave_budget(vpt_ctx *c, size_t maxPaths)
+{
+    if (!c || maxPaths == 0) return fail(VPT_ERR_ARG, "vpt_set_wave_budget: bad argument");
+    c->waveBudget = maxPaths;
+    return VPT_OK;
+}
 int vpt_generate_sky(vpt_ctx *c, const VptSkyParams *params, const float *tables)
 {
     if (!c || !params || !tables) return fail(VPT_ERR_ARG, "vpt_generate_sky: null argument");
@@ -385,7 +392,7 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     a.countSteps = c->countSteps;
     // wave size: as many samples per wave as fit a 16 M-path budget
     const int shardSamples = sampleBegin < c->spp ? (c->spp - sampleBegin + sampleStep - 1) / sampleStep : 0;
-    int samplesPerWave = (int)((size_t)(16u << 20) / (size_t)a.nSlots);
+    int samplesPerWave = (int)(c->waveBudget / (size_t)a.nSlots);
     if (samplesPerWave < 1) samplesPerWave = 1;
     if (samplesPerWave > shardSamples) samplesPerWave = shardSamples > 0 ? shardSamples : 1;
     if (c->wave.nSlots != a.nSlots || c->wave.maxSamplesInWave < samplesPerWave)

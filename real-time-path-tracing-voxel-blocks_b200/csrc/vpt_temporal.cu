@@ -5,11 +5,13 @@
 // HistoryFix and HistoryClamping branch on hl <= 4, AtrousSmem on hl >= 3 — and in the first frames hl sits exactly on
 // those integers (n frames of history -> n +- an ulp from the bilinear weight normalisation and the footprint quality).
 // One ulp of difference flips the branch for half the image. So the chain that decides hl — view vector, world position,
-// reprojected uv, N.V of both frames, the bilinear weights, the custom-weight history-length fetch and the footprint
-// arithmetic — is the EXACT class (vpt::ex::, explicit round-to-nearest intrinsics, compensated dot / Mat3*v like the
+// reprojected uv, N.V of both frames, the parallax and disocclusion thresholds of the tap-validity tests, the averaged and
+// re-projected normals, the bilinear
+// weights, the custom-weight history-length fetch and the footprint arithmetic — is the EXACT class (vpt::ex::, explicit round-to-nearest intrinsics, compensated dot / Mat3*v like the
 // reference's LinearMath): historyLength is bit-identical to the oracle, every implementation takes the same branches
-// (the same reasoning as the exact class for primary hits). Everything else (parallax, disocclusion thresholds, normal
-// tests, the 12-tap history fetches, the blends) is the fast class.
+// (the same reasoning as the exact class for primary hits) — including the normal sign test: an axis-aligned voxel scene
+// is full of exact cancellations (dot == 0), which fast arithmetic turns into +-1e-9. Only the 12-tap history fetches
+// and the blends (no decisions) are the fast class.
 #include "vpt_denoise_common.cuh"
 
 namespace vpt {
@@ -131,6 +133,44 @@ VPT_DEV float exSampleBilinearCustom1(const float *tex, const ExBilinear &b, int
     return ex::divf(out, sum);
 }
 
+VPT_DEV f3 exAdd3(f3 a, f3 b) { return {ex::addf(a.x, b.x), ex::addf(a.y, b.y), ex::addf(a.z, b.z)}; }
+VPT_DEV f3 exScale3(f3 a, float s) { return {ex::mulf(a.x, s), ex::mulf(a.y, s), ex::mulf(a.z, s)}; }
+VPT_DEV f3 exDiv3(f3 a, float s) { return {ex::divf(a.x, s), ex::divf(a.y, s), ex::divf(a.z, s)}; }
+// Quat (LinearMath.h:1311-1366) in the exact class: an axis-aligned voxel scene is full of EXACT cancellations (a 3x3 normal
+// average perpendicular to the history normal gives dot == 0), so the sign test below must round like the oracle
+VPT_DEV quat exQmul(quat p, quat q)
+{
+    return {exAdd3(exAdd3(exScale3(q.v, p.w), exScale3(p.v, q.w)), ex::cross(p.v, q.v)), ex::subf(ex::mulf(p.w, q.w), ex::dot(p.v, q.v))};
+}
+VPT_DEV quat exRotationBetween(f3 p, f3 q)
+{
+    quat r = {ex::cross(p, q), ex::addf(__fsqrt_rn(ex::mulf(ex::dot(p, p), ex::dot(q, q))), ex::dot(p, q))};
+    const float n = __fsqrt_rn(ex::addf(ex::addf(ex::addf(ex::mulf(r.v.x, r.v.x), ex::mulf(r.v.y, r.v.y)), ex::mulf(r.v.z, r.v.z)), ex::mulf(r.w, r.w)));
+    return {exDiv3(r.v, n), ex::divf(r.w, n)};
+}
+VPT_DEV f3 exQrotate(quat q, f3 v) { return exQmul(exQmul(q, quat{v, 0.0f}), quat{-q.v, q.w}).v; }
+// parallaxInPixels (TemporalAccumulation.h:29-40): uv of X seen from camPos minus uvZero, in pixels
+VPT_DEV float exParallaxInPixels(f3 X, f2 uvZero, f3 camPos, const float *worldToUv, f2 rectSize)
+{
+    const f3 h = ex::mulMat3(worldToUv, ex::normalize(exSub3(X, camPos)));
+    const float dx = ex::mulf(ex::subf(ex::divf(h.x, h.z), uvZero.x), rectSize.x), dy = ex::mulf(ex::subf(ex::divf(h.y, h.z), uvZero.y), rectSize.y);
+    return __fsqrt_rn(ex::addf(ex::mulf(dx, dx), ex::mulf(dy, dy)));
+}
+
+// SampleBicubicSmoothStep (Sampler.h:652-698), xyz only
+VPT_DEV f3 exSampleSmoothStep3(const float4 *tex, const ExBilinear &b, int W, int H)
+{
+    const float fx2 = ex::mulf(b.fx, b.fx), fy2 = ex::mulf(b.fy, b.fy), fx3 = ex::mulf(fx2, b.fx), fy3 = ex::mulf(fy2, b.fy);
+    const float w1x = ex::addf(ex::mulf(-2.0f, fx3), ex::mulf(3.0f, fx2)), w1y = ex::addf(ex::mulf(-2.0f, fy3), ex::mulf(3.0f, fy2));
+    const float w0x = ex::subf(1.0f, w1x), w0y = ex::subf(1.0f, w1y);
+    const int xs[4] = {b.x0, b.x0 + 1, b.x0, b.x0 + 1}, ys[4] = {b.y0, b.y0, b.y0 + 1, b.y0 + 1};
+    const float ws[4] = {ex::mulf(w0x, w0y), ex::mulf(w1x, w0y), ex::mulf(w0x, w1y), ex::mulf(w1x, w1y)};
+    f3 out = F3(0.0f); float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sum = ex::addf(sum, ws[i]); out = exAdd3(out, exScale3(xyz(ld4(tex, W, H, xs[i], ys[i])), ws[i])); }
+    return exDiv3(out, sum);
+}
+
 // ------------------------------------------------------------------------------------------------ temporal
 struct TemporalArgs
 {
@@ -149,14 +189,13 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
     // launch-uniform: rotation between the previous and current view directions, once per CTA
     __shared__ quat prevToCurS;
     if (threadIdx.x == 0 && threadIdx.y == 0)
-        prevToCurS = rotationBetween(F3(a.prevCam.dir[0], a.prevCam.dir[1], a.prevCam.dir[2]), F3(a.cam.dir[0], a.cam.dir[1], a.cam.dir[2]));
+        prevToCurS = exRotationBetween(F3(a.prevCam.dir[0], a.prevCam.dir[1], a.prevCam.dir[2]), F3(a.cam.dir[0], a.cam.dir[1], a.cam.dir[2]));
     __syncthreads();
     PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
     const float z = __ldg(a.depth + pix);
     if (z > a.denoisingRange) return;
     const Cam cam = loadCam(a.cam), prevCam = loadCam(a.prevCam);
     const quat prevToCur = prevToCurS;
-    const f2 pixelUv = {(float(x) + 0.5f) * (1.0f / (float)W), (float(y) + 0.5f) * (1.0f / (float)H)};
     const f3 n = xyz(__ldg(a.normalRough + pix));
     // ---- exact class: the chain that decides historyLength
     const f2 curUV = {ex::mulf(ex::addf(float(x), 0.5f), cam.invResX), ex::mulf(ex::addf(float(y), 0.5f), cam.invResY)};
@@ -178,35 +217,37 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
         for (int j = -1; j <= 1; ++j)
         {
             if (i == 0 && j == 0) continue;
-            nAvg += xyz(ld4(a.normalRough, W, H, x + i, y + j));
+            nAvg = exAdd3(nAvg, xyz(ld4(a.normalRough, W, H, x + i, y + j)));
         }
-    nAvg /= 9.0f;
+    nAvg = exDiv3(nAvg, 9.0f);
     const float m1 = luminance(illum), m2 = m1 * m1;
-    const f3 camDelta = prevCam.pos - cam.pos;
+    // ---- exact class: everything a tap-validity decision depends on (parallax, disocclusion thresholds, expected depth)
+    const f2 pixelUv = {ex::mulf(ex::addf(float(x), 0.5f), ex::divf(1.0f, (float)W)), ex::mulf(ex::addf(float(y), 0.5f), ex::divf(1.0f, (float)H))};
+    const f3 camDelta = exSub3(prevCam.pos, cam.pos);
     const f2 rect = {(float)W, (float)H};
-    const float par1 = parallaxInPixels(prevWorldPos + camDelta, pixelUv, prevCam, rect);
-    const float par2 = parallaxInPixels(prevWorldPos - camDelta, prevUV, cam, rect);
+    const float par1 = exParallaxInPixels(exAdd3(prevWorldPos, camDelta), pixelUv, prevCam.pos, a.prevCam.worldToUv, rect);
+    const float par2 = exParallaxInPixels(exSub3(prevWorldPos, camDelta), prevUV, cam.pos, a.cam.worldToUv, rect);
     const float parMax = fmaxr(par1, par2);
-    const float thrBonus = a.disocclusionThreshold + (1.5f / H);
-    const float thrAltBonus = a.disocclusionThresholdAlternate + (1.5f / H);
-    const float disThr = lerpf(thrBonus, thrAltBonus, 0.0f);
-
-    const f3 curNormalAvg = normalize(nAvg);
-    const float estPrevDepth = length(prevWorldPos - prevCam.pos);
+    const float thrBonus = ex::addf(a.disocclusionThreshold, ex::divf(1.5f, (float)H));
+    const float thrAltBonus = ex::addf(a.disocclusionThresholdAlternate, ex::divf(1.5f, (float)H));
+    const float disThr = exLerp(thrBonus, thrAltBonus, 0.0f);
+    const f3 toPrev = exSub3(prevWorldPos, prevCam.pos);
+    const float estPrevDepth = __fsqrt_rn(ex::dot(toPrev, toPrev));
     const int bx = bil.x0, by = bil.y0;
-    const float pixelSize = (cam.tanHalfFovX / (cam.resX / 2)) * z;
-    const float frustumSize = pixelSize * (float)min(W, H);
-    const float slopeScale = 1.0f / lerpf(lerpf(0.05f, 1.0f, NoV), 1.0f, saturate(parMax / 30.0f));
+    const float pixelSize = ex::mulf(ex::divf(cam.tanHalfFovX, ex::divf(cam.resX, 2.0f)), z);
+    const float frustumSize = ex::mulf(pixelSize, (float)min(W, H));
+    const float slopeScale = ex::divf(1.0f, exLerp(exLerp(0.05f, 1.0f, NoV), 1.0f, saturate(ex::divf(parMax, 30.0f))));
     float thr[4];
     {
-        const float base = saturate(disThr * slopeScale) * frustumSize;
+        const float base = ex::mulf(saturate(ex::mulf(disThr, slopeScale)), frustumSize);
         const int px0 = bx, py0 = by, px1 = bx + 1, py1 = by + 1;
         float rx0 = (px0 >= 0) ? 1.0f : 0.0f, ry0 = (py0 >= 0) ? 1.0f : 0.0f, rx1 = (px1 >= 0) ? 1.0f : 0.0f, ry1 = (py1 >= 0) ? 1.0f : 0.0f;
         rx0 *= (px0 < W) ? 1.0f : 0.0f; ry0 *= (py0 < H) ? 1.0f : 0.0f; rx1 *= (px1 < W) ? 1.0f : 0.0f; ry1 *= (py1 < H) ? 1.0f : 0.0f;
         const float inScreen[4] = {rx0 * ry0, rx1 * ry0, rx0 * ry1, rx1 * ry1};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { thr[i] = base * inScreen[i]; thr[i] -= 1e-6f; }
+        for (int i = 0; i < 4; ++i) thr[i] = ex::subf(ex::mulf(base, inScreen[i]), 1e-6f);
     }
+    const f3 curNormalAvg = ex::normalize(nAvg);
     const int bic[4][2][2] = {{{0, -1}, {-1, 0}}, {{1, -1}, {2, 0}}, {{-1, 1}, {0, 2}}, {{2, 1}, {1, 2}}};
     const int bilTap[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
     float bicubicValid = 1.0f;
@@ -216,20 +257,21 @@ __global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_const
         for (int j = 0; j < 2; ++j)
         {
             float pz = ld1(a.prevDepth, W, H, bx + bic[i][j][0], by + bic[i][j][1]);
-            bicubicValid *= fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
+            bicubicValid *= fabsf(ex::subf(pz, estPrevDepth)) > thr[i] ? 0.0f : 1.0f;
         }
     float tv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
         float pz = ld1(a.prevDepth, W, H, bx + bilTap[i][0], by + bilTap[i][1]);
-        float v = fabsf(pz - estPrevDepth) > thr[i] ? 0.0f : 1.0f;
+        float v = fabsf(ex::subf(pz, estPrevDepth)) > thr[i] ? 0.0f : 1.0f;
         bicubicValid *= v; tv[i] = v;
     }
     f4 tapsValid = {tv[0], tv[1], tv[2], tv[3]};
-    const f3 prevNFlat = normalize(sampleSmoothStep3(a.prevNormalRough, prevUV, W, H));
-    const f3 prevNRot = normalize(qrotate(prevToCur, prevNFlat));
-    if (dot(curNormalAvg, prevNRot) < 0.0f) { tapsValid = F4(0.0f); bicubicValid = 0.0f; }
+    const f3 prevNFlat = ex::normalize(exSampleSmoothStep3(a.prevNormalRough, bil, W, H));
+    const f3 prevNRot = ex::normalize(exQrotate(prevToCur, prevNFlat));
+    if (ex::dot(curNormalAvg, prevNRot) < 0.0f) { tapsValid = F4(0.0f); bicubicValid = 0.0f; }
+    // ---- fast class: the history fetches and blends
     const bool useBicubic = bicubicValid > 0;
     f4 prevIllum; f3 prevFast;
     if (useBicubic)

@@ -41,7 +41,7 @@ EXPORTS = [
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
-    "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
+    "vpt_set_wave_budget", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
 
 
 class VptError(RuntimeError):
@@ -274,6 +274,9 @@ class Vpt:
         sky = np.zeros((h.value, w.value, 4), np.float32); sun = np.zeros((sh.value, sw.value, 4), np.float32); sd = np.zeros(3, np.float32)
         _check(self.L.vpt_read_sky(self.ctx, _p(sky), _p(sun), _p(sd)), "vpt_read_sky")
         return sky, sun, sd
+
+    def set_wave_budget(self, max_paths):
+        _check(self.L.vpt_set_wave_budget(self.ctx, C.c_size_t(int(max_paths))), "vpt_set_wave_budget")
 
     def tonemap(self, params):
         """vpt_tonemap on IlluminationOutput: (rgb8[h,w,3] top row first, ldr[h,w,4])."""

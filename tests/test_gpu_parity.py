@@ -192,4 +192,68 @@ def test_denoised_output_passes_reference_imagediff_thresholds(libs):
             r = imagediff.compare(imagediff.to_png8(g.read("IlluminationOutput")), imagediff.to_png8(o.read("IlluminationOutput")))
             assert r["isIdentical"] or r["isVeryClose"], (f, r)
             assert r["pixelDifferenceRatio"] <= 5e-3, (f, r)   # pixels off by more than 0.01*255 in some channel (trace is the fast arithmetic class)
+    # every decision of the temporal pass is the exact arithmetic class: the history length stays bit-identical over frames
     assert np.array_equal(g.read("HistoryLength"), o.read("HistoryLength"))
+
+
+def test_multi_wave_render_equals_single_wave(libs):
+    """More samples than one wave holds: the sample loop runs wave by wave (accumulate carries the partial sum). A wave budget
+    of one sample per wave must give bit-identical planes to the single-wave render, and match the oracle."""
+    vpt, O = libs
+    W, H = 192, 128
+    inp = common.scene_inputs((2, 1, 2))
+    cam = common.scene_camera(W, H)
+    g1 = common.setup(vpt.Vpt(W, H), inp, spp=6, total=3, diffuse=1)
+    g2 = common.setup(vpt.Vpt(W, H), inp, spp=6, total=3, diffuse=1)
+    g2.set_wave_budget(2 * W * H)          # 2 samples per wave -> 3 waves
+    o = common.setup(O.Oracle(W, H), inp, spp=6, total=3, diffuse=1)
+    for f in range(2):
+        g1.render(cam, cam, f); g2.render(cam, cam, f); o.render(cam, cam, f)
+        for name in ("Illumination", "Depth", "NormalRoughness", "PrimaryHits"):
+            assert np.array_equal(g1.read(name), g2.read(name)), (f, name)
+        assert np.array_equal(g1.read_reservoirs(f & 1), g2.read_reservoirs(f & 1))
+        mean_rel, outliers, _ = common.rel_err_stats(g2.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert mean_rel <= 1e-3 and outliers <= 1e-2, (f, mean_rel, outliers)
+    assert g1.counters()[0] == g2.counters()[0]
+
+
+def test_world_larger_than_shared_memory_walks_the_mask_through_l2(libs):
+    """8 x 2 x 8 chunks (256 x 64 x 256 voxels): both traversal masks are 1.2 MB, beyond shared memory, so the DDA engine runs
+    its global-memory variant (ddaKernel<kSmem=false>) — same bit-exact primary hits, same radiance tolerance. Also a chunk
+    grid with chunksY > 1 (the reference's chunk index cx + CX*(cz + CZ*cy))."""
+    vpt, O = libs
+    W, H = 224, 128
+    inp = common.scene_inputs((8, 2, 8))
+    g, o = _pair(libs, W, H, inp, spp=2, total=3, diffuse=1)
+    assert np.array_equal(g.get_grid(), o.get_grid())
+    pos = [100.3, 40.7, 90.2]
+    cam = vpt.camera_from_scene(W, H, pos, [-0.5, -0.35, 0.6], 90.0)
+    outside = vpt.camera_from_scene(W, H, [-20.5, 70.2, -14.1], [0.6, -0.45, 0.55], 75.0)   # origin outside the grid: entry clip
+    for f, c in enumerate((cam, cam, outside)):
+        g.render(c, c, f); o.render(c, c, f)
+        hg, ho = g.read("PrimaryHits"), o.read("PrimaryHits")
+        assert np.array_equal(hg, ho), (f, int((hg != ho).any(-1).sum()))
+        assert (ho[..., 3] >= 0).mean() > 0.2
+        assert np.array_equal(g.read("Depth"), o.read("Depth"))
+        mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert mean_rel <= 1e-3 and outliers <= 1e-2, (f, mean_rel, outliers)
+
+
+def test_set_voxel_edits_update_both_traversal_masks(libs):
+    """VoxelEngine::setVoxelAtGlobal equivalents: adding a block ABOVE the skyline (raises GridView::upH and rebuilds the
+    upward mask), removing blocks, adding below — primary hits stay bit-exact after every edit."""
+    vpt, O = libs
+    W, H = 160, 96
+    inp = common.scene_inputs((2, 1, 2))
+    g, o = _pair(libs, W, H, inp, spp=1, total=3, diffuse=1)
+    cam = common.scene_camera(W, H)
+    edits = [(30, 30, 38, 3), (30, 31, 38, 3), (31, 29, 39, 2),       # a pillar above everything (y = 29..31)
+             (33, 8, 40, 0), (33, 9, 40, 0), (34, 9, 40, 0),          # dig
+             (36, 12, 36, 7)]                                          # place below the skyline
+    for f, (x, y, z, bid) in enumerate(edits):
+        g.set_voxel(x, y, z, bid); o.set_voxel(x, y, z, bid)
+        g.render(cam, cam, f); o.render(cam, cam, f)
+        assert np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits")), (f, (x, y, z, bid))
+        mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert mean_rel <= 1e-3 and outliers <= 1.5e-2, (f, mean_rel, outliers)
+    assert np.array_equal(g.get_grid(), o.get_grid())
