@@ -225,6 +225,12 @@ int vpt_denoise_external(vpt_ctx *ctx, const VptDenoisingParams *params, const V
 /* ---- outputs. BufferManager::GetBuffer2D (renderer/core/BufferManager.h:84) + OfflineBackend::storeFrameInBatch. */
 int vpt_read_buffer(vpt_ctx *ctx, VptBufferName name, void *host, size_t bytes);
 int vpt_write_buffer(vpt_ctx *ctx, VptBufferName name, const void *host, size_t bytes);
+/* Pipelined read-back (OfflineBackend::storeFrameInBatch without stalling the frame loop): the copy is queued on a copy
+ * stream behind everything submitted so far and returns at once; `host` should be pinned. The next vpt_denoise /
+ * vpt_render that would overwrite the plane waits for the copy on the DEVICE, so the transfer overlaps the next frame's
+ * trace. vpt_sync (or vpt_read_wait) completes it. */
+int vpt_read_buffer_async(vpt_ctx *ctx, VptBufferName name, void *host, size_t bytes);
+int vpt_read_wait(vpt_ctx *ctx);
 /* BufferManager::reservoirBuffer (BufferManager.cpp:206-207): plane `parity` of the 2 x W x H reservoir array. */
 int vpt_read_reservoirs(vpt_ctx *ctx, int parity, VptReservoir *host, size_t bytes);
 int vpt_write_reservoirs(vpt_ctx *ctx, int parity, const VptReservoir *host, size_t bytes);

@@ -39,6 +39,9 @@ struct vpt_ctx
     int device = 0, width = 0, height = 0, smCount = 0;
     size_t smemOptIn = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;       // pipelined read-backs (vpt_read_buffer_async)
+    cudaEvent_t copyReady = nullptr, copyDone = nullptr;
+    bool copyPending = false, copyPendingTraceWritten = false;
     // tables
     uint8_t *sobol = nullptr, *scrambling = nullptr, *ranking = nullptr;
     // grid
@@ -108,6 +111,9 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     c->device = device; c->width = width; c->height = height; c->smCount = prop.multiProcessorCount;
     c->smemOptIn = prop.sharedMemPerBlockOptin;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->copyReady, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->copyDone, cudaEventDisableTiming));
     const size_t n = c->npix();
     auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
         cudaError_t r = cudaMalloc(p, bytes);
@@ -170,6 +176,7 @@ void vpt_destroy(vpt_ctx *c)
 
 int vpt_sync(vpt_ctx *c)
 {
+    if (c && c->copyStream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->copyStream); c->copyPending = false; }
     if (!c) return fail(VPT_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
@@ -368,6 +375,7 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     if (!c->sky) return fail(VPT_ERR_STATE, "vpt_render: no sky (vpt_set_sky)");
     if ((int)cam->resolution[0] != c->width || (int)cam->resolution[1] != c->height) return fail(VPT_ERR_ARG, "vpt_render: camera resolution != context size");
     CU(cudaSetDevice(c->device));
+    if (c->copyPending && c->copyPendingTraceWritten) { CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0)); c->copyPending = false; }
     c->cur ^= 1;
     TraceArgs a;
     std::memset(&a, 0, sizeof a);
@@ -555,6 +563,8 @@ int vpt_denoise(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, c
     if (p->enableHitDistanceReconstruction || p->enablePrePass)
         return fail(VPT_ERR_ARG, "vpt_denoise: HitDistReconstruction / PrePass are off in the shipped settings and not built (SURVEY 8a D2/D3)");
     CU(cudaSetDevice(c->device));
+    // a pipelined read-back of the previous frame's planes must finish before this chain overwrites them (device-side wait)
+    if (c->copyPending) { CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0)); c->copyPending = false; }
     return denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, 0, c->height, c->profiling, false);
 }
 
@@ -605,6 +615,34 @@ int vpt_read_buffer(vpt_ctx *c, VptBufferName name, void *host, size_t bytes)
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_read_buffer_async(vpt_ctx *c, VptBufferName name, void *host, size_t bytes)
+{
+    if (!c || !host) return fail(VPT_ERR_ARG, "vpt_read_buffer_async: null argument");
+    void *p; size_t have;
+    int rc = planeInfo(c, name, &p, &have);
+    if (rc) return rc;
+    if (have != bytes) return fail(VPT_ERR_ARG, "vpt_read_buffer_async: size mismatch");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->copyReady, c->stream));
+    CU(cudaStreamWaitEvent(c->copyStream, c->copyReady, 0));
+    CU(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    CU(cudaEventRecord(c->copyDone, c->copyStream));
+    c->copyPending = true;
+    // planes the trace writes must also survive until the copy is done; IlluminationOutput and the history planes are
+    // only touched by the denoiser, so their copy may overlap the whole next trace
+    c->copyPendingTraceWritten = !(name == VPT_BUF_IlluminationOutput || name == VPT_BUF_IlluminationPing || name == VPT_BUF_IlluminationPong ||
+                                   name == VPT_BUF_PrevIllumination || name == VPT_BUF_PrevFastIllumination || name == VPT_BUF_HistoryLength ||
+                                   name == VPT_BUF_PrevHistoryLength);
+    return VPT_OK;
+}
+int vpt_read_wait(vpt_ctx *c)
+{
+    if (!c) return fail(VPT_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copyStream));
+    c->copyPending = false;
     return VPT_OK;
 }
 int vpt_write_buffer(vpt_ctx *c, VptBufferName name, const void *host, size_t bytes)

@@ -41,7 +41,7 @@ EXPORTS = [
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
-    "vpt_set_wave_budget", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
+    "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
 
 
 class VptError(RuntimeError):
@@ -274,6 +274,13 @@ class Vpt:
         sky = np.zeros((h.value, w.value, 4), np.float32); sun = np.zeros((sh.value, sw.value, 4), np.float32); sd = np.zeros(3, np.float32)
         _check(self.L.vpt_read_sky(self.ctx, _p(sky), _p(sun), _p(sd)), "vpt_read_sky")
         return sky, sun, sd
+
+    def read_async(self, name, out):
+        """Pipelined read-back into `out` (pinned host array); completes at read_wait() / sync()."""
+        _check(self.L.vpt_read_buffer_async(self.ctx, BUF[name], _p(out), C.c_size_t(out.nbytes)), "vpt_read_buffer_async")
+
+    def read_wait(self):
+        _check(self.L.vpt_read_wait(self.ctx), "vpt_read_wait")
 
     def set_wave_budget(self, max_paths):
         _check(self.L.vpt_set_wave_budget(self.ctx, C.c_size_t(int(max_paths))), "vpt_set_wave_budget")

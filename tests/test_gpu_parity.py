@@ -257,3 +257,26 @@ def test_set_voxel_edits_update_both_traversal_masks(libs):
         mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
         assert mean_rel <= 1e-3 and outliers <= 1.5e-2, (f, mean_rel, outliers)
     assert np.array_equal(g.get_grid(), o.get_grid())
+
+
+def test_pipelined_readback_returns_the_frame_it_was_queued_for(libs):
+    """vpt_read_buffer_async: the copy queued after frame f must hold frame f even though frame f+1 is submitted right behind
+    it (the next denoise waits for the copy on the device before overwriting the plane)."""
+    import torch
+    vpt, O = libs
+    W, H = 320, 192
+    inp = common.scene_inputs((2, 1, 2))
+    g = common.setup(vpt.Vpt(W, H), inp, spp=1, total=3, diffuse=1)
+    ref = common.setup(vpt.Vpt(W, H), inp, spp=1, total=3, diffuse=1)
+    p = S.default_denoising_params()
+    cam = common.scene_camera(W, H)
+    bufs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy() for _ in range(4)]
+    want = []
+    for f in range(4):
+        ref.render(cam, cam, f); ref.denoise(p, cam, cam, f, f + 1)
+        want.append(ref.read("IlluminationOutput"))
+        g.render(cam, cam, f); g.denoise(p, cam, cam, f, f + 1)
+        g.read_async("IlluminationOutput", bufs[f])
+    g.read_wait()
+    for f in range(4):
+        assert np.array_equal(bufs[f], want[f]), f
