@@ -367,7 +367,7 @@ int vpt_set_trace_params(vpt_ctx *c, int spp, int totalBounceLimit, int diffuseB
     return VPT_OK;
 }
 
-int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
+static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, bool resolve)
 {
     if (!c || !cam || !prevCam || sampleBegin < 0 || sampleStep < 1) return fail(VPT_ERR_ARG, "vpt_render: bad argument");
     if (!c->occ) return fail(VPT_ERR_STATE, "vpt_render: no voxel grid (vpt_set_grid / vpt_generate_terrain)");
@@ -398,6 +398,7 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
     // a path continues past its first hit only through a specular surface or with a diffuse limit above 1
     a.depthRounds = (c->anySpecular || c->diffuseBounceLimit > 1) ? c->totalBounceLimit : 1;
     a.countSteps = c->countSteps;
+    a.resolveSpp = (resolve && c->spp > 1) ? (float)c->spp : 0.0f;
     // wave size: as many samples per wave as fit a 16 M-path budget
     const int shardSamples = sampleBegin < c->spp ? (c->spp - sampleBegin + sampleStep - 1) / sampleStep : 0;
     int samplesPerWave = (int)(c->waveBudget / (size_t)a.nSlots);
@@ -444,11 +445,14 @@ int vpt_resolve(vpt_ctx *c)
     }
     return VPT_OK;
 }
+int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
+{
+    return renderImpl(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, false);
+}
 int vpt_render(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex)
 {
-    int rc = vpt_render_shard(c, cam, prevCam, iterationIndex, 0, 1);
-    if (rc) return rc;
-    return vpt_resolve(c);
+    // == vpt_render_shard(0, 1) + vpt_resolve, with the division fused into the last accumulate
+    return renderImpl(c, cam, prevCam, iterationIndex, 0, 1, true);
 }
 int vpt_begin_external_frame(vpt_ctx *c) { if (!c) return VPT_ERR_ARG; c->cur ^= 1; return VPT_OK; }
 

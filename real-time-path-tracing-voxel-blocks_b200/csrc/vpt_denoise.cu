@@ -136,8 +136,9 @@ struct FireflyArgs
     float weightThreshold, minWeight, normalThreshold, depthSigma, phiLuminance;
     FireflyPatch *patches;
 };
-// 3x3 bilateral replacement of a firefly's colour and reservoir (FireflyFilter.h:112-251), one thread per list entry,
-// reading only pre-pass values.
+// 3x3 bilateral replacement of a firefly's colour and reservoir (FireflyFilter.h:112-251), reading only pre-pass values.
+// Eight lanes per list entry — one per neighbour, so the six dependent loads of a tap are issued for all taps at once —
+// reduced with width-8 shuffles (four entries per warp).
 __global__ void __launch_bounds__(128) fireflyFilterKernel(const __grid_constant__ FireflyArgs a)
 {
     const int W = a.W, H = a.H;
@@ -145,9 +146,14 @@ __global__ void __launch_bounds__(128) fireflyFilterKernel(const __grid_constant
     const float weightThreshold = a.weightThreshold, minWeight = a.minWeight, normalThreshold = a.normalThreshold, depthSigma = a.depthSigma;
     const float4 *illum = a.illum; const float4 *normalRough = a.normalRough; const float *depth = a.depth, *material = a.material;
     const VptReservoir *res = a.res;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const int groupsTotal = gridDim.x * (blockDim.x >> 3);
+    const int rounds = (n + groupsTotal - 1) / groupsTotal;
+    for (int rnd = 0; rnd < rounds; ++rnd)
     {
-        const int4 ent = __ldg(a.fireflyList + e);
+        const int e = rnd * groupsTotal + (blockIdx.x * blockDim.x + threadIdx.x) / 8;
+        const bool have = e < n; // whole 8-lane groups agree; the shuffles below are executed by all 32 lanes
+        const int4 ent = have ? __ldg(a.fireflyList + e) : make_int4(0, 0, 0, 0);
         const size_t pix = (size_t)ent.x;
         const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
         const int neighborValidCount = ent.y;
@@ -164,49 +170,74 @@ __global__ void __launch_bounds__(128) fireflyFilterKernel(const __grid_constant
         const float centerMaterial = __ldg(material + pix);
         const f3 centerWorldPos = worldPosFromPixel(cam, x, y, centerDepth);
         const float gaussian[3] = {1.0f, 2.0f, 1.0f};
-        f4 filteredColor = centerColor4; float filteredWeight = 1.0f;
-        f4 fallbackColor = centerColor4 * (gaussian[0] * gaussian[0]); float fallbackWeight = gaussian[0] * gaussian[0];
         const float depthScale = fmaxf(fabsf(centerDepth), 1.0f);
         const float normalWeightParam = normalWeightParam2(1.0f, 0.25f);
-        VptReservoir best = reservoir; float bestScore = FLT_MAX; bool hasReplacement = false;
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx)
+        // this lane's neighbour, in the reference's scan order (dy outer, dx inner, centre skipped)
+        const int k = sub < 4 ? sub : sub + 1;
+        const int dy = k / 3 - 1, dx = k % 3 - 1;
+        f4 fil = F4(0.0f), fal = F4(0.0f);
+        float filW = 0.0f, falW = 0.0f, score = FLT_MAX;
+        VptReservoir nr = reservoir;
+        const int sx = x + dx, sy = y + dy;
+        if (have && !(sx < 0 || sy < 0 || sx >= W || sy >= H))
+        {
+            const size_t sp = (size_t)sy * W + sx;
+            const float gw = gaussian[abs(dx)] * gaussian[abs(dy)];
+            const f4 sc4 = F4(__ldg(illum + sp));
+            fal = sc4 * gw; falW = gw;
+            const float sd = __ldg(depth + sp);
+            f3 sn = xyz(__ldg(normalRough + sp));
+            const float snLen = length(sn);
+            bool ok = !(sd > kDenoisingRange) && snLen > 0.0f;
+            float nd = 0.0f;
+            if (ok) { sn /= snLen; nd = dot(centerNormal, sn); ok = !(nd < normalThreshold) && !(fabsf(__ldg(material + sp) - centerMaterial) > 0.5f); }
+            if (ok)
             {
-                if (dx == 0 && dy == 0) continue;
-                const int sx = x + dx, sy = y + dy;
-                if (sx < 0 || sy < 0 || sx >= W || sy >= H) continue;
-                const size_t sp = (size_t)sy * W + sx;
-                const float gw = gaussian[abs(dx)] * gaussian[abs(dy)];
-                const f4 sc4 = F4(__ldg(illum + sp));
-                fallbackColor += sc4 * gw; fallbackWeight += gw;
-                const float sd = __ldg(depth + sp);
-                if (sd > kDenoisingRange) continue;
-                f3 sn = xyz(__ldg(normalRough + sp));
-                const float snLen = length(sn);
-                if (snLen <= 0.0f) continue;
-                sn /= snLen;
-                const float nd = dot(centerNormal, sn);
-                if (nd < normalThreshold) continue;
-                if (fabsf(__ldg(material + sp) - centerMaterial) > 0.5f) continue;
                 const f3 swp = worldPosFromPixel(cam, sx, sy, sd);
-                const float geomW = planeDistWeightAtrous(centerWorldPos, centerNormal, swp, depthSigma * depthScale);
-                if (geomW <= 0.0f) continue;
+                ok = planeDistWeightAtrous(centerWorldPos, centerNormal, swp, depthSigma * depthScale) > 0.0f;
+            }
+            if (ok)
+            {
                 const float normalW = nonExpWeight(acosApprox(clampf(nd, -1.0f, 1.0f)), normalWeightParam, 0.0f);
                 const float depthW = expf(-fabsf(sd - centerDepth) / (depthScale * depthSigma + 1e-6f));
                 const float lumW = expf(-fabsf(luminance(xyz(sc4)) - centerLum) * a.phiLuminance);
-                const float total = gw * geomW * normalW * depthW * lumW;
-                if (total > 1e-5f) { filteredColor += sc4 * total; filteredWeight += total; }
-                const VptReservoir nr = ldRes(res + sp);
+                const float total = gw * normalW * depthW * lumW;
+                if (total > 1e-5f) { fil = sc4 * total; filW = total; }
+                nr = ldRes(res + sp);
                 const bool nValid = nr.lightData != 0 && isfinite(nr.weightSum) && nr.weightSum > 0.0f && nr.weightSum < currentWeight;
                 if (nValid)
                 {
                     const float depthTerm = fabsf(sd - centerDepth) / (depthScale + 1e-6f);
                     const float normalTerm = 1.0f - clampf(nd, 0.0f, 1.0f);
                     const float weightDiff = fabsf(nr.weightSum - currentWeight);
-                    const float score = depthTerm + normalTerm + 0.25f * weightDiff;
-                    if (score < bestScore) { bestScore = score; best = nr; hasReplacement = true; }
+                    score = depthTerm + normalTerm + 0.25f * weightDiff;
                 }
             }
+        }
+        // width-8 reductions: sums, and the best (lowest score, earliest neighbour on ties) replacement reservoir
+        int bestK = score < FLT_MAX ? sub : 8;
+        float bestScore = score;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1)
+        {
+            fil.x += __shfl_xor_sync(0xffffffffu, fil.x, off, 8); fil.y += __shfl_xor_sync(0xffffffffu, fil.y, off, 8);
+            fil.z += __shfl_xor_sync(0xffffffffu, fil.z, off, 8); fil.w += __shfl_xor_sync(0xffffffffu, fil.w, off, 8);
+            fal.x += __shfl_xor_sync(0xffffffffu, fal.x, off, 8); fal.y += __shfl_xor_sync(0xffffffffu, fal.y, off, 8);
+            fal.z += __shfl_xor_sync(0xffffffffu, fal.z, off, 8); fal.w += __shfl_xor_sync(0xffffffffu, fal.w, off, 8);
+            filW += __shfl_xor_sync(0xffffffffu, filW, off, 8); falW += __shfl_xor_sync(0xffffffffu, falW, off, 8);
+            const float os = __shfl_xor_sync(0xffffffffu, bestScore, off, 8);
+            const int ok2 = __shfl_xor_sync(0xffffffffu, bestK, off, 8);
+            if (os < bestScore || (os == bestScore && ok2 < bestK)) { bestScore = os; bestK = ok2; }
+        }
+        const bool hasReplacement = bestK < 8;
+        const int srcLane = (lane & ~7) | (hasReplacement ? bestK : 0);
+        VptReservoir best;
+        best.lightData = __shfl_sync(0xffffffffu, nr.lightData, srcLane); best.uvData = __shfl_sync(0xffffffffu, nr.uvData, srcLane);
+        best.weightSum = __shfl_sync(0xffffffffu, nr.weightSum, srcLane); best.targetPdf = __shfl_sync(0xffffffffu, nr.targetPdf, srcLane);
+        best.M = __shfl_sync(0xffffffffu, nr.M, srcLane);
+        if (!have || sub != 0) continue;
+        const f4 filteredColor = centerColor4 + fil; const float filteredWeight = 1.0f + filW;
+        const f4 fallbackColor = centerColor4 * (gaussian[0] * gaussian[0]) + fal; const float fallbackWeight = gaussian[0] * gaussian[0] + falW;
         f4 outColor;
         if (filteredWeight > 0.0f) outColor = filteredColor / filteredWeight;
         else if (fallbackWeight > 0.0f) outColor = fallbackColor / fallbackWeight;
@@ -664,7 +695,7 @@ cudaError_t launchPrep(const DenoiseLaunch &d, int prepRow0, int prepRow1, bool 
         f.res = d.b.reservoirs; f.counters = d.counters; f.fireflyList = d.fireflyList; f.maxList = maxPatches;
         f.weightThreshold = 80.0f; f.minWeight = 5.0f; f.normalThreshold = 0.8f; f.depthSigma = 0.02f; f.phiLuminance = d.p.phiLuminance;
         f.patches = patches;
-        fireflyFilterKernel<<<64, 128, 0, d.stream>>>(f);
+        fireflyFilterKernel<<<148, 128, 0, d.stream>>>(f);
         fireflyApplyKernel<<<64, 256, 0, d.stream>>>(patches, d.counters, maxPatches, d.b.illumination, d.b.reservoirs);
     }
     return cudaGetLastError();

@@ -110,6 +110,7 @@ struct TraceArgs
     FastDiv divPartSlots;
     int depthRounds;             // 1 when no path can continue past its first hit (all-diffuse materials, diffuse limit 1)
     int countSteps;              // DDA step statistics on/off
+    float resolveSpp;            // > 0: the last wave's accumulate also divides by spp (vpt_render); 0: leave the sum (vpt_render_shard)
 };
 
 struct WaveWorkspace

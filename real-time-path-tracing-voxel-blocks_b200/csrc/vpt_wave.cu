@@ -485,6 +485,13 @@ enum : uint32_t
 };
 constexpr int kRandShift = 16, kDepthShift = 24, kDiffuseShift = 28;
 constexpr int kShadeThreads = 256;
+#define VPT_SHADE_MINB_DEFAULT 4
+#ifndef VPT_S3_MINB
+#define VPT_S3_MINB 3 // measured: S3 (temporal ReSTIR, the heaviest stage) prefers 3 CTAs/SM (85 regs), S5 6
+#endif
+#ifndef VPT_S5_MINB
+#define VPT_S5_MINB 6
+#endif
 #ifndef VPT_SHADE_MINB
 #define VPT_SHADE_MINB 4 // measured on B200 (r1 variants): 4 resident CTAs/SM (<= 64 regs) is the optimum for S1-S3: shade 1.94 -> 1.61 ms
 #endif
@@ -1013,7 +1020,7 @@ VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float
 
 // ------------------------------------------------------------------------------------------------ S3
 // Temporal ReSTIR: candidates from the previous frame + the bias-correction rays (closesthit.cu:636-760).
-__global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
+__global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
@@ -1189,7 +1196,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_const
 
 // ------------------------------------------------------------------------------------------------ S5
 // Shade with the surviving reservoir, store it, accumulate, spawn the continuation ray (closesthit.cu:822-851, RayGen.cu:71-84).
-__global__ void __launch_bounds__(kShadeThreads) shade5Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+__global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, int *__restrict__ nextList,
                                                               unsigned *nextCount, unsigned *qCount)
 {
@@ -1302,6 +1309,8 @@ __global__ void __launch_bounds__(kShadeThreads) accumulateKernel(const __grid_c
         if (sl == 0 && haveDepth) depth0 = v.w;
     }
     if (haveDepth) a.cur.depth[pix] = depth0;
+    // vpt_render (unsharded): the division by spp of vpt_resolve, fused into the last wave's accumulate
+    if (a.resolveSpp > 0.0f) { sum.x = sum.x / a.resolveSpp; sum.y = sum.y / a.resolveSpp; sum.z = sum.z / a.resolveSpp; }
     a.illumination[pix] = make_float4(sum.x, sum.y, sum.z, depth0);
 }
 
@@ -1422,7 +1431,11 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
                 }
                 shade5Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, nextList, cnt + kCntList + depth + 1, cnt + 2 * pair); ++nl; mark(1, st);
             }
-            accumulateKernel<<<gridSlots, kShadeThreads, 0, st>>>(a); ++nl; mark(1, st);
+            {
+                TraceArgs acc = a;
+                if (first + maxSamplesInWave < shardSamples) acc.resolveSpp = 0.0f; // only the last wave resolves
+                accumulateKernel<<<gridSlots, kShadeThreads, 0, st>>>(acc); ++nl; mark(1, st);
+            }
             VPT_TRY(cudaGetLastError());
             if (overlap)
             {
