@@ -310,6 +310,15 @@ def main():
         except Exception as ex:  # the baseline is reported, never required for the product path
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
+    # the dominant kernel of the whole step is the DDA engine: issue-bound, so its "roofline" is the issue-slot one (ncu figures
+    # committed under profiles/); reported next to the HBM roofline of the dominant denoiser kernel
+    trace_eff = None
+    ep = os.path.join(ROOT, "profiles", "trace_efficiency.json")
+    if os.path.exists(ep):
+        try:
+            trace_eff = json.load(open(ep))
+        except Exception:
+            trace_eff = None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
@@ -323,7 +332,7 @@ def main():
                     "h2d_bytes_per_step": 2 * 212 + 68 + 64, "d2h_bytes_per_step": npix * 16,
                     "note": "vpt_render + vpt_denoise + vpt_read_buffer_async(IlluminationOutput) into pinned host memory each frame (double-buffered, every copy complete inside the timed region); inputs per frame are "
                             "the two cameras + parameter blocks (scene is resident, as in the reference)"},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "trace_efficiency_ncu": trace_eff, "kernels": kernels, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
