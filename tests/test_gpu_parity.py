@@ -280,3 +280,79 @@ def test_pipelined_readback_returns_the_frame_it_was_queued_for(libs):
     g.read_wait()
     for f in range(4):
         assert np.array_equal(bufs[f], want[f]), f
+
+
+def test_cfg4_shape_sample_shards_sum_to_the_unsharded_render(libs):
+    """BASELINE config 4 shape (3840x2160, many spp, limits 4/1, spp-sharded) on ONE GPU, as a size-independent property:
+    the four sample shards {k : k mod 4 == r} summed (what ncclAllReduce does across ranks) and resolved equal the
+    unsharded render of the same 8 spp up to fp32 summation order. At this size 8 spp are two waves (16 Mi-path budget)."""
+    vpt, O = libs
+    W, H, spp = 3840, 2160, 8
+    inp = common.scene_inputs((4, 1, 4))
+    cam = common.scene_camera(W, H, (4, 1, 4))
+    g = common.setup(vpt.Vpt(W, H), inp, spp=spp, total=4, diffuse=1)
+    g.render(cam, cam, 0)
+    full = g.read("Illumination")
+    depth = g.read("Depth")
+    hits = g.read("PrimaryHits")
+    assert np.isfinite(full).all() and (hits[..., 3] >= 0).mean() > 0.3
+    acc = np.zeros_like(full[..., :3], dtype=np.float64)
+    s = common.setup(vpt.Vpt(W, H), inp, spp=spp, total=4, diffuse=1)
+    for r in range(4):
+        s.render_shard(cam, cam, 0, r, 4)
+        part = s.read("Illumination")
+        acc += part[..., :3]
+        if r == 0:
+            assert np.array_equal(part[..., 3], full[..., 3]) and np.array_equal(s.read("Depth"), depth)   # sample 0 owns depth / G-buffer
+            assert np.array_equal(s.read("PrimaryHits"), hits)
+    mean_rel, outliers, _ = common.rel_err_stats((acc / spp).astype(np.float32), full[..., :3])
+    assert mean_rel <= 1e-6 and outliers == 0.0, (mean_rel, outliers)
+
+
+def test_cfg5_shape_large_world_matches_oracle(libs):
+    """BASELINE config 5 world (32 x 8 x 32 chunks = 1024 x 256 x 1024 voxels, 256 MiB of ids, 2 x 33 MiB of traversal masks walked
+    through L2), limits 8/2: terrain ids bit-exact, primary hits bit-exact and radiance within tolerance against the oracle at a
+    resolution the oracle finishes in seconds (rays cross up to ~1000 voxels: the divergence / grid-residency stress)."""
+    vpt, O = libs
+    chunks = (32, 8, 32)
+    W, H = 256, 144
+    inp = common.scene_inputs(chunks)
+    g, o = _pair(libs, W, H, inp, spp=2, total=8, diffuse=2)
+    gg, og = g.get_grid(), o.get_grid()
+    assert gg.size == 32 * 8 * 32 * 32768 and np.array_equal(gg, og)
+    del gg, og
+    cam = vpt.camera_from_scene(W, H, [500.3, 150.7, 480.2], [0.55, -0.22, 0.62], 90.0)
+    far = vpt.camera_from_scene(W, H, [-200.0, 300.0, -150.0], [0.62, -0.3, 0.6], 60.0)       # outside the grid, looking in
+    for f, c in enumerate((cam, far)):
+        g.render(c, c, f); o.render(c, c, f)
+        hg, ho = g.read("PrimaryHits"), o.read("PrimaryHits")
+        assert np.array_equal(hg, ho), (f, int((hg != ho).any(-1).sum()))
+        assert (ho[..., 3] >= 0).mean() > 0.2
+        assert np.array_equal(g.read("Depth"), o.read("Depth"))
+        mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert mean_rel <= 1e-3 and outliers <= 2e-2, (f, mean_rel, outliers)
+    rays, steps = g.counters()
+    assert steps / rays > 20     # long rays
+
+
+def test_cfg3_full_size_denoiser_alone_matches_oracle(libs):
+    """BASELINE config 3 at its full size: the denoiser chain alone on the synthetic G-buffer + noisy radiance at 3840x2160
+    (vpt_denoise_external: H2D of the five planes, chain, D2H), 3 frames, against the oracle."""
+    vpt, O = libs
+    W, H = 3840, 2160
+    g, o = vpt.Vpt(W, H), O.Oracle(W, H)
+    p = S.default_denoising_params()
+    cam = vpt.camera_init(W, H)
+    cam[6:9] = (0.0, 6.0, 0.0)
+    cam = vpt.camera_set_yaw_pitch(cam, 0.0, 0.0)
+    for f in range(3):
+        gb = S.synthetic_gbuffer(W, H, f)
+        out = g.denoise_external(p, cam, cam, f, f + 1, gb)
+        o.begin_external_frame()
+        for name in ("Illumination", "Depth", "NormalRoughness", "Material", "Albedo"):
+            o.write(name, gb[name])
+        o.denoise(p, cam, cam, f, f + 1)
+        ref = o.read("IlluminationOutput")
+        mean_rel, outliers, dmax = common.rel_err_stats(out, ref)
+        assert mean_rel <= 5e-5 and outliers <= 5e-3, (f, mean_rel, outliers, dmax)
+        assert np.array_equal(g.read("HistoryLength"), o.read("HistoryLength")), f
