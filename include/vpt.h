@@ -297,6 +297,20 @@ int vpt_load_sky_settings(const char *yamlPath, VptSkyParams *params);
  * rgb8: W*H*3 bytes, top row first (may be NULL); rgbaLDR: W*H float4 sRGB-encoded, bottom row first (may be NULL). */
 int vpt_tonemap(vpt_ctx *ctx, const VptToneMappingParams *params, uint8_t *rgb8, float *rgbaLDR);
 
+/* ---- world chunk files (SURVEY 8f "next" row 4, I/O part): the reference's content-addressed raw chunk format
+ * (renderer/core/WorldSceneManager.cpp:240-308: 32768 bytes per chunk in GetLinearId order, file name = FNV-1a-64 of the
+ * bytes as 16 hex digits + ".bin") and the scene file that lists them (SceneConfigParser::SaveToFile / LoadFromFile,
+ * renderer/core/SceneConfig.cpp:95-148: sections camera, chunk_config, chunks "index: hash"). Host only. */
+void vpt_chunk_hash(const uint8_t *chunk32768, char *hex17);
+/* WorldSceneManager::SaveScene (:310-359): writes every chunk to chunkDir/<hash>.bin and the scene file. cam9 = position,
+ * direction, up. Returns VPT_ERR_IO if anything could not be written. */
+int vpt_save_world(const char *sceneYamlPath, const char *chunkDir, int chunksX, int chunksY, int chunksZ, const uint8_t *ids,
+                   const float *cam9, float fov);
+/* WorldSceneManager::LoadScene (:361-458), chunk part: ids holds the runtime grid (chunksX*Y*Z*32768 bytes) and is overwritten
+ * chunk by chunk for every "index: hash" record whose file exists and has the right size; bad records are skipped like the
+ * reference does. loaded/failed (may be NULL) receive the record counts. Returns VPT_ERR_IO when the scene file cannot be opened. */
+int vpt_load_world(const char *sceneYamlPath, const char *chunkDir, int chunksX, int chunksY, int chunksZ, uint8_t *ids, int *loaded, int *failed);
+
 /* Test hook (no device work): the launch-invariant division the kernels use for index decoding. */
 void vpt_debug_fastdiv(uint32_t n, uint32_t d, uint32_t *q, uint32_t *r);
 

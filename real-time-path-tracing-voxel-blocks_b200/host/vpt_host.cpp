@@ -462,6 +462,71 @@ extern "C" void vpt_sky_state(const VptSkyParams *p, const float *tables, float 
     }
 }
 
+// ---- world chunk files (renderer/core/WorldSceneManager.cpp:240-308, 310-458; SceneConfig.cpp:95-148)
+extern "C" void vpt_chunk_hash(const uint8_t *chunk, char *hex17)
+{
+    unsigned long long hash = 1469598103934665603ull;               // FNV-1a 64 offset basis
+    for (size_t i = 0; i < 32768; ++i) { hash ^= (unsigned long long)chunk[i]; hash *= 1099511628211ull; }
+    std::snprintf(hex17, 17, "%016llx", hash);
+}
+static std::string float3ToStringLikeReference(const float *v)
+{
+    std::ostringstream oss;                                         // SceneConfigParser::float3ToString: "[x, y, z]"
+    oss << "[" << v[0] << ", " << v[1] << ", " << v[2] << "]";
+    return oss.str();
+}
+extern "C" int vpt_save_world(const char *sceneYamlPath, const char *chunkDir, int cx, int cy, int cz, const uint8_t *ids, const float *cam9, float fov)
+{
+    if (!sceneYamlPath || !chunkDir || !ids || !cam9 || cx <= 0 || cy <= 0 || cz <= 0) return VPT_ERR_ARG;
+    const int total = cx * cy * cz;
+    bool ok = true;
+    std::vector<std::string> hashes((size_t)total);
+    for (int i = 0; i < total; ++i)
+    {
+        char hex[17];
+        vpt_chunk_hash(ids + (size_t)i * 32768, hex);
+        hashes[(size_t)i] = hex;
+        std::ofstream out(std::string(chunkDir) + "/" + hex + ".bin", std::ios::binary | std::ios::out | std::ios::trunc);
+        if (!out.is_open()) { ok = false; continue; }
+        out.write((const char *)(ids + (size_t)i * 32768), 32768);
+        if (!out.good()) ok = false;
+    }
+    std::ofstream file(sceneYamlPath);
+    if (!file.is_open()) return VPT_ERR_IO;
+    const float zero3[3] = {0.0f, 0.0f, 0.0f}, one3[3] = {1.0f, 1.0f, 1.0f};
+    file << "# Scene Configuration File\n# Generated automatically\n\n";
+    file << "camera:\n  position: " << float3ToStringLikeReference(cam9) << "\n  direction: " << float3ToStringLikeReference(cam9 + 3)
+         << "\n  up: " << float3ToStringLikeReference(cam9 + 6) << "\n  fov: " << fov << "\n\n";
+    file << "character:\n  position: " << float3ToStringLikeReference(zero3) << "\n  rotation: " << float3ToStringLikeReference(zero3)
+         << "\n  scale: " << float3ToStringLikeReference(one3) << "\n";
+    file << "\nchunk_config:\n  chunksX: " << cx << "\n  chunksY: " << cy << "\n  chunksZ: " << cz << "\n";
+    file << "\nchunks:\n";
+    for (int i = 0; i < total; ++i) file << "  " << i << ": " << hashes[(size_t)i] << "\n";
+    return (ok && file.good()) ? VPT_OK : VPT_ERR_IO;
+}
+extern "C" int vpt_load_world(const char *sceneYamlPath, const char *chunkDir, int cx, int cy, int cz, uint8_t *ids, int *loaded, int *failed)
+{
+    if (!sceneYamlPath || !chunkDir || !ids || cx <= 0 || cy <= 0 || cz <= 0) return VPT_ERR_ARG;
+    const unsigned total = (unsigned)(cx * cy * cz);
+    int nOk = 0, nBad = 0;
+    const int rc = parseSection(sceneYamlPath, "chunks", [&](const std::string &key, const std::string &value) {
+        int index = -1;
+        if (!parseInt(key, index) || index < 0) return;
+        if ((unsigned)index >= total) { ++nBad; return; }               // "Chunk index out of range in scene file"
+        std::ifstream in(std::string(chunkDir) + "/" + value + ".bin", std::ios::binary | std::ios::in | std::ios::ate);
+        if (!in.is_open() || (long long)in.tellg() != 32768) { ++nBad; return; }   // missing file / size mismatch: skipped
+        in.seekg(0);
+        std::vector<char> buf(32768);
+        in.read(buf.data(), 32768);
+        if (in.gcount() != 32768) { ++nBad; return; }
+        std::memcpy(ids + (size_t)index * 32768, buf.data(), 32768);
+        ++nOk;
+    });
+    if (loaded) *loaded = nOk;
+    if (failed) *failed = nBad;
+    return rc;
+}
+
 // Test hook: the magic-number division used by the kernels (csrc/vpt_fastdiv.h), evaluated on the host.
 extern "C" void vpt_debug_fastdiv(uint32_t n, uint32_t d, uint32_t *q, uint32_t *r)
 {

@@ -99,6 +99,7 @@ int main(int argc, char *argv[])
     int width = 3840, height = 2160;
     std::string outputPrefix = "offline_render", sceneFile = "data/scene/scene_export.yaml";
     std::string settingsFile = "data/settings/global_settings.yaml", tablesFile = "data/bluenoise_tables.bin", skyTablesFile = "data/sky_tables.bin";
+    std::string worldChunkDir, saveWorldDir; // WorldSceneManager chunk storage: load the scene's "chunks:" records / save the world
     int totalFrames = 64;
     std::vector<int> savedFrames = {1, 4, 16, 64};
     int spp = 1, totalBounce = 3, diffuseBounce = 1;
@@ -115,6 +116,8 @@ int main(int argc, char *argv[])
         else if (arg == "--settings" && i + 1 < argc) settingsFile = argv[++i];
         else if (arg == "--tables" && i + 1 < argc) tablesFile = argv[++i];
         else if (arg == "--sky-tables" && i + 1 < argc) skyTablesFile = argv[++i];
+        else if (arg == "--world-chunks" && i + 1 < argc) worldChunkDir = argv[++i];
+        else if (arg == "--save-world" && i + 1 < argc) saveWorldDir = argv[++i];
         else if (arg == "--test-canonical" || arg == "--test" || arg == "--update-canonical")
             std::printf("note: %s ignored (data/canonical/canonical_render.png is not part of the reference tree)\n", arg.c_str());
         else if (arg == "--canonical-image" && i + 1 < argc) ++i;
@@ -136,7 +139,8 @@ int main(int argc, char *argv[])
                         "  --width <int> --height <int> --output <prefix> --scene <file> --frames <int>\n"
                         "  --test-canonical --update-canonical --canonical-image <path> --comment <text>\n"
                         "  --test-sequence --test-remove20 --test-remove-circle   (accepted, ignored)\n"
-                        "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file> --sky-tables <file>\n", argv[0]);
+                        "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file> --sky-tables <file>\n"
+                        "  --world-chunks <dir>  load the chunk files the scene lists (WorldSceneManager::LoadScene)   --save-world <dir>  write them\n", argv[0]);
             return 0;
         }
     }
@@ -167,6 +171,27 @@ int main(int argc, char *argv[])
     std::vector<float> noise((size_t)chunks[0] * chunks[1] * chunks[2] * 1024);
     vpt_perlin_noise_chunks(chunks[0], chunks[1], chunks[2], 124, noise.data());
     CHECK(vpt_generate_terrain(ctx, chunks[0], chunks[1], chunks[2], noise.data()));
+    if (!worldChunkDir.empty() || !saveWorldDir.empty())
+    {
+        // WorldSceneManager::LoadScene / SaveScene, chunk part (renderer/core/WorldSceneManager.cpp:310-458)
+        std::vector<uint8_t> ids((size_t)chunks[0] * chunks[1] * chunks[2] * 32768);
+        CHECK(vpt_get_grid(ctx, ids.data(), ids.size()));
+        if (!worldChunkDir.empty())
+        {
+            int loaded = 0, failed = 0;
+            if (vpt_load_world(sceneFile.c_str(), worldChunkDir.c_str(), chunks[0], chunks[1], chunks[2], ids.data(), &loaded, &failed) != VPT_OK)
+                std::printf("Scene file not found: %s (no chunks loaded)\n", sceneFile.c_str());
+            std::printf("World chunks: %d loaded, %d failed from %s\n", loaded, failed, worldChunkDir.c_str());
+            if (loaded > 0) CHECK(vpt_set_grid(ctx, chunks[0], chunks[1], chunks[2], ids.data()));
+        }
+        if (!saveWorldDir.empty())
+        {
+            const std::string sceneOut = saveWorldDir + "/scene.yaml";
+            if (vpt_save_world(sceneOut.c_str(), saveWorldDir.c_str(), chunks[0], chunks[1], chunks[2], ids.data(), cam9, fov) != VPT_OK)
+                std::fprintf(stderr, "Failed to save the world to %s\n", saveWorldDir.c_str());
+            else std::printf("Saved scene config to: %s\n", sceneOut.c_str());
+        }
+    }
     // terrain materials (data/assets/materials.yaml order; textures out of scope -> flat albedo stand-ins)
     const MaterialRow rows[12] = {{0.76f, 0.70f, 0.50f, 0.8f}, {0.45f, 0.33f, 0.22f, 0.9f}, {0.55f, 0.52f, 0.48f, 0.85f}, {0.40f, 0.30f, 0.20f, 0.9f},
                                   {0.76f, 0.70f, 0.50f, 0.8f}, {0.80f, 0.75f, 0.60f, 0.7f}, {0.50f, 0.50f, 0.52f, 0.85f}, {0.60f, 0.60f, 0.58f, 0.6f},

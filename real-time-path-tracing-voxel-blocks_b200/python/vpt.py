@@ -41,7 +41,7 @@ EXPORTS = [
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
-    "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
+    "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
 
 
 class VptError(RuntimeError):
@@ -151,6 +151,29 @@ def load_sky_settings(path):
     p["timeOfDay"], p["sunAxisAngle"], p["sunAxisRotate"], p["skyBrightness"] = 0.25, 45.0, 0.0, 1.0
     rc = lib().vpt_load_sky_settings(path.encode(), _p(p))
     return p, rc
+
+
+def chunk_hash(chunk):
+    """FNV-1a-64 of a 32768-byte chunk as 16 hex digits (WorldSceneManager.cpp:240-258)."""
+    c = np.ascontiguousarray(chunk, np.uint8).ravel()
+    assert c.size == 32768
+    out = C.create_string_buffer(17)
+    lib().vpt_chunk_hash(_p(c), out)
+    return out.value.decode()
+
+
+def save_world(scene_path, chunk_dir, chunks, ids, cam9, fov=90.0):
+    ids = np.ascontiguousarray(ids, np.uint8).ravel()
+    cam9 = np.ascontiguousarray(cam9, np.float32)
+    return lib().vpt_save_world(scene_path.encode(), chunk_dir.encode(), chunks[0], chunks[1], chunks[2], _p(ids), _p(cam9), C.c_float(fov))
+
+
+def load_world(scene_path, chunk_dir, chunks, ids):
+    """Overwrites `ids` (runtime grid, chunk-major) with the chunk files the scene lists; returns (rc, loaded, failed)."""
+    assert ids.dtype == np.uint8 and ids.flags["C_CONTIGUOUS"] and ids.size == chunks[0] * chunks[1] * chunks[2] * 32768
+    ok, bad = C.c_int(), C.c_int()
+    rc = lib().vpt_load_world(scene_path.encode(), chunk_dir.encode(), chunks[0], chunks[1], chunks[2], _p(ids), C.byref(ok), C.byref(bad))
+    return rc, ok.value, bad.value
 
 
 def sky_state(params, tables):
