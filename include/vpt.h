@@ -174,6 +174,22 @@ int vpt_set_materials(vpt_ctx *ctx, const VptMaterial *materials, int count, con
  * their alias tables (shaders/AliasTable.cu:66-153) and the sun direction. */
 int vpt_set_sky(vpt_ctx *ctx, const float *skyRGBA, int skyW, int skyH, const float *sunRGBA, int sunW, int sunH,
                 const VptAliasBin *skyAlias, const VptAliasBin *sunAlias, const float *sunDir /*[3]*/);
+/* Textured materials (SURVEY 8a S5 / 8f "next" row 3; closesthit.cu:166-254, sampler state TextureManager.cu:222-240: wrap
+ * addressing, trilinear, normalised coordinates, no sRGB, mip levels down to 4x4). The reference feeds NVTT-encoded BC7/BC5/BC4
+ * blocks to the texture unit — neither is reproducible — so this build filters UNCOMPRESSED RGBA8 mip chains in software
+ * (fp32): nTextures square power-of-two textures, texture t has levels[t] levels of (widths[t] >> l)^2 RGBA8 texels (r = low
+ * byte), all levels of all textures concatenated in `texels`. slots4[m] = albedo, normal, roughness, metallic texture index
+ * of material m (-1 = none; single-channel maps are read from .r); texSize2[m] = MaterialParameter::texSize. nTextures = 0
+ * removes them. Must follow vpt_set_materials (same material count). */
+int vpt_set_textures(vpt_ctx *ctx, int nTextures, const int32_t *widths, const int32_t *levels, const uint32_t *texels, int nMaterials,
+                     const int32_t *slots4, const float *texSize2);
+/* Mip chain of one square power-of-two RGBA8 image the way TextureManager::init builds it (renderer/assets/TextureManager.cu:
+ * 82-115, 216-217, 395-411): level l+1 = per-channel 2x2 box average of level l, truncated to 8 bits; levels stop at 4x4
+ * (numLods = log2(width) - 1; images smaller than 4x4 keep 1 level). Host only. out receives all levels concatenated (the layout
+ * vpt_set_textures takes) and must hold vpt_mip_chain_texels(width) texels (0 for an invalid width). Returns the number of levels, 0 on a bad argument. */
+int vpt_mip_chain_texels(int width);
+int vpt_build_mip_chain(const uint32_t *level0, int width, uint32_t *out);
+
 /* SkyParams (renderer/core/GlobalSettings.h:188-204) */
 typedef struct VptSkyParams
 {

@@ -217,6 +217,20 @@ class Oracle:
         assert b.size == 256
         self.L.orc_set_materials(self.ctx, _p(m), m.size, _p(b))
 
+    def set_textures(self, textures, slots, tex_size):
+        widths = np.array([t[0].shape[0] for t in textures], np.int32)
+        levels = np.array([len(t) for t in textures], np.int32)
+        texels = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(l, np.uint32).ravel() for t in textures for l in t])
+                                      if textures else np.zeros(1, np.uint32))
+        slots = np.ascontiguousarray(slots, np.int32).reshape(-1, 4)
+        tex_size = np.ascontiguousarray(tex_size, np.float32).reshape(-1, 2)
+        self.L.orc_set_textures(self.ctx, len(textures), _p(widths), _p(levels), _p(texels), slots.shape[0], _p(slots), _p(tex_size))
+
+    def tex_sample(self, tex, u, v, lod):
+        out = np.zeros(4, np.float32)
+        self.L.orc_tex_sample(self.ctx, int(tex), C.c_float(u), C.c_float(v), C.c_float(lod), _p(out))
+        return out
+
     def set_sky(self, sky, sun, sky_alias, sun_alias, sun_dir):
         sky = np.ascontiguousarray(sky, np.float32)
         sun = np.ascontiguousarray(sun, np.float32)

@@ -93,6 +93,36 @@ int orc_set_sky(orc_ctx *c, const float *sky, int skyW, int skyH, const float *s
     s.sunDir = {sunDir[0], sunDir[1], sunDir[2]};
     return 0;
 }
+// Uncompressed RGBA8 mip chains + per-material texture slots (albedo, normal, roughness, metallic; -1 = none) and texSize.
+int orc_set_textures(orc_ctx *c, int nTextures, const int *widths, const int *levels, const uint32_t *texels, int nMaterials,
+                     const int32_t *slots4, const float *texSize2)
+{
+    c->sc.textures.assign((size_t)nTextures, Texture());
+    size_t off = 0;
+    for (int t = 0; t < nTextures; ++t)
+    {
+        Texture &tx = c->sc.textures[(size_t)t];
+        tx.width = widths[t]; tx.levels = levels[t];
+        size_t n = 0;
+        for (int l = 0; l < tx.levels; ++l) { tx.levelOffset.push_back(n); n += (size_t)(tx.width >> l) * (tx.width >> l); }
+        tx.texels.assign(texels + off, texels + off + n);
+        off += n;
+    }
+    c->sc.matTex.assign((size_t)nMaterials, MaterialTextures());
+    for (int m = 0; m < nMaterials; ++m)
+    {
+        MaterialTextures &mt = c->sc.matTex[(size_t)m];
+        mt.albedo = slots4[m * 4]; mt.normal = slots4[m * 4 + 1]; mt.roughness = slots4[m * 4 + 2]; mt.metallic = slots4[m * 4 + 3];
+        mt.texSizeX = texSize2[m * 2]; mt.texSizeY = texSize2[m * 2 + 1];
+    }
+    return 0;
+}
+// test hook: one trilinear fetch (tex2DLod restatement)
+void orc_tex_sample(orc_ctx *c, int tex, float u, float v, float lod, float *out4)
+{
+    const f4 r = tex2DLod(c->sc.textures[(size_t)tex], u, v, lod);
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
 int orc_set_trace_params(orc_ctx *c, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir)
 {
     c->sc.tp = {spp, totalBounceLimit, diffuseBounceLimit, enableRestir};

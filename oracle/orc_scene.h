@@ -67,6 +67,17 @@ inline void cameraUpdate(Camera &c)
     c.posDelta = {0, 0, 0};
     cameraUpdateMatrices(c);
 }
+// Camera::getRayConeWidth (Camera.h:133-149): angular width of the pixel
+inline float getRayConeWidth(const Camera &c, int ix, int iy)
+{
+    const f2 pixelCenter = {((float)ix + 0.5f) - c.resolution.x / 2, ((float)iy + 0.5f) - c.resolution.y / 2};
+    const f2 pixelOffset = {copysignf(0.5f, pixelCenter.x), copysignf(0.5f, pixelCenter.y)};
+    const f2 uvNear = {(pixelCenter.x - pixelOffset.x) * c.inversedResolution.x * 2, (pixelCenter.y - pixelOffset.y) * c.inversedResolution.y * 2};
+    const f2 uvFar = {(pixelCenter.x + pixelOffset.x) * c.inversedResolution.x * 2, (pixelCenter.y + pixelOffset.y) * c.inversedResolution.y * 2};
+    const f2 pn = {uvNear.x * c.tanHalfFov.x, uvNear.y * c.tanHalfFov.y}, pf = {uvFar.x * c.tanHalfFov.x, uvFar.y * c.tanHalfFov.y};
+    const float angleNear = atanf(sqrtf(pn.x * pn.x + pn.y * pn.y)), angleFar = atanf(sqrtf(pf.x * pf.x + pf.y * pf.y));
+    return angleFar - angleNear;
+}
 inline f3 uvToWorldDirection(const Camera &c, f2 uv) { return normalize(mul(c.uvToWorld, F3(uv.x, uv.y, 1.0f))); }
 inline f2 worldDirectionToUV(const Camera &c, f3 d)
 {

@@ -365,12 +365,55 @@ struct GBufferSet
 };
 struct TraceParams { int spp = 1, totalBounceLimit = 3, diffuseBounceLimit = 1, enableRestir = 1; };
 
+// Textured materials (closesthit.cu:166-254; sampler state TextureManager.cu:222-240: wrap addressing, linear filter, linear
+// mip filter, normalised coordinates, no sRGB, levels down to 4x4: maxLod = log2(width) - 2). The reference feeds BC7/BC5/BC4
+// blocks encoded by NVTT to the texture unit; neither the encoder nor the unit's 8-bit filter weights are reproducible, so the
+// restatement (and the CUDA path) filter UNCOMPRESSED RGBA8 mip chains supplied by the caller in software, in fp32.
+struct Texture
+{
+    int width = 0, levels = 0;
+    std::vector<uint32_t> texels;      // all levels, level l is (width >> l)^2 texels, RGBA8 little endian (r = low byte)
+    std::vector<size_t> levelOffset;
+};
+struct MaterialTextures { int albedo = -1, normal = -1, roughness = -1, metallic = -1; float texSizeX = 1024.0f, texSizeY = 1024.0f; };
+inline f4 texelRGBA(const Texture &t, int level, int x, int y)
+{
+    const int n = t.width >> level;
+    x = ((x % n) + n) % n; y = ((y % n) + n) % n;    // cudaAddressModeWrap
+    const uint32_t v = t.texels[t.levelOffset[level] + (size_t)y * n + x];
+    return {(float)(v & 0xff) / 255.0f, (float)((v >> 8) & 0xff) / 255.0f, (float)((v >> 16) & 0xff) / 255.0f, (float)(v >> 24) / 255.0f};
+}
+inline f4 texBilinear(const Texture &t, int level, float u, float v)
+{
+    const int n = t.width >> level;
+    const float x = u * n - 0.5f, y = v * n - 0.5f;
+    const float fx = std::floor(x), fy = std::floor(y);
+    const float a = x - fx, b = y - fy;
+    const int i = (int)fx, j = (int)fy;
+    const f4 t00 = texelRGBA(t, level, i, j), t10 = texelRGBA(t, level, i + 1, j), t01 = texelRGBA(t, level, i, j + 1), t11 = texelRGBA(t, level, i + 1, j + 1);
+    return ((1.0f - a) * (1.0f - b)) * t00 + (a * (1.0f - b)) * t10 + ((1.0f - a) * b) * t01 + (a * b) * t11;
+}
+// tex2DLod with trilinear filtering
+inline f4 tex2DLod(const Texture &t, float u, float v, float lod)
+{
+    const float maxLod = (float)(t.levels - 1);
+    lod = lod < 0.0f ? 0.0f : (lod > maxLod ? maxLod : lod);   // also maps -inf / NaN-free inputs into range
+    if (!(lod >= 0.0f)) lod = 0.0f;
+    const int l0 = (int)std::floor(lod);
+    const int l1 = l0 + 1 < t.levels ? l0 + 1 : l0;
+    const float beta = lod - (float)l0;
+    const f4 c0 = texBilinear(t, l0, u, v), c1 = texBilinear(t, l1, u, v);
+    return c0 + beta * (c1 - c0);
+}
+
 struct Scene
 {
     int width = 0, height = 0;
     Tables tables;
     Grid grid;
     std::vector<Material> materials;
+    std::vector<Texture> textures;
+    std::vector<MaterialTextures> matTex; // empty or one entry per material
     uint16_t blockToMaterial[256] = {0};
     Sky sky;
     TraceParams tp;
@@ -571,6 +614,7 @@ struct RayData
 {
     f3 pos; float distance; f3 wo, wi; unsigned depth; f3 radiance, bsdfOverPdf; float pdf;
     bool hitFirstDiffuseSurface, shouldTerminate, isCurrentBounceDiffuse, isLastBounceDiffuse, hitFrontFace, transmissionEvent;
+    float rayConeWidth, rayConeSpread;
 };
 
 // __miss__radiance (miss.cu:9-82)
@@ -671,13 +715,44 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
     Surface s;
     s.geoNormal = geoNormal;
     s.wo = rd.wo;
-    s.albedo = max3f(F3(mat.albedo[0], mat.albedo[1], mat.albedo[2]), F3(0.001f));
+    // texture coordinates: world-grid UV by the dominant normal axis (closesthit.cu:166-187), ray-cone LOD (:194-200)
+    const size_t matIndex = sc.blockToMaterial[h.id];
+    const MaterialTextures *mt = matIndex < sc.matTex.size() ? &sc.matTex[matIndex] : nullptr;
+    f2 texCoords = {0.0f, 0.0f};
+    if (mat.useWorldGridUV)
+    {
+        if (fabsf(geoNormal.x) > 0.9f) texCoords = {fmodf(rd.pos.z, mat.uvScale), fmodf(rd.pos.y, mat.uvScale)};
+        else if (fabsf(geoNormal.y) > 0.9f) texCoords = {fmodf(rd.pos.x, mat.uvScale), fmodf(rd.pos.z, mat.uvScale)};
+        else if (fabsf(geoNormal.z) > 0.9f) texCoords = {fmodf(rd.pos.x, mat.uvScale), fmodf(rd.pos.y, mat.uvScale)};
+    }
+    rd.rayConeWidth += rd.rayConeSpread * rd.distance;
+    texCoords = {texCoords.x / mat.uvScale, texCoords.y / mat.uvScale};
+    float lod = 0.0f;
+    if (mt)
+    {
+        const float texMip0Size = sqrtf(mt->texSizeX * mt->texSizeX + mt->texSizeY * mt->texSizeY);
+        lod = log2f(rd.rayConeWidth / fmaxr(dot(geoNormal, rd.wo), 0.2f) / mat.uvScale * 2.0f * texMip0Size) - 3.0f;
+    }
+    s.albedo = F3(mat.albedo[0], mat.albedo[1], mat.albedo[2]);
+    if (mt && mt->albedo >= 0) s.albedo = s.albedo * xyz(tex2DLod(sc.textures[mt->albedo], texCoords.x, texCoords.y, lod));
+    s.albedo = max3f(s.albedo, F3(0.001f));
     s.roughness = mat.roughness;
+    if (mt && mt->roughness >= 0) s.roughness = tex2DLod(sc.textures[mt->roughness], texCoords.x, texCoords.y, lod).x;
     if (rd.hitFirstDiffuseSurface) s.roughness = fminr(s.roughness * 2.0f + 0.1f, 1.0f);
     const bool isDiffuse = s.roughness > kRoughnessThreshold;
     s.metallic = mat.metallic != 0;
+    if (mt && mt->metallic >= 0) s.metallic = tex2DLod(sc.textures[mt->metallic], texCoords.x, texCoords.y, lod).x > 0.5f;
     s.translucency = mat.translucency;
-    s.normal = lerp3(geoNormal, geoNormal, 0.2f); // no normal map: state.normal = geoNormal (closesthit.cu:251-254)
+    if (mt && mt->normal >= 0)
+    {
+        const f3 texNormal = xyz(tex2DLod(sc.textures[mt->normal], texCoords.x, texCoords.y, lod));
+        f3 nm = normalize(texNormal - F3(0.5f));
+        nm.x = -nm.x; nm.y = -nm.y;
+        alignVector(geoNormal, nm);
+        s.normal = lerp3(geoNormal, nm, 0.2f); // normalMapStrength (closesthit.cu:253-254)
+    }
+    else
+        s.normal = lerp3(geoNormal, geoNormal, 0.2f); // no normal map: state.normal = geoNormal (closesthit.cu:251-254)
     rd.isCurrentBounceDiffuse = isDiffuse;
 
     if (gbufferPass)
@@ -946,6 +1021,8 @@ inline f3 tracePath(PixelCtx &c, bool ownsGBuffer, float &primaryDist)
     rd.pos = c.cam->pos;
     rd.wi = uvToWorldDirection(*c.cam, sampleUv);
     f3 radiance = F3(0.0f), throughput = F3(1.0f);
+    rd.rayConeWidth = 0.0f;
+    rd.rayConeSpread = getRayConeWidth(*c.cam, c.px, c.py); // RayGen.cu:134-135
     rd.depth = 0;
     primaryDist = kRayMax;
     bool terminated = false;

@@ -52,6 +52,7 @@ struct vpt_ctx
     // materials / sky
     VptMaterial *materials = nullptr; int nMaterials = 0;
     uint16_t *blockToMaterial = nullptr;
+    uint32_t *texels = nullptr; int4 *texDescs = nullptr, *matTexSlots = nullptr; float *matTexMip0Size = nullptr; int nTextures = 0;
     float4 *sky = nullptr, *sun = nullptr;
     VptAliasBin *skyAlias = nullptr, *sunAlias = nullptr;
     int skyW = 0, skyH = 0, sunW = 0, sunH = 0;
@@ -74,6 +75,7 @@ struct vpt_ctx
     TraceProfile traceProf;
     TraceStreams traceStreams;
     bool overlapParts = false; // two-stream part overlap: measured, no gain (see vpt_wave.cu launchTrace)
+    bool texSpecular = false; // a roughness map exists: any texel may be specular
     bool anySpecular = false; // a non-diffuse, non-emissive material exists: paths may continue past their first hit
     int countSteps = 1;
     size_t waveBudget = (size_t)16u << 20;
@@ -270,6 +272,7 @@ int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_
     if (c->materials) cudaFree(c->materials);
     CU(cudaMalloc((void **)&c->materials, (size_t)count * sizeof(VptMaterial)));
     c->nMaterials = count;
+    c->nTextures = 0; c->texSpecular = false; // texture slots are per material: vpt_set_textures must follow
     c->anySpecular = false;
     for (int i = 0; i < count; ++i)
         if (!m[i].isEmissive && !(m[i].roughness > 0.00001f)) c->anySpecular = true; // isDiffuse = roughness > 1e-5 (Bsdf.h:5)
@@ -299,6 +302,46 @@ int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *s
     return VPT_OK;
 }
 
+int vpt_set_textures(vpt_ctx *c, int nTextures, const int32_t *widths, const int32_t *levels, const uint32_t *texels, int nMaterials,
+                     const int32_t *slots4, const float *texSize2)
+{
+    if (!c || nTextures < 0) return fail(VPT_ERR_ARG, "vpt_set_textures: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (void *p : {(void *)c->texels, (void *)c->texDescs, (void *)c->matTexSlots, (void *)c->matTexMip0Size}) if (p) cudaFree(p);
+    c->texels = nullptr; c->texDescs = nullptr; c->matTexSlots = nullptr; c->matTexMip0Size = nullptr; c->nTextures = 0; c->texSpecular = false;
+    if (nTextures == 0) return VPT_OK;
+    if (!widths || !levels || !texels || !slots4 || !texSize2) return fail(VPT_ERR_ARG, "vpt_set_textures: null argument");
+    if (nMaterials != c->nMaterials) return fail(VPT_ERR_ARG, "vpt_set_textures: material count differs from vpt_set_materials");
+    std::vector<int4> descs((size_t)nTextures);
+    size_t total = 0;
+    for (int t = 0; t < nTextures; ++t)
+    {
+        const int w = widths[t], l = levels[t];
+        if (w <= 0 || (w & (w - 1)) || l < 1 || (w >> (l - 1)) < 1) return fail(VPT_ERR_ARG, "vpt_set_textures: textures must be square powers of two with 1..log2(w)+1 levels");
+        if (total > 0x7fffffffu) return fail(VPT_ERR_ARG, "vpt_set_textures: more than 2^31 texels");
+        descs[(size_t)t] = make_int4((int)total, w, l, 0);
+        for (int k = 0; k < l; ++k) total += (size_t)(w >> k) * (w >> k);
+    }
+    std::vector<int4> slots((size_t)nMaterials);
+    std::vector<float> mip0((size_t)nMaterials);
+    for (int m = 0; m < nMaterials; ++m)
+    {
+        for (int k = 0; k < 4; ++k) if (slots4[m * 4 + k] >= nTextures) return fail(VPT_ERR_ARG, "vpt_set_textures: texture index out of range");
+        slots[(size_t)m] = make_int4(slots4[m * 4], slots4[m * 4 + 1], slots4[m * 4 + 2], slots4[m * 4 + 3]);
+        mip0[(size_t)m] = sqrtf(texSize2[m * 2] * texSize2[m * 2] + texSize2[m * 2 + 1] * texSize2[m * 2 + 1]); // texSize.length(), host IEEE like the oracle
+    }
+    CU(cudaMalloc((void **)&c->texels, total * 4)); CU(cudaMalloc((void **)&c->texDescs, descs.size() * sizeof(int4)));
+    CU(cudaMalloc((void **)&c->matTexSlots, slots.size() * sizeof(int4))); CU(cudaMalloc((void **)&c->matTexMip0Size, mip0.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(c->texels, texels, total * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->texDescs, descs.data(), descs.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->matTexSlots, slots.data(), slots.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->matTexMip0Size, mip0.data(), mip0.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->nTextures = nTextures;
+    for (int m = 0; m < nMaterials; ++m) if (slots4[m * 4 + 2] >= 0) c->texSpecular = true;
+    return VPT_OK;
+}
 int vpt_set_wave_budget(vpt_ctx *c, size_t maxPaths)
 {
     if (!c || maxPaths == 0) return fail(VPT_ERR_ARG, "vpt_set_wave_budget: bad argument");
@@ -396,7 +439,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.divSlots = makeFastDiv(a.nSlots); a.divTilesX = makeFastDiv(a.tilesX);
     a.divSkyW = makeFastDiv(c->skyW); a.divSunW = makeFastDiv(c->sunW);
     // a path continues past its first hit only through a specular surface or with a diffuse limit above 1
-    a.depthRounds = (c->anySpecular || c->diffuseBounceLimit > 1) ? c->totalBounceLimit : 1;
+    a.depthRounds = (c->anySpecular || c->texSpecular || c->diffuseBounceLimit > 1) ? c->totalBounceLimit : 1;
     a.countSteps = c->countSteps;
     a.resolveSpp = (resolve && c->spp > 1) ? (float)c->spp : 0.0f;
     // wave size: as many samples per wave as fit a 16 M-path budget
@@ -414,6 +457,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.wb = c->wave.wb;
     a.sobol = c->sobol; a.scrambling = c->scrambling; a.ranking = c->ranking;
     a.materials = c->materials; a.blockToMaterial = c->blockToMaterial;
+    a.texels = c->texels; a.texDescs = c->texDescs; a.matTexSlots = c->matTexSlots; a.matTexMip0Size = c->matTexMip0Size; a.nTextures = c->nTextures;
     a.sky = c->sky; a.sun = c->sun; a.skyAlias = c->skyAlias; a.sunAlias = c->sunAlias;
     a.skyW = c->skyW; a.skyH = c->skyH; a.sunW = c->sunW; a.sunH = c->sunH;
     a.sunDir[0] = c->sunDir[0]; a.sunDir[1] = c->sunDir[1]; a.sunDir[2] = c->sunDir[2];

@@ -51,6 +51,8 @@ struct WaveBuffers
     uint32_t *hitPacked; // (linear voxel index << 3) | face, 0xFFFFFFFF = miss
     float4 *surfA;      // spawn position xyz, hit distance
     float4 *surfB;      // wo xyz, bits: face | material index << 3
+    float4 *surfC;      // textured scenes only: shading normal xyz, roughness (regularised)
+    float4 *surfD;      // textured scenes only: albedo rgb, metallic
     uint32_t *pflag;    // path flags (vpt_wave.cu: F_*)
     float4 *candA;      // sun idx, sun weightSum, sun targetPdf, sky idx
     float4 *candB;      // sky weightSum, sky targetPdf
@@ -92,6 +94,12 @@ struct TraceArgs
     int skyW, skyH, sunW, sunH;
     float sunDir[3];
     float sunCosThetaMax;
+    // textured materials (optional): RGBA8 mip chains, per-texture (first texel, width, levels), per-material slots + |texSize|
+    const uint32_t *texels;
+    const int4 *texDescs;
+    const int4 *matTexSlots;
+    const float *matTexMip0Size;
+    int nTextures;
     GBufferPtrs cur, prev;
     float4 *illumination;
     VptReservoir *resCur;

@@ -556,8 +556,49 @@ VPT_DEV Ctx makeCtx(const TraceArgs &a, const PathId &id, int randIdx)
 }
 VPT_DEV f3 camPos(const TraceArgs &a) { return F3(a.cam.pos[0], a.cam.pos[1], a.cam.pos[2]); }
 
+// ---- textured materials (closesthit.cu:166-254): software trilinear over RGBA8 mip chains, wrap addressing
+VPT_DEV f4 texelRGBA(const TraceArgs &a, int4 d, int level, int x, int y)
+{
+    const int n = d.y >> level;
+    x &= n - 1; y &= n - 1;                                     // power-of-two wrap (two's complement handles negatives)
+    const int w2 = d.y * d.y, n2 = n * n;
+    const uint32_t v = __ldg(a.texels + (size_t)d.x + (size_t)((4 * w2 - 4 * n2) / 3) + (size_t)y * n + x);
+    return {(float)(v & 0xffu) / 255.0f, (float)((v >> 8) & 0xffu) / 255.0f, (float)((v >> 16) & 0xffu) / 255.0f, (float)(v >> 24) / 255.0f};
+}
+VPT_DEV f4 texBilinear(const TraceArgs &a, int4 d, int level, float u, float v)
+{
+    const int n = d.y >> level;
+    const float x = u * n - 0.5f, y = v * n - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float wa = x - fx, wb = y - fy;
+    const int i = (int)fx, j = (int)fy;
+    const f4 t00 = texelRGBA(a, d, level, i, j), t10 = texelRGBA(a, d, level, i + 1, j), t01 = texelRGBA(a, d, level, i, j + 1), t11 = texelRGBA(a, d, level, i + 1, j + 1);
+    return ((1.0f - wa) * (1.0f - wb)) * t00 + (wa * (1.0f - wb)) * t10 + ((1.0f - wa) * wb) * t01 + (wa * wb) * t11;
+}
+VPT_DEV f4 tex2DLod(const TraceArgs &a, int tex, float u, float v, float lod)
+{
+    const int4 d = __ldg(a.texDescs + tex);
+    const float maxLod = (float)(d.z - 1);
+    lod = lod < 0.0f ? 0.0f : (lod > maxLod ? maxLod : lod);
+    if (!(lod >= 0.0f)) lod = 0.0f;
+    const int l0 = (int)floorf(lod);
+    const int l1 = l0 + 1 < d.z ? l0 + 1 : l0;
+    const float beta = lod - (float)l0;
+    const f4 c0 = texBilinear(a, d, l0, u, v), c1 = texBilinear(a, d, l1, u, v);
+    return c0 + beta * (c1 - c0);
+}
+// Camera::getRayConeWidth (Camera.h:133-149)
+VPT_DEV float rayConeSpread(const VptCamera &c, int ix, int iy)
+{
+    const float pcx = ((float)ix + 0.5f) - c.resolution[0] / 2, pcy = ((float)iy + 0.5f) - c.resolution[1] / 2;
+    const float ox = copysignf(0.5f, pcx), oy = copysignf(0.5f, pcy);
+    const float nx = (pcx - ox) * c.inversedResolution[0] * 2 * c.tanHalfFov[0], ny = (pcy - oy) * c.inversedResolution[1] * 2 * c.tanHalfFov[1];
+    const float fx = (pcx + ox) * c.inversedResolution[0] * 2 * c.tanHalfFov[0], fy = (pcy + oy) * c.inversedResolution[1] * 2 * c.tanHalfFov[1];
+    return atanf(sqrtf(fx * fx + fy * fy)) - atanf(sqrtf(nx * nx + ny * ny));
+}
+
 // Surface of the current hit, rebuilt from the 32-byte record S1 wrote (closesthit.cu:160-256 without textures).
-VPT_DEV Surface loadSurface(const TraceArgs &a, int p, int depth)
+template <bool kTex> VPT_DEV Surface loadSurface(const TraceArgs &a, int p, int depth)
 {
     const float4 sa = __ldg(a.wb.surfA + p), sb = __ldg(a.wb.surfB + p);
     const uint32_t bits = __float_as_uint(sb.w);
@@ -566,12 +607,19 @@ VPT_DEV Surface loadSurface(const TraceArgs &a, int p, int depth)
     Surface s;
     s.pos = xyz(sa); s.depth = sa.w; s.wo = xyz(sb);
     s.geoNormal = faceNormal(face, -s.wo);
+    s.translucency = __ldg(&mat->translucency);
+    if (kTex)
+    {
+        // textured scene: S1 stored what it fetched
+        const float4 sc = __ldg(a.wb.surfC + p), sd = __ldg(a.wb.surfD + p);
+        s.normal = xyz(sc); s.roughness = sc.w; s.albedo = xyz(sd); s.metallic = sd.w != 0.0f;
+        return s;
+    }
     s.normal = lerp3(s.geoNormal, s.geoNormal, 0.2f);
     s.albedo = max3f(F3(__ldg(&mat->albedo[0]), __ldg(&mat->albedo[1]), __ldg(&mat->albedo[2])), F3(0.001f));
     s.roughness = __ldg(&mat->roughness);
     if (depth > 0) s.roughness = fminr(s.roughness * 2.0f + 0.1f, 1.0f);
     s.metallic = __ldg(&mat->metallic) != 0;
-    s.translucency = __ldg(&mat->translucency);
     return s;
 }
 VPT_DEV void storeLight(const TraceArgs &a, float4 *A, float4 *B, int i, const LightSample &l)
@@ -669,7 +717,7 @@ __global__ void __launch_bounds__(kShadeThreads) genKernel(const __grid_constant
 
 // ------------------------------------------------------------------------------------------------ S1
 // __miss__radiance, and __closesthit__radiance up to the BSDF-candidate ray (closesthit.cu:96-468).
-__global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
@@ -692,6 +740,7 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(co
         const uint32_t hp = a.wb.hitPacked[p];
         const float t = a.wb.hitT[p];
         const bool gbufferPass = owns && depth == 0;
+        float coneWidth = depth == 0 ? 0.0f : __ldg(a.wb.dirT + p).w; // rayData->rayConeWidth (RayGen.cu:134, closesthit.cu:195)
         uint32_t nf = F_LIVE | ((uint32_t)depth << kDepthShift);
         int newDiffuse = diffuseBounce;
         f3 radiance = F3(0.0f);
@@ -736,13 +785,41 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(co
                 Surface s;
                 s.geoNormal = geoNormal;
                 s.wo = -d;
-                s.albedo = max3f(matAlbedo, F3(0.001f));
+                s.albedo = matAlbedo;
                 s.roughness = __ldg(&mat->roughness);
-                if (depth > 0) s.roughness = fminr(s.roughness * 2.0f + 0.1f, 1.0f);
-                const bool isDiffuse = s.roughness > kRoughnessThreshold;
                 s.metallic = __ldg(&mat->metallic) != 0;
                 s.translucency = __ldg(&mat->translucency);
-                s.normal = lerp3(geoNormal, geoNormal, 0.2f);
+                s.normal = geoNormal;
+                if (kTex)
+                {
+                    // world-grid UV by the dominant normal axis + ray-cone LOD (closesthit.cu:166-200), then the four maps (:202-250)
+                    const float uvScale = __ldg(&mat->uvScale);
+                    f2 tc = {0.0f, 0.0f};
+                    if (__ldg(&mat->useWorldGridUV))
+                    {
+                        if (fabsf(geoNormal.x) > 0.9f) tc = {fmodf(frontPos.z, uvScale), fmodf(frontPos.y, uvScale)};
+                        else if (fabsf(geoNormal.y) > 0.9f) tc = {fmodf(frontPos.x, uvScale), fmodf(frontPos.z, uvScale)};
+                        else if (fabsf(geoNormal.z) > 0.9f) tc = {fmodf(frontPos.x, uvScale), fmodf(frontPos.y, uvScale)};
+                    }
+                    tc = {tc.x / uvScale, tc.y / uvScale};
+                    coneWidth += rayConeSpread(a.cam, id.px, id.py) * distance;
+                    const int4 slots = __ldg(a.matTexSlots + matIndex);
+                    const float lod = log2f(coneWidth / fmaxr(dot(geoNormal, s.wo), 0.2f) / uvScale * 2.0f * __ldg(a.matTexMip0Size + matIndex)) - 3.0f;
+                    if (slots.x >= 0) s.albedo = s.albedo * xyz(tex2DLod(a, slots.x, tc.x, tc.y, lod));
+                    if (slots.z >= 0) s.roughness = tex2DLod(a, slots.z, tc.x, tc.y, lod).x;
+                    if (slots.w >= 0) s.metallic = tex2DLod(a, slots.w, tc.x, tc.y, lod).x > 0.5f;
+                    if (slots.y >= 0)
+                    {
+                        f3 nm = normalize(xyz(tex2DLod(a, slots.y, tc.x, tc.y, lod)) - F3(0.5f));
+                        nm.x = -nm.x; nm.y = -nm.y;
+                        alignVector(geoNormal, nm);
+                        s.normal = nm;
+                    }
+                }
+                s.albedo = max3f(s.albedo, F3(0.001f));
+                if (depth > 0) s.roughness = fminr(s.roughness * 2.0f + 0.1f, 1.0f);
+                const bool isDiffuse = s.roughness > kRoughnessThreshold;
+                s.normal = lerp3(geoNormal, s.normal, 0.2f);
                 if (gbufferPass)
                 {
                     a.cur.material[pix] = (float)__ldg(&mat->materialId);
@@ -832,13 +909,18 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(co
                 {
                     nf |= F_CONT;
                     needSurf = true;
-                    a.wb.nextD[p] = make_float4(bsdfWi.x, bsdfWi.y, bsdfWi.z, 0.0f);
+                    a.wb.nextD[p] = make_float4(bsdfWi.x, bsdfWi.y, bsdfWi.z, coneWidth);
                     a.wb.bop[p] = make_float4(bsdfOverPdf.x, bsdfOverPdf.y, bsdfOverPdf.z, 0.0f);
                 }
                 if (needSurf)
                 {
                     a.wb.surfA[p] = make_float4(frontPos.x, frontPos.y, frontPos.z, distance);
                     a.wb.surfB[p] = make_float4(s.wo.x, s.wo.y, s.wo.z, __uint_as_float((uint32_t)face | (matIndex << 3)));
+                    if (kTex)
+                    {
+                        a.wb.surfC[p] = make_float4(s.normal.x, s.normal.y, s.normal.z, s.roughness);
+                        a.wb.surfD[p] = make_float4(s.albedo.x, s.albedo.y, s.albedo.z, s.metallic ? 1.0f : 0.0f);
+                    }
                 }
             }
         }
@@ -862,7 +944,7 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(co
 
 // ------------------------------------------------------------------------------------------------ S2
 // RIS: classify the BSDF candidate, merge the three reservoirs, cast the winner's visibility ray (closesthit.cu:470-634).
-__global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
@@ -877,7 +959,7 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade2Kernel(co
     {
         const PathId id = pathId(a, p);
         Ctx c = makeCtx(a, id, (int)((fl >> kRandShift) & 0xffu));
-        const Surface s = loadSurface(a, p, depth);
+        const Surface s = loadSurface<kTex>(a, p, depth);
         const f3 sunD = c.sunDir();
         const bool skipSun = (dot(s.normal, sunD) < 0.0f || dot(s.geoNormal, sunD) < 0.0f);
         const int nSun = skipSun ? 0 : 1;
@@ -1020,7 +1102,7 @@ VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float
 
 // ------------------------------------------------------------------------------------------------ S3
 // Temporal ReSTIR: candidates from the previous frame + the bias-correction rays (closesthit.cu:636-760).
-__global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
+template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
@@ -1033,7 +1115,7 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const
     {
         const PathId id = pathId(a, p);
         Ctx c = makeCtx(a, id, (int)((fl >> kRandShift) & 0xffu));
-        const Surface s = loadSurface(a, p, 0);
+        const Surface s = loadSurface<kTex>(a, p, 0);
         VptReservoir ris = loadRis(a, p);
         LightSample lightSample = loadLight(a.wb.lightA, a.wb.lightB, p);
         // resolve the RIS winner's visibility (closesthit.cu:602-634)
@@ -1196,7 +1278,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_const
 
 // ------------------------------------------------------------------------------------------------ S5
 // Shade with the surviving reservoir, store it, accumulate, spawn the continuation ray (closesthit.cu:822-851, RayGen.cu:71-84).
-__global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, int *__restrict__ nextList,
                                                               unsigned *nextCount, unsigned *qCount)
 {
@@ -1213,7 +1295,7 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const
         const PathId id = pathId(a, p);
         if (fl & F_RIS)
         {
-            const Surface s = loadSurface(a, p, depth);
+            const Surface s = loadSurface<kTex>(a, p, depth);
             const bool useRestir = (fl & F_RESTIR) != 0;
             VptReservoir shading;
             LightSample lightSample;
@@ -1270,7 +1352,7 @@ __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const
             th.x *= bo.x; th.y *= bo.y; th.z *= bo.z;
             a.wb.thr[p] = th;
             a.wb.org[p] = make_float4(sa.x, sa.y, sa.z, 0.0f);
-            a.wb.dirT[p] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+            a.wb.dirT[p] = make_float4(nd.x, nd.y, nd.z, nd.w); // .w = accumulated ray-cone width
             want = prepareRay(a.grid, xyz(sa), xyz(nd), 0.0f, (uint32_t)p, r);
             if (!want) { a.wb.hitPacked[p] = kHitMiss; a.wb.hitT[p] = kRayMax; }
             a.wb.pflag[p] = F_LIVE | (fl & (0xffu << kRandShift)) | (fl & (0xfu << kDiffuseShift));
@@ -1331,7 +1413,7 @@ static void carveAll(char *base, WaveBuffers &wb, int nSlots, int samples)
     const size_t N = (size_t)nSlots * samples, S = (size_t)nSlots;
     char *cur = base;
     carve(cur, wb.dirT, N); carve(cur, wb.org, N); carve(cur, wb.hitT, N); carve(cur, wb.hitPacked, N);
-    carve(cur, wb.surfA, N); carve(cur, wb.surfB, N); carve(cur, wb.pflag, N);
+    carve(cur, wb.surfA, N); carve(cur, wb.surfB, N); carve(cur, wb.surfC, N); carve(cur, wb.surfD, N); carve(cur, wb.pflag, N);
     carve(cur, wb.candA, N); carve(cur, wb.candB, N); carve(cur, wb.dir1, N);
     carve(cur, wb.ris, N); carve(cur, wb.lightA, N); carve(cur, wb.lightB, N);
     carve(cur, wb.vis1, N); carve(cur, wb.vis2, N); carve(cur, wb.vis4, N);
@@ -1375,6 +1457,8 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
     // gain — a shading kernel's thousands of pending CTAs keep back-filling the SMs, so the other part's 1024-thread
     // DDA CTA (173 KiB of shared memory) only gets in at the tail. One part unless the caller passes side streams.
     const int nParts = (overlap && nTiles >= 2) ? 2 : 1;
+    const bool tex = a.nTextures > 0;
+#define KTEX(k) (tex ? k<true> : k<false>)
 #define VPT_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
     for (int first = 0; first < shardSamples; first += maxSamplesInWave)
     {
@@ -1418,18 +1502,18 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
                 int *nextList = (depth + 1 < a.depthRounds) ? ((depth + 1) & 1 ? a.wb.listA : a.wb.listB) : nullptr;
                 const unsigned *listCount = cnt + kCntList + depth;
                 VPT_TRY(dda(pair, true, nullptr)); ++pair;
-                shade1Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
+                KTEX(shade1Kernel)<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
                 VPT_TRY(dda(pair, false, a.wb.vis1)); ++pair;
-                shade2Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
+                KTEX(shade2Kernel)<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
                 VPT_TRY(dda(pair, false, a.wb.vis2)); ++pair;
                 if (depth == 0 && restirWave)
                 {
-                    shade3Kernel<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
+                    KTEX(shade3Kernel)<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
                     VPT_TRY(dda(pair, false, a.wb.vis3)); ++pair;
                     shade4Kernel<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
                     VPT_TRY(dda(pair, false, a.wb.vis4)); ++pair;
                 }
-                shade5Kernel<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, nextList, cnt + kCntList + depth + 1, cnt + 2 * pair); ++nl; mark(1, st);
+                KTEX(shade5Kernel)<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, nextList, cnt + kCntList + depth + 1, cnt + 2 * pair); ++nl; mark(1, st);
             }
             {
                 TraceArgs acc = a;

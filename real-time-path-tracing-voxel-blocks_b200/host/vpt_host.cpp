@@ -463,6 +463,48 @@ extern "C" void vpt_sky_state(const VptSkyParams *p, const float *tables, float 
 }
 
 // ---- world chunk files (renderer/core/WorldSceneManager.cpp:240-308, 310-458; SceneConfig.cpp:95-148)
+// ---- texture mip chains (TextureManager.cu:82-115, 216-217, 395-411): 2x2 box average per channel, truncated, down to 4x4
+static int mipLevels(int width)
+{
+    if (width <= 0 || (width & (width - 1))) return -1;
+    int lg = 0;
+    while ((1 << lg) < width) ++lg;
+    return lg >= 2 ? lg - 1 : 1;
+}
+extern "C" int vpt_mip_chain_texels(int width)
+{
+    const int levels = mipLevels(width);
+    if (levels < 0) return 0;
+    long long n = 0;
+    for (int l = 0; l < levels; ++l) n += (long long)(width >> l) * (width >> l);
+    return n > 0x7fffffffLL ? 0 : (int)n;
+}
+extern "C" int vpt_build_mip_chain(const uint32_t *level0, int width, uint32_t *out)
+{
+    const int levels = mipLevels(width);
+    if (levels < 0 || !level0 || !out) return 0;
+    std::memcpy(out, level0, (size_t)width * width * 4);
+    const uint32_t *src = out;
+    uint32_t *dst = out + (size_t)width * width;
+    for (int l = 1; l < levels; ++l)
+    {
+        const int n = width >> l, sn = n * 2;
+        for (int y = 0; y < n; ++y)
+            for (int x = 0; x < n; ++x)
+            {
+                const uint32_t a = src[(size_t)(2 * y) * sn + 2 * x], b = src[(size_t)(2 * y) * sn + 2 * x + 1];
+                const uint32_t c = src[(size_t)(2 * y + 1) * sn + 2 * x], d = src[(size_t)(2 * y + 1) * sn + 2 * x + 1];
+                uint32_t v = 0;
+                for (int ch = 0; ch < 32; ch += 8) // (float sum) * 0.25 truncated == integer sum >> 2 (sum <= 1020 is exact in fp32)
+                    v |= ((((a >> ch) & 0xffu) + ((b >> ch) & 0xffu) + ((c >> ch) & 0xffu) + ((d >> ch) & 0xffu)) >> 2) << ch;
+                dst[(size_t)y * n + x] = v;
+            }
+        src = dst;
+        dst += (size_t)n * n;
+    }
+    return levels;
+}
+
 extern "C" void vpt_chunk_hash(const uint8_t *chunk, char *hex17)
 {
     unsigned long long hash = 1469598103934665603ull;               // FNV-1a 64 offset basis

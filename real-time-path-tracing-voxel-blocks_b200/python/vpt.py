@@ -41,7 +41,38 @@ EXPORTS = [
     "vpt_denoise_band", "vpt_camera_init", "vpt_camera_update", "vpt_camera_from_scene", "vpt_perlin_noise_chunks",
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
-    "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings"]
+    "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain"]
+
+
+def pack_textures(textures, slots, tex_size):
+    """Flatten a list of mip chains into the arrays vpt_set_textures takes (shared with the oracle binding)."""
+    widths = np.array([t[0].shape[0] for t in textures], np.int32)
+    levels = np.array([len(t) for t in textures], np.int32)
+    texels = np.concatenate([np.ascontiguousarray(l, np.uint32).ravel() for t in textures for l in t]) if textures else np.zeros(1, np.uint32)
+    slots = np.ascontiguousarray(slots, np.int32).reshape(-1, 4)
+    tex_size = np.ascontiguousarray(tex_size, np.float32).reshape(-1, 2)
+    assert slots.shape[0] == tex_size.shape[0]
+    return widths, levels, np.ascontiguousarray(texels), slots, tex_size
+
+
+def build_mip_chain(level0):
+    """vpt_build_mip_chain on one (n,n) uint32 RGBA8 image -> list of levels (host only)."""
+    level0 = np.ascontiguousarray(level0, np.uint32)
+    n = level0.shape[0]
+    total = lib().vpt_mip_chain_texels(n)
+    if total <= 0:
+        raise VptError("vpt_mip_chain_texels(%d) failed: textures must be square powers of two" % n)
+    out = np.zeros(total, np.uint32)
+    nl = lib().vpt_build_mip_chain(_p(level0), n, _p(out))
+    if nl <= 0:
+        raise VptError("vpt_build_mip_chain failed")
+    chain, off = [], 0
+    for l in range(nl):
+        w = n >> l
+        chain.append(out[off:off + w * w].reshape(w, w).copy())
+        off += w * w
+    return chain
 
 
 class VptError(RuntimeError):
@@ -275,6 +306,13 @@ class Vpt:
         b = np.ascontiguousarray(block_to_material, np.uint16)
         assert m.dtype.itemsize == 48 and b.size == 256
         _check(self.L.vpt_set_materials(self.ctx, _p(m), m.size, _p(b)), "vpt_set_materials")
+
+    def set_textures(self, textures, slots, tex_size):
+        """textures: list of (levels-list of (n,n) uint32 RGBA8 arrays); slots: (nMaterials,4) int32 albedo/normal/roughness/metallic
+        texture index or -1; tex_size: (nMaterials,2) float32 MaterialParameter::texSize. An empty list removes the textures."""
+        widths, levels, texels, slots, tex_size = pack_textures(textures, slots, tex_size)
+        _check(self.L.vpt_set_textures(self.ctx, len(textures), _p(widths), _p(levels), _p(texels), slots.shape[0], _p(slots), _p(tex_size)),
+               "vpt_set_textures")
 
     def set_sky(self, sky, sun, sky_alias, sun_alias, sun_dir):
         sky = np.ascontiguousarray(sky, np.float32)
