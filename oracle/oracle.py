@@ -169,6 +169,12 @@ def max_threads():
     return int(lib().orc_max_threads())
 
 
+def prepass_rotator(frame_index):
+    out = np.zeros(4, np.float32)
+    lib().orc_prepass_rotator(int(frame_index), _p(out))
+    return out
+
+
 class Oracle:
     def __init__(self, width, height):
         self.L = lib()

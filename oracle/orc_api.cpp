@@ -168,6 +168,7 @@ int orc_denoise(orc_ctx *c, const DenoisingParams *p, const Camera *cam, const C
     denoiseRun(c->sc, c->ds, *cam, *prevCam, *p, frameNum, iterationIndex);
     return 0;
 }
+void orc_prepass_rotator(int frameIndex, float *rot4) { prePassRotator(frameIndex, rot4); }
 // Single passes, for per-pass parity tests (same argument meaning as the kernels in Denoiser.cu)
 int orc_pass_temporal(orc_ctx *c, const DenoisingParams *p, const Camera *cam, const Camera *prevCam) { temporalAccumulation(c->sc, c->ds, *cam, *prevCam, *p); return 0; }
 int orc_pass_history_fix(orc_ctx *c, const Camera *cam) { historyFix(c->sc, c->ds, *cam); return 0; }

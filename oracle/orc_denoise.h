@@ -689,6 +689,145 @@ inline void atrous(Scene &sc, const std::vector<f4> &in, std::vector<f4> &out, c
         }
 }
 
+// ------------------------------------------------------------------ HitDistReconstruction<8,2> (HitDistReconstruction.h:50-161)
+// 5x5 weighted fill of the hit distance (illumination.w) into IlluminationPing. Default off in the shipped settings.
+inline float expApprox(float x) { return 1.0f / (x * x - x + 1.0f); }                                  // DenoiserCommon.h:62-65
+inline float expWeight(float x, float px, float py, float scale) { return expApprox(-scale * fabsf(x * px + py)); } // :67-70
+inline float gaussianWeight(float r) { return expf(-0.66f * r * r); }                                  // :48-51
+inline float bilateralWeight(float z, float zc)                                                         // :53-60
+{
+    const float t = fabsf(z - zc) * (1.0f / (fmaxr(fabsf(z), fabsf(zc)) + 1e-6f));
+    return linearStep(0.03f, 0.0f, t);
+}
+inline void hitDistReconstruction(Scene &sc, DenoiseState &ds)
+{
+    const int W = sc.width, H = sc.height;
+    const GBufferSet &g = sc.gb[sc.cur];
+    const f2 invRes = {1.0f / (float)W, 1.0f / (float)H};
+    // GetNormalWeightParams(1,1,1) (:11-17): the reference evaluates this in double (atan(m*0.75/(1.0-0.75)), 0.5f*M_PI/180)
+    const double lobeAngle = std::atan(1.0 * 0.75 / (1.0 - 0.75)) * (double)lerpf(1.0f, 1.0f, 1.0f);
+    const float nParam = (float)(1.0 / std::max(lobeAngle, (double)(0.5f * 3.14159265358979323846 / 180.0)));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+        {
+            const size_t pix = (size_t)y * W + x;
+            const float cz = fabsf(g.depth[pix]);
+            if (cz > kDenoisingRange) continue;
+            const f3 cn = xyz(g.normalRoughness[pix]);
+            const f4 ci = sc.illumination[pix];
+            const float chd = ci.w;
+            const f2 pixelUv = {((float)x + 0.5f) * invRes.x, ((float)y + 0.5f) * invRes.y};
+            float sumW = 1000.0f * (chd != 0.0f ? 1.0f : 0.0f);
+            float sumHD = chd * sumW;
+            for (int dy = -2; dy <= 2; ++dy)
+                for (int dx = -2; dx <= 2; ++dx)
+                {
+                    if (dx == 0 && dy == 0) continue;
+                    const f3 sn = xyz(ldc(g.normalRoughness, W, H, x + dx, y + dy));
+                    const float sz = fabsf(ldc(g.depth, W, H, x + dx, y + dy));
+                    float shd = ldc(sc.illumination, W, H, x + dx, y + dy).w;
+                    const float angle = acosApprox(saturate(dot(cn, sn)));
+                    const f2 uv = {pixelUv.x + (float)dx * invRes.x, pixelUv.y + (float)dy * invRes.y};
+                    float w = (saturate(uv.x) == uv.x && saturate(uv.y) == uv.y) ? 1.0f : 0.0f;   // IsInScreen (:43-46)
+                    w *= gaussianWeight(sqrtf((float)(dx * dx + dy * dy)) * 0.5f);
+                    w *= bilateralWeight(sz, cz);
+                    float dw = w * expWeight(angle, nParam, 0.0f, 3.0f);
+                    shd = dw == 0.0f ? 0.0f : shd;                                                  // Denanify
+                    dw *= (shd != 0.0f) ? 1.0f : 0.0f;
+                    sumHD += shd * dw;
+                    sumW += dw;
+                }
+            sumHD /= fmaxr(sumW, 1e-6f);
+            ds.ping[pix] = {ci.x, ci.y, ci.z, sumHD};
+        }
+}
+
+// ------------------------------------------------------------------ PrePass (PrePass.h:6-149)
+// 8-tap Poisson pre-blur of IlluminationPing into IlluminationBuffer, radius from the hit distance; rotator from
+// Weyl1D(0.5, frameIndex). Quirks kept: the G-buffer taps are read at round(floor(p)+0.5) = floor(p)+1 while the radiance
+// tap (a linear-filter texture fetch at a texel centre = that texel, clamp addressing) is read at floor(p).
+inline float weyl1D(float p, int n)                                                                      // DenoiserCommon.h:336-339
+{
+    const int32_t m = (int32_t)((uint32_t)n * 10368889u);   // int multiply wraps
+    float ip;
+    return modff(p + (float)m / 16777216.0f, &ip);
+}
+inline void prePassRotator(int frameIndex, float rot[4])
+{
+    const float angle = weyl1D(0.5f, frameIndex) * (90.0f * kPiOver180);
+    const float ca = cosf(angle), sa = sinf(angle);
+    rot[0] = ca; rot[1] = sa; rot[2] = -sa; rot[3] = ca;                                                 // GetRotator (:328-334)
+}
+inline float specMagicCurve(float roughness, float power = 0.25f)                                        // :390-395
+{
+    float f = 1.0f - exp2f(-200.0f * roughness * roughness);
+    f *= powf(saturate(roughness), power);
+    return f;
+}
+inline void prePass(Scene &sc, DenoiseState &ds, const Camera &cam, int frameIndex)
+{
+    const int W = sc.width, H = sc.height;
+    const GBufferSet &g = sc.gb[sc.cur];
+    const f2 invRes = {1.0f / (float)W, 1.0f / (float)H};
+    static const float kPoisson8[8][3] = {
+        {-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f}, {-0.3487388f, +0.4037880f, +0.5335386f},
+        {+0.1023042f, +0.6439373f, +0.6520134f}, {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
+        {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+    float rot[4];
+    prePassRotator(frameIndex, rot);
+    const float unproject = cam.tanHalfFov.x / (cam.resolution.x / 2);                                    // Camera.h:128-131
+    const float nParam = normalWeightParam2(1.0f, 0.25f * 0.5f);
+    std::vector<f4> out(sc.illumination);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+        {
+            const size_t pix = (size_t)y * W + x;
+            const float cz = g.depth[pix];
+            if (cz > kDenoisingRange) continue;
+            const float cMat = g.material[pix];
+            const f3 cn = xyz(g.normalRoughness[pix]);
+            const f3 cpos = worldPosFromPixel(cam, x, y, cz);
+            const f2 pixelUv = {((float)x + 0.5f) * invRes.x, ((float)y + 0.5f) * invRes.y};
+            f4 acc = ds.ping[pix];
+            const float frustumSize = (float)std::min(W, H) * unproject * cz;                             // PixelRadiusToWorld
+            const float hitDist = acc.w == 0.0f ? 1.0f : acc.w;
+            float blurRadius = 30.0f * saturate(hitDist / frustumSize);
+            if (acc.w == 0.0f) blurRadius = fmaxr(blurRadius, 1.0f);
+            // GetHitDistanceWeightParams(hitDist, 1/9) (:397-405)
+            const float norm = lerpf(0.0005f, 1.0f, fminr(1.0f / 9.0f, specMagicCurve(1.0f)));
+            const float hdA = 1.0f / norm, hdB = -(acc.w * hdA);
+            float weightSum = 1.0f;
+            for (int i = 0; i < 8; ++i)
+            {
+                const f2 rv = {kPoisson8[i][0] * rot[0] + kPoisson8[i][1] * rot[1], kPoisson8[i][0] * rot[2] + kPoisson8[i][1] * rot[3]};
+                f2 uv = {pixelUv.x * (float)W + rv.x * blurRadius, pixelUv.y * (float)H + rv.y * blurRadius};
+                uv = {floorf(uv.x) + 0.5f, floorf(uv.y) + 0.5f};
+                const int gx = (int)roundf(uv.x), gy = (int)roundf(uv.y);   // G-buffer tap (samplePosInt)
+                const int tx = (int)floorf(uv.x), ty = (int)floorf(uv.y);   // radiance tap (texel centre)
+                uv = {uv.x * invRes.x, uv.y * invRes.y};
+                const float sMat = ldc(g.material, W, H, gx, gy);
+                const f3 sn = xyz(ldc(g.normalRoughness, W, H, gx, gy));
+                const float sz = ldc(g.depth, W, H, gx, gy);
+                const f3 spos = worldPosFromPixel(cam, gx, gy, sz);
+                float w = (uv.x >= 0.0f && uv.x < 1.0f && uv.y >= 0.0f && uv.y < 1.0f) ? 1.0f : 0.0f; // IsInScreenNearest
+                w *= (sz < kDenoisingRange) ? 1.0f : 0.0f;
+                w *= (cMat == sMat) ? 1.0f : 0.0f;
+                w *= (fabsf(dot(spos - cpos, cn)) / cz > 0.003f) ? 0.0f : 1.0f;                          // GetPlaneDistanceWeight (:300-305)
+                w *= nonExpWeight(acosApprox(dot(cn, sn)), nParam, 0.0f);
+                f4 sv = ldc(ds.ping, W, H, tx, ty);
+                if (w == 0.0f) sv = F4(0.0f);                                                            // Denanify
+                w *= lerpf(0.2f, 1.0f, expWeight(sv.w, hdA, hdB, 3.0f));
+                w *= gaussianWeight(kPoisson8[i][2]);
+                weightSum += w;
+                acc += sv * w;
+            }
+            out[pix] = acc / weightSum;
+        }
+    sc.illumination.swap(out);
+}
+
 // ------------------------------------------------------------------ Denoiser::run (Denoiser.cu:24-408)
 // iterationIndex is the value AFTER the render's post-increment (GlobalSettings::iterationIndex).
 inline void denoiseRun(Scene &sc, DenoiseState &ds, const Camera &cam, const Camera &prevCam, const DenoisingParams &p,
@@ -700,8 +839,10 @@ inline void denoiseRun(Scene &sc, DenoiseState &ds, const Camera &cam, const Cam
     const int usedIter = iterationIndex > 0 ? iterationIndex - 1 : 0;
     if (p.enableFireflyFilter) fireflyFilter(sc, cam, usedIter & 1, 80.0f, 5.0f, 0.8f, 0.02f, p.phiLuminance);
     int finalBuf = 0; // 0 illum, 1 ping, 2 pong, 3 prevIllum
+    if (p.enableHitDistanceReconstruction) { hitDistReconstruction(sc, ds); finalBuf = 1; }
     for (size_t i = 0; i < npix; ++i)
         if (g.depth[i] > kDenoisingRange) ds.illumOutput[i] = sc.illumination[i]; // BufferCopySky
+    if (p.enablePrePass) prePass(sc, ds, cam, iterationIndex); // reads Ping (stale scratch when the reconstruction is off), writes Illumination
     if (frameNum == 0)
     {
         ds.prevIllum = sc.illumination; ds.prevFastIllum = sc.illumination;

@@ -529,13 +529,17 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
     launches += p->enableFireflyFilter ? 3 : 1; c->ranFirefly = true;
     if (p->enableFireflyFilter && (rc = halo(c->illumination, 4, 2))) return rc; // 5x5 noisy moments in HistoryClamping
     CU(rec(EV_FIREFLY));
+    int finalBuf = 0;
+    // HitDistReconstruction -> Ping, PrePass Ping -> Illumination (Denoiser.cu:86-119; off in the shipped settings). Their
+    // times are booked under the sky-copy stage.
+    if (p->enableHitDistanceReconstruction) { CU(launchHitDist(d)); launches++; finalBuf = 1; }
+    if (p->enablePrePass) { CU(launchPrePass(d, iterationIndex)); launches++; }
     if (frameNum == 0)
     {
         CU(launchFrame0Init(d)); launches++;
         if ((rc = halo(c->prevIllum, 4, 2))) return rc;
     }
     CU(rec(EV_SKY));
-    int finalBuf = 0;
     if (p->enableTemporalAccumulation && frameNum > 0)
     {
         // band mode: static camera or small motion — history taps stay within the guard band exchanged at the end of the last frame
@@ -608,8 +612,6 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
 int vpt_denoise(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex)
 {
     if (!c || !p || !cam || !prevCam) return fail(VPT_ERR_ARG, "vpt_denoise: null argument");
-    if (p->enableHitDistanceReconstruction || p->enablePrePass)
-        return fail(VPT_ERR_ARG, "vpt_denoise: HitDistReconstruction / PrePass are off in the shipped settings and not built (SURVEY 8a D2/D3)");
     CU(cudaSetDevice(c->device));
     // a pipelined read-back of the previous frame's planes must finish before this chain overwrites them (device-side wait)
     if (c->copyPending) { CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0)); c->copyPending = false; }

@@ -579,6 +579,116 @@ __global__ void __launch_bounds__(kBX *kBY) atrousFirstKernel(const __grid_const
     }
 }
 
+#ifndef VPT_ATROUS_V3
+#define VPT_ATROUS_V3 1
+#endif
+#ifndef VPT_ATROUS_MINB
+#define VPT_ATROUS_MINB 3
+#endif
+#if VPT_ATROUS_V3
+// Atrous (Atrous.h:6-158): 3x3 taps at stride `step`, hashed sub-stride jitter for step > 4. kComposite: the last
+// pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky, BufferCopy.h:36-116).
+// The pass is latency-bound when each tap's radiance load waits for that tap's weight (ncu r1g: issue 54 %, 7.4 stalled
+// cycles per issue on the long scoreboard): here the three loads of four taps at a time are issued back to back before any
+// of them is consumed, and CTAs whose taps cannot leave the image (all but the border ring) skip the clamp/inside logic.
+template <bool kComposite, bool kInterior>
+VPT_DEV void atrousBody(const AtrousArgs &a, int x, int y)
+{
+    const int W = a.W, H = a.H;
+    const int pix = y * W + x;
+    const float4 g = __ldg(a.G + pix);
+    if (g.w > kSkyZs) return;
+    const uint32_t cMat = __ldg(a.MQ + pix) & 0xffffu;
+    const float hl = __ldg(a.histLen + pix);
+    const f4 cv = F4(__ldg(a.in + pix));
+    const f3 cn = {g.x, g.y, g.z};
+    const int stepSize = (int)a.step;
+    float lobeFrac = a.lobeAngleFraction / sqrtf((float)stepSize);
+    lobeFrac = lerpf(0.99f, lobeFrac, saturate(hl / 5.0f));
+    const float cLum = luminance(xyz(cv));
+    const float phiInv = 1.0f / fmaxr(1.0e-4f, a.phiLuminance * sqrtf(cv.w));
+    const float nParam = normalWeightParam2(1.0f, lobeFrac);
+    const PlaneTest pt = planeTest(a.view, x, y, cn, g.w, a.depthThreshold);
+    float sumW = 0.44198f * 0.44198f;
+    f4 sum = cv * f4{sumW, sumW, sumW, sumW * sumW};
+    int offx = 0, offy = 0;
+    if (stepSize > 4)
+    {
+        uint32_t zorder = seqExplode((uint32_t)x) | (seqExplode((uint32_t)y) << 1);
+        uint32_t seed = seqHash(a.frameIndex + 0x035F9F29u);
+        uint32_t st = seed ^ (seqHash(zorder) + 0x9E3779B9u + (seed << 6) + (seed >> 2));
+        st = seqHash(st); const float u0 = st / 4294967295.0f;
+        st = seqHash(st); const float u1 = st / 4294967295.0f;
+        offx = (int)((float)stepSize * 0.5f * (u0 - 0.5f));
+        offy = (int)((float)stepSize * 0.5f * (u1 - 0.5f));
+    }
+    const int bx = x + offx, by = y + offy;
+    // tap coordinates are small integers: base + k*step in fp32 is exact, identical to converting the integer sum
+    const float fbx = (float)bx, fby = (float)by, fstep = (float)stepSize;
+    constexpr int tx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, ty[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+    {
+        float4 sg[4], sv[4];
+        uint32_t sm[4];
+        float fx[4], fy[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int t = half * 4 + k;
+            int sx = bx + tx[t] * stepSize, sy = by + ty[t] * stepSize;
+            if (kInterior) { ok[k] = true; fx[k] = fbx + (float)tx[t] * fstep; fy[k] = fby + (float)ty[t] * fstep; }
+            else
+            {
+                ok[k] = sx >= 0 && sy >= 0 && sx < W && sy < H;
+                sx = clampi(sx, 0, W - 1); sy = clampi(sy, 0, H - 1);
+                fx[k] = (float)sx; fy[k] = (float)sy;
+            }
+            const int sp = sy * W + sx;
+            sg[k] = __ldg(a.G + sp);
+            sm[k] = __ldg(a.MQ + sp);
+            sv[k] = __ldg(a.in + sp);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int t = half * 4 + k;
+            constexpr float k3[2] = {0.44198f, 0.27901f};
+            float w = k3[tx[t] & 1] * k3[ty[t] & 1];
+            w = (ok[k] && sg[k].w < kSkyZs && (sm[k] & 0xffffu) == cMat && planeNear(pt, sg[k].w, fx[k], fy[k])) ? w : 0.0f;
+            w *= normalWeight(dot(cn, F3(sg[k].x, sg[k].y, sg[k].z)), nParam);
+            if (w > 1e-4f)
+            {
+                const f4 v = F4(sv[k]);
+                const float lumW = fabsf(cLum - luminance(xyz(v))) * phiInv;
+                w *= __expf(-lumW);
+                sumW += w;
+                sum += f4{w, w, w, w * w} * v;
+            }
+        }
+    }
+    const f4 res = sum / f4{sumW, sumW, sumW, sumW * sumW};
+    if (kComposite)
+    {
+        const float4 al = __ldg(a.albedo + pix);
+        a.out[pix] = make_float4(res.x * al.x, res.y * al.y, res.z * al.z, 0.0f);
+    }
+    else
+        a.out[pix] = toFloat4(res);
+}
+template <bool kComposite>
+__global__ void __launch_bounds__(kBX *kAtrousBY, VPT_ATROUS_MINB) atrousKernel(const __grid_constant__ AtrousArgs a)
+{
+    const int x0 = blockIdx.x * kBX, y0 = a.rowBegin + blockIdx.y * kAtrousBY;
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= a.W || y >= a.rowEnd) return;
+    const int m = (int)a.step + (a.step > 4 ? (int)a.step / 4 + 1 : 0); // tap reach incl. the jitter (|off| <= step/4)
+    const bool interior = x0 - m >= 0 && x0 + kBX - 1 + m < a.W && y0 - m >= 0 && y0 + kAtrousBY - 1 + m < a.H; // CTA-uniform
+    if (interior) atrousBody<kComposite, true>(a, x, y);
+    else atrousBody<kComposite, false>(a, x, y);
+}
+#else
 // Atrous (Atrous.h:6-158): 3x3 taps at stride `step`, hashed sub-stride jitter for step > 4. kComposite: the last
 // pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky, BufferCopy.h:36-116).
 template <bool kComposite>
@@ -648,6 +758,122 @@ __global__ void __launch_bounds__(kBX *kAtrousBY) atrousKernel(const __grid_cons
     }
     else
         a.out[pix] = toFloat4(res);
+}
+
+#endif
+
+// ------------------------------------------------------------------------------------------------ HitDistReconstruction / PrePass
+// Both are off in the shipped settings (global_settings.yaml); they read the reference-layout planes directly.
+VPT_DEV float expApprox(float x) { return 1.0f / (x * x - x + 1.0f); }
+VPT_DEV float expWeight(float x, float px, float py, float scale) { return expApprox(-scale * fabsf(x * px + py)); }
+VPT_DEV float gaussianWeight(float r) { return __expf(-0.66f * r * r); }
+VPT_DEV float bilateralWeight(float z, float zc)
+{
+    const float t = fabsf(z - zc) * (1.0f / (fmaxr(fabsf(z), fabsf(zc)) + 1e-6f));
+    return linearStep(0.03f, 0.0f, t);
+}
+// HitDistReconstruction<8,2> (HitDistReconstruction.h:50-161): 5x5 weighted fill of illumination.w -> IlluminationPing
+__global__ void __launch_bounds__(kBX *kBY) hitDistKernel(int W, int H, int rowBegin, int rowEnd, float nParam, const float *__restrict__ depth,
+                                                          const float4 *__restrict__ normalRough, const float4 *__restrict__ illum, float4 *__restrict__ ping)
+{
+    PIXEL_GUARD(W, rowBegin, rowEnd)
+    const float cz = fabsf(__ldg(depth + pix));
+    if (cz > kDenoisingRange) return;
+    const f3 cn = xyz(F4(__ldg(normalRough + pix)));
+    const float4 ci = __ldg(illum + pix);
+    const float chd = ci.w;
+    const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+    const float pu = ((float)x + 0.5f) * invW, pv = ((float)y + 0.5f) * invH;
+    float sumW = 1000.0f * (chd != 0.0f ? 1.0f : 0.0f);
+    float sumHD = chd * sumW;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx)
+        {
+            if (dx == 0 && dy == 0) continue;
+            const size_t sp = (size_t)clampi(y + dy, 0, H - 1) * W + clampi(x + dx, 0, W - 1);
+            const f3 sn = xyz(F4(__ldg(normalRough + sp)));
+            const float sz = fabsf(__ldg(depth + sp));
+            float shd = __ldg(illum + sp).w;
+            const float angle = acosApprox(saturate(dot(cn, sn)));
+            const float u = pu + (float)dx * invW, v = pv + (float)dy * invH;
+            float w = (saturate(u) == u && saturate(v) == v) ? 1.0f : 0.0f;
+            w *= gaussianWeight(sqrtf((float)(dx * dx + dy * dy)) * 0.5f);
+            w *= bilateralWeight(sz, cz);
+            float dw = w * expWeight(angle, nParam, 0.0f, 3.0f);
+            shd = dw == 0.0f ? 0.0f : shd;
+            dw *= (shd != 0.0f) ? 1.0f : 0.0f;
+            sumHD += shd * dw;
+            sumW += dw;
+        }
+    sumHD /= fmaxr(sumW, 1e-6f);
+    ping[pix] = make_float4(ci.x, ci.y, ci.z, sumHD);
+}
+
+// PrePass (PrePass.h:6-149): 8-tap Poisson pre-blur of IlluminationPing -> Illumination. The G-buffer taps sit one pixel
+// up/right of the radiance tap (round(floor(p)+0.5) vs the texel centre), as in the reference.
+struct PrePassArgs
+{
+    int W, H, rowBegin, rowEnd;
+    VptCamera cam;
+    float rot[4], hdA, nParam, unproject;
+    const float *depth, *material;
+    const float4 *normalRough, *ping;
+    float4 *illum;
+};
+__global__ void __launch_bounds__(kBX *kBY) prePassKernel(const __grid_constant__ PrePassArgs a)
+{
+    const int W = a.W, H = a.H;
+    PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
+    const float cz = __ldg(a.depth + pix);
+    if (cz > kDenoisingRange) return;
+    const Cam cam = loadCam(a.cam);
+    const float cMat = __ldg(a.material + pix);
+    const f3 cn = xyz(F4(__ldg(a.normalRough + pix)));
+    const f3 cpos = worldPosFromPixel(cam, x, y, cz);
+    const float pu = ((float)x + 0.5f) * cam.invResX, pv = ((float)y + 0.5f) * cam.invResY;
+    f4 acc = F4(__ldg(a.ping + pix));
+    // the blur radius positions the taps: exact class
+    const float frustumSize = __fmul_rn(__fmul_rn((float)min(W, H), a.unproject), cz);
+    const float hitDist = acc.w == 0.0f ? 1.0f : acc.w;
+    float blurRadius = __fmul_rn(30.0f, saturate(__fdiv_rn(hitDist, frustumSize)));
+    if (acc.w == 0.0f) blurRadius = fmaxr(blurRadius, 1.0f);
+    const float hdB = -(acc.w * a.hdA);
+    float weightSum = 1.0f;
+    const float poisson[8][3] = {
+        {-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f}, {-0.3487388f, +0.4037880f, +0.5335386f},
+        {+0.1023042f, +0.6439373f, +0.6520134f}, {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
+        {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        // tap position: every operation rounded separately (the floor() decides which texel is read)
+        const float rx = __fadd_rn(__fmul_rn(poisson[i][0], a.rot[0]), __fmul_rn(poisson[i][1], a.rot[1]));
+        const float ry = __fadd_rn(__fmul_rn(poisson[i][0], a.rot[2]), __fmul_rn(poisson[i][1], a.rot[3]));
+        const float fx = floorf(__fadd_rn(__fmul_rn(pu, (float)W), __fmul_rn(rx, blurRadius))) + 0.5f;
+        const float fy = floorf(__fadd_rn(__fmul_rn(pv, (float)H), __fmul_rn(ry, blurRadius))) + 0.5f;
+        const int gx = (int)roundf(fx), gy = (int)roundf(fy);
+        const int tx = (int)floorf(fx), ty = (int)floorf(fy);
+        const float u = fx * cam.invResX, v = fy * cam.invResY;
+        const size_t gp = (size_t)clampi(gy, 0, H - 1) * W + clampi(gx, 0, W - 1);
+        const float sMat = __ldg(a.material + gp);
+        const f3 sn = xyz(F4(__ldg(a.normalRough + gp)));
+        const float sz = __ldg(a.depth + gp);
+        const f3 spos = worldPosFromPixel(cam, gx, gy, sz);
+        float w = (u >= 0.0f && u < 1.0f && v >= 0.0f && v < 1.0f) ? 1.0f : 0.0f;
+        w *= (sz < kDenoisingRange) ? 1.0f : 0.0f;
+        w *= (cMat == sMat) ? 1.0f : 0.0f;
+        w *= (fabsf(dot(spos - cpos, cn)) / cz > 0.003f) ? 0.0f : 1.0f;
+        w *= nonExpWeight(acosApprox(dot(cn, sn)), a.nParam, 0.0f);
+        f4 sv = F4(__ldg(a.ping + (size_t)clampi(ty, 0, H - 1) * W + clampi(tx, 0, W - 1)));
+        if (w == 0.0f) sv = F4(0.0f);
+        w *= lerpf(0.2f, 1.0f, expWeight(sv.w, a.hdA, hdB, 3.0f));
+        w *= gaussianWeight(poisson[i][2]);
+        weightSum += w;
+        acc += sv * w;
+    }
+    a.illum[pix] = toFloat4(acc / weightSum);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -743,6 +969,35 @@ cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, 
     const dim3 grid((d.width + kBX - 1) / kBX, (d.rowEnd - d.rowBegin + kAtrousBY - 1) / kAtrousBY), block(kBX, kAtrousBY);
     if (composite) atrousKernel<true><<<grid, block, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
     else atrousKernel<false><<<grid, block, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
+    return cudaGetLastError();
+}
+cudaError_t launchHitDist(const DenoiseLaunch &d)
+{
+    // GetNormalWeightParams(1,1,1) (HitDistReconstruction.h:11-17), evaluated in double like the reference's literals
+    const double lobeAngle = std::atan(1.0 * 0.75 / (1.0 - 0.75));
+    const float nParam = (float)(1.0 / std::max(lobeAngle, (double)(0.5f * 3.14159265358979323846 / 180.0)));
+    hitDistKernel<<<gridFor(d), kBlock, 0, d.stream>>>(d.width, d.height, d.rowBegin, d.rowEnd, nParam, d.b.cur.depth, d.b.cur.normalRoughness,
+                                                       d.b.illumination, d.b.ping);
+    return cudaGetLastError();
+}
+cudaError_t launchPrePass(const DenoiseLaunch &d, int frameIndex)
+{
+    PrePassArgs a;
+    a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd; a.cam = d.cam;
+    // launch-uniform values on the host (same libm as the oracle): Weyl1D rotator (DenoiserCommon.h:328-339), hit-distance
+    // weight scale (:383-405 with roughness 1, nonLinearAccumSpeed 1/9), normal weight parameter
+    const int32_t m = (int32_t)((uint32_t)frameIndex * 10368889u);
+    float ip;
+    const float angle = std::modf(0.5f + (float)m / 16777216.0f, &ip) * (90.0f * 0.017453292519943295f);
+    a.rot[0] = cosf(angle); a.rot[1] = sinf(angle); a.rot[2] = -a.rot[1]; a.rot[3] = a.rot[0];
+    const float smc = (1.0f - exp2f(-200.0f)) * powf(1.0f, 0.25f);
+    const float norm = 0.0005f + std::min(1.0f / 9.0f, smc) * (1.0f - 0.0005f);
+    a.hdA = 1.0f / norm;
+    const float tanHalf = 1.0f * 1.0f * 0.125f / (1.0f - 0.125f + 1e-6f);
+    a.nParam = 1.0f / std::max(atanf(tanHalf), 1e-6f);
+    a.unproject = d.cam.tanHalfFov[0] / (d.cam.resolution[0] / 2); // Camera::getPixelWorldSizeScaleToDepth (Camera.h:128-131)
+    a.depth = d.b.cur.depth; a.material = d.b.cur.material; a.normalRough = d.b.cur.normalRoughness; a.ping = d.b.ping; a.illum = d.b.illumination;
+    prePassKernel<<<gridFor(d), kBlock, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launchCompositeNonSky(const DenoiseLaunch &d, const float4 *finalBuf)

@@ -220,5 +220,7 @@ cudaError_t launchAtrousSmem(const DenoiseLaunch &d, const float4 *in, float4 *o
 cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step, bool composite);
 cudaError_t launchCompositeNonSky(const DenoiseLaunch &d, const float4 *finalBuf);
 cudaError_t launchFrame0Init(const DenoiseLaunch &d);
+cudaError_t launchHitDist(const DenoiseLaunch &d);                 // IlluminationBuffer.w -> IlluminationPing (default off)
+cudaError_t launchPrePass(const DenoiseLaunch &d, int frameIndex); // IlluminationPing -> IlluminationBuffer (default off)
 
 } // namespace vpt
