@@ -183,6 +183,24 @@ int vpt_set_sky(vpt_ctx *ctx, const float *skyRGBA, int skyW, int skyH, const fl
  * removes them. Must follow vpt_set_materials (same material count). */
 int vpt_set_textures(vpt_ctx *ctx, int nTextures, const int32_t *widths, const int32_t *levels, const uint32_t *texels, int nMaterials,
                      const int32_t *slots4, const float *texSize2);
+/* Asset tables: materials.yaml -> MaterialParameter rows in file order (materialId = index, MaterialManager.cpp:85-100;
+ * defaults MaterialDefinition.h:18-28; metallic float -> bool; emissive materials carry emissive_radiance in albedo, :151-167) and
+ * blocks.yaml -> block id -> material index (MaterialManager.cpp:104-120; unmapped -> 0). paths (may be NULL) receives the texture
+ * files of each material as the reference resolves them ("data/" + the YAML value, AssetRegistry.cpp:86-97), "" = none.
+ * blocksYamlPath / blockToMaterial256 may be NULL. Host only. */
+typedef struct VptMaterialTexturePaths
+{
+    char albedo[256];
+    char normal[256];
+    char roughness[256];
+    char metallic[256];
+} VptMaterialTexturePaths;
+int vpt_load_materials(const char *materialsYamlPath, const char *blocksYamlPath, VptMaterial *materials, VptMaterialTexturePaths *paths,
+                       int maxMaterials, int *count, uint16_t *blockToMaterial256);
+/* PNG decode to RGBA8 words (r = low byte), what stbi_load gives TextureManager::init (TextureManager.cu:178-200): 8/16-bit grey,
+ * grey+alpha, RGB, palette, RGBA; non-interlaced. Grey is replicated to rgb, missing alpha = 255. out == NULL only queries
+ * width/height/channels (channels = the file's channel count, as stb reports it). Host only. */
+int vpt_load_png_rgba8(const char *path, uint32_t *out, size_t maxTexels, int *width, int *height, int *channels);
 /* Mip chain of one square power-of-two RGBA8 image the way TextureManager::init builds it (renderer/assets/TextureManager.cu:
  * 82-115, 216-217, 395-411): level l+1 = per-channel 2x2 box average of level l, truncated to 8 bits; levels stop at 4x4
  * (numLods = log2(width) - 1; images smaller than 4x4 keep 1 level). Host only. out receives all levels concatenated (the layout

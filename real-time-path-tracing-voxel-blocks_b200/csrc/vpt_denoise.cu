@@ -368,7 +368,10 @@ struct ClampArgs
     float *prevHistLen;
 };
 constexpr int kClampTW = kBX + 4, kClampTH = kBY + 4;
-__global__ void __launch_bounds__(kBX *kBY) historyClampKernel(const __grid_constant__ ClampArgs a)
+#ifndef VPT_HCLAMP_MINB
+#define VPT_HCLAMP_MINB 1
+#endif
+__global__ void __launch_bounds__(kBX *kBY, VPT_HCLAMP_MINB) historyClampKernel(const __grid_constant__ ClampArgs a)
 {
     // 12 channels per pixel: responsive YCoCg (3), its squares (3), noisy rgb (3), noisy luminance^2 (1), pad (2)
     __shared__ float4 tA[3][kClampTH][kClampTW];
@@ -493,7 +496,10 @@ VPT_DEV bool planeNear(const PlaneTest &p, float zsTap, float x, float y)
 }
 
 // AtrousSmem (AtrousSmem.h:66-303): first spatial pass on the freshly written history.
-__global__ void __launch_bounds__(kBX *kBY) atrousFirstKernel(const __grid_constant__ AtrousArgs a)
+#ifndef VPT_AFIRST_MINB
+#define VPT_AFIRST_MINB 3 // measured: 1 (101 regs) 72.5 us, 2 72.7, 3 (80 regs) 64.5, 4 (64 regs, spills) 71.7
+#endif
+__global__ void __launch_bounds__(kBX *kBY, VPT_AFIRST_MINB) atrousFirstKernel(const __grid_constant__ AtrousArgs a)
 {
     const int W = a.W, H = a.H;
     PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(kBX *kBY) atrousFirstKernel(const __grid_const
 #define VPT_ATROUS_V3 1
 #endif
 #ifndef VPT_ATROUS_MINB
-#define VPT_ATROUS_MINB 3
+#define VPT_ATROUS_MINB 5 // measured on B200 (r1 variants), three passes: 2 -> 253 us, 3 -> 185, 4 -> 165, 5 -> 159, 6 -> 159 (spills)
 #endif
 #if VPT_ATROUS_V3
 // Atrous (Atrous.h:6-158): 3x3 taps at stride `step`, hashed sub-stride jitter for step > 4. kComposite: the last

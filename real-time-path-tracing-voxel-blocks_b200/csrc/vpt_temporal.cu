@@ -183,7 +183,10 @@ struct TemporalArgs
     float *histLen;
     unsigned *fixCount; int *fixList; // pixels that end with historyLength <= 4: HistoryFix's work list
 };
-__global__ void __launch_bounds__(kBX *kBY, 3) temporalKernel(const __grid_constant__ TemporalArgs a)
+#ifndef VPT_TEMPORAL_MINB
+#define VPT_TEMPORAL_MINB 4 // measured: 2 -> 223 us, 3 (80 regs) -> 176, 4 (64 regs) -> 162, 5 -> 162
+#endif
+__global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(const __grid_constant__ TemporalArgs a)
 {
     const int W = a.W, H = a.H;
     // launch-uniform: rotation between the previous and current view directions, once per CTA

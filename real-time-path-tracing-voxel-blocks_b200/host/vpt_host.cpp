@@ -16,7 +16,10 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <fstream>
+#include <iterator>
+#include <map>
 #include <random>
 #include <sstream>
 #include <string>
@@ -463,6 +466,320 @@ extern "C" void vpt_sky_state(const VptSkyParams *p, const float *tables, float 
 }
 
 // ---- world chunk files (renderer/core/WorldSceneManager.cpp:240-308, 310-458; SceneConfig.cpp:95-148)
+// ---- material / block tables (AssetRegistry.cpp:60-150, 260-300; MaterialManager.cpp:58-120, 151-190; MaterialDefinition.h:18-28)
+namespace {
+struct YamlLine { int indent; std::string key, value; bool item; };
+// "  - key: value  # comment" -> indent of the key, item flag for a leading "- "; quotes stripped
+bool splitYamlLine(const std::string &raw, YamlLine &o)
+{
+    size_t i = 0;
+    while (i < raw.size() && raw[i] == ' ') ++i;
+    if (i >= raw.size() || raw[i] == '#') return false;
+    o.item = false;
+    if (raw[i] == '-' && i + 1 < raw.size() && raw[i + 1] == ' ') { o.item = true; i += 2; while (i < raw.size() && raw[i] == ' ') ++i; }
+    o.indent = (int)i;
+    const size_t colon = raw.find(':', i);
+    if (colon == std::string::npos) return false;
+    o.key = trim(raw.substr(i, colon - i));
+    std::string v = raw.substr(colon + 1);
+    bool inQuote = false;
+    for (size_t k = 0; k < v.size(); ++k)
+    {
+        if (v[k] == '"') inQuote = !inQuote;
+        else if (v[k] == '#' && !inQuote) { v = v.substr(0, k); break; }
+    }
+    v = trim(v);
+    if (v.size() >= 2 && v.front() == '"' && v.back() == '"') v = v.substr(1, v.size() - 2);
+    o.value = v;
+    return true;
+}
+void copyPath(char *dst, const std::string &v) { std::string p = "data/" + v; std::strncpy(dst, p.c_str(), 255); dst[255] = 0; }
+} // namespace
+
+extern "C" int vpt_load_materials(const char *materialsYamlPath, const char *blocksYamlPath, VptMaterial *materials, VptMaterialTexturePaths *paths,
+                                  int maxMaterials, int *count, uint16_t *blockToMaterial256)
+{
+    if (!materialsYamlPath || !materials || !count || maxMaterials <= 0) return VPT_ERR_ARG;
+    std::ifstream mf(materialsYamlPath);
+    if (!mf.is_open()) return VPT_ERR_IO;
+    std::map<std::string, int> idToIndex;
+    std::vector<std::array<float, 3>> emissive;
+    std::string line, sub;
+    int n = 0, itemIndent = -1;
+    bool inList = false;
+    while (std::getline(mf, line))
+    {
+        YamlLine y;
+        if (!splitYamlLine(line, y)) continue;
+        if (y.indent == 0) { inList = (y.key == "materials"); continue; }
+        if (!inList) continue;
+        if (y.item)
+        {
+            if (n >= maxMaterials) return VPT_ERR_ARG;
+            VptMaterial &m = materials[n];
+            std::memset(&m, 0, sizeof m);
+            m.albedo[0] = m.albedo[1] = m.albedo[2] = 1.0f; m.roughness = 0.5f; m.uvScale = 1.0f; // MaterialProperties defaults
+            m.materialId = n;
+            if (paths) std::memset(&paths[n], 0, sizeof paths[n]);
+            emissive.push_back({0.0f, 0.0f, 0.0f});
+            itemIndent = y.indent; sub.clear();
+            ++n;
+        }
+        if (n == 0) continue;
+        VptMaterial &m = materials[n - 1];
+        if (y.indent == itemIndent)
+        {
+            sub = (y.value.empty() && (y.key == "textures" || y.key == "properties")) ? y.key : std::string();
+            if (y.key == "id") idToIndex[y.value] = n - 1;
+            continue;
+        }
+        if (sub == "textures" && paths)
+        {
+            if (y.key == "albedo") copyPath(paths[n - 1].albedo, y.value);
+            else if (y.key == "normal") copyPath(paths[n - 1].normal, y.value);
+            else if (y.key == "roughness") copyPath(paths[n - 1].roughness, y.value);
+            else if (y.key == "metallic") copyPath(paths[n - 1].metallic, y.value);
+        }
+        else if (sub == "properties")
+        {
+            float f; int32_t b;
+            if (y.key == "albedo") parseFloat3(y.value, m.albedo);
+            else if (y.key == "roughness") parseFloat(y.value, m.roughness);
+            else if (y.key == "metallic") { if (parseFloat(y.value, f)) m.metallic = f != 0.0f ? 1 : 0; } // float -> bool (0.8 -> true)
+            else if (y.key == "uv_scale") parseFloat(y.value, m.uvScale);
+            else if (y.key == "translucency") parseFloat(y.value, m.translucency);
+            else if (y.key == "is_emissive") { if (parseBool(y.value, b)) m.isEmissive = b; }
+            else if (y.key == "is_thinfilm") { if (parseBool(y.value, b)) m.isThinfilm = b; }
+            else if (y.key == "use_world_grid_uv") { if (parseBool(y.value, b)) m.useWorldGridUV = b; }
+            else if (y.key == "emissive_radiance") parseFloat3(y.value, emissive[(size_t)n - 1].data());
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        if (materials[i].isEmissive) { materials[i].albedo[0] = emissive[(size_t)i][0]; materials[i].albedo[1] = emissive[(size_t)i][1]; materials[i].albedo[2] = emissive[(size_t)i][2]; }
+    *count = n;
+    if (n == 0) return VPT_ERR_IO; // "No materials found in registry" (MaterialManager.cpp:64-68)
+    if (blockToMaterial256)
+    {
+        std::memset(blockToMaterial256, 0, 256 * sizeof(uint16_t)); // unmapped blocks -> material 0 (getMaterialIndexForBlock default)
+        if (!blocksYamlPath) return VPT_OK;
+        std::ifstream bf(blocksYamlPath);
+        if (!bf.is_open()) return VPT_ERR_IO;
+        int blockId = -1; inList = false;
+        while (std::getline(bf, line))
+        {
+            YamlLine y;
+            if (!splitYamlLine(line, y)) continue;
+            if (y.indent == 0) { inList = (y.key == "blocks"); continue; }
+            if (!inList) continue;
+            if (y.item) { blockId = -1; itemIndent = y.indent; }
+            if (y.indent != itemIndent) continue;
+            if (y.key == "id") { int v; if (parseInt(y.value, v)) blockId = v; }
+            else if (y.key == "material" && blockId >= 0 && blockId < 256 && y.value != "null" && !y.value.empty())
+            {
+                auto it = idToIndex.find(y.value);
+                if (it != idToIndex.end()) blockToMaterial256[blockId] = (uint16_t)it->second;
+            }
+        }
+    }
+    return VPT_OK;
+}
+
+// ---- PNG reader (the reference decodes data/textures/*.png with stb_image, TextureManager.cu:178): 8/16-bit, grey / grey+alpha /
+// RGB / palette / RGBA, non-interlaced; zlib stream inflated here (stored, fixed and dynamic Huffman blocks). No dependency.
+namespace {
+struct BitReader
+{
+    const uint8_t *p, *end;
+    uint32_t acc = 0; int n = 0;
+    bool need(int k) { while (n < k) { if (p >= end) return false; acc |= (uint32_t)*p++ << n; n += 8; } return true; }
+    bool bits(int k, uint32_t &v) { if (k == 0) { v = 0; return true; } if (!need(k)) return false; v = acc & ((1u << k) - 1u); acc >>= k; n -= k; return true; }
+};
+struct Huffman
+{
+    uint16_t count[16], symbol[288];
+    void build(const uint8_t *len, int nsym)
+    {
+        std::memset(count, 0, sizeof count);
+        for (int i = 0; i < nsym; ++i) count[len[i]]++;
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + count[i];
+        for (int i = 0; i < nsym; ++i) if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
+    }
+    int decode(BitReader &br) const
+    {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l <= 15; ++l)
+        {
+            uint32_t b;
+            if (!br.bits(1, b)) return -1;
+            code |= (int)b;
+            const int c = count[l];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+bool inflateZlib(const uint8_t *src, size_t n, std::vector<uint8_t> &out, size_t expected)
+{
+    if (n < 6) return false;
+    BitReader br{src + 2, src + n};
+    out.clear(); out.reserve(expected);
+    static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint32_t final = 0;
+    while (!final)
+    {
+        uint32_t type;
+        if (!br.bits(1, final) || !br.bits(2, type)) return false;
+        if (type == 0)
+        {
+            br.acc = 0; br.n = 0; // byte align (the accumulator only ever holds bits of bytes already consumed)
+            if (br.end - br.p < 4) return false;
+            const unsigned len = br.p[0] | (br.p[1] << 8);
+            br.p += 4;
+            if ((size_t)(br.end - br.p) < len) return false;
+            out.insert(out.end(), br.p, br.p + len);
+            br.p += len;
+            continue;
+        }
+        if (type == 3) return false;
+        Huffman lit, dist;
+        uint8_t lens[320];
+        if (type == 1)
+        {
+            for (int i = 0; i < 144; ++i) lens[i] = 8;
+            for (int i = 144; i < 256; ++i) lens[i] = 9;
+            for (int i = 256; i < 280; ++i) lens[i] = 7;
+            for (int i = 280; i < 288; ++i) lens[i] = 8;
+            lit.build(lens, 288);
+            for (int i = 0; i < 30; ++i) lens[i] = 5;
+            dist.build(lens, 30);
+        }
+        else
+        {
+            uint32_t hlit, hdist, hclen;
+            if (!br.bits(5, hlit) || !br.bits(5, hdist) || !br.bits(4, hclen)) return false;
+            hlit += 257; hdist += 1; hclen += 4;
+            uint8_t cl[19] = {0};
+            for (uint32_t i = 0; i < hclen; ++i) { uint32_t v; if (!br.bits(3, v)) return false; cl[order[i]] = (uint8_t)v; }
+            Huffman clh; clh.build(cl, 19);
+            uint32_t i = 0;
+            while (i < hlit + hdist)
+            {
+                const int sym = clh.decode(br);
+                if (sym < 0) return false;
+                if (sym < 16) { lens[i++] = (uint8_t)sym; continue; }
+                uint32_t rep, prev = 0;
+                if (sym == 16) { if (i == 0) return false; prev = lens[i - 1]; if (!br.bits(2, rep)) return false; rep += 3; }
+                else if (sym == 17) { if (!br.bits(3, rep)) return false; rep += 3; }
+                else { if (!br.bits(7, rep)) return false; rep += 11; }
+                if (i + rep > hlit + hdist) return false;
+                while (rep--) lens[i++] = (uint8_t)prev;
+            }
+            lit.build(lens, (int)hlit);
+            dist.build(lens + hlit, (int)hdist);
+        }
+        for (;;)
+        {
+            const int sym = lit.decode(br);
+            if (sym < 0) return false;
+            if (sym < 256) { out.push_back((uint8_t)sym); continue; }
+            if (sym == 256) break;
+            if (sym > 285) return false;
+            uint32_t eb;
+            if (!br.bits(lext[sym - 257], eb)) return false;
+            const size_t len = lbase[sym - 257] + eb;
+            const int ds = dist.decode(br);
+            if (ds < 0 || ds > 29) return false;
+            if (!br.bits(dext[ds], eb)) return false;
+            const size_t d = dbase[ds] + eb;
+            if (d > out.size()) return false;
+            const size_t from = out.size() - d;
+            for (size_t k = 0; k < len; ++k) out.push_back(out[from + k]);
+        }
+    }
+    return true;
+}
+inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+} // namespace
+
+extern "C" int vpt_load_png_rgba8(const char *path, uint32_t *out, size_t maxTexels, int *width, int *height, int *channels)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) return VPT_ERR_IO;
+    std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 33 || std::memcmp(file.data(), sig, 8) != 0) return VPT_ERR_IO;
+    uint32_t W = 0, H = 0; int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, palette, trns;
+    size_t pos = 8;
+    while (pos + 12 <= file.size())
+    {
+        const uint32_t len = be32(&file[pos]);
+        const uint8_t *type = &file[pos + 4], *data = &file[pos + 8];
+        if (pos + 12 + (size_t)len > file.size()) return VPT_ERR_IO;
+        if (!std::memcmp(type, "IHDR", 4) && len >= 13) { W = be32(data); H = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12]; }
+        else if (!std::memcmp(type, "PLTE", 4)) palette.assign(data, data + len);
+        else if (!std::memcmp(type, "tRNS", 4)) trns.assign(data, data + len);
+        else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!std::memcmp(type, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (W == 0 || H == 0 || interlace != 0 || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8)) return VPT_ERR_IO;
+    const int nch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (nch == 0) return VPT_ERR_IO;
+    if (width) *width = (int)W;
+    if (height) *height = (int)H;
+    if (channels) *channels = ctype == 3 ? (trns.empty() ? 3 : 4) : nch; // what stbi_load(..., 0) reports
+    if (!out) return VPT_OK; // size query
+    if ((size_t)W * H > maxTexels) return VPT_ERR_ARG;
+    const size_t bpp = (size_t)nch * (depth / 8), stride = bpp * W;
+    std::vector<uint8_t> raw;
+    if (!inflateZlib(idat.data(), idat.size(), raw, (stride + 1) * H) || raw.size() < (stride + 1) * H) return VPT_ERR_IO;
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    for (uint32_t y = 0; y < H; ++y)
+    {
+        const uint8_t *row = &raw[(stride + 1) * y];
+        const int filter = row[0];
+        for (size_t i = 0; i < stride; ++i)
+        {
+            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+            int pred = 0;
+            if (filter == 1) pred = a;
+            else if (filter == 2) pred = b;
+            else if (filter == 3) pred = (a + b) >> 1;
+            else if (filter == 4) { const int pp = a + b - c, pa = std::abs(pp - a), pb = std::abs(pp - b), pc = std::abs(pp - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (filter != 0) return VPT_ERR_IO;
+            cur[i] = (uint8_t)(row[1 + i] + pred);
+        }
+        for (uint32_t x = 0; x < W; ++x)
+        {
+            const uint8_t *px = &cur[x * bpp];
+            const int s = depth / 8; // 16-bit samples: the high byte (stb's 8-bit conversion)
+            uint32_t r, g, b, al = 255;
+            if (ctype == 0) { r = g = b = px[0]; }
+            else if (ctype == 4) { r = g = b = px[0]; al = px[s]; }
+            else if (ctype == 2) { r = px[0]; g = px[s]; b = px[2 * s]; }
+            else if (ctype == 6) { r = px[0]; g = px[s]; b = px[2 * s]; al = px[3 * s]; }
+            else
+            {
+                const size_t k = px[0];
+                if (k * 3 + 2 >= palette.size()) return VPT_ERR_IO;
+                r = palette[k * 3]; g = palette[k * 3 + 1]; b = palette[k * 3 + 2];
+                if (k < trns.size()) al = trns[k];
+            }
+            out[(size_t)y * W + x] = r | (g << 8) | (b << 16) | (al << 24);
+        }
+        prev.swap(cur);
+    }
+    return VPT_OK;
+}
+
 // ---- texture mip chains (TextureManager.cu:82-115, 216-217, 395-411): 2x2 box average per channel, truncated, down to 4x4
 static int mipLevels(int width)
 {

@@ -99,6 +99,8 @@ int main(int argc, char *argv[])
     int width = 3840, height = 2160;
     std::string outputPrefix = "offline_render", sceneFile = "data/scene/scene_export.yaml";
     std::string settingsFile = "data/settings/global_settings.yaml", tablesFile = "data/bluenoise_tables.bin", skyTablesFile = "data/sky_tables.bin";
+    std::string assetsDir, dataRoot = "."; // --assets: materials.yaml/blocks.yaml directory (reference: data/assets); texture paths resolve against --data-root
+    bool useTextures = true;
     std::string worldChunkDir, saveWorldDir; // WorldSceneManager chunk storage: load the scene's "chunks:" records / save the world
     int totalFrames = 64;
     std::vector<int> savedFrames = {1, 4, 16, 64};
@@ -116,6 +118,9 @@ int main(int argc, char *argv[])
         else if (arg == "--settings" && i + 1 < argc) settingsFile = argv[++i];
         else if (arg == "--tables" && i + 1 < argc) tablesFile = argv[++i];
         else if (arg == "--sky-tables" && i + 1 < argc) skyTablesFile = argv[++i];
+        else if (arg == "--assets" && i + 1 < argc) assetsDir = argv[++i];
+        else if (arg == "--data-root" && i + 1 < argc) dataRoot = argv[++i];
+        else if (arg == "--no-textures") useTextures = false;
         else if (arg == "--world-chunks" && i + 1 < argc) worldChunkDir = argv[++i];
         else if (arg == "--save-world" && i + 1 < argc) saveWorldDir = argv[++i];
         else if (arg == "--test-canonical" || arg == "--test" || arg == "--update-canonical")
@@ -140,6 +145,7 @@ int main(int argc, char *argv[])
                         "  --test-canonical --update-canonical --canonical-image <path> --comment <text>\n"
                         "  --test-sequence --test-remove20 --test-remove-circle   (accepted, ignored)\n"
                         "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file> --sky-tables <file>\n"
+                        "  --assets <dir>  materials.yaml + blocks.yaml (reference: data/assets) with their textures under --data-root <dir> (default .); --no-textures\n"
                         "  --world-chunks <dir>  load the chunk files the scene lists (WorldSceneManager::LoadScene)   --save-world <dir>  write them\n", argv[0]);
             return 0;
         }
@@ -205,7 +211,55 @@ int main(int argc, char *argv[])
     }
     uint16_t b2m[256] = {0};
     for (int b = 1; b <= 12; ++b) b2m[b] = (uint16_t)(b - 1);
-    CHECK(vpt_set_materials(ctx, mats, 12, b2m));
+    if (assetsDir.empty()) CHECK(vpt_set_materials(ctx, mats, 12, b2m));
+    else
+    {
+        // AssetRegistry + MaterialManager::init + TextureManager::init (renderer/assets/): the reference's own tables and textures
+        std::vector<VptMaterial> am(256);
+        std::vector<VptMaterialTexturePaths> ap(256);
+        int nm = 0;
+        if (vpt_load_materials((assetsDir + "/materials.yaml").c_str(), (assetsDir + "/blocks.yaml").c_str(), am.data(), ap.data(), 256, &nm, b2m) != VPT_OK)
+        { std::fprintf(stderr, "Error: cannot load %s/materials.yaml + blocks.yaml\n", assetsDir.c_str()); return 1; }
+        CHECK(vpt_set_materials(ctx, am.data(), nm, b2m));
+        std::printf("Materials: %d from %s\n", nm, assetsDir.c_str());
+        if (useTextures)
+        {
+            std::vector<std::string> names;            // unique texture files, first use first
+            std::vector<int32_t> slots((size_t)nm * 4, -1), widths, levels;
+            std::vector<float> texSize((size_t)nm * 2, 1024.0f); // MaterialParameter::texSize default (SystemParameter.h:29)
+            std::vector<uint32_t> texels;
+            for (int m = 0; m < nm; ++m)
+            {
+                const char *pp[4] = {ap[(size_t)m].albedo, ap[(size_t)m].normal, ap[(size_t)m].roughness, ap[(size_t)m].metallic};
+                for (int k = 0; k < 4; ++k)
+                {
+                    if (!pp[k][0]) continue;
+                    const std::string file = dataRoot + "/" + (std::strncmp(pp[k], "data/", 5) == 0 ? pp[k] + 5 : pp[k]);
+                    size_t t = 0;
+                    while (t < names.size() && names[t] != file) ++t;
+                    if (t == names.size())
+                    {
+                        int w = 0, h = 0, ch = 0;
+                        if (vpt_load_png_rgba8(file.c_str(), nullptr, 0, &w, &h, &ch) != VPT_OK || w != h || vpt_mip_chain_texels(w) == 0)
+                        { std::fprintf(stderr, "Warning: texture %s missing or not a square power of two, slot left empty\n", file.c_str()); continue; }
+                        std::vector<uint32_t> img((size_t)w * h);
+                        if (vpt_load_png_rgba8(file.c_str(), img.data(), img.size(), &w, &h, &ch) != VPT_OK) continue;
+                        const size_t base = texels.size();
+                        texels.resize(base + (size_t)vpt_mip_chain_texels(w));
+                        levels.push_back(vpt_build_mip_chain(img.data(), w, texels.data() + base));
+                        widths.push_back(w);
+                        names.push_back(file);
+                    }
+                    slots[(size_t)m * 4 + k] = (int32_t)t;
+                }
+            }
+            if (!names.empty())
+            {
+                CHECK(vpt_set_textures(ctx, (int)names.size(), widths.data(), levels.data(), texels.data(), nm, slots.data(), texSize.data()));
+                std::printf("Textures: %zu files, %.1f MB of RGBA8 mip chains\n", names.size(), texels.size() * 4.0 / 1048576.0);
+            }
+        }
+    }
     // SkyModel::init/update (mainOffline.cpp:191 -> OfflineBackend::init -> SkyModel; Sky.cu:355-396): Hosek-Wilkie sky + solar
     // disc evaluated on the device from the "sky" section of the settings file
     {

@@ -42,7 +42,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8"]
 
 
 def pack_textures(textures, slots, tex_size):
@@ -54,6 +54,34 @@ def pack_textures(textures, slots, tex_size):
     tex_size = np.ascontiguousarray(tex_size, np.float32).reshape(-1, 2)
     assert slots.shape[0] == tex_size.shape[0]
     return widths, levels, np.ascontiguousarray(texels), slots, tex_size
+
+
+def load_png_rgba8(path):
+    """vpt_load_png_rgba8 -> ((h,w) uint32 RGBA8, channels)."""
+    w, h, ch = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().vpt_load_png_rgba8(path.encode(), None, C.c_size_t(0), C.byref(w), C.byref(h), C.byref(ch))
+    if rc != 0:
+        raise VptError("vpt_load_png_rgba8(%s) failed (%d)" % (path, rc))
+    out = np.zeros((h.value, w.value), np.uint32)
+    rc = lib().vpt_load_png_rgba8(path.encode(), _p(out), C.c_size_t(out.size), C.byref(w), C.byref(h), C.byref(ch))
+    if rc != 0:
+        raise VptError("vpt_load_png_rgba8(%s) failed (%d)" % (path, rc))
+    return out, ch.value
+
+
+def load_materials(materials_yaml, blocks_yaml=None, max_materials=256):
+    """vpt_load_materials -> (materials structured array, block->material uint16[256], list of 4-tuples of texture paths)."""
+    import vpt_scenes as S
+    mats = np.zeros(max_materials, S.MATERIAL_DTYPE)
+    paths = np.zeros((max_materials, 4, 256), np.uint8)
+    b2m = np.zeros(256, np.uint16)
+    n = C.c_int()
+    rc = lib().vpt_load_materials(materials_yaml.encode(), blocks_yaml.encode() if blocks_yaml else None, _p(mats), _p(paths), max_materials,
+                                  C.byref(n), _p(b2m))
+    if rc != 0:
+        raise VptError("vpt_load_materials failed (%d)" % rc)
+    names = [tuple(bytes(paths[i, k]).split(b"\0")[0].decode() for k in range(4)) for i in range(n.value)]
+    return mats[:n.value].copy(), b2m, names
 
 
 def build_mip_chain(level0):

@@ -201,3 +201,196 @@ def test_textured_specular_chain_matches_oracle(oracle_lib):
     assert np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits"))
     m, outl, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
     assert m <= 1e-3 and outl <= 1e-2, (m, outl)
+
+
+# ---------------------------------------------------------------------------------------------- asset loaders (host only)
+MATERIALS_YAML = """# Material Definition File
+materials:
+  # terrain
+  - id: sand
+    name: "Sand Material"
+    textures:
+      albedo: "textures/sand_albedo.png"
+      normal: "textures/sand_normal.png"
+      roughness: "textures/sand_rough.png"
+    properties:
+      uv_scale: 2.5
+      use_world_grid_uv: true
+      roughness: 0.8
+      metallic: 0.0
+
+  - id: metal
+    name: "Metal # not a comment"
+    textures:
+      albedo: "textures/sand_albedo.png"   # shared file
+      metallic: "textures/metal_metal.png"
+    properties:
+      albedo: [0.9, 0.8, 0.7]
+      metallic: 0.8
+      translucency: 0.25
+      is_thinfilm: true
+
+  - id: lantern
+    name: "Lantern"
+    properties:
+      is_emissive: true
+      emissive_radiance: [10.0, 8.0, 6.0]
+"""
+BLOCKS_YAML = """blocks:
+  - id: 0
+    name: "Empty"
+    material: null
+  - id: 1
+    name: "Sand"
+    type: BlockTypeSand
+    material: sand
+    model: null
+  - id: 2
+    name: "Metal"
+    material: metal
+  - id: 13
+    name: "Lantern"
+    material: lantern
+    is_emissive: true
+  - id: 14
+    name: "Ghost"
+    material: does_not_exist
+"""
+
+
+def test_material_and_block_tables_loader(tmp_path):
+    """AssetRegistry / MaterialManager::init semantics: file order = material index, MaterialProperties defaults, metallic
+    float -> bool, emissive radiance moves into albedo, "data/" + texture path, unknown materials and unmapped blocks -> 0."""
+    import vpt
+    (tmp_path / "materials.yaml").write_text(MATERIALS_YAML)
+    (tmp_path / "blocks.yaml").write_text(BLOCKS_YAML)
+    m, b2m, names = vpt.load_materials(str(tmp_path / "materials.yaml"), str(tmp_path / "blocks.yaml"))
+    assert len(m) == 3 and list(m["materialId"]) == [0, 1, 2]
+    assert np.allclose(m["albedo"][0], 1.0) and m["roughness"][0] == np.float32(0.8) and m["uvScale"][0] == 2.5
+    assert m["useWorldGridUV"][0] == 1 and m["metallic"][0] == 0
+    assert np.allclose(m["albedo"][1], [0.9, 0.8, 0.7]) and m["metallic"][1] == 1 and m["roughness"][1] == 0.5 and m["uvScale"][1] == 1.0
+    assert m["translucency"][1] == 0.25 and m["isThinfilm"][1] == 1 and m["useWorldGridUV"][1] == 0
+    assert m["isEmissive"][2] == 1 and np.allclose(m["albedo"][2], [10.0, 8.0, 6.0])
+    assert names[0] == ("data/textures/sand_albedo.png", "data/textures/sand_normal.png", "data/textures/sand_rough.png", "")
+    assert names[1] == ("data/textures/sand_albedo.png", "", "", "data/textures/metal_metal.png") and names[2] == ("", "", "", "")
+    assert b2m[0] == 0 and b2m[1] == 0 and b2m[2] == 1 and b2m[13] == 2 and b2m[14] == 0 and b2m[200] == 0
+    with pytest.raises(vpt.VptError):
+        vpt.load_materials(str(tmp_path / "missing.yaml"))
+
+
+def test_reference_asset_tables_when_present():
+    """Live check in the build container: the reference's own data/assets tables give the 12 terrain materials of
+    vpt_scenes.default_materials() (roughness / uv scale / flags; the stand-in albedo differs by design)."""
+    import os
+    import vpt
+    root = "/root/reference/data/assets"
+    if not os.path.exists(root + "/materials.yaml"):
+        pytest.skip("reference tree not present")
+    m, b2m, names = vpt.load_materials(root + "/materials.yaml", root + "/blocks.yaml")
+    dm, db = S.default_materials()
+    for k in ("roughness", "uvScale", "metallic", "materialId", "useWorldGridUV", "isEmissive", "translucency"):
+        assert np.array_equal(m[:12][k], dm[k]), k
+    assert np.array_equal(b2m[1:13], db[1:13])
+    assert all(n[0].startswith("data/textures/") and n[0].endswith(".png") for n in names[:12])
+
+
+def test_png_reader_matches_pil(tmp_path):
+    """Every colour type / bit depth the reader takes, with stored, fixed-Huffman and dynamic-Huffman zlib streams."""
+    PIL = pytest.importorskip("PIL.Image")
+    import vpt
+    rng = np.random.default_rng(11)
+    n = 64
+    smooth = (np.add.outer(np.arange(n), np.arange(n)) * 2 % 256).astype(np.uint8)
+    noise = rng.integers(0, 256, (n, n), dtype=np.uint8)
+    cases = []
+    for name, base in (("smooth", smooth), ("noise", noise)):
+        rgb = np.stack([base, base.T, 255 - base], -1)
+        cases += [(name + "_L", PIL.fromarray(base, "L")), (name + "_RGB", PIL.fromarray(rgb, "RGB")),
+                  (name + "_RGBA", PIL.fromarray(np.concatenate([rgb, noise[..., None]], -1), "RGBA")),
+                  (name + "_LA", PIL.fromarray(np.stack([base, noise], -1), "LA")),
+                  (name + "_P", PIL.fromarray(rgb, "RGB").quantize(17))]
+    cases.append(("wide_L16", PIL.fromarray((smooth.astype(np.uint16) * 257), "I;16")))
+    for name, im in cases:
+        for level in (0, 1, 9):
+            path = str(tmp_path / ("%s_%d.png" % (name, level)))
+            im.save(path, compress_level=level)
+            got, ch = vpt.load_png_rgba8(path)
+            ref_im = PIL.open(path)
+            if ref_im.mode == "I;16":
+                ref = (np.asarray(ref_im) >> 8).astype(np.uint8)
+                ref = np.stack([ref, ref, ref, np.full_like(ref, 255)], -1)
+            else:
+                ref = np.asarray(ref_im.convert("RGBA"))
+            ref = ref.astype(np.uint32)
+            refw = ref[..., 0] | (ref[..., 1] << 8) | (ref[..., 2] << 16) | (ref[..., 3] << 24)
+            assert np.array_equal(got, refw), (name, level)
+    # non-square image, truncated file, not a PNG
+    PIL.fromarray(rng.integers(0, 256, (5, 9, 3), dtype=np.uint8), "RGB").save(str(tmp_path / "r.png"))
+    got, ch = vpt.load_png_rgba8(str(tmp_path / "r.png"))
+    assert got.shape == (5, 9) and ch == 3
+    data = open(str(tmp_path / "r.png"), "rb").read()
+    open(str(tmp_path / "trunc.png"), "wb").write(data[:len(data) // 2])
+    open(str(tmp_path / "junk.png"), "wb").write(b"not a png at all, just bytes" * 4)
+    for bad in ("trunc.png", "junk.png", "nope.png"):
+        with pytest.raises(vpt.VptError):
+            vpt.load_png_rgba8(str(tmp_path / bad))
+
+
+def test_reference_textures_decode_like_pil_when_present():
+    import os
+    PIL = pytest.importorskip("PIL.Image")
+    import vpt
+    d = "/root/reference/data/textures"
+    if not os.path.isdir(d):
+        pytest.skip("reference tree not present")
+    for f in ("rocky_trail_albedo.png", "rocky_trail_rough.png", "beaten-up-metal1_metal.png"):
+        got, ch = vpt.load_png_rgba8(os.path.join(d, f))
+        ref = np.asarray(PIL.open(os.path.join(d, f)).convert("RGBA")).astype(np.uint32)
+        assert np.array_equal(got, ref[..., 0] | (ref[..., 1] << 8) | (ref[..., 2] << 16) | (ref[..., 3] << 24)), f
+        chain = vpt.build_mip_chain(got)
+        assert len(chain) == 9 and chain[-1].shape == (4, 4)      # numLods = log2(1024) - 1 (TextureManager.cu:216-217)
+
+
+@pytest.mark.gpu
+def test_vpt_offline_with_asset_tables_and_textures(tmp_path):
+    """The offline entry end to end with an assets directory: materials.yaml + blocks.yaml + PNG textures are loaded, mip
+    chains built and the textured render differs from the flat-albedo one; frames are written like mainOffline does."""
+    import os
+    import subprocess
+    PIL = pytest.importorskip("PIL.Image")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "real-time-path-tracing-voxel-blocks_b200")
+    exe = os.path.join(pkg, "vpt_offline")
+    (tmp_path / "assets").mkdir()
+    (tmp_path / "textures").mkdir()
+    names = ["sand", "soil", "cliff", "trunk", "unused1", "unused2", "rocks", "grass", "stone", "plank", "wood", "leaves"]
+    mats = "materials:\n"
+    blocks = "blocks:\n  - id: 0\n    material: null\n"
+    for i, nme in enumerate(names):
+        mats += ("  - id: %s\n    textures:\n      albedo: \"textures/%s_albedo.png\"\n      normal: \"textures/n.png\"\n      roughness: \"textures/r.png\"\n"
+                 "    properties:\n      uv_scale: 2.5\n      use_world_grid_uv: true\n      roughness: 0.8\n" % (nme, nme))
+        blocks += "  - id: %d\n    material: %s\n" % (i + 1, nme)
+        img = procedural_texture(64, 40 + i)
+        rgba = np.stack([(img >> s) & 0xff for s in (0, 8, 16)], -1).astype(np.uint8)
+        PIL.fromarray(rgba, "RGB").save(str(tmp_path / "textures" / ("%s_albedo.png" % nme)))
+    nimg = procedural_texture(128, 7, "normal")
+    PIL.fromarray(np.stack([(nimg >> s) & 0xff for s in (0, 8, 16)], -1).astype(np.uint8), "RGB").save(str(tmp_path / "textures" / "n.png"))
+    PIL.fromarray(((procedural_texture(32, 9, "mono") & 0xff) // 2 + 100).astype(np.uint8), "L").save(str(tmp_path / "textures" / "r.png"))
+    (tmp_path / "assets" / "materials.yaml").write_text(mats)
+    (tmp_path / "assets" / "blocks.yaml").write_text(blocks)
+    (tmp_path / "scene.yaml").write_text("camera:\n  position: [35.6184, 11.8733, 42.0387]\n  direction: [-0.321564, -0.0129988, -0.946799]\n  up: [0, 1, 0]\n  fov: 90\n")
+    (tmp_path / "settings.yaml").write_text("denoising:\n  atrousIterationNum: 1\npostprocess:\n  manualExposure: 0.8\nsky:\n  timeOfDay: 0.25\n  sunAxisAngle: 45\n")
+    common_args = [exe, "--width", "320", "--height", "192", "--frames", "4", "--spp", "2", "--scene", str(tmp_path / "scene.yaml"),
+                   "--settings", str(tmp_path / "settings.yaml"), "--tables", os.path.join(pkg, "data", "bluenoise_tables.bin"),
+                   "--sky-tables", os.path.join(pkg, "data", "sky_tables.bin")]
+    a = subprocess.run(common_args + ["--output", str(tmp_path / "flat")], capture_output=True, text=True, timeout=300)
+    b = subprocess.run(common_args + ["--output", str(tmp_path / "tex"), "--assets", str(tmp_path / "assets"), "--data-root", str(tmp_path)],
+                       capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stdout[-2000:] + a.stderr[-2000:]
+    assert b.returncode == 0, b.stdout[-2000:] + b.stderr[-2000:]
+    assert "Materials: 12" in b.stdout and "Textures: 14 files" in b.stdout, b.stdout[-2000:]
+    fa = np.asarray(PIL.open(str(tmp_path / "flat_0004.png")).convert("RGB")).astype(np.float32)
+    fb = np.asarray(PIL.open(str(tmp_path / "tex_0004.png")).convert("RGB")).astype(np.float32)
+    assert fa.shape == fb.shape == (192, 320, 3)
+    assert np.abs(fa - fb).mean() > 2.0          # 8-bit levels: the textures are visible
+    assert fb.std() > 5.0 and np.isfinite(fb).all()
