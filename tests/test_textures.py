@@ -389,8 +389,8 @@ def test_vpt_offline_with_asset_tables_and_textures(tmp_path):
     assert a.returncode == 0, a.stdout[-2000:] + a.stderr[-2000:]
     assert b.returncode == 0, b.stdout[-2000:] + b.stderr[-2000:]
     assert "Materials: 12" in b.stdout and "Textures: 14 files" in b.stdout, b.stdout[-2000:]
-    fa = np.asarray(PIL.open(str(tmp_path / "flat_0004.png")).convert("RGB")).astype(np.float32)
-    fb = np.asarray(PIL.open(str(tmp_path / "tex_0004.png")).convert("RGB")).astype(np.float32)
+    fa = np.asarray(PIL.open(str(tmp_path / "flat_0003.png")).convert("RGB")).astype(np.float32)
+    fb = np.asarray(PIL.open(str(tmp_path / "tex_0003.png")).convert("RGB")).astype(np.float32)
     assert fa.shape == fb.shape == (192, 320, 3)
     assert np.abs(fa - fb).mean() > 2.0          # 8-bit levels: the textures are visible
     assert fb.std() > 5.0 and np.isfinite(fb).all()
