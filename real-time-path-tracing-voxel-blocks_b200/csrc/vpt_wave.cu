@@ -497,9 +497,27 @@ constexpr int kShadeThreads = 256;
 #endif
 constexpr int kCntWords = 256, kCntList = 128; // cnt[2k], cnt[2k+1] = count / cursor of the k-th DDA launch; cnt[128+d] = active paths at depth d
 
-// Queue reservation with ONE atomic per CTA. Every thread of the CTA calls it (convergent); n = entries wanted.
+#ifndef VPT_RESERVE_WARP
+#define VPT_RESERVE_WARP 0
+#endif
+// Queue reservation. Every thread of the CTA calls it (convergent); n = entries wanted. Default: ONE atomic per CTA (scan over
+// the CTA, three barriers). VPT_RESERVE_WARP=1: one atomic per warp and no barrier (A/B variant).
 VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
 {
+#if VPT_RESERVE_WARP
+    const unsigned lane = threadIdx.x & 31;
+    unsigned incl = n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (unsigned)off) incl += v;
+    }
+    unsigned base = 0;
+    if (lane == 31 && incl) base = atomicAdd(counter, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - n;
+#else
     __shared__ unsigned warpSum[kShadeThreads / 32];
     __shared__ unsigned ctaBase;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -523,6 +541,7 @@ VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
     const unsigned r = ctaBase + warpSum[warp] + incl - n;
     __syncthreads();
     return r;
+#endif
 }
 
 struct PathId { int p, slot, sl, px, py, k; bool inImage; };

@@ -5,7 +5,8 @@ NAME=$1; EXTRA=$2
 cd "$(dirname "$0")/../real-time-path-tracing-voxel-blocks_b200"
 B=build_$NAME; mkdir -p $B
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ -I../include"
-for f in wave denoise; do $NV -prec-div=false -prec-sqrt=false -ftz=true $EXTRA -c csrc/vpt_$f.cu -o $B/vpt_$f.o & done
+$NV -use_fast_math $EXTRA -c csrc/vpt_wave.cu -o $B/vpt_wave.o &
+for f in denoise; do $NV -prec-div=false -prec-sqrt=false -ftz=true $EXTRA -c csrc/vpt_$f.cu -o $B/vpt_$f.o & done
 for f in dda api; do $NV -prec-div=false -prec-sqrt=false $EXTRA -c csrc/vpt_$f.cu -o $B/vpt_$f.o & done
 $NV -prec-div=false -prec-sqrt=false $EXTRA -c csrc/vpt_temporal.cu -o $B/vpt_temporal.o &
 $NV -fmad=false $EXTRA -c csrc/vpt_grid.cu -o $B/vpt_grid.o &
