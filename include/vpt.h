@@ -168,6 +168,21 @@ int vpt_set_voxel(vpt_ctx *ctx, int x, int y, int z, int blockId);
 /* initVoxelsMultiChunk + GenerateVoxelChunk (voxelengine/VoxelSceneGen.cu:341-388, 61-165): noise is
  * chunks x 32 x 32 floats, noise[chunk][z][x]. Runs on the device. */
 int vpt_generate_terrain(vpt_ctx *ctx, int chunksX, int chunksY, int chunksZ, const float *noise);
+/* The block picker (VoxelEngine::performRayTraversal, voxelengine/VoxelEngine.cu:1040-1166; result type
+ * VoxelEngine.h:85-93): walks the resident grid from `origin` along `direction` (the reference passes camera.pos / camera.dir)
+ * with the reference's comparison order and tMax += tDelta accumulation, at most 1000 voxels, stopping when it leaves the
+ * grid (an origin outside the grid finds nothing). deletePos / deleteBlockId = first solid voxel; createPos = the last empty
+ * voxel before it. VoxelEngine::update (:906-985) then calls deleteBlock(deletePos) or addBlock(createPos, id): vpt_set_voxel. */
+typedef struct VptPickResult
+{
+    int32_t hasSpaceToCreate;
+    int32_t hitSurface;
+    int32_t createPos[3];
+    int32_t deletePos[3];
+    int32_t deleteBlockId;
+} VptPickResult;
+int vpt_pick_voxel(vpt_ctx *ctx, const float *origin /*[3]*/, const float *direction /*[3]*/, VptPickResult *out);
+
 /* MaterialManager (renderer/assets/MaterialManager.cpp:85-120): material table + block id -> material index. */
 int vpt_set_materials(vpt_ctx *ctx, const VptMaterial *materials, int count, const uint16_t *blockToMaterial /*[256]*/);
 /* SkyModel buffers (renderer/sky/Sky.cu:355-396): RGBA32F sky (equal-area sphere map) and sun-disk maps with

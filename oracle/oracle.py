@@ -217,6 +217,13 @@ class Oracle:
     def set_voxel(self, x, y, z, block_id):
         return self.L.orc_set_voxel(self.ctx, x, y, z, block_id)
 
+    def pick_voxel(self, origin, direction):
+        o = np.ascontiguousarray(origin, np.float32); d = np.ascontiguousarray(direction, np.float32)
+        out = np.zeros(9, np.int32)
+        self.L.orc_pick_voxel(self.ctx, _p(o), _p(d), _p(out))
+        return dict(hasSpaceToCreate=int(out[0]), hitSurface=int(out[1]), createPos=tuple(int(v) for v in out[2:5]),
+                    deletePos=tuple(int(v) for v in out[5:8]), deleteBlockId=int(out[8]))
+
     def set_materials(self, materials, block_to_material):
         m = np.ascontiguousarray(materials, MATERIAL_DTYPE)
         b = np.ascontiguousarray(block_to_material, np.uint16)

@@ -4,7 +4,9 @@
 #include "orc_denoise.h"
 #include "orc_sky.h"
 #include <omp.h>
+#include <cfloat>
 #include <cstdio>
+#include <cstring>
 
 using namespace orc;
 
@@ -122,6 +124,50 @@ void orc_tex_sample(orc_ctx *c, int tex, float u, float v, float lod, float *out
 {
     const f4 r = tex2DLod(c->sc.textures[(size_t)tex], u, v, lod);
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+// The block picker, restated from VoxelEngine::performRayTraversal (voxelengine/VoxelEngine.cu:1040-1166). out9 = hasSpaceToCreate,
+// hitSurface, createPos xyz, deletePos xyz, deleteBlockId.
+int orc_pick_voxel(orc_ctx *c, const float *origin, const float *direction, int32_t *out9)
+{
+    const Grid &g = c->sc.grid;
+    int32_t res[9] = {0, 0, -1, -1, -1, -1, -1, -1, -1};
+    const float len = std::sqrt(direction[0] * direction[0] + direction[1] * direction[1] + direction[2] * direction[2]);
+    if (!(len <= 1e-8f))
+    {
+        const int dims[3] = {g.W(), g.H(), g.D()};
+        float dir[3], tDelta[3], tNext[3];
+        int cell[3], inc[3];
+        for (int k = 0; k < 3; ++k)
+        {
+            dir[k] = direction[k] / len;
+            cell[k] = (int)std::floor(origin[k]);
+            inc[k] = dir[k] > 0.0f ? 1 : -1;
+            const bool flat = std::fabs(dir[k]) < 1e-8f;
+            tDelta[k] = flat ? FLT_MAX : 1.0f / std::fabs(dir[k]);
+            const float wall = inc[k] > 0 ? (float)(cell[k] + 1) : (float)cell[k];
+            tNext[k] = flat ? FLT_MAX : (wall - origin[k]) / dir[k];
+        }
+        for (int visited = 0; visited < 1000; ++visited)
+        {
+            bool inside = true;
+            for (int k = 0; k < 3; ++k) inside = inside && cell[k] >= 0 && cell[k] < dims[k];
+            if (!inside) break;
+            const int id = g.at(cell[0], cell[1], cell[2]);
+            if (id != 0)
+            {
+                res[1] = 1; res[5] = cell[0]; res[6] = cell[1]; res[7] = cell[2]; res[8] = id;
+                break;
+            }
+            res[0] = 1; res[2] = cell[0]; res[3] = cell[1]; res[4] = cell[2];
+            int k;
+            if (tNext[0] < tNext[1]) k = tNext[0] < tNext[2] ? 0 : 2;
+            else k = tNext[1] < tNext[2] ? 1 : 2;
+            cell[k] += inc[k];
+            tNext[k] += tDelta[k];
+        }
+    }
+    std::memcpy(out9, res, sizeof res);
+    return 0;
 }
 int orc_set_trace_params(orc_ctx *c, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir)
 {

@@ -52,6 +52,7 @@ struct vpt_ctx
     // materials / sky
     VptMaterial *materials = nullptr; int nMaterials = 0;
     uint16_t *blockToMaterial = nullptr;
+    VptPickResult *pickDev = nullptr;
     uint32_t *texels = nullptr; int4 *texDescs = nullptr, *matTexSlots = nullptr; float *matTexMip0Size = nullptr; int nTextures = 0;
     float4 *sky = nullptr, *sun = nullptr;
     VptAliasBin *skyAlias = nullptr, *sunAlias = nullptr;
@@ -261,6 +262,18 @@ int vpt_set_voxel(vpt_ctx *c, int x, int y, int z, int blockId)
     if (x < 0 || y < 0 || z < 0 || x >= c->cx * 32 || y >= c->cy * 32 || z >= c->cz * 32) return VPT_OK; // reference ignores out-of-range edits
     CU(cudaSetDevice(c->device));
     CU(launchSetVoxel(c->idsChunk, c->idsLinear, c->occ, &c->upH, c->cx, c->cy, c->cz, x, y, z, blockId, c->stream));
+    return VPT_OK;
+}
+
+int vpt_pick_voxel(vpt_ctx *c, const float *origin, const float *direction, VptPickResult *out)
+{
+    if (!c || !origin || !direction || !out) return fail(VPT_ERR_ARG, "vpt_pick_voxel: null argument");
+    if (!c->idsLinear) return fail(VPT_ERR_STATE, "vpt_pick_voxel: no grid set");
+    CU(cudaSetDevice(c->device));
+    if (!c->pickDev) CU(cudaMalloc((void **)&c->pickDev, sizeof(VptPickResult)));
+    CU(launchPick(c->idsLinear, c->cx, c->cy, c->cz, origin, direction, c->pickDev, c->stream));
+    CU(cudaMemcpyAsync(out, c->pickDev, sizeof(VptPickResult), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return VPT_OK;
 }
 

@@ -157,4 +157,56 @@ cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ,
     return cudaGetLastError();
 }
 
+// The block picker (VoxelEngine::performRayTraversal, voxelengine/VoxelEngine.cu:1040-1166): one Amanatides-Woo walk from the
+// camera along camera.dir over the resident ids, IEEE arithmetic throughout (this TU is built -fmad=false; divisions and the
+// square root are the round-to-nearest intrinsics), at most 1000 voxels, stops when it leaves the grid. One thread.
+__global__ void pickKernel(const uint8_t *__restrict__ idsLinear, int W, int H, int D, float ox, float oy, float oz, float dx, float dy, float dz,
+                           VptPickResult *out)
+{
+    VptPickResult r;
+    r.hasSpaceToCreate = 0; r.hitSurface = 0; r.deleteBlockId = -1;
+    for (int k = 0; k < 3; ++k) { r.createPos[k] = -1; r.deletePos[k] = -1; }
+    const float len = __fsqrt_rn(dx * dx + dy * dy + dz * dz);
+    if (!(len <= 1e-8f))
+    {
+        const float o[3] = {ox, oy, oz}, d[3] = {__fdiv_rn(dx, len), __fdiv_rn(dy, len), __fdiv_rn(dz, len)};
+        const int dim[3] = {W, H, D};
+        int v[3], step[3];
+        float tDelta[3], tMax[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            v[k] = (int)floorf(o[k]);
+            step[k] = d[k] > 0.0f ? 1 : -1;
+            const bool flat = fabsf(d[k]) < 1e-8f;
+            tDelta[k] = flat ? 3.402823466e+38f : __fdiv_rn(1.0f, fabsf(d[k]));
+            const float boundary = step[k] > 0 ? (float)(v[k] + 1) : (float)v[k];
+            tMax[k] = flat ? 3.402823466e+38f : __fdiv_rn(boundary - o[k], d[k]);
+        }
+        for (int it = 0; it < 1000; ++it)
+        {
+            if (v[0] < 0 || v[0] >= W || v[1] < 0 || v[1] >= H || v[2] < 0 || v[2] >= D) break;
+            const int id = idsLinear[(size_t)v[0] + (size_t)W * ((size_t)v[2] + (size_t)D * (size_t)v[1])];
+            if (id == 0) { r.hasSpaceToCreate = 1; r.createPos[0] = v[0]; r.createPos[1] = v[1]; r.createPos[2] = v[2]; }
+            else
+            {
+                r.hitSurface = 1; r.deleteBlockId = id;
+                r.deletePos[0] = v[0]; r.deletePos[1] = v[1]; r.deletePos[2] = v[2];
+                break;
+            }
+            // x only when strictly smallest, y over z only when strictly smaller, z otherwise (the reference's comparison order)
+            const int axis = tMax[0] < tMax[1] ? (tMax[0] < tMax[2] ? 0 : 2) : (tMax[1] < tMax[2] ? 1 : 2);
+            v[axis] += step[axis];
+            tMax[axis] = tMax[axis] + tDelta[axis];
+        }
+        (void)dim;
+    }
+    *out = r;
+}
+cudaError_t launchPick(const uint8_t *idsLinear, int cx, int cy, int cz, const float *origin, const float *dir, VptPickResult *outDev, cudaStream_t s)
+{
+    pickKernel<<<1, 1, 0, s>>>(idsLinear, cx * 32, cy * 32, cz * 32, origin[0], origin[1], origin[2], dir[0], dir[1], dir[2], outDev);
+    return cudaGetLastError();
+}
+
 } // namespace vpt

@@ -190,6 +190,7 @@ cudaError_t launchSkySun(const float *sunDir, float brightness, const float *sol
 
 cudaError_t launchRepackGrid(const uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHDev, int *upHHost, int cx, int cy, int cz, cudaStream_t s);
 cudaError_t launchSetVoxel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *occ, int *upHHost, int cx, int cy, int cz, int x, int y, int z, int id, cudaStream_t s);
+cudaError_t launchPick(const uint8_t *idsLinear, int cx, int cy, int cz, const float *origin, const float *dir, VptPickResult *outDev, cudaStream_t s);
 cudaError_t launchGenerateTerrain(const float *noise, uint8_t *idsChunk, int cx, int cy, int cz, cudaStream_t s);
 
 // Pixel-space view-vector basis of the current camera: M*(u,v,1) = M0 + x*Mx + y*My (vpt_denoise.cu)

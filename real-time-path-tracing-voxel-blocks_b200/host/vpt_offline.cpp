@@ -7,8 +7,8 @@
 // (renderer/core/OfflineBackend.cpp:191-221: y-flip, clamp to [0,1], *255). Out of scope here, as in SURVEY §2:
 // the wall-clock / history dependent post effects (auto-exposure, bloom, lens flare, vignette); the deterministic part —
 // FilmicToneMapping with the manual exposure of the settings file, sRGB, the PNG conversion — runs on the device (vpt_tonemap),
-// scripted edit tests (--test-sequence / --test-remove20 / --test-remove-circle are accepted and ignored with a
-// notice), canonical comparison (the golden PNG is absent from the reference tree).
+// canonical comparison (the golden PNG is absent from the reference tree). The scripted edit tests (--test-sequence /
+// --test-remove20 / --test-remove-circle, mainOffline.cpp:168-188, 279-393) run through the picker: vpt_pick_voxel + vpt_set_voxel.
 // New flags of this build: --spp N, --bounces T D, --chunks X Y Z, --exposure E, --tables PATH, --sky-tables PATH.
 #include "../../include/vpt.h"
 #include <algorithm>
@@ -101,6 +101,11 @@ int main(int argc, char *argv[])
     std::string settingsFile = "data/settings/global_settings.yaml", tablesFile = "data/bluenoise_tables.bin", skyTablesFile = "data/sky_tables.bin";
     std::string assetsDir, dataRoot = "."; // --assets: materials.yaml/blocks.yaml directory (reference: data/assets); texture paths resolve against --data-root
     bool useTextures = true;
+    // scripted block edits (mainOffline.cpp:43-51, 168-188, 279-393): clicks are consumed by the next frame's VoxelEngine::update
+    bool enableTestSequence = false, enableRemovalStressTest = false, enableCircularRemovalTest = false;
+    const int removalTestClickCount = 20, circularTestViewDirections = 8, circularTestRemovalsPerDirection = 5;
+    const int circularTestTotalRemovals = circularTestViewDirections * circularTestRemovalsPerDirection;
+    const float circularYawAmplitude = 12.0f * 3.14159265358979323846f / 180.0f, circularPitchAmplitude = 6.0f * 3.14159265358979323846f / 180.0f;
     std::string worldChunkDir, saveWorldDir; // WorldSceneManager chunk storage: load the scene's "chunks:" records / save the world
     int totalFrames = 64;
     std::vector<int> savedFrames = {1, 4, 16, 64};
@@ -127,8 +132,9 @@ int main(int argc, char *argv[])
             std::printf("note: %s ignored (data/canonical/canonical_render.png is not part of the reference tree)\n", arg.c_str());
         else if (arg == "--canonical-image" && i + 1 < argc) ++i;
         else if (arg == "--comment" && i + 1 < argc) ++i;
-        else if (arg == "--test-sequence" || arg == "--test-remove20" || arg == "--test-remove-circle")
-            std::printf("note: %s ignored (scripted block edits are outside the hot path)\n", arg.c_str());
+        else if (arg == "--test-sequence") enableTestSequence = true;
+        else if (arg == "--test-remove20") enableRemovalStressTest = true;
+        else if (arg == "--test-remove-circle") enableCircularRemovalTest = true;
         else if (arg == "--frames" && i + 1 < argc)
         {
             totalFrames = std::atoi(argv[++i]);
@@ -143,7 +149,7 @@ int main(int argc, char *argv[])
             std::printf("Offline Voxel Path Tracer (B200-native hot path)\nUsage: %s [options]\n"
                         "  --width <int> --height <int> --output <prefix> --scene <file> --frames <int>\n"
                         "  --test-canonical --update-canonical --canonical-image <path> --comment <text>\n"
-                        "  --test-sequence --test-remove20 --test-remove-circle   (accepted, ignored)\n"
+                        "  --test-sequence --test-remove20 --test-remove-circle   scripted block edits through the picker (vpt_pick_voxel + vpt_set_voxel)\n"
                         "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file> --sky-tables <file>\n"
                         "  --assets <dir>  materials.yaml + blocks.yaml (reference: data/assets) with their textures under --data-root <dir> (default .); --no-textures\n"
                         "  --world-chunks <dir>  load the chunk files the scene lists (WorldSceneManager::LoadScene)   --save-world <dir>  write them\n", argv[0]);
@@ -279,6 +285,17 @@ int main(int argc, char *argv[])
     std::printf("Camera setup - Position: (%g, %g, %g)\nCamera setup - Direction: (%g, %g, %g)\nCamera setup - FOV: %g degrees\n",
                 camera.pos[0], camera.pos[1], camera.pos[2], camera.dir[0], camera.dir[1], camera.dir[2], fov);
 
+    // scripted click sequences (VoxelEngine::configureOfflineClickSequence): removal tests click block id 0, the placement test
+    // cycles 16, 0, 16 (VoxelEngine.cu:906-945). Block 16 is an instanced lantern mesh in the reference: here it is a plain voxel.
+    std::vector<int> clickSequence;
+    if (enableCircularRemovalTest) { clickSequence.assign((size_t)circularTestTotalRemovals, 0); std::printf("Offline circular removal test enabled: %d view directions, %d deletions each.\n", circularTestViewDirections, circularTestRemovalsPerDirection); }
+    else if (enableRemovalStressTest) { clickSequence.assign((size_t)removalTestClickCount, 0); std::printf("Offline removal stress test enabled: %d scripted deletions.\n", removalTestClickCount); }
+    size_t clickIndex = 0, defaultClickIndex = 0;
+    bool clickPending = false;
+    int removalClickCounter = 0, circularRemovalsPerformed = 0, lastCircularDirectionIndex = -1, blocksRemoved = 0, blocksPlaced = 0;
+    bool circularOrientationReset = false;
+    const float baseCameraYaw = camera.yaw, baseCameraPitch = camera.pitch;
+
     int iterationIndex = 0; // GlobalSettings::iterationIndex, reset for a fresh offline run (mainOffline.cpp:252)
     double traceMs = 0, denoiseMs = 0;
     const auto t0 = std::chrono::steady_clock::now();
@@ -286,7 +303,40 @@ int main(int argc, char *argv[])
     {
         const int frameNumber = f + 1;
         historyCamera = camera;
+        if (enableCircularRemovalTest)
+        {
+            if (circularRemovalsPerformed < circularTestTotalRemovals)
+            {
+                const int directionIndex = circularRemovalsPerformed / circularTestRemovalsPerDirection;
+                if (directionIndex != lastCircularDirectionIndex)
+                {
+                    const float angle = (float)directionIndex * (6.28318530717958647692f / (float)circularTestViewDirections);
+                    const float yawOffset = (float)(circularYawAmplitude * std::cos(angle)), pitchOffset = (float)(circularPitchAmplitude * std::sin(angle));
+                    camera.yaw = baseCameraYaw + yawOffset; camera.pitch = baseCameraPitch + pitchOffset;
+                    std::printf("CIRCULAR TEST: Switching to view direction #%d (yaw offset %g, pitch offset %g)\n", directionIndex + 1, yawOffset, pitchOffset);
+                    lastCircularDirectionIndex = directionIndex;
+                }
+            }
+            else if (!circularOrientationReset)
+            {
+                camera.yaw = baseCameraYaw; camera.pitch = baseCameraPitch; circularOrientationReset = true;
+                std::printf("CIRCULAR TEST: Restored base camera orientation after scripted removals.\n");
+            }
+        }
         vpt_camera_update(&camera);
+        // VoxelEngine::update (OfflineBackend::renderFrame -> VoxelEngine.cu:876-985): pick along the camera ray, apply a pending click
+        if (clickPending)
+        {
+            clickPending = false;
+            int blockId;
+            if (!clickSequence.empty()) { const size_t i = std::min(clickIndex, clickSequence.size() - 1); blockId = clickSequence[i]; if (i + 1 < clickSequence.size()) clickIndex = i + 1; else clickIndex = i; }
+            else { static const int defaultSequence[3] = {16, 0, 16}; blockId = defaultSequence[defaultClickIndex % 3]; ++defaultClickIndex; }
+            VptPickResult pick;
+            CHECK(vpt_pick_voxel(ctx, camera.pos, camera.dir, &pick));
+            if (pick.hitSurface) std::printf("CAMERA RAY DEBUG: Hit block at (%d,%d,%d)\n", pick.deletePos[0], pick.deletePos[1], pick.deletePos[2]);
+            if (blockId == 0) { if (pick.hitSurface) { CHECK(vpt_set_voxel(ctx, pick.deletePos[0], pick.deletePos[1], pick.deletePos[2], 0)); ++blocksRemoved; } }
+            else if (pick.hasSpaceToCreate && pick.hitSurface) { CHECK(vpt_set_voxel(ctx, pick.createPos[0], pick.createPos[1], pick.createPos[2], blockId)); ++blocksPlaced; }
+        }
         CHECK(vpt_render(ctx, &camera, &historyCamera, iterationIndex)); // render() post-increments the index
         ++iterationIndex;
         CHECK(vpt_denoise(ctx, &dn, &camera, &historyCamera, f, iterationIndex));
@@ -304,7 +354,33 @@ int main(int argc, char *argv[])
             if (!writePng(name, width, height, rgb)) std::fprintf(stderr, "Failed to save image to: %s\n", name);
             else std::printf("Saved frame %d/%d -> %s\n", frameNumber, totalFrames, name);
         }
+        if (enableCircularRemovalTest)
+        {
+            if (circularRemovalsPerformed < circularTestTotalRemovals)
+            {
+                ++circularRemovalsPerformed;
+                std::printf("CIRCULAR TEST: Frame %d deleting block #%d (direction %d, ID=0)...\n", frameNumber, circularRemovalsPerformed,
+                            std::min(circularTestViewDirections - 1, (circularRemovalsPerformed - 1) / circularTestRemovalsPerDirection) + 1);
+                clickPending = true;
+            }
+        }
+        else if (enableRemovalStressTest)
+        {
+            if (removalClickCounter < removalTestClickCount)
+            {
+                ++removalClickCounter;
+                std::printf("REMOVAL TEST: Frame %d deleting block #%d (ID=0)...\n", frameNumber, removalClickCounter);
+                clickPending = true;
+            }
+        }
+        else if (enableTestSequence && (frameNumber == 2 || frameNumber == 5 || frameNumber == 8))
+        {
+            std::printf("TEST FRAME %d: %s light block...\n", frameNumber, frameNumber == 5 ? "Removing" : "Placing");
+            clickPending = true;
+        }
     }
+    if (enableCircularRemovalTest || enableRemovalStressTest || enableTestSequence)
+        std::printf("Scripted edits: %d blocks removed, %d placed\n", blocksRemoved, blocksPlaced);
     const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::printf("Rendering completed successfully!\nAverage per frame: path trace %.3f ms, denoiser %.3f ms (device), whole %.3f ms (wall)\n",
                 traceMs / totalFrames, denoiseMs / totalFrames, wall / totalFrames);

@@ -42,7 +42,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel"]
 
 
 def pack_textures(textures, slots, tex_size):
@@ -328,6 +328,14 @@ class Vpt:
 
     def set_voxel(self, x, y, z, block_id):
         _check(self.L.vpt_set_voxel(self.ctx, x, y, z, block_id), "vpt_set_voxel")
+
+    def pick_voxel(self, origin, direction):
+        """vpt_pick_voxel -> dict(hasSpaceToCreate, hitSurface, createPos, deletePos, deleteBlockId)."""
+        o = np.ascontiguousarray(origin, np.float32); d = np.ascontiguousarray(direction, np.float32)
+        out = np.zeros(9, np.int32)
+        _check(self.L.vpt_pick_voxel(self.ctx, _p(o), _p(d), _p(out)), "vpt_pick_voxel")
+        return dict(hasSpaceToCreate=int(out[0]), hitSurface=int(out[1]), createPos=tuple(int(v) for v in out[2:5]),
+                    deletePos=tuple(int(v) for v in out[5:8]), deleteBlockId=int(out[8]))
 
     def set_materials(self, materials, block_to_material):
         m = np.ascontiguousarray(materials)
