@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small end-to-end case for compute-sanitizer memcheck: every kernel of the product path at a tiny size (trace with ReSTIR,
-continuation depth rounds, multi-wave, edits, generated sky, denoiser chain incl. firefly / history-fix lists, tone map)."""
+continuation depth rounds, multi-wave, edits, generated sky, denoiser chain incl. firefly / history-fix lists, tone map, textured materials, HitDistReconstruction / PrePass, the block picker)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,6 +22,17 @@ for f in range(6):
     g.denoise(p, cam, prev, f, f + 1)
     prev = cam
     cam = vpt.camera_set_yaw_pitch(cam, cam[15] + np.float32(0.01), cam[16])
+# textured materials + the default-off denoiser passes + the picker
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import test_textures as T
+g.set_textures(*T.textured_scene(vpt, len(mats), size=32))
+p2 = p.copy(); p2["enableHitDistanceReconstruction"] = 1; p2["enablePrePass"] = 1; p2["atrousIterationNum"] = 1
+for f in range(6, 9):
+    pk = g.pick_voxel(cam[6:9], cam[9:12])
+    if pk["hitSurface"]: g.set_voxel(*pk["deletePos"], 0)
+    g.render(cam, prev, f)
+    g.denoise(p2, cam, prev, f, f + 1)
+    prev = cam
 rgb8, ldr = g.tonemap(vpt.default_tonemapping_params())
 out = g.read("IlluminationOutput")
 assert np.isfinite(out).all() and rgb8.shape == (H, W, 3)
