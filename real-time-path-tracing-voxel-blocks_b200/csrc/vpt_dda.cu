@@ -27,6 +27,9 @@ constexpr int kDdaThreads = 1024;
 #ifndef VPT_DDA_REFILL
 #define VPT_DDA_REFILL 20
 #endif
+#ifndef VPT_DDA_BREAK
+#define VPT_DDA_BREAK 1
+#endif
 constexpr int kChunk = VPT_DDA_CHUNK;        // rays reserved per warp per atomic
 constexpr int kRefillBelow = VPT_DDA_REFILL; // re-arm idle lanes when <= this many lanes are live
 constexpr unsigned kFull = 0xffffffffu;
@@ -148,6 +151,21 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                 uint32_t word;
                 if (kSmem) word = occS[(unsigned)lin >> 5];
                 else word = __ldg(occG + ((unsigned)lin >> 5));
+#define VPT_DDA_ADVANCE()                                                                          \
+    do {                                                                                           \
+        const bool xy = tX < tY;                                                                   \
+        const float tA = xy ? tX : tY;                                                             \
+        const bool az = tA < tZ;                                                                   \
+        tCur = az ? tA : tZ;                                                                       \
+        const int dd = az ? (xy ? dX : dY) : dZ;                                                   \
+        /* tCur IS the advanced axis' tMax: three conditional adds, no dt select */                \
+        if (az && xy) tX = __fadd_rn(tX, dtX);                                                     \
+        if (az && !xy) tY = __fadd_rn(tY, dtY);                                                    \
+        if (!az) tZ = __fadd_rn(tZ, dtZ);                                                          \
+        lin += dd;                                                                                 \
+        lastD = dd;                                                                                \
+        if (kStats) stepsAcc += live ? 1u : 0u;                                                    \
+    } while (0)
                 if ((word >> (lin & 31)) & 1u)
                 {
                     // solid voxel or shell: once per ray (twice for a ray whose origin voxel lies before tmin)
@@ -160,21 +178,15 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                         live = false;
                         lin = parkLin; dX = 0; dY = 0; dZ = 0; // parked: steps in place on an empty spare word
                     }
+#if VPT_DDA_BREAK
+                    // leave the unrolled block: the divergent region then closes once per block, not once per step, and a
+                    // finished lane has nothing to do before the next ballot anyway
+                    else VPT_DDA_ADVANCE();
+                    break;
+#endif
                 }
                 // advance the axis with the smallest tMax: X<Y ? (X<Z ? X : Z) : (Y<Z ? Y : Z)  ==  A = min(X,Y); A<Z ? A : Z
-                const bool xy = tX < tY;
-                const float tA = xy ? tX : tY;
-                const bool az = tA < tZ;
-                tCur = az ? tA : tZ;
-                const int dd = az ? (xy ? dX : dY) : dZ;
-                const float dt = az ? (xy ? dtX : dtY) : dtZ;
-                const float tN = __fadd_rn(tCur, dt);
-                if (az && xy) tX = tN;
-                if (az && !xy) tY = tN;
-                if (!az) tZ = tN;
-                lin += dd;
-                lastD = dd;
-                if (kStats) stepsAcc += live ? 1u : 0u;
+                VPT_DDA_ADVANCE();
             }
             const unsigned act = __ballot_sync(kFull, live);
             if (act == 0u) break;

@@ -544,6 +544,17 @@ VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
 #endif
 }
 
+#ifndef VPT_PREFETCH
+#define VPT_PREFETCH 0 // measured on B200: shading 1.504 ms without, 1.524 ms with (CCTL.E.PF1 per plane): off
+#endif
+// A stage thread's first loads are a dependent chain (path flags -> liveness test -> the state planes): the planes' lines are
+// requested while the flags are still in flight (no register, no scoreboard; ncu r1i: 17 % of S1's stall samples sat there).
+template <typename T> VPT_DEV void prefetchL1(const T *ptr)
+{
+#if VPT_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#endif
+}
 struct PathId { int p, slot, sl, px, py, k; bool inImage; };
 VPT_DEV PathId pathId(const TraceArgs &a, int p)
 {
@@ -743,6 +754,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
     const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
     const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
+    if (act) { prefetchL1(a.wb.hitPacked + p); prefetchL1(a.wb.hitT + p); prefetchL1(a.wb.dirT + p); if (depth > 0) prefetchL1(a.wb.org + p); }
     const uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_LIVE);
     bool want = false;
@@ -970,6 +982,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
     const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
     const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
+    if (act) { prefetchL1(a.wb.surfA + p); prefetchL1(a.wb.surfB + p); prefetchL1(a.wb.candA + p); prefetchL1(a.wb.candB + p); prefetchL1(a.wb.dir1 + p); }
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS);
     bool want = false;
@@ -1121,11 +1134,20 @@ VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float
 
 // ------------------------------------------------------------------------------------------------ S3
 // Temporal ReSTIR: candidates from the previous frame + the bias-correction rays (closesthit.cu:636-760).
+#ifndef VPT_S3_UNROLL
+#define VPT_S3_UNROLL 0
+#endif
+#if VPT_S3_UNROLL
+#define VPT_S3_LOOP _Pragma("unroll")
+#else
+#define VPT_S3_LOOP _Pragma("unroll 1")
+#endif
 template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
     bool act = idx < a.partSlots;
+    if (act) { prefetchL1(a.wb.surfA + p); prefetchL1(a.wb.surfB + p); prefetchL1(a.wb.ris + p); prefetchL1(a.wb.lightA + p); prefetchL1(a.wb.lightB + p); }
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS) && (fl & F_RESTIR);
     unsigned nWant = 0;
@@ -1165,7 +1187,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MIN
         }
         unsigned cached = 0, rayMask = 0;
         int selectedLoopIdx = -1;
-#pragma unroll 1
+VPT_S3_LOOP
         for (int i = 0; i < nTemporal; ++i)
         {
             int ix = id.px + offx[i], iy = id.py + offy[i];
@@ -1191,7 +1213,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MIN
         const bool valid = isValidReservoir(restir);
         if (valid)
         {
-#pragma unroll 1
+VPT_S3_LOOP
             for (int i = 0; i < nTemporal; ++i)
             {
                 if ((cached & (1u << i)) == 0) continue;
@@ -1305,6 +1327,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
     const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
     const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
+    if (act) { prefetchL1(a.wb.surfA + p); prefetchL1(a.wb.surfB + p); prefetchL1(a.wb.ris + p); prefetchL1(a.wb.lightA + p); prefetchL1(a.wb.lightB + p); prefetchL1(a.wb.thr + p); }
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & (F_RIS | F_CONT));
     bool cont = false, want = false;
