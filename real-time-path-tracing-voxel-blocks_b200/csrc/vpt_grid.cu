@@ -73,6 +73,8 @@ __global__ void maxSolidYKernel(const uint8_t *__restrict__ idsLinear, int *upH,
 // Padded traversal masks (GridView): one thread per bit of the padded volume, x fastest, so the 32 lanes of a warp
 // are the 32 bits of one word -> __ballot_sync builds it. The one-voxel shell (and the row padding beyond it) is solid.
 // Mask 0 is the grid; mask 1 (the upward mask, for rays with dir.y > 0) is additionally solid from y = upH up.
+// Words are stored BIT-REVERSED (voxel k of a word at bit 31-k): the DDA tests `(int)(word << (lin & 31)) < 0`, a shift
+// whose count is the low five bits of lin as they are, and a sign test (2 instructions instead of shift + and + compare).
 __global__ void repackMaskKernel(const uint8_t *__restrict__ idsLinear, uint32_t *__restrict__ occ, int W, int H, int D, int Wp, int upH)
 {
     const int Dp = D + 2, Hp = H + 2;
@@ -90,8 +92,8 @@ __global__ void repackMaskKernel(const uint8_t *__restrict__ idsLinear, uint32_t
         if (x < 0 || y < 0 || z < 0 || x >= W || y >= H || z >= D) shell = true;
         else solid = __ldg(idsLinear + ((size_t)y * D + z) * W + x) != 0;
     }
-    const unsigned word0 = __ballot_sync(0xffffffffu, solid || shell);
-    const unsigned word1 = __ballot_sync(0xffffffffu, solid || shell || y >= upH);
+    const unsigned word0 = __brev(__ballot_sync(0xffffffffu, solid || shell));
+    const unsigned word1 = __brev(__ballot_sync(0xffffffffu, solid || shell || y >= upH));
     if ((threadIdx.x & 31) == 0)
     {
         if (i < total) { occ[i >> 5] = word0; occ[(total >> 5) + (i >> 5)] = word1; }
@@ -107,7 +109,7 @@ __global__ void setVoxelKernel(uint8_t *idsChunk, uint8_t *idsLinear, uint32_t *
     idsLinear[((size_t)y * D + z) * W + x] = (uint8_t)id;
     const size_t linP = ((size_t)(y + 1) * Dp + (z + 1)) * Wp + (x + 1);
     const size_t maskWords = (size_t)(Wp / 32) * (H + 2) * Dp;
-    const uint32_t bit = 1u << (linP & 31);
+    const uint32_t bit = 0x80000000u >> (linP & 31); // bit-reversed words
     uint32_t w = occ[linP >> 5];
     occ[linP >> 5] = id ? (w | bit) : (w & ~bit);
     if (y < upH) // above upH the upward mask stays solid
