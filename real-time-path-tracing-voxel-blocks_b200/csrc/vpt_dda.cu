@@ -30,6 +30,9 @@ constexpr int kDdaThreads = 1024;
 #ifndef VPT_DDA_UNROLL
 #define VPT_DDA_UNROLL 16 // steps between warp ballots; measured on B200 (DDA ms/frame): 3 -> 1.196, 4 -> 1.121, 6 -> 1.037, 8 -> 0.993, 12 -> 0.961, 16 -> 0.945, 24 -> 0.946, 32 -> 0.963
 #endif
+#ifndef VPT_DDA_MULHI
+#define VPT_DDA_MULHI 0 // lin >> 5 as IMAD.HI (fma pipe) instead of SHF + LOP3: measured slower (0.983 vs 0.943 ms)
+#endif
 #ifndef VPT_DDA_BREAK
 #define VPT_DDA_BREAK 1
 #endif
@@ -152,7 +155,11 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
             for (int u = 0; u < VPT_DDA_UNROLL; ++u)
             {
                 uint32_t word;
+#if VPT_DDA_MULHI
+                if (kSmem) word = occS[__umulhi((unsigned)lin, 0x08000000u)]; // lin >> 5 on the fma pipe (the alu pipe is the bottleneck)
+#else
                 if (kSmem) word = occS[(unsigned)lin >> 5];
+#endif
                 else word = __ldg(occG + ((unsigned)lin >> 5));
 #define VPT_DDA_ADVANCE()                                                                          \
     do {                                                                                           \
