@@ -9,7 +9,7 @@
 //    whole in shared memory, so a step is one LDS + bit test; worlds whose mask exceeds shared memory walk it
 //    through L1/L2 (kSmem = false).
 //  * the mask has a solid one-voxel shell: leaving the grid is "hitting" the shell — the step loop has NO bounds
-//    arithmetic. 22 SASS instructions per step. Rays with dir.y > 0 walk a second copy of the mask that is solid
+//    arithmetic. 18 SASS instructions per step (words are stored bit-reversed: shift + sign test). Rays with dir.y > 0 walk a second copy of the mask that is solid
 //    from the highest solid voxel up (GridView::upH): they retire as soon as nothing can be above them.
 //  * warp-level ray compaction: a warp reserves chunks of the prepared-ray queue (one atomic per 128 rays); whenever
 //    at most kRefillBelow lanes still hold a live ray, the idle lanes are re-armed from the queue
