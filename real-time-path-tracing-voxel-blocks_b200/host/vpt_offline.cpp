@@ -217,6 +217,12 @@ int main(int argc, char *argv[])
     }
     uint16_t b2m[256] = {0};
     for (int b = 1; b <= 12; ++b) b2m[b] = (uint16_t)(b - 1);
+    if (assetsDir.empty())
+    {
+        // the reference always loads data/assets relative to the working directory (AssetRegistry::loadFromYAML): do the same when it is there
+        std::ifstream probe("data/assets/materials.yaml");
+        if (probe.is_open()) { assetsDir = "data/assets"; if (dataRoot == ".") dataRoot = "data"; }
+    }
     if (assetsDir.empty()) CHECK(vpt_set_materials(ctx, mats, 12, b2m));
     else
     {
