@@ -401,9 +401,12 @@ struct Ctx
         const VptCamera &pc = a.prevCam;
         if (x < 0 || y < 0 || x >= pc.resolution[0] || y >= pc.resolution[1]) return false;
         const size_t i = (size_t)y * a.width + x;
-        s.depth = __ldg(a.prev.depth + i);
-        if (s.depth == kRayMax) return false;
+        // every plane of the pixel is requested before the depth test consumes the first: one round trip, not two
+        const float depth = __ldg(a.prev.depth + i);
         const float4 nr = __ldg(a.prev.normalRoughness + i), gt = __ldg(a.prev.geoNormalThinfilm + i), mp = __ldg(a.prev.materialParameter + i);
+        const float4 al = __ldg(a.prev.albedo + i);
+        s.depth = depth;
+        if (s.depth == kRayMax) return false;
         const float j0 = blueNoise(prevSampleIndex, 0), j1 = blueNoise(prevSampleIndex, 1);
         f2 prevUV = {(float(x) + j0) * pc.inversedResolution[0], (float(y) + j1) * pc.inversedResolution[1]};
         f3 viewDir = uvToWorldDirection(pc, prevUV);
@@ -411,7 +414,7 @@ struct Ctx
         s.wo = -viewDir;
         s.normal = xyz(nr);
         s.geoNormal = xyz(gt);
-        s.albedo = xyz(__ldg(a.prev.albedo + i));
+        s.albedo = xyz(al);
         s.roughness = nr.w;
         s.metallic = (mp.x == 1.0f);
         s.translucency = mp.y;
@@ -555,6 +558,10 @@ template <typename T> VPT_DEV void prefetchL1(const T *ptr)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 #endif
 }
+template <typename T> VPT_DEV void prefetchLine(const T *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+#ifndef VPT_S3_PREFETCH
+#define VPT_S3_PREFETCH 0 // measured on B200: prefetch.global.L1 of the candidates' lines makes S3 slower (shading 1.568 vs 1.514 ms)
+#endif
 struct PathId { int p, slot, sl, px, py, k; bool inImage; };
 VPT_DEV PathId pathId(const TraceArgs &a, int p)
 {
@@ -1185,6 +1192,24 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MIN
             const f2 dsk = concentricSampleDisk(c.rnd2()) * 64.0f;
             offx[2] = (int)dsk.x; offy[2] = (int)dsk.y;
         }
+#if VPT_S3_PREFETCH
+        // S3 is bound by its chain of dependent gathers (depth -> G-buffer planes -> reservoir -> sky texel, per candidate and
+        // again in the bias-correction loop: ~20 round trips per thread). The three candidates' previous-frame lines are
+        // requested up front, all in flight together; the loops below then find them in L1.
+#pragma unroll
+        for (int i = 0; i < nTemporal; ++i)
+        {
+            int ix = id.px + offx[i], iy = id.py + offy[i];
+            clampIntoView(ix, iy, a.width, a.height);
+            if (ix >= 0 && iy >= 0 && ix < a.width && iy < a.height)
+            {
+                const size_t q = (size_t)iy * a.width + ix;
+                prefetchLine(a.prev.depth + q); prefetchLine(a.prev.normalRoughness + q); prefetchLine(a.prev.geoNormalThinfilm + q);
+                prefetchLine(a.prev.materialParameter + q); prefetchLine(a.prev.albedo + q);
+                prefetchLine(a.resPrev + q); prefetchLine(reinterpret_cast<const char *>(a.resPrev + q) + 16);
+            }
+        }
+#endif
         unsigned cached = 0, rayMask = 0;
         int selectedLoopIdx = -1;
 VPT_S3_LOOP
@@ -1193,13 +1218,15 @@ VPT_S3_LOOP
             int ix = id.px + offx[i], iy = id.py + offy[i];
             clampIntoView(ix, iy, a.width, a.height);
             Surface ts;
+            // the candidate's reservoir travels with its surface planes (same pixel): requested before the validation
+            const bool inView = ix >= 0 && iy >= 0 && ix < a.width && iy < a.height; // getPrevSurface's own test
+            VptReservoir pr = inView ? loadPrevReservoir(a, ix, iy, mCap) : emptyReservoir();
             if (!c.getPrevSurface(ts, ix, iy)) continue;
             const bool nOk = dot(s.normal, ts.geoNormal) >= 0.5f;
             const bool dOk = fabsf(expectedPrevDepth - ts.depth) <= 0.1f * fmaxr(expectedPrevDepth, ts.depth);
             const bool rOk = fabsf(s.roughness - ts.roughness) <= 0.5f * fmaxr(s.roughness, ts.roughness);
             if (!(nOk && dOk && rOk)) continue;
             cached |= (1u << i);
-            VptReservoir pr = loadPrevReservoir(a, ix, iy, mCap);
             float neighborWeight = 0;
             LightSample cand = noLight();
             if (isValidReservoir(pr))
