@@ -9,7 +9,13 @@ namespace vpt {
 
 constexpr float kDenoisingRange = 500000.0f;
 constexpr float kSkyZs = 1.0e20f; // zs above this = sky (depth is kRayMax = 1e27 there)
-constexpr int kBX = 32, kBY = 8, kAtrousBY = 8; // (32x32 a-trous CTAs were measured slower: 71 vs 61 us)
+#ifndef VPT_DN_BY
+#define VPT_DN_BY 8
+#endif
+#ifndef VPT_ATROUS_BY
+#define VPT_ATROUS_BY 8
+#endif
+constexpr int kBX = 32, kBY = VPT_DN_BY, kAtrousBY = VPT_ATROUS_BY; // (32x32 a-trous CTAs were measured slower: 71 vs 61 us)
 
 // a*a - b*b style cancellations: no FMA contraction (the oracle is built -ffp-contract=off)
 VPT_DEV float subSq(float a, float b) { return __fsub_rn(a, __fmul_rn(b, b)); }

@@ -487,16 +487,22 @@ enum : uint32_t
     F_VISHAVE1 = 1u << 10 // the RIS winner's visibility was resolved (direction = lightA)
 };
 constexpr int kRandShift = 16, kDepthShift = 24, kDiffuseShift = 28;
-constexpr int kShadeThreads = 256;
-#define VPT_SHADE_MINB_DEFAULT 4
+// Stage CTAs: 128 threads. Measured on B200 (shading ms/frame, same register budgets): 512 -> 1.710, 256 -> 1.504, 128 -> 1.443,
+// 96 -> 1.473, 64 -> 1.439: the CTA-wide queue reservation (three barriers) stalls fewer warps in a smaller CTA, and 128 keeps
+// the same-address atomics at 65 k per launch. Resident CTAs per SM (register budget) per stage, from the same variant runs:
+// S1/S2 8 (64 regs; 7 -> 1.476, 10 -> 1.566), S3 7 (73 regs; 5 -> 1.485, 6 -> 1.443, 7 -> 1.434), S5 16 (12 -> 1.443, 16 -> 1.439).
+#ifndef VPT_SHADE_THREADS
+#define VPT_SHADE_THREADS 128
+#endif
+constexpr int kShadeThreads = VPT_SHADE_THREADS;
 #ifndef VPT_S3_MINB
-#define VPT_S3_MINB 3 // measured: S3 (temporal ReSTIR, the heaviest stage) prefers 3 CTAs/SM (85 regs), S5 6
+#define VPT_S3_MINB 7
 #endif
 #ifndef VPT_S5_MINB
-#define VPT_S5_MINB 6
+#define VPT_S5_MINB 16
 #endif
 #ifndef VPT_SHADE_MINB
-#define VPT_SHADE_MINB 4 // measured on B200 (r1 variants): 4 resident CTAs/SM (<= 64 regs) is the optimum for S1-S3: shade 1.94 -> 1.61 ms
+#define VPT_SHADE_MINB 8
 #endif
 constexpr int kCntWords = 256, kCntList = 128; // cnt[2k], cnt[2k+1] = count / cursor of the k-th DDA launch; cnt[128+d] = active paths at depth d
 
