@@ -511,7 +511,7 @@ constexpr int kCntWords = 256, kCntList = 128; // cnt[2k], cnt[2k+1] = count / c
 #endif
 // Queue reservation. Every thread of the CTA calls it (convergent); n = entries wanted. Default: ONE atomic per CTA (scan over
 // the CTA, three barriers). VPT_RESERVE_WARP=1: one atomic per warp and no barrier (A/B variant).
-VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
+template <int kSite = 0> VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
 {
 #if VPT_RESERVE_WARP
     const unsigned lane = threadIdx.x & 31;
@@ -547,9 +547,8 @@ VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
         ctaBase = tot ? atomicAdd(counter, tot) : 0u;
     }
     __syncthreads();
-    const unsigned r = ctaBase + warpSum[warp] + incl - n;
-    __syncthreads();
-    return r;
+    // no trailing barrier: a kernel's second reservation (S5) is another instantiation with its own shared words
+    return ctaBase + warpSum[warp] + incl - n;
 #endif
 }
 
@@ -1435,7 +1434,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
     }
     if (nextList)
     {
-        const unsigned lpos = ctaReserve(cont ? 1u : 0u, nextCount);
+        const unsigned lpos = ctaReserve<1>(cont ? 1u : 0u, nextCount);
         if (cont) nextList[lpos] = p;
     }
     const unsigned pos = ctaReserve(want ? 1u : 0u, qCount);
