@@ -28,10 +28,13 @@ constexpr int kDdaThreads = 1024;
 #define VPT_DDA_REFILL 20
 #endif
 #ifndef VPT_DDA_UNROLL
-#define VPT_DDA_UNROLL 16 // steps between warp ballots; measured on B200 (DDA ms/frame): 3 -> 1.196, 4 -> 1.121, 6 -> 1.037, 8 -> 0.993, 12 -> 0.961, 16 -> 0.945, 24 -> 0.946, 32 -> 0.963
+#define VPT_DDA_UNROLL 32 // closest-hit launches (coherent primary rays): 16 -> 0.947, 32 -> 0.933, 48 -> 0.939, 64 -> 0.933 ms of DDA per frame. Both kinds, earlier sweep: measured on B200 (DDA ms/frame): 3 -> 1.196, 4 -> 1.121, 6 -> 1.037, 8 -> 0.993, 12 -> 0.961, 16 -> 0.945, 24 -> 0.946, 32 -> 0.963
 #endif
 #ifndef VPT_DDA_MULHI
 #define VPT_DDA_MULHI 0 // lin >> 5 as IMAD.HI (fma pipe) instead of SHF + LOP3: measured slower (0.983 vs 0.943 ms)
+#endif
+#ifndef VPT_DDA_UNROLL_ANY
+#define VPT_DDA_UNROLL_ANY 16 // any-hit launches (ray lengths vary more): 8 -> 0.981, 12 -> 0.953, 16 -> 0.947, 24 -> 0.951
 #endif
 #ifndef VPT_DDA_BREAK
 #define VPT_DDA_BREAK 1
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         for (;;)
         {
 #pragma unroll
-            for (int u = 0; u < VPT_DDA_UNROLL; ++u)
+            for (int u = 0; u < (kClosest ? VPT_DDA_UNROLL : VPT_DDA_UNROLL_ANY); ++u)
             {
                 uint32_t word;
 #if VPT_DDA_MULHI
