@@ -13,6 +13,7 @@
 // is full of exact cancellations (dot == 0), which fast arithmetic turns into +-1e-9. Only the 12-tap history fetches
 // and the blends (no decisions) are the fast class.
 #include "vpt_denoise_common.cuh"
+#include <cmath>
 
 namespace vpt {
 
@@ -182,6 +183,7 @@ struct TemporalArgs
     float4 *ping, *pong;
     float *histLen;
     unsigned *fixCount; int *fixList; // pixels that end with historyLength <= 4: HistoryFix's work list
+    float prevToCur[4];               // Quat rotationBetween(prevCam.dir, cam.dir), xyz + w
 };
 #ifndef VPT_TEMPORAL_MINB
 #define VPT_TEMPORAL_MINB 4 // measured: 2 -> 223 us, 3 (80 regs) -> 176, 4 (64 regs) -> 162, 5 -> 162
@@ -189,16 +191,12 @@ struct TemporalArgs
 __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(const __grid_constant__ TemporalArgs a)
 {
     const int W = a.W, H = a.H;
-    // launch-uniform: rotation between the previous and current view directions, once per CTA
-    __shared__ quat prevToCurS;
-    if (threadIdx.x == 0 && threadIdx.y == 0)
-        prevToCurS = exRotationBetween(F3(a.prevCam.dir[0], a.prevCam.dir[1], a.prevCam.dir[2]), F3(a.cam.dir[0], a.cam.dir[1], a.cam.dir[2]));
-    __syncthreads();
     PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
     const float z = __ldg(a.depth + pix);
     if (z > a.denoisingRange) return;
     const Cam cam = loadCam(a.cam), prevCam = loadCam(a.prevCam);
-    const quat prevToCur = prevToCurS;
+    // launch-uniform: rotation between the previous and current view directions, evaluated on the host (hostRotationBetween)
+    const quat prevToCur = {F3(a.prevToCur[0], a.prevToCur[1], a.prevToCur[2]), a.prevToCur[3]};
     const f3 n = xyz(__ldg(a.normalRough + pix));
     // ---- exact class: the chain that decides historyLength
     const f2 curUV = {ex::mulf(ex::addf(float(x), 0.5f), cam.invResX), ex::mulf(ex::addf(float(y), 0.5f), cam.invResY)};
@@ -321,6 +319,49 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     }
 }
 
+// Host twin of exRotationBetween (same IEEE operations: products and sums rounded one by one, error-free transforms through
+// fmaf, correctly rounded sqrt and division), so the launch-uniform quaternion costs no barrier in the kernel. It used to be
+// computed by thread 0 of every CTA behind a __syncthreads (12 % of the kernel's stall samples, ncu r1k).
+namespace {
+struct HC { float v, err; };
+inline HC hTwoProd(float a, float b) { volatile float ab = a * b; return {ab, std::fmaf(a, b, -ab)}; }
+inline float hDop(float a, float b, float c, float d)
+{
+    volatile float cd = c * d;
+    const float err = std::fmaf(-c, d, cd);
+    const float r = std::fmaf(a, b, -cd);
+    volatile float s = r + err;
+    return s;
+}
+inline HC hTwoSum(float a, float b)
+{
+    volatile float s = a + b, delta = s - a;
+    volatile float t0 = s - delta, t1 = a - t0, t2 = b - delta, e = t1 + t2;
+    return {s, e};
+}
+inline float hInner3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    const HC p0 = hTwoProd(a0, b0), p1 = hTwoProd(a1, b1), p2 = hTwoProd(a2, b2);
+    const HC s12 = hTwoSum(p1.v, p2.v);
+    volatile float e0 = p2.err + s12.err, e1 = p1.err + e0;
+    const HC s = hTwoSum(p0.v, s12.v);
+    volatile float e2 = e1 + s.err, e3 = p0.err + e2, r = s.v + e3;
+    return r;
+}
+void hostRotationBetween(const float *p, const float *q, float *out4)
+{
+    const float cx = hDop(p[1], q[2], p[2], q[1]), cy = hDop(p[2], q[0], p[0], q[2]), cz = hDop(p[0], q[1], p[1], q[0]);
+    const float pp = hInner3(p[0], p[0], p[1], p[1], p[2], p[2]), qq = hInner3(q[0], q[0], q[1], q[1], q[2], q[2]);
+    const float pq = hInner3(p[0], q[0], p[1], q[1], p[2], q[2]);
+    volatile float ppqq = pp * qq;
+    volatile float w = std::sqrt((float)ppqq) + pq;
+    volatile float xx = cx * cx, yy = cy * cy, zz = cz * cz, ww = w * w;
+    volatile float s0 = xx + yy, s1 = s0 + zz, s2 = s1 + ww;
+    const float n = std::sqrt((float)s2);
+    out4[0] = cx / n; out4[1] = cy / n; out4[2] = cz / n; out4[3] = w / n;
+}
+} // namespace
+
 cudaError_t launchTemporal(const DenoiseLaunch &d)
 {
     const dim3 grid((d.width + kBX - 1) / kBX, (d.rowEnd - d.rowBegin + kBY - 1) / kBY), block(kBX, kBY);
@@ -334,6 +375,7 @@ cudaError_t launchTemporal(const DenoiseLaunch &d)
     a.normalRough = d.b.cur.normalRoughness; a.prevNormalRough = d.b.prev.normalRoughness;
     a.illum = d.b.illumination; a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum;
     a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength; a.fixCount = d.counters + 1; a.fixList = d.fixList;
+    hostRotationBetween(d.prevCam.dir, d.cam.dir, a.prevToCur);
     temporalKernel<<<grid, block, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
