@@ -184,6 +184,7 @@ struct TemporalArgs
     float *histLen;
     unsigned *fixCount; int *fixList; // pixels that end with historyLength <= 4: HistoryFix's work list
     float prevToCur[4];               // Quat rotationBetween(prevCam.dir, cam.dir), xyz + w
+    float invW, invH, disThr, unproject; // launch-uniform IEEE quotients / sums, evaluated once on the host
 };
 #ifndef VPT_TEMPORAL_MINB
 #define VPT_TEMPORAL_MINB 4 // measured: 2 -> 223 us, 3 (80 regs) -> 176, 4 (64 regs) -> 162, 5 -> 162
@@ -223,19 +224,17 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     nAvg = exDiv3(nAvg, 9.0f);
     const float m1 = luminance(illum), m2 = m1 * m1;
     // ---- exact class: everything a tap-validity decision depends on (parallax, disocclusion thresholds, expected depth)
-    const f2 pixelUv = {ex::mulf(ex::addf(float(x), 0.5f), ex::divf(1.0f, (float)W)), ex::mulf(ex::addf(float(y), 0.5f), ex::divf(1.0f, (float)H))};
+    const f2 pixelUv = {ex::mulf(ex::addf(float(x), 0.5f), a.invW), ex::mulf(ex::addf(float(y), 0.5f), a.invH)};
     const f3 camDelta = exSub3(prevCam.pos, cam.pos);
     const f2 rect = {(float)W, (float)H};
     const float par1 = exParallaxInPixels(exAdd3(prevWorldPos, camDelta), pixelUv, prevCam.pos, a.prevCam.worldToUv, rect);
     const float par2 = exParallaxInPixels(exSub3(prevWorldPos, camDelta), prevUV, cam.pos, a.cam.worldToUv, rect);
     const float parMax = fmaxr(par1, par2);
-    const float thrBonus = ex::addf(a.disocclusionThreshold, ex::divf(1.5f, (float)H));
-    const float thrAltBonus = ex::addf(a.disocclusionThresholdAlternate, ex::divf(1.5f, (float)H));
-    const float disThr = exLerp(thrBonus, thrAltBonus, 0.0f);
+    const float disThr = a.disThr; // lerp(threshold + 1.5/H, alternate + 1.5/H, 0): launch-uniform, from the host
     const f3 toPrev = exSub3(prevWorldPos, prevCam.pos);
     const float estPrevDepth = __fsqrt_rn(ex::dot(toPrev, toPrev));
     const int bx = bil.x0, by = bil.y0;
-    const float pixelSize = ex::mulf(ex::divf(cam.tanHalfFovX, ex::divf(cam.resX, 2.0f)), z);
+    const float pixelSize = ex::mulf(a.unproject, z); // unproject = tanHalfFov.x / (resolution.x / 2), from the host
     const float frustumSize = ex::mulf(pixelSize, (float)min(W, H));
     const float slopeScale = ex::divf(1.0f, exLerp(exLerp(0.05f, 1.0f, NoV), 1.0f, saturate(ex::divf(parMax, 30.0f))));
     float thr[4];
@@ -376,6 +375,13 @@ cudaError_t launchTemporal(const DenoiseLaunch &d)
     a.illum = d.b.illumination; a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum;
     a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength; a.fixCount = d.counters + 1; a.fixList = d.fixList;
     hostRotationBetween(d.prevCam.dir, d.cam.dir, a.prevToCur);
+    {
+        volatile float invW = 1.0f / (float)d.width, invH = 1.0f / (float)d.height, q = 1.5f / (float)d.height;
+        volatile float thrBonus = d.p.disocclusionThreshold + q, thrAlt = d.p.disocclusionThresholdAlternate + q;
+        volatile float diff = thrAlt - thrBonus, scaled = 0.0f * diff, dis = thrBonus + scaled; // exLerp(thrBonus, thrAlt, 0)
+        volatile float half = d.cam.resolution[0] / 2.0f, unproject = d.cam.tanHalfFov[0] / half;
+        a.invW = invW; a.invH = invH; a.disThr = dis; a.unproject = unproject;
+    }
     temporalKernel<<<grid, block, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
