@@ -185,6 +185,7 @@ struct TemporalArgs
     unsigned *fixCount; int *fixList; // pixels that end with historyLength <= 4: HistoryFix's work list
     float prevToCur[4];               // Quat rotationBetween(prevCam.dir, cam.dir), xyz + w
     float invW, invH, disThr, unproject; // launch-uniform IEEE quotients / sums, evaluated once on the host
+    int identityRotation;
 };
 #ifndef VPT_TEMPORAL_MINB
 #define VPT_TEMPORAL_MINB 4 // measured: 2 -> 223 us, 3 (80 regs) -> 176, 4 (64 regs) -> 162, 5 -> 162
@@ -269,7 +270,9 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     }
     f4 tapsValid = {tv[0], tv[1], tv[2], tv[3]};
     const f3 prevNFlat = ex::normalize(exSampleSmoothStep3(a.prevNormalRough, bil, W, H));
-    const f3 prevNRot = ex::normalize(exQrotate(prevToCur, prevNFlat));
+    // identity rotation (static camera: q = (0,0,0,1) exactly): q v q^-1 = v up to the sign of a zero, which the sign test
+    // below cannot see; launch-uniform branch
+    const f3 prevNRot = ex::normalize(a.identityRotation ? prevNFlat : exQrotate(prevToCur, prevNFlat));
     if (ex::dot(curNormalAvg, prevNRot) < 0.0f) { tapsValid = F4(0.0f); bicubicValid = 0.0f; }
     // ---- fast class: the history fetches and blends
     const bool useBicubic = bicubicValid > 0;
@@ -375,6 +378,7 @@ cudaError_t launchTemporal(const DenoiseLaunch &d)
     a.illum = d.b.illumination; a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum;
     a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength; a.fixCount = d.counters + 1; a.fixList = d.fixList;
     hostRotationBetween(d.prevCam.dir, d.cam.dir, a.prevToCur);
+    a.identityRotation = (a.prevToCur[0] == 0.0f && a.prevToCur[1] == 0.0f && a.prevToCur[2] == 0.0f && a.prevToCur[3] == 1.0f) ? 1 : 0;
     {
         volatile float invW = 1.0f / (float)d.width, invH = 1.0f / (float)d.height, q = 1.5f / (float)d.height;
         volatile float thrBonus = d.p.disocclusionThreshold + q, thrAlt = d.p.disocclusionThresholdAlternate + q;
