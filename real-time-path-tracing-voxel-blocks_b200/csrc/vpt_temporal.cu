@@ -14,6 +14,7 @@
 // and the blends (no decisions) are the fast class.
 #include "vpt_denoise_common.cuh"
 #include <cmath>
+#include <cstring>
 
 namespace vpt {
 
@@ -185,7 +186,7 @@ struct TemporalArgs
     unsigned *fixCount; int *fixList; // pixels that end with historyLength <= 4: HistoryFix's work list
     float prevToCur[4];               // Quat rotationBetween(prevCam.dir, cam.dir), xyz + w
     float invW, invH, disThr, unproject; // launch-uniform IEEE quotients / sums, evaluated once on the host
-    int identityRotation;
+    int identityRotation, staticCamera;
 };
 #ifndef VPT_TEMPORAL_MINB
 #define VPT_TEMPORAL_MINB 4 // measured: 2 -> 223 us, 3 (80 regs) -> 176, 4 (64 regs) -> 162, 5 -> 162
@@ -228,8 +229,21 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     const f2 pixelUv = {ex::mulf(ex::addf(float(x), 0.5f), a.invW), ex::mulf(ex::addf(float(y), 0.5f), a.invH)};
     const f3 camDelta = exSub3(prevCam.pos, cam.pos);
     const f2 rect = {(float)W, (float)H};
-    const float par1 = exParallaxInPixels(exAdd3(prevWorldPos, camDelta), pixelUv, prevCam.pos, a.prevCam.worldToUv, rect);
-    const float par2 = exParallaxInPixels(exSub3(prevWorldPos, camDelta), prevUV, cam.pos, a.cam.worldToUv, rect);
+    float par1, par2;
+    if (a.staticCamera)
+    {
+        // prevCam == cam bit for bit: camDelta = 0, both parallax terms re-project the same point with the same camera, i.e.
+        // they repeat the operations that produced prevUV. par2 = |prevUV - prevUV| = 0, par1 = |prevUV - pixelUv| in pixels:
+        // the same values without two more normalize / Mat3 / divide chains (launch-uniform branch).
+        const float dx = ex::mulf(ex::subf(prevUV.x, pixelUv.x), rect.x), dy = ex::mulf(ex::subf(prevUV.y, pixelUv.y), rect.y);
+        par1 = __fsqrt_rn(ex::addf(ex::mulf(dx, dx), ex::mulf(dy, dy)));
+        par2 = 0.0f;
+    }
+    else
+    {
+        par1 = exParallaxInPixels(exAdd3(prevWorldPos, camDelta), pixelUv, prevCam.pos, a.prevCam.worldToUv, rect);
+        par2 = exParallaxInPixels(exSub3(prevWorldPos, camDelta), prevUV, cam.pos, a.cam.worldToUv, rect);
+    }
     const float parMax = fmaxr(par1, par2);
     const float disThr = a.disThr; // lerp(threshold + 1.5/H, alternate + 1.5/H, 0): launch-uniform, from the host
     const f3 toPrev = exSub3(prevWorldPos, prevCam.pos);
@@ -378,6 +392,7 @@ cudaError_t launchTemporal(const DenoiseLaunch &d)
     a.illum = d.b.illumination; a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum;
     a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength; a.fixCount = d.counters + 1; a.fixList = d.fixList;
     hostRotationBetween(d.prevCam.dir, d.cam.dir, a.prevToCur);
+    a.staticCamera = (std::memcmp(d.cam.pos, d.prevCam.pos, sizeof d.cam.pos) == 0 && std::memcmp(d.cam.worldToUv, d.prevCam.worldToUv, sizeof d.cam.worldToUv) == 0) ? 1 : 0;
     a.identityRotation = (a.prevToCur[0] == 0.0f && a.prevToCur[1] == 0.0f && a.prevToCur[2] == 0.0f && a.prevToCur[3] == 1.0f) ? 1 : 0;
     {
         volatile float invW = 1.0f / (float)d.width, invH = 1.0f / (float)d.height, q = 1.5f / (float)d.height;
