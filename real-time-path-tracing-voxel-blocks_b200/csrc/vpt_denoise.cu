@@ -473,6 +473,7 @@ struct AtrousArgs
     DnView view;
     float phiLuminance, depthThreshold, lobeAngleFraction;
     unsigned frameIndex, step;
+    float nParamFull; // GetNormalWeightParam2(1, lobe fraction) of a pixel with historyLength >= 5 (launch-uniform), from the host
     const float4 *in, *G;
     const uint32_t *MQ;
     const float *histLen;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_AFIRST_MINB) atrousFirstKernel(c
     const f3 cn = {g.x, g.y, g.z};
     const uint32_t cMat = __ldg(a.MQ + pix) >> 16;
     const float hl = __ldg(a.histLen + pix);
-    const float nParam = normalWeightParam2(1.0f, a.lobeAngleFraction);
+    const float nParam = a.nParamFull; // GetNormalWeightParam2(1, lobeAngleFraction): launch-uniform, from the host
     if (hl >= 3.0f)
     {
         // the 3x3 neighbourhood is read once: gaussian variance prefilter, then the edge-stopping filter
@@ -609,11 +610,17 @@ VPT_DEV void atrousBody(const AtrousArgs &a, int x, int y)
     const f4 cv = F4(__ldg(a.in + pix));
     const f3 cn = {g.x, g.y, g.z};
     const int stepSize = (int)a.step;
-    float lobeFrac = a.lobeAngleFraction / sqrtf((float)stepSize);
-    lobeFrac = lerpf(0.99f, lobeFrac, saturate(hl / 5.0f));
     const float cLum = luminance(xyz(cv));
     const float phiInv = 1.0f / fmaxr(1.0e-4f, a.phiLuminance * sqrtf(cv.w));
-    const float nParam = normalWeightParam2(1.0f, lobeFrac);
+    // the lobe relaxation saturates at historyLength 5: converged pixels share one launch-uniform parameter and the
+    // sqrt / divide / atanf chain only runs for warps that hold a young pixel
+    float nParam = a.nParamFull;
+    if (hl < 5.0f)
+    {
+        float lobeFrac = a.lobeAngleFraction / sqrtf((float)stepSize);
+        lobeFrac = lerpf(0.99f, lobeFrac, saturate(hl / 5.0f));
+        nParam = normalWeightParam2(1.0f, lobeFrac);
+    }
     const PlaneTest pt = planeTest(a.view, x, y, cn, g.w, a.depthThreshold);
     float sumW = 0.44198f * 0.44198f;
     f4 sum = cv * f4{sumW, sumW, sumW, sumW * sumW};
@@ -962,6 +969,18 @@ static AtrousArgs atrousArgs(const DenoiseLaunch &d, const float4 *in, float4 *o
     a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd; a.view = d.view;
     a.phiLuminance = d.p.phiLuminance; a.depthThreshold = d.p.depthThreshold; a.lobeAngleFraction = d.p.lobeAngleFraction;
     a.frameIndex = frameIndex; a.step = step;
+    {
+        // GetNormalWeightParam2(1, f) = 1 / max(atan(f / (1 - f + 1e-6)), 1e-6) (DenoiserCommon.h:373-388) with the lobe fraction of a
+        // converged pixel: the first pass uses lobeAngleFraction itself (AtrousSmem.h), pass `step` lerp(0.99, fraction / sqrt(step), 1)
+        volatile float frac = d.p.lobeAngleFraction;
+        if (step != 1u)
+        {
+            volatile float f0 = d.p.lobeAngleFraction / std::sqrt((float)step), diff = f0 - 0.99f, l = 0.99f + diff;
+            frac = l;
+        }
+        volatile float fs = std::min(std::max((float)frac, 0.0f), 1.0f), num = 1.0f * 1.0f * fs, den = 1.0f - fs + 1e-6f, th = num / den;
+        a.nParamFull = 1.0f / std::max(std::atan((float)th), 1e-6f);
+    }
     a.in = in; a.G = d.G; a.MQ = d.MQ; a.histLen = d.b.historyLength; a.albedo = d.b.cur.albedo; a.out = out;
     return a;
 }
