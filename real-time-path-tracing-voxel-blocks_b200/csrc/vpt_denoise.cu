@@ -586,13 +586,9 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_AFIRST_MINB) atrousFirstKernel(c
     }
 }
 
-#ifndef VPT_ATROUS_V3
-#define VPT_ATROUS_V3 1
-#endif
 #ifndef VPT_ATROUS_MINB
 #define VPT_ATROUS_MINB 5 // measured on B200 (r1 variants), three passes: 2 -> 253 us, 3 -> 185, 4 -> 165, 5 -> 159, 6 -> 159 (spills)
 #endif
-#if VPT_ATROUS_V3
 // Atrous (Atrous.h:6-158): 3x3 taps at stride `step`, hashed sub-stride jitter for step > 4. kComposite: the last
 // pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky, BufferCopy.h:36-116).
 // The pass is latency-bound when each tap's radiance load waits for that tap's weight (ncu r1g: issue 54 %, 7.4 stalled
@@ -701,79 +697,6 @@ __global__ void __launch_bounds__(kBX *kAtrousBY, VPT_ATROUS_MINB) atrousKernel(
     if (interior) atrousBody<kComposite, true>(a, x, y);
     else atrousBody<kComposite, false>(a, x, y);
 }
-#else
-// Atrous (Atrous.h:6-158): 3x3 taps at stride `step`, hashed sub-stride jitter for step > 4. kComposite: the last
-// pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky, BufferCopy.h:36-116).
-template <bool kComposite>
-__global__ void __launch_bounds__(kBX *kAtrousBY) atrousKernel(const __grid_constant__ AtrousArgs a)
-{
-    const int W = a.W, H = a.H;
-    const int x = blockIdx.x * kBX + threadIdx.x;
-    const int y = a.rowBegin + blockIdx.y * kAtrousBY + threadIdx.y;
-    if (x >= W || y >= a.rowEnd) return;
-    const size_t pix = (size_t)y * W + x;
-    const float4 g = __ldg(a.G + pix);
-    if (g.w > kSkyZs) return;
-    const uint32_t cMat = __ldg(a.MQ + pix) & 0xffffu;
-    const f3 cn = {g.x, g.y, g.z};
-    const float hl = __ldg(a.histLen + pix);
-    const int stepSize = (int)a.step;
-    float lobeFrac = a.lobeAngleFraction / sqrtf((float)stepSize);
-    lobeFrac = lerpf(0.99f, lobeFrac, saturate(hl / 5.0f));
-    const f4 cv = F4(__ldg(a.in + pix));
-    const float cLum = luminance(xyz(cv));
-    const float phiInv = 1.0f / fmaxr(1.0e-4f, a.phiLuminance * sqrtf(cv.w));
-    const float nParam = normalWeightParam2(1.0f, lobeFrac);
-    const PlaneTest pt = planeTest(a.view, x, y, cn, g.w, a.depthThreshold);
-    float sumW = 0.44198f * 0.44198f;
-    f4 sum = cv * f4{sumW, sumW, sumW, sumW * sumW};
-    const float k3[2] = {0.44198f, 0.27901f};
-    int offx = 0, offy = 0;
-    if (stepSize > 4)
-    {
-        uint32_t zorder = seqExplode((uint32_t)x) | (seqExplode((uint32_t)y) << 1);
-        uint32_t seed = seqHash(a.frameIndex + 0x035F9F29u);
-        uint32_t st = seed ^ (seqHash(zorder) + 0x9E3779B9u + (seed << 6) + (seed >> 2));
-        st = seqHash(st); const float u0 = st / 4294967295.0f;
-        st = seqHash(st); const float u1 = st / 4294967295.0f;
-        offx = (int)((float)stepSize * 0.5f * (u0 - 0.5f));
-        offy = (int)((float)stepSize * 0.5f * (u1 - 0.5f));
-    }
-#pragma unroll
-    for (int yy = -1; yy <= 1; yy++)
-#pragma unroll
-        for (int xx = -1; xx <= 1; xx++)
-        {
-            if (xx == 0 && yy == 0) continue;
-            const int sx = x + offx + xx * stepSize, sy = y + offy + yy * stepSize;
-            const bool inside = sx >= 0 && sy >= 0 && sx < W && sy < H;
-            const int qx = clampi(sx, 0, W - 1), qy = clampi(sy, 0, H - 1);
-            const size_t sp = (size_t)qy * W + qx;
-            const float4 sg = __ldg(a.G + sp);
-            const uint32_t sMat = __ldg(a.MQ + sp) & 0xffffu;
-            float w = k3[abs(xx)] * k3[abs(yy)];
-            w = (inside && sg.w < kSkyZs && sMat == cMat && planeNear(pt, sg.w, (float)qx, (float)qy)) ? w : 0.0f;
-            w *= normalWeight(dot(cn, F3(sg.x, sg.y, sg.z)), nParam);
-            if (w > 1e-4f)
-            {
-                const f4 sv = F4(__ldg(a.in + sp));
-                const float lumW = fabsf(cLum - luminance(xyz(sv))) * phiInv;
-                w *= __expf(-lumW);
-                sumW += w;
-                sum += f4{w, w, w, w * w} * sv;
-            }
-        }
-    const f4 res = sum / f4{sumW, sumW, sumW, sumW * sumW};
-    if (kComposite)
-    {
-        const float4 al = __ldg(a.albedo + pix);
-        a.out[pix] = make_float4(res.x * al.x, res.y * al.y, res.z * al.z, 0.0f);
-    }
-    else
-        a.out[pix] = toFloat4(res);
-}
-
-#endif
 
 // ------------------------------------------------------------------------------------------------ HitDistReconstruction / PrePass
 // Both are off in the shipped settings (global_settings.yaml); they read the reference-layout planes directly.

@@ -144,12 +144,6 @@ VPT_DEV quat exQmul(quat p, quat q)
 {
     return {exAdd3(exAdd3(exScale3(q.v, p.w), exScale3(p.v, q.w)), ex::cross(p.v, q.v)), ex::subf(ex::mulf(p.w, q.w), ex::dot(p.v, q.v))};
 }
-VPT_DEV quat exRotationBetween(f3 p, f3 q)
-{
-    quat r = {ex::cross(p, q), ex::addf(__fsqrt_rn(ex::mulf(ex::dot(p, p), ex::dot(q, q))), ex::dot(p, q))};
-    const float n = __fsqrt_rn(ex::addf(ex::addf(ex::addf(ex::mulf(r.v.x, r.v.x), ex::mulf(r.v.y, r.v.y)), ex::mulf(r.v.z, r.v.z)), ex::mulf(r.w, r.w)));
-    return {exDiv3(r.v, n), ex::divf(r.w, n)};
-}
 VPT_DEV f3 exQrotate(quat q, f3 v) { return exQmul(exQmul(q, quat{v, 0.0f}), quat{-q.v, q.w}).v; }
 // parallaxInPixels (TemporalAccumulation.h:29-40): uv of X seen from camPos minus uvZero, in pixels
 VPT_DEV float exParallaxInPixels(f3 X, f2 uvZero, f3 camPos, const float *worldToUv, f2 rectSize)
@@ -335,7 +329,7 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     }
 }
 
-// Host twin of exRotationBetween (same IEEE operations: products and sums rounded one by one, error-free transforms through
+// Quat::rotationBetween (LinearMath.h:1311-1366) on the host (same IEEE operations: products and sums rounded one by one, error-free transforms through
 // fmaf, correctly rounded sqrt and division), so the launch-uniform quaternion costs no barrier in the kernel. It used to be
 // computed by thread 0 of every CTA behind a __syncthreads (12 % of the kernel's stall samples, ncu r1k).
 namespace {

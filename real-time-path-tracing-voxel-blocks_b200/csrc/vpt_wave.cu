@@ -552,21 +552,6 @@ template <int kSite = 0> VPT_DEV unsigned ctaReserve(unsigned n, unsigned *count
 #endif
 }
 
-#ifndef VPT_PREFETCH
-#define VPT_PREFETCH 0 // measured on B200: shading 1.504 ms without, 1.524 ms with (CCTL.E.PF1 per plane): off
-#endif
-// A stage thread's first loads are a dependent chain (path flags -> liveness test -> the state planes): the planes' lines are
-// requested while the flags are still in flight (no register, no scoreboard; ncu r1i: 17 % of S1's stall samples sat there).
-template <typename T> VPT_DEV void prefetchL1(const T *ptr)
-{
-#if VPT_PREFETCH
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-#endif
-}
-template <typename T> VPT_DEV void prefetchLine(const T *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-#ifndef VPT_S3_PREFETCH
-#define VPT_S3_PREFETCH 0 // measured on B200: prefetch.global.L1 of the candidates' lines makes S3 slower (shading 1.568 vs 1.514 ms)
-#endif
 struct PathId { int p, slot, sl, px, py, k; bool inImage; };
 VPT_DEV PathId pathId(const TraceArgs &a, int p)
 {
@@ -766,7 +751,6 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
     const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
     const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
-    if (act) { prefetchL1(a.wb.hitPacked + p); prefetchL1(a.wb.hitT + p); prefetchL1(a.wb.dirT + p); if (depth > 0) prefetchL1(a.wb.org + p); }
     const uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_LIVE);
     bool want = false;
@@ -994,7 +978,6 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
     const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
     const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
-    if (act) { prefetchL1(a.wb.surfA + p); prefetchL1(a.wb.surfB + p); prefetchL1(a.wb.candA + p); prefetchL1(a.wb.candB + p); prefetchL1(a.wb.dir1 + p); }
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS);
     bool want = false;
@@ -1159,7 +1142,6 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MIN
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
     bool act = idx < a.partSlots;
-    if (act) { prefetchL1(a.wb.surfA + p); prefetchL1(a.wb.surfB + p); prefetchL1(a.wb.ris + p); prefetchL1(a.wb.lightA + p); prefetchL1(a.wb.lightB + p); }
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & F_RIS) && (fl & F_RESTIR);
     unsigned nWant = 0;
@@ -1197,24 +1179,6 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MIN
             const f2 dsk = concentricSampleDisk(c.rnd2()) * 64.0f;
             offx[2] = (int)dsk.x; offy[2] = (int)dsk.y;
         }
-#if VPT_S3_PREFETCH
-        // S3 is bound by its chain of dependent gathers (depth -> G-buffer planes -> reservoir -> sky texel, per candidate and
-        // again in the bias-correction loop: ~20 round trips per thread). The three candidates' previous-frame lines are
-        // requested up front, all in flight together; the loops below then find them in L1.
-#pragma unroll
-        for (int i = 0; i < nTemporal; ++i)
-        {
-            int ix = id.px + offx[i], iy = id.py + offy[i];
-            clampIntoView(ix, iy, a.width, a.height);
-            if (ix >= 0 && iy >= 0 && ix < a.width && iy < a.height)
-            {
-                const size_t q = (size_t)iy * a.width + ix;
-                prefetchLine(a.prev.depth + q); prefetchLine(a.prev.normalRoughness + q); prefetchLine(a.prev.geoNormalThinfilm + q);
-                prefetchLine(a.prev.materialParameter + q); prefetchLine(a.prev.albedo + q);
-                prefetchLine(a.resPrev + q); prefetchLine(reinterpret_cast<const char *>(a.resPrev + q) + 16);
-            }
-        }
-#endif
         unsigned cached = 0, rayMask = 0;
         int selectedLoopIdx = -1;
 VPT_S3_LOOP
@@ -1359,7 +1323,6 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
     const int n = list ? (int)__ldg(listCount) : a.partPaths;
     bool act = idx < n;
     const int p = act ? (list ? __ldg(list + idx) : partPath(a, idx)) : 0;
-    if (act) { prefetchL1(a.wb.surfA + p); prefetchL1(a.wb.surfB + p); prefetchL1(a.wb.ris + p); prefetchL1(a.wb.lightA + p); prefetchL1(a.wb.lightB + p); prefetchL1(a.wb.thr + p); }
     uint32_t fl = act ? a.wb.pflag[p] : 0u;
     act = act && (fl & (F_RIS | F_CONT));
     bool cont = false, want = false;
