@@ -716,30 +716,36 @@ VPT_DEV f3 missEmission(const Ctx &c, f3 rayDir)
 // RayGen.cu:102-135: jittered primary ray, exact arithmetic up to the prepared DDA state.
 __global__ void __launch_bounds__(kShadeThreads) genKernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
+    // Every path spawns exactly one primary ray, so its queue slot is its own index: no reservation, no barrier (the CTA-wide
+    // reservation was 37 % of this kernel's stall samples, ncu r1k). A path without a ray to trace (a tile pixel outside the
+    // image, a ray that misses the grid) queues a ray that starts on the shell corner (padded voxel 0): the engine retires
+    // it on its first test as a miss, which is the result such a path needs.
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
+    if (idx == 0) atomicAdd(qCount, (unsigned)a.partPaths);
+    if (idx >= a.partPaths) return;
+    const int p = partPath(a, idx);
+    const PathId id = pathId(a, p);
+    uint32_t fl = 0;
     bool want = false;
     PreparedRay r;
-    if (idx < a.partPaths)
+    if (id.inImage)
     {
-        const int p = partPath(a, idx);
-        const PathId id = pathId(a, p);
-        uint32_t fl = 0;
-        if (id.inImage)
-        {
-            Ctx c = makeCtx(a, id, 0);
-            const f2 jitter = c.rnd2();
-            const f2 sampleUv = {ex::mulf(ex::addf(float(id.px), jitter.x), a.cam.inversedResolution[0]),
-                                 ex::mulf(ex::addf(float(id.py), jitter.y), a.cam.inversedResolution[1])};
-            const f3 dir = ex::normalize(ex::mulMat3(a.cam.uvToWorld, F3(sampleUv.x, sampleUv.y, 1.0f)));
-            a.wb.dirT[p] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-            fl = F_LIVE | ((uint32_t)c.randIdx << kRandShift);
-            want = prepareRay(a.grid, camPos(a), dir, 0.0f, (uint32_t)p, r);
-            if (!want) { a.wb.hitPacked[p] = kHitMiss; a.wb.hitT[p] = kRayMax; }
-        }
-        a.wb.pflag[p] = fl;
+        Ctx c = makeCtx(a, id, 0);
+        const f2 jitter = c.rnd2();
+        const f2 sampleUv = {ex::mulf(ex::addf(float(id.px), jitter.x), a.cam.inversedResolution[0]),
+                             ex::mulf(ex::addf(float(id.py), jitter.y), a.cam.inversedResolution[1])};
+        const f3 dir = ex::normalize(ex::mulMat3(a.cam.uvToWorld, F3(sampleUv.x, sampleUv.y, 1.0f)));
+        a.wb.dirT[p] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        fl = F_LIVE | ((uint32_t)c.randIdx << kRandShift);
+        want = prepareRay(a.grid, camPos(a), dir, 0.0f, (uint32_t)p, r);
     }
-    const unsigned pos = ctaReserve(want ? 1u : 0u, qCount);
-    if (want) storePreparedRay(a.wb.queue, pos, r);
+    a.wb.pflag[p] = fl;
+    if (!want)
+    {
+        r.tMaxX = r.tMaxY = r.tMaxZ = r.tCur = 0.0f; r.tDeltaX = r.tDeltaY = r.tDeltaZ = r.tmin = 0.0f;
+        r.lin = 0; r.meta = 6u << 4; r.result = (uint32_t)p; r.pad = 0u;
+    }
+    storePreparedRay(a.wb.queue, (unsigned)idx, r);
 }
 
 // ------------------------------------------------------------------------------------------------ S1
