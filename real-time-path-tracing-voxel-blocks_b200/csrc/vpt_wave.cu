@@ -1387,7 +1387,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
             if (depth == 0 && id.k == 0)
                 storeReservoir(a.resCur + (size_t)id.py * a.width + id.px, a.enableRestir ? shading : emptyReservoir());
         }
-        if (fl & F_CONT)
+        if ((fl & F_CONT) && nextList) // the last depth round traces nothing further: no continuation state, no reservations
         {
             cont = true;
             const float4 sa = __ldg(a.wb.surfA + p), nd = __ldg(a.wb.nextD + p), bo = __ldg(a.wb.bop + p);
@@ -1401,13 +1401,13 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
             a.wb.pflag[p] = F_LIVE | (fl & (0xffu << kRandShift)) | (fl & (0xfu << kDiffuseShift));
         }
     }
-    if (nextList)
+    if (nextList) // launch-uniform
     {
         const unsigned lpos = ctaReserve<1>(cont ? 1u : 0u, nextCount);
         if (cont) nextList[lpos] = p;
+        const unsigned pos = ctaReserve(want ? 1u : 0u, qCount);
+        if (want) storePreparedRay(a.wb.queue, pos, r);
     }
-    const unsigned pos = ctaReserve(want ? 1u : 0u, qCount);
-    if (want) storePreparedRay(a.wb.queue, pos, r);
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
