@@ -258,6 +258,12 @@ int vpt_render(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamer
  * the un-normalised radiance SUM in Illumination; vpt_resolve divides by spp (after the cross-GPU sum). */
 int vpt_render_shard(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamera, int iterationIndex,
                      int sampleBegin, int sampleStep);
+/* Same shard, but its FIRST sample (sampleBegin) owns this context's G-buffer, reservoir plane and temporal ReSTIR pass — every
+ * rank then runs the reference's whole per-frame algorithm (RayGen.cu:102-181: one ReSTIR sample + spp-1 plain samples) on its own
+ * sample subset with rank-local ReSTIR state ("keep it rank-local"), so the ranks do equal work. The sum over ranks is
+ * an average of independent frames; it is NOT bit-comparable to one GPU rendering N x spp (vpt_render_shard is). */
+int vpt_render_shard_local(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamera, int iterationIndex,
+                           int sampleBegin, int sampleStep);
 int vpt_resolve(vpt_ctx *ctx);
 /* Denoiser::run (renderer/denoising/Denoiser.cu:24-408). frameNum == OfflineBackend::getFrameNum();
  * iterationIndex is the POST-increment GlobalSettings::iterationIndex the reference reads there (:37,296). */

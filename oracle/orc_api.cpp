@@ -177,7 +177,17 @@ int orc_set_trace_params(orc_ctx *c, int spp, int totalBounceLimit, int diffuseB
 
 // OptixRenderer::render for the sample shard {k = sampleBegin, sampleBegin+sampleStep, ...}.
 // Leaves the un-normalised radiance SUM in Illumination (w = primary distance on the shard owning k=0).
+static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, int ownerSample);
 int orc_render_shard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
+{
+    return renderShard(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, 0);
+}
+// rank-local owner: the shard's first sample owns the G-buffer, the reservoir and the ReSTIR pass
+int orc_render_shard_local(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
+{
+    return renderShard(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, sampleBegin);
+}
+static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, int ownerSample)
 {
     Scene &sc = c->sc;
     sc.cur ^= 1;
@@ -187,7 +197,7 @@ int orc_render_shard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int i
         for (int x = 0; x < sc.width; ++x)
         {
             f4 acc;
-            renderPixel(sc, *cam, *prevCam, iterationIndex, x, y, sampleBegin, sampleStep, &acc, rays, steps);
+            renderPixel(sc, *cam, *prevCam, iterationIndex, x, y, sampleBegin, sampleStep, &acc, rays, steps, ownerSample);
             sc.illumination[(size_t)y * sc.width + x] = acc;
         }
     sc.rayCount = rays; sc.stepCount = steps;

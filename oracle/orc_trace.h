@@ -1058,9 +1058,10 @@ inline f3 tracePath(PixelCtx &c, bool ownsGBuffer, float &primaryDist)
 }
 
 // One pixel of OptixRenderer::render: spp samples, sample 0 owns G-buffer / depth / reservoir.
-// `sampleBegin/sampleStep` shard the spp loop (multi-GPU: rank r renders k = r, r+n, ...).
+// `sampleBegin/sampleStep` shard the spp loop (multi-GPU: rank r renders k = r, r+n, ...). ownerSample = the sample that owns
+// the G-buffer / reservoir / ReSTIR pass: 0 (the reference), or sampleBegin for a rank-local owner.
 inline void renderPixel(Scene &sc, const Camera &cam, const Camera &prevCam, int iterationIndex, int px, int py,
-                        int sampleBegin, int sampleStep, f4 *accumOut, uint64_t &rays, uint64_t &steps)
+                        int sampleBegin, int sampleStep, f4 *accumOut, uint64_t &rays, uint64_t &steps, int ownerSample = 0)
 {
     PixelCtx c{&sc, &cam, &prevCam, px, py, iterationIndex, 0, 0, 0, 0, 0};
     const int spp = sc.tp.spp;
@@ -1070,11 +1071,11 @@ inline void renderPixel(Scene &sc, const Camera &cam, const Camera &prevCam, int
     for (int k = sampleBegin; k < spp; k += sampleStep)
     {
         c.sampleIndex = iterationIndex * spp + k;
-        c.prevSampleIndex = (iterationIndex - 1) * spp;
+        c.prevSampleIndex = (iterationIndex - 1) * spp + ownerSample; // the previous frame's owner sample (its G-buffer jitter)
         float pd;
-        f3 r = tracePath(c, k == 0, pd);
+        f3 r = tracePath(c, k == ownerSample, pd);
         sum += r;
-        if (k == 0) { depth0 = pd; haveDepth = true; }
+        if (k == ownerSample) { depth0 = pd; haveDepth = true; }
     }
     size_t pix = (size_t)py * sc.width + px;
     if (haveDepth) sc.gb[sc.cur].depth[pix] = depth0;

@@ -423,7 +423,7 @@ int vpt_set_trace_params(vpt_ctx *c, int spp, int totalBounceLimit, int diffuseB
     return VPT_OK;
 }
 
-static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, bool resolve)
+static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, bool resolve, bool localOwner = false)
 {
     if (!c || !cam || !prevCam || sampleBegin < 0 || sampleStep < 1) return fail(VPT_ERR_ARG, "vpt_render: bad argument");
     if (!c->occ) return fail(VPT_ERR_STATE, "vpt_render: no voxel grid (vpt_set_grid / vpt_generate_terrain)");
@@ -439,6 +439,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.width = c->width; a.height = c->height;
     a.iterationIndex = iterationIndex; a.spp = c->spp; a.totalBounceLimit = c->totalBounceLimit; a.diffuseBounceLimit = c->diffuseBounceLimit;
     a.enableRestir = c->enableRestir; a.sampleBegin = sampleBegin; a.sampleStep = sampleStep;
+    a.ownerSample = localOwner ? sampleBegin : 0;
     a.grid.W = c->cx * 32; a.grid.H = c->cy * 32; a.grid.D = c->cz * 32;
     a.grid.Wp = paddedW(a.grid.W); a.grid.Hp = a.grid.H + 2; a.grid.Dp = a.grid.D + 2;
     a.grid.maskWords = (int)paddedMaskWords(a.grid.W, a.grid.H, a.grid.D);
@@ -505,6 +506,10 @@ int vpt_resolve(vpt_ctx *c)
 int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
 {
     return renderImpl(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, false);
+}
+int vpt_render_shard_local(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
+{
+    return renderImpl(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, false, true);
 }
 int vpt_render(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex)
 {

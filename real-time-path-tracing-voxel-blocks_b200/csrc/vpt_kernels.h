@@ -84,6 +84,7 @@ struct TraceArgs
     int width, height;
     int iterationIndex, spp, totalBounceLimit, diffuseBounceLimit, enableRestir;
     int sampleBegin, sampleStep;
+    int ownerSample; // the sample that owns the G-buffer, the reservoir and the temporal ReSTIR pass: 0, or sampleBegin with a rank-local owner
     GridView grid;
     int occInSmem;
     const uint8_t *sobol, *scrambling, *ranking;

@@ -577,7 +577,7 @@ VPT_DEV int partPath(const TraceArgs &a, int idx)
 }
 VPT_DEV Ctx makeCtx(const TraceArgs &a, const PathId &id, int randIdx)
 {
-    Ctx c{a, id.px, id.py, a.iterationIndex * a.spp + id.k, (a.iterationIndex - 1) * a.spp, randIdx, 0ull, 0ull, 0ull};
+    Ctx c{a, id.px, id.py, a.iterationIndex * a.spp + id.k, (a.iterationIndex - 1) * a.spp + a.ownerSample, randIdx, 0ull, 0ull, 0ull};
     c.loadKeys();
     return c;
 }
@@ -764,7 +764,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
     if (act)
     {
         const PathId id = pathId(a, p);
-        const bool owns = (id.k == 0);
+        const bool owns = (id.k == a.ownerSample);
         Ctx c = makeCtx(a, id, (int)((fl >> kRandShift) & 0xffu));
         const int diffuseBounce = (int)(fl >> kDiffuseShift);
         const size_t pix = (size_t)id.py * a.width + id.px;
@@ -1384,7 +1384,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
                 }
                 a.wb.rad[p] = acc;
             }
-            if (depth == 0 && id.k == 0)
+            if (depth == 0 && id.k == a.ownerSample)
                 storeReservoir(a.resCur + (size_t)id.py * a.width + id.px, a.enableRestir ? shading : emptyReservoir());
         }
         if ((fl & F_CONT) && nextList) // the last depth round traces nothing further: no continuation state, no reservations
@@ -1421,7 +1421,7 @@ __global__ void __launch_bounds__(kShadeThreads) accumulateKernel(const __grid_c
     if (!id.inImage) return;
     const size_t pix = (size_t)id.py * a.width + id.px;
     const bool first = a.waveFirst == 0;
-    const bool haveDepth = first && a.sampleBegin == 0;
+    const bool haveDepth = first && a.sampleBegin == a.ownerSample;
     float4 prev = first ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : a.illumination[pix];
     f3 sum = {prev.x, prev.y, prev.z};
     float depth0 = prev.w;
@@ -1508,7 +1508,7 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
         a.waveFirst = first;
         a.samplesInWave = shardSamples - first < maxSamplesInWave ? shardSamples - first : maxSamplesInWave;
         a.nPaths = a.nSlots * a.samplesInWave;
-        const bool restirWave = a.enableRestir && a.sampleBegin == 0 && first == 0;
+        const bool restirWave = a.enableRestir && a.sampleBegin == a.ownerSample && first == 0;
         VPT_TRY(cudaMemsetAsync(wb0.cnt, 0, 2 * kCntWords * sizeof(unsigned), s));
         if (overlap) VPT_TRY(cudaEventRecord(ts->fork, s));
         size_t queueBase = 0, listBase = 0;

@@ -27,9 +27,14 @@ def row_bands(height, nranks):
     return b
 
 
-def render_sharded(ctx, cam, prev_cam, iteration_index, rank, nranks, allreduce_sum):
-    """One spp-sharded frame: ctx is a vpt.Vpt or an oracle.Oracle; allreduce_sum(ctx) sums Illumination over ranks."""
+def render_sharded(ctx, cam, prev_cam, iteration_index, rank, nranks, allreduce_sum, local_owner=False):
+    """One spp-sharded frame: ctx is a vpt.Vpt or an oracle.Oracle; allreduce_sum(ctx) sums Illumination over ranks.
+    local_owner: every rank's first sample owns that rank's G-buffer / reservoirs / ReSTIR pass (equal work per rank; the sum is
+    an average of independent frames instead of one frame of nranks x spp samples with a single ReSTIR sample)."""
     begin, step = sample_shard(rank, nranks)
-    ctx.render_shard(cam, prev_cam, iteration_index, begin, step)
+    if local_owner:
+        ctx.render_shard_local(cam, prev_cam, iteration_index, begin, step)
+    else:
+        ctx.render_shard(cam, prev_cam, iteration_index, begin, step)
     allreduce_sum(ctx)
     ctx.resolve()

@@ -356,3 +356,29 @@ def test_cfg3_full_size_denoiser_alone_matches_oracle(libs):
         mean_rel, outliers, dmax = common.rel_err_stats(out, ref)
         assert mean_rel <= 5e-5 and outliers <= 5e-3, (f, mean_rel, outliers, dmax)
         assert np.array_equal(g.read("HistoryLength"), o.read("HistoryLength")), f
+
+
+def test_shard_with_rank_local_owner_matches_oracle(libs):
+    """vpt_render_shard_local: the shard's first sample owns the G-buffer, the reservoir and the ReSTIR pass (rank-local state
+    over two frames, temporal reuse included). Shard (1, 2) of 4 spp: samples 1 and 3, owner sample 1."""
+    W, H = 256, 160
+    inp = common.scene_inputs((2, 1, 2))
+    g, o = _pair(libs, W, H, inp, spp=4, total=3, diffuse=1)
+    cam = common.scene_camera(W, H)
+    for f in range(2):
+        g.render_shard_local(cam, cam, f, 1, 2)
+        o.render_shard_local(cam, cam, f, 1, 2)
+        assert np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits")), f
+        for name in ("Depth", "Material", "NormalRoughness", "Albedo"):
+            assert np.array_equal(g.read(name), o.read(name)), (f, name)
+        m, outl, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert m <= 1e-3 and outl <= 1e-2, (f, m, outl)
+    rg, ro = g.read_reservoirs(1), o.read_reservoirs(1)
+    assert (ro["M"] > 0).mean() > 0.3
+    assert (rg["lightData"] == ro["lightData"]).mean() > 0.99
+    # shard (0, 1) in local mode is the plain render's un-normalised sum
+    g2, _ = _pair(libs, W, H, inp, spp=4, total=3, diffuse=1)
+    g3, _ = _pair(libs, W, H, inp, spp=4, total=3, diffuse=1)
+    g2.render_shard_local(cam, cam, 0, 0, 1)
+    g3.render_shard(cam, cam, 0, 0, 1)
+    assert np.array_equal(g2.read("Illumination"), g3.read("Illumination"))

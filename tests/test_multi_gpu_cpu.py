@@ -64,3 +64,67 @@ def test_spp_sharding_gloo_world2():
     assert res[1] < 1e-5, res          # sum of shards / spp == full render (fp32 summation order only)
     assert res[2] and res[3]           # depth channel carried by the sample-0 shard; rank 0 owns the G-buffer
     assert oth[1] is False             # rank 1 never writes the G-buffer
+
+
+def _worker_local(rank, world, port, q):
+    """Rank-local owner mode (vpt_render_shard_local): every rank owns a G-buffer and runs its own ReSTIR pass."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "real-time-path-tracing-voxel-blocks_b200", "python"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import common
+    import oracle as O
+    import vpt_scenes as S
+    import vpt_shard
+    O.set_threads(2)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    W, H, spp = 96, 64, 4
+    inp = common.scene_inputs((2, 1, 2), noise_fn=O.perlin_noise_chunks, alias_fn=O.build_alias_table)
+    o = common.setup(O.Oracle(W, H), inp, spp=spp, total=3, diffuse=1)
+    cam = O.camera_from_scene(W, H, S.SCENE_CAMERA["position"], S.SCENE_CAMERA["direction"], 90.0)
+    own = []
+
+    def allreduce(ctx):
+        own.append(ctx.read("Illumination").copy())
+        t = torch.from_numpy(ctx.read("Illumination"))
+        dist.all_reduce(t)
+        ctx.write("Illumination", t.numpy())
+
+    for f in range(2):
+        vpt_shard.render_sharded(o, cam, cam, f, rank, world, allreduce, local_owner=True)
+    summed = o.read("Illumination")
+    owns = bool((o.read("Depth") != 0).any())
+    res = o.read_reservoirs(1)
+    valid_res = float((res["M"] > 0).mean())
+    if rank == 0:
+        # the same two shards rendered one after the other in this process must add up to the all-reduced image
+        parts = []
+        for r in range(world):
+            ctx = common.setup(O.Oracle(W, H), inp, spp=spp, total=3, diffuse=1)
+            for f in range(2):
+                ctx.render_shard_local(cam, cam, f, r, world)
+            parts.append(ctx.read("Illumination"))
+        ref = (parts[0][..., :3] + parts[1][..., :3]) / np.float32(spp)
+        q.put(("result", float(np.abs(summed[..., :3] - ref).max()), owns, valid_res))
+    else:
+        q.put(("other", owns, valid_res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_spp_sharding_local_owner_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker_local, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    res = [g for g in got if g[0] == "result"][0]
+    other = [g for g in got if g[0] == "other"][0]
+    assert res[1] <= 1e-5, res                      # all-reduced sum == the two shards added up (fp32 summation order)
+    assert res[2] and other[1]                      # BOTH ranks own a G-buffer
+    assert res[3] > 0.3 and other[2] > 0.3          # ... and keep ReSTIR reservoirs of their own
