@@ -642,7 +642,7 @@ bool inflateZlib(const uint8_t *src, size_t n, std::vector<uint8_t> &out, size_t
             if (br.end - br.p < 4) return false;
             const unsigned len = br.p[0] | (br.p[1] << 8);
             br.p += 4;
-            if ((size_t)(br.end - br.p) < len) return false;
+            if ((size_t)(br.end - br.p) < len || out.size() + len > expected + 65536) return false;
             out.insert(out.end(), br.p, br.p + len);
             br.p += len;
             continue;
@@ -688,6 +688,7 @@ bool inflateZlib(const uint8_t *src, size_t n, std::vector<uint8_t> &out, size_t
         {
             const int sym = lit.decode(br);
             if (sym < 0) return false;
+            if (out.size() > expected) return false; // more data than the image holds: corrupt stream
             if (sym < 256) { out.push_back((uint8_t)sym); continue; }
             if (sym == 256) break;
             if (sym > 285) return false;
@@ -730,7 +731,7 @@ extern "C" int vpt_load_png_rgba8(const char *path, uint32_t *out, size_t maxTex
         else if (!std::memcmp(type, "IEND", 4)) break;
         pos += 12 + (size_t)len;
     }
-    if (W == 0 || H == 0 || interlace != 0 || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8)) return VPT_ERR_IO;
+    if (W == 0 || H == 0 || W > 32768u || H > 32768u || interlace != 0 || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8)) return VPT_ERR_IO;
     const int nch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (nch == 0) return VPT_ERR_IO;
     if (width) *width = (int)W;

@@ -394,3 +394,31 @@ def test_vpt_offline_with_asset_tables_and_textures(tmp_path):
     assert fa.shape == fb.shape == (192, 320, 3)
     assert np.abs(fa - fb).mean() > 2.0          # 8-bit levels: the textures are visible
     assert fb.std() > 5.0 and np.isfinite(fb).all()
+
+
+def test_png_reader_survives_corrupt_streams(tmp_path):
+    """Mutated and truncated files must come back as an error or as some image — never a crash or a runaway allocation."""
+    PIL = pytest.importorskip("PIL.Image")
+    import vpt
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (48, 48, 3), dtype=np.uint8)
+    img[:24] = np.arange(48, dtype=np.uint8)[None, :, None]
+    src = str(tmp_path / "a.png")
+    PIL.fromarray(img, "RGB").save(src, compress_level=6)
+    data = open(src, "rb").read()
+    dst = str(tmp_path / "b.png")
+    ok = bad = 0
+    for it in range(400):
+        d = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            d[int(rng.integers(8, len(d)))] = int(rng.integers(0, 256))
+        if it % 7 == 0:
+            d = d[: int(rng.integers(20, len(d)))]
+        open(dst, "wb").write(bytes(d))
+        try:
+            got, _ = vpt.load_png_rgba8(dst)
+            assert got.ndim == 2 and got.size <= 32768 * 32768
+            ok += 1
+        except vpt.VptError:
+            bad += 1
+    assert bad > 50 and ok + bad == 400
