@@ -163,7 +163,9 @@ int vpt_set_tables(vpt_ctx *ctx, const uint8_t *sobol, const uint8_t *scrambling
  * cx + CX*(cz + CZ*cy) (VoxelEngine.cu:221-224), 32768 bytes per chunk in GetLinearId order (VoxelMath.h:120-127). */
 int vpt_set_grid(vpt_ctx *ctx, int chunksX, int chunksY, int chunksZ, const uint8_t *ids);
 int vpt_get_grid(vpt_ctx *ctx, uint8_t *ids_out, size_t bytes);
-/* VoxelEngine::setVoxelAtGlobal (VoxelEngine.cu:265-276). */
+/* VoxelEngine::setVoxelAtGlobal (VoxelEngine.cu:265-276). 
+ * The first edit after a render keeps a snapshot of the traversal masks: that frame's temporal-ReSTIR bias rays walk the world as
+ * the previous render saw it (sysParam.prevTopObject, closesthit.cu:736-755). */
 int vpt_set_voxel(vpt_ctx *ctx, int x, int y, int z, int blockId);
 /* initVoxelsMultiChunk + GenerateVoxelChunk (voxelengine/VoxelSceneGen.cu:341-388, 61-165): noise is
  * chunks x 32 x 32 floats, noise[chunk][z][x]. Runs on the device. */

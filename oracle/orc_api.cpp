@@ -57,11 +57,13 @@ int orc_set_grid(orc_ctx *c, int cx, int cy, int cz, const uint8_t *ids)
 {
     c->sc.grid.cx = cx; c->sc.grid.cy = cy; c->sc.grid.cz = cz;
     c->sc.grid.ids.assign(ids, ids + (size_t)cx * cy * cz * 32768);
+    c->sc.havePrevGrid = false; // a new world has no previous state
     return 0;
 }
 int orc_generate_terrain(orc_ctx *c, int cx, int cy, int cz, const float *noise)
 {
     generateTerrain(c->sc.grid, cx, cy, cz, noise);
+    c->sc.havePrevGrid = false;
     return 0;
 }
 int orc_get_grid(orc_ctx *c, uint8_t *out, size_t bytes)
@@ -74,6 +76,7 @@ int orc_set_voxel(orc_ctx *c, int x, int y, int z, int id)
 {
     Grid &g = c->sc.grid;
     if (x < 0 || y < 0 || z < 0 || x >= g.W() || y >= g.H() || z >= g.D()) return 1;
+    if (!c->sc.havePrevGrid) { c->sc.prevGrid = g; c->sc.havePrevGrid = true; } // the world the previous render saw
     g.ids[g.index(x, y, z)] = (uint8_t)id;
     return 0;
 }
@@ -201,6 +204,7 @@ static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int
             sc.illumination[(size_t)y * sc.width + x] = acc;
         }
     sc.rayCount = rays; sc.stepCount = steps;
+    sc.havePrevGrid = false; // the next frame's previous world is this one unless an edit takes a new snapshot
     return 0;
 }
 // Divide the (possibly all-reduced) radiance sum by spp.

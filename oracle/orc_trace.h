@@ -411,6 +411,7 @@ struct Scene
     int width = 0, height = 0;
     Tables tables;
     Grid grid;
+    Grid prevGrid; bool havePrevGrid = false; // snapshot taken by the first edit after a render (the reference's prevTopObject)
     std::vector<Material> materials;
     std::vector<Texture> textures;
     std::vector<MaterialTextures> matTex; // empty or one entry per material
@@ -450,6 +451,13 @@ struct PixelCtx
     Hit trace(f3 o, f3 d, float tmin, float tmax)
     {
         Hit h = ddaTrace(sc->grid, o, d, tmin, tmax);
+        ++rays; steps += (uint64_t)h.steps;
+        return h;
+    }
+    // against the world as the previous render saw it (usePrevBvh / sysParam.prevTopObject, closesthit.cu:736-755)
+    Hit tracePrev(f3 o, f3 d, float tmin, float tmax)
+    {
+        Hit h = ddaTrace(sc->havePrevGrid ? sc->prevGrid : sc->grid, o, d, tmin, tmax);
         ++rays; steps += (uint64_t)h.steps;
         return h;
     }
@@ -977,7 +985,7 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
                 {
                     const float extraRayOffset = 0.01f + 0.01f * ts.depth;
                     // previous BVH == current grid (static scene)
-                    Hit nh = c.trace(ts.pos, lightSample.position, extraRayOffset, kRayMax);
+                    Hit nh = c.tracePrev(ts.pos, lightSample.position, extraRayOffset, kRayMax);
                     if (nh.hit) ps = 0.0f;
                 }
                 Reservoir pr = sc.reservoirs[prevBase + (size_t)idx.y * sc.width + idx.x];

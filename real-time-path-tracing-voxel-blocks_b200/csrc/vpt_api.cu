@@ -49,6 +49,9 @@ struct vpt_ctx
     uint8_t *idsChunk = nullptr, *idsLinear = nullptr;
     uint32_t *occ = nullptr;
     int *upHDev = nullptr; int upH = 0; // highest solid y + 1 (GridView::upH)
+    // the world as the PREVIOUS render saw it (the reference's prevTopObject, closesthit.cu:736-755): a snapshot of the masks
+    // taken by the first edit after a render, walked by the bias-correction rays of the temporal ReSTIR pass
+    uint32_t *occPrev = nullptr; size_t occPrevWords = 0; int upHPrev = 0; bool prevSnapshot = false;
     // materials / sky
     VptMaterial *materials = nullptr; int nMaterials = 0;
     uint16_t *blockToMaterial = nullptr;
@@ -163,7 +166,7 @@ void vpt_destroy(vpt_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
                     c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
-                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList};
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
     {
@@ -226,6 +229,7 @@ int vpt_set_grid(vpt_ctx *c, int cx, int cy, int cz, const uint8_t *ids)
     int rc = allocGrid(c, cx, cy, cz);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->idsChunk, ids, (size_t)cx * cy * cz * 32768, cudaMemcpyHostToDevice, c->stream));
+    c->prevSnapshot = false; // a new world has no previous state
     CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, c->upHDev, &c->upH, cx, cy, cz, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return VPT_OK;
@@ -241,6 +245,7 @@ int vpt_generate_terrain(vpt_ctx *c, int cx, int cy, int cz, const float *noise)
     CU(cudaMalloc((void **)&dNoise, nb));
     CU(cudaMemcpyAsync(dNoise, noise, nb, cudaMemcpyHostToDevice, c->stream));
     CU(launchGenerateTerrain(dNoise, c->idsChunk, cx, cy, cz, c->stream));
+    c->prevSnapshot = false; // a new world has no previous state
     CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, c->upHDev, &c->upH, cx, cy, cz, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFree(dNoise));
@@ -261,6 +266,13 @@ int vpt_set_voxel(vpt_ctx *c, int x, int y, int z, int blockId)
     if (!c || !c->idsChunk) return fail(VPT_ERR_STATE, "vpt_set_voxel: no grid set");
     if (x < 0 || y < 0 || z < 0 || x >= c->cx * 32 || y >= c->cy * 32 || z >= c->cz * 32) return VPT_OK; // reference ignores out-of-range edits
     CU(cudaSetDevice(c->device));
+    if (!c->prevSnapshot)
+    {
+        const size_t words = paddedOccWords(c->cx * 32, c->cy * 32, c->cz * 32);
+        if (c->occPrevWords != words) { if (c->occPrev) cudaFree(c->occPrev); c->occPrev = nullptr; CU(cudaMalloc((void **)&c->occPrev, words * 4)); c->occPrevWords = words; }
+        CU(cudaMemcpyAsync(c->occPrev, c->occ, words * 4, cudaMemcpyDeviceToDevice, c->stream));
+        c->upHPrev = c->upH; c->prevSnapshot = true;
+    }
     CU(launchSetVoxel(c->idsChunk, c->idsLinear, c->occ, &c->upH, c->cx, c->cy, c->cz, x, y, z, blockId, c->stream));
     return VPT_OK;
 }
@@ -445,6 +457,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.grid.maskWords = (int)paddedMaskWords(a.grid.W, a.grid.H, a.grid.D);
     a.grid.occWords = 2 * a.grid.maskWords + 4; a.grid.parkLin = 2 * a.grid.maskWords * 32;
     a.grid.upH = c->upH;
+    a.occPrev = c->prevSnapshot ? c->occPrev : nullptr; a.upHPrev = c->upHPrev;
     a.grid.occ = c->occ; a.grid.idsLinear = c->idsLinear;
     a.grid.divW = makeFastDiv(a.grid.W); a.grid.divD = makeFastDiv(a.grid.D);
     a.grid.divWp = makeFastDiv(a.grid.Wp); a.grid.divDp = makeFastDiv(a.grid.Dp);
@@ -487,6 +500,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     int launches = 0;
     c->traceProf.enabled = c->profiling;
     CU(launchTrace(a, c->wave.maxSamplesInWave, c->stream, c->overlapParts ? &c->traceStreams : nullptr, c->smCount, c->smemOptIn, &launches, &c->traceProf));
+    c->prevSnapshot = false; // the next frame's "previous world" is this one unless an edit takes a new snapshot
     if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE1], c->stream));
     c->haveTrace = c->profiling; c->ranResolve = false; c->launchesRender = launches;
     return VPT_OK;

@@ -257,6 +257,22 @@ def test_set_voxel_edits_update_both_traversal_masks(libs):
         mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
         assert mean_rel <= 1e-3 and outliers <= 1.5e-2, (f, mean_rel, outliers)
     assert np.array_equal(g.get_grid(), o.get_grid())
+    # many edits before ONE frame: a wall in front of the camera, then its removal. The bias-correction rays of the temporal
+    # ReSTIR pass walk the world as the previous render saw it (the reference's prevTopObject, closesthit.cu:736-755): only
+    # the first edit after a render snapshots it.
+    f = len(edits)
+    for bid in (5, 0):
+        for yy in range(9, 16):
+            for xx in range(28, 36):
+                g.set_voxel(xx, yy, 34, bid); o.set_voxel(xx, yy, 34, bid)
+        for _ in range(2):                      # the frame right after the edit (previous world differs), then a settled one
+            g.render(cam, cam, f); o.render(cam, cam, f)
+            assert np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits")), (f, bid)
+            mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+            assert mean_rel <= 1e-3 and outliers <= 1.5e-2, (f, bid, mean_rel, outliers)
+            rg, ro = g.read_reservoirs(f & 1), o.read_reservoirs(f & 1)
+            assert (rg["lightData"] == ro["lightData"]).mean() > 0.99, (f, bid)
+            f += 1
 
 
 def test_pipelined_readback_returns_the_frame_it_was_queued_for(libs):
