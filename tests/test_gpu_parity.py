@@ -398,3 +398,24 @@ def test_shard_with_rank_local_owner_matches_oracle(libs):
     g2.render_shard_local(cam, cam, 0, 0, 1)
     g3.render_shard(cam, cam, 0, 0, 1)
     assert np.array_equal(g2.read("Illumination"), g3.read("Illumination"))
+
+
+def test_emissive_material_early_out_matches_oracle(libs):
+    """closesthit.cu:101-122 on the device: emissive primary hits return their radiance and write the sky-like G-buffer."""
+    W, H = 256, 160
+    inp = common.scene_inputs((2, 1, 2))
+    mats = inp["materials"].copy()
+    mats[1]["isEmissive"] = 1
+    mats[1]["albedo"] = (5.0, 4.0, 3.0)
+    g, o = _pair(libs, W, H, dict(inp, materials=mats), spp=2, total=3, diffuse=1)
+    cam = common.scene_camera(W, H)
+    for f in range(2):
+        g.render(cam, cam, f)
+        o.render(cam, cam, f)
+        assert np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits")), f
+        for name in ("Depth", "Material", "NormalRoughness", "Albedo"):
+            assert np.array_equal(g.read(name), o.read(name)), (f, name)
+        m, outl, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        assert m <= 1e-3 and outl <= 1e-2, (f, m, outl)
+    ill = g.read("Illumination")[..., :3]
+    assert (np.abs(ill - np.float32([5.0, 4.0, 3.0])).max(-1) < 1e-6).mean() > 0.02   # emissive pixels are there
