@@ -11,7 +11,7 @@
 //  * the mask has a solid one-voxel shell: leaving the grid is "hitting" the shell — the step loop has NO bounds
 //    arithmetic. 18 SASS instructions per step (words are stored bit-reversed: shift + sign test). Rays with dir.y > 0 walk a second copy of the mask that is solid
 //    from the highest solid voxel up (GridView::upH): they retire as soon as nothing can be above them.
-//  * warp-level ray compaction: a warp reserves chunks of the prepared-ray queue (one atomic per 128 rays); whenever
+//  * warp-level ray compaction: a warp reserves chunks of the prepared-ray queue (one atomic per 64 rays); whenever
 //    at most kRefillBelow lanes still hold a live ray, the idle lanes are re-armed from the queue
 //    (__ballot_sync/__popc slot assignment), so the step loop runs with most lanes active regardless of how
 //    different the trip counts are. Lanes without a ray are parked on a spare all-zero mask word with zero
