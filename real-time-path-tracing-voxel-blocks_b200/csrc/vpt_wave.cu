@@ -504,6 +504,9 @@ constexpr int kShadeThreads = VPT_SHADE_THREADS;
 #ifndef VPT_SHADE_MINB
 #define VPT_SHADE_MINB 8
 #endif
+#ifndef VPT_S2_MINB
+#define VPT_S2_MINB VPT_SHADE_MINB
+#endif
 constexpr int kCntWords = 256, kCntList = 128; // cnt[2k], cnt[2k+1] = count / cursor of the k-th DDA launch; cnt[128+d] = active paths at depth d
 
 #ifndef VPT_RESERVE_WARP
@@ -977,7 +980,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
 
 // ------------------------------------------------------------------------------------------------ S2
 // RIS: classify the BSDF candidate, merge the three reservoirs, cast the winner's visibility ray (closesthit.cu:470-634).
-template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
