@@ -218,6 +218,27 @@ int vpt_load_materials(const char *materialsYamlPath, const char *blocksYamlPath
  * grey+alpha, RGB, palette, RGBA; non-interlaced. Grey is replicated to rgb, missing alpha = 255. out == NULL only queries
  * width/height/channels (channels = the file's channel count, as stb reports it). Host only. */
 int vpt_load_png_rgba8(const char *path, uint32_t *out, size_t maxTexels, int *width, int *height, int *channels);
+/* The reference's image-diff tool (renderer/util/ImageDiff.cpp:95-372; thresholds :119-121; docs/image-diffing-system.md), which
+ * mainOffline --test-canonical applies to its last frame (mainOffline.cpp:422-497): pixels whose per-channel difference exceeds
+ * 0.01 of full scale, RMSE over all samples, global SSIM of the 3x3-gaussian filtered luma (K1 0.01, K2 0.03, L 255);
+ * IDENTICAL = no different pixel, VERY CLOSE = SSIM > 0.99 and RMSE < 1, CLOSE = SSIM > 0.95 and RMSE < 5. The images are RGBA8
+ * words (vpt_load_png_rgba8 layout); `channels` = how many of r,g,b,a take part (min of the two files' channel counts).
+ * Sums are taken in double. Host only. Returns VPT_ERR_ARG for images of different size. */
+typedef struct VptImageDiffResult
+{
+    int32_t differentPixels;
+    int32_t totalPixels;
+    float pixelDifferenceRatio;
+    float rmse;
+    float ssim;
+    int32_t isIdentical;
+    int32_t isVeryClose;
+    int32_t isClose;
+} VptImageDiffResult;
+int vpt_image_diff(const uint32_t *imageA, const uint32_t *imageB, int width, int height, int channels, VptImageDiffResult *result);
+/* ImageDiff::compare(pathA, pathB) on two PNG files; diffPngOrNull != NULL also writes the difference picture of
+ * ImageDiff::generateDiffImage (:138-190: |a - b| per channel, amplified 3x, capped at 255, RGB). VPT_ERR_IO if a file cannot be read. */
+int vpt_image_diff_files(const char *pngA, const char *pngB, VptImageDiffResult *result, const char *diffPngOrNull);
 /* Mip chain of one square power-of-two RGBA8 image the way TextureManager::init builds it (renderer/assets/TextureManager.cu:
  * 82-115, 216-217, 395-411): level l+1 = per-channel 2x2 box average of level l, truncated to 8 bits; levels stop at 4x4
  * (numLods = log2(width) - 1; images smaller than 4x4 keep 1 level). Host only. out receives all levels concatenated (the layout

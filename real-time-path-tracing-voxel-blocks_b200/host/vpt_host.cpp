@@ -781,6 +781,138 @@ extern "C" int vpt_load_png_rgba8(const char *path, uint32_t *out, size_t maxTex
     return VPT_OK;
 }
 
+// ---- image diff (ImageDiff.cpp:95-372): different-pixel count, RMSE, global SSIM on the 3x3-gaussian filtered luma
+extern "C" int vpt_image_diff(const uint32_t *A, const uint32_t *B, int w, int h, int channels, VptImageDiffResult *r)
+{
+    if (!A || !B || !r || w <= 0 || h <= 0 || channels < 1 || channels > 4) return VPT_ERR_ARG;
+    const size_t n = (size_t)w * h;
+    auto ch = [](uint32_t v, int c) -> int { return (int)((v >> (8 * c)) & 0xffu); };
+    size_t different = 0;
+    double sq = 0.0;
+    std::vector<float> ga(n), gb(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        bool diff = false;
+        for (int c = 0; c < channels; ++c)
+        {
+            const int d = ch(A[i], c) - ch(B[i], c);
+            if ((float)std::abs(d) / 255.0f > 0.01f) diff = true;
+            sq += (double)d * d;
+        }
+        different += diff ? 1 : 0;
+        // luma of the first three channels (grey images: the single channel)
+        if (channels >= 3)
+        {
+            ga[i] = 0.299f * ch(A[i], 0) + 0.587f * ch(A[i], 1) + 0.114f * ch(A[i], 2);
+            gb[i] = 0.299f * ch(B[i], 0) + 0.587f * ch(B[i], 1) + 0.114f * ch(B[i], 2);
+        }
+        else { ga[i] = (float)ch(A[i], 0); gb[i] = (float)ch(B[i], 0); }
+    }
+    auto blur = [&](const std::vector<float> &src) {
+        std::vector<float> out(n);
+        static const float k[3] = {1.0f, 2.0f, 1.0f};
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+            {
+                float acc = 0.0f;
+                for (int ky = -1; ky <= 1; ++ky)
+                    for (int kx = -1; kx <= 1; ++kx)
+                    {
+                        const int yy = std::min(std::max(y + ky, 0), h - 1), xx = std::min(std::max(x + kx, 0), w - 1);
+                        acc += src[(size_t)yy * w + xx] * (k[ky + 1] * k[kx + 1] / 16.0f);
+                    }
+                out[(size_t)y * w + x] = acc;
+            }
+        return out;
+    };
+    const std::vector<float> fa = blur(ga), fb = blur(gb);
+    double ma = 0.0, mb = 0.0;
+    for (size_t i = 0; i < n; ++i) { ma += fa[i]; mb += fb[i]; }
+    ma /= (double)n; mb /= (double)n;
+    double va = 0.0, vb = 0.0, cov = 0.0;
+    for (size_t i = 0; i < n; ++i) { const double da = fa[i] - ma, db = fb[i] - mb; va += da * da; vb += db * db; cov += da * db; }
+    const double dn = n > 1 ? (double)(n - 1) : 1.0;
+    va /= dn; vb /= dn; cov /= dn;
+    const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+    const double ssim = ((2.0 * ma * mb + C1) * (2.0 * cov + C2)) / ((ma * ma + mb * mb + C1) * (va + vb + C2));
+    r->differentPixels = (int32_t)different; r->totalPixels = (int32_t)n;
+    r->pixelDifferenceRatio = (float)((double)different / (double)n);
+    r->rmse = (float)std::sqrt(sq / ((double)n * channels));
+    r->ssim = (float)ssim;
+    r->isIdentical = different == 0 ? 1 : 0;
+    r->isVeryClose = (r->ssim > 0.99f && r->rmse < 1.0f) ? 1 : 0;
+    r->isClose = (r->ssim > 0.95f && r->rmse < 5.0f) ? 1 : 0;
+    return VPT_OK;
+}
+
+// minimal RGB8 PNG writer for the difference picture (zlib "stored" blocks)
+namespace {
+uint32_t crcOf(const uint8_t *d, size_t n, uint32_t crc)
+{
+    static uint32_t table[256]; static bool init = false;
+    if (!init) { for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; } init = true; }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ d[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+void putBe32(std::vector<uint8_t> &v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+void pngChunk(std::vector<uint8_t> &out, const char *type, const std::vector<uint8_t> &data)
+{
+    putBe32(out, (uint32_t)data.size());
+    std::vector<uint8_t> td(type, type + 4);
+    td.insert(td.end(), data.begin(), data.end());
+    out.insert(out.end(), td.begin(), td.end());
+    putBe32(out, crcOf(td.data(), td.size(), 0xFFFFFFFFu) ^ 0xFFFFFFFFu);
+}
+bool writeRgbPng(const char *path, int w, int h, const std::vector<uint8_t> &rgb)
+{
+    std::vector<uint8_t> raw;
+    raw.reserve((size_t)h * ((size_t)w * 3 + 1));
+    for (int y = 0; y < h; ++y) { raw.push_back(0); raw.insert(raw.end(), rgb.begin() + (size_t)y * w * 3, rgb.begin() + (size_t)(y + 1) * w * 3); }
+    std::vector<uint8_t> z = {0x78, 0x01};
+    uint32_t a = 1, b = 0;
+    for (uint8_t v : raw) { a = (a + v) % 65521u; b = (b + a) % 65521u; }
+    for (size_t pos = 0; pos < raw.size();)
+    {
+        const size_t n = std::min<size_t>(65535, raw.size() - pos);
+        z.push_back(pos + n == raw.size() ? 1 : 0);
+        z.push_back((uint8_t)(n & 0xff)); z.push_back((uint8_t)(n >> 8)); z.push_back((uint8_t)(~n & 0xff)); z.push_back((uint8_t)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
+        pos += n;
+    }
+    putBe32(z, (b << 16) | a);
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A}, ihdr;
+    putBe32(ihdr, (uint32_t)w); putBe32(ihdr, (uint32_t)h);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+    pngChunk(out, "IHDR", ihdr); pngChunk(out, "IDAT", z); pngChunk(out, "IEND", {});
+    std::ofstream f(path, std::ios::binary);
+    if (!f.is_open()) return false;
+    f.write((const char *)out.data(), (std::streamsize)out.size());
+    return (bool)f;
+}
+} // namespace
+
+extern "C" int vpt_image_diff_files(const char *pngA, const char *pngB, VptImageDiffResult *r, const char *diffPng)
+{
+    if (!pngA || !pngB || !r) return VPT_ERR_ARG;
+    int wa = 0, ha = 0, ca = 0, wb = 0, hb = 0, cb = 0;
+    if (vpt_load_png_rgba8(pngA, nullptr, 0, &wa, &ha, &ca) != VPT_OK || vpt_load_png_rgba8(pngB, nullptr, 0, &wb, &hb, &cb) != VPT_OK) return VPT_ERR_IO;
+    if (wa != wb || ha != hb) return VPT_ERR_ARG; // "Cannot compare images of different sizes"
+    std::vector<uint32_t> A((size_t)wa * ha), B((size_t)wb * hb);
+    if (vpt_load_png_rgba8(pngA, A.data(), A.size(), &wa, &ha, &ca) != VPT_OK || vpt_load_png_rgba8(pngB, B.data(), B.size(), &wb, &hb, &cb) != VPT_OK) return VPT_ERR_IO;
+    const int channels = std::min(ca, cb);
+    const int rc = vpt_image_diff(A.data(), B.data(), wa, ha, channels, r);
+    if (rc != VPT_OK || !diffPng) return rc;
+    std::vector<uint8_t> rgb((size_t)wa * ha * 3);
+    for (size_t i = 0; i < A.size(); ++i)
+    {
+        int d[3];
+        for (int c = 0; c < 3; ++c) d[c] = std::abs((int)((A[i] >> (8 * c)) & 0xffu) - (int)((B[i] >> (8 * c)) & 0xffu));
+        if (channels < 3) { d[1] = d[0]; d[2] = d[0]; }
+        for (int c = 0; c < 3; ++c) rgb[i * 3 + c] = (uint8_t)std::min(255.0f, (float)d[c] * 3.0f);
+    }
+    return writeRgbPng(diffPng, wa, ha, rgb) ? VPT_OK : VPT_ERR_IO;
+}
+
 // ---- texture mip chains (TextureManager.cu:82-115, 216-217, 395-411): 2x2 box average per channel, truncated, down to 4x4
 static int mipLevels(int width)
 {

@@ -7,7 +7,8 @@
 // (renderer/core/OfflineBackend.cpp:191-221: y-flip, clamp to [0,1], *255). Out of scope here, as in SURVEY §2:
 // the wall-clock / history dependent post effects (auto-exposure, bloom, lens flare, vignette); the deterministic part —
 // FilmicToneMapping with the manual exposure of the settings file, sRGB, the PNG conversion — runs on the device (vpt_tonemap),
-// canonical comparison (the golden PNG is absent from the reference tree). The scripted edit tests (--test-sequence /
+// (the canonical comparison --test-canonical / --update-canonical / --canonical-image runs the reference's ImageDiff criteria
+// through vpt_image_diff_files; the golden PNG itself is absent from the reference tree). The scripted edit tests (--test-sequence /
 // --test-remove20 / --test-remove-circle, mainOffline.cpp:168-188, 279-393) run through the picker: vpt_pick_voxel + vpt_set_voxel.
 // New flags of this build: --spp N, --bounces T D, --chunks X Y Z, --exposure E, --tables PATH, --sky-tables PATH.
 #include "../../include/vpt.h"
@@ -101,6 +102,8 @@ int main(int argc, char *argv[])
     std::string settingsFile = "data/settings/global_settings.yaml", tablesFile = "data/bluenoise_tables.bin", skyTablesFile = "data/sky_tables.bin";
     std::string assetsDir, dataRoot = "."; // --assets: materials.yaml/blocks.yaml directory (reference: data/assets); texture paths resolve against --data-root
     bool useTextures = true;
+    bool testCanonical = false, updateCanonical = false; // mainOffline.cpp:41-42, 422-497
+    std::string canonicalImagePath = "../../data/canonical/canonical_render.png"; // the reference's default (mainOffline.cpp:41)
     // scripted block edits (mainOffline.cpp:43-51, 168-188, 279-393): clicks are consumed by the next frame's VoxelEngine::update
     bool enableTestSequence = false, enableRemovalStressTest = false, enableCircularRemovalTest = false;
     const int removalTestClickCount = 20, circularTestViewDirections = 8, circularTestRemovalsPerDirection = 5;
@@ -128,9 +131,9 @@ int main(int argc, char *argv[])
         else if (arg == "--no-textures") useTextures = false;
         else if (arg == "--world-chunks" && i + 1 < argc) worldChunkDir = argv[++i];
         else if (arg == "--save-world" && i + 1 < argc) saveWorldDir = argv[++i];
-        else if (arg == "--test-canonical" || arg == "--test" || arg == "--update-canonical")
-            std::printf("note: %s ignored (data/canonical/canonical_render.png is not part of the reference tree)\n", arg.c_str());
-        else if (arg == "--canonical-image" && i + 1 < argc) ++i;
+        else if (arg == "--test-canonical" || arg == "--test") testCanonical = true;
+        else if (arg == "--update-canonical") updateCanonical = true;
+        else if (arg == "--canonical-image" && i + 1 < argc) canonicalImagePath = argv[++i];
         else if (arg == "--comment" && i + 1 < argc) ++i;
         else if (arg == "--test-sequence") enableTestSequence = true;
         else if (arg == "--test-remove20") enableRemovalStressTest = true;
@@ -391,5 +394,48 @@ int main(int argc, char *argv[])
     std::printf("Rendering completed successfully!\nAverage per frame: path trace %.3f ms, denoiser %.3f ms (device), whole %.3f ms (wall)\n",
                 traceMs / totalFrames, denoiseMs / totalFrames, wall / totalFrames);
     vpt_destroy(ctx);
+    // canonical image testing / updating on the last frame (mainOffline.cpp:422-497; ImageDiff::compare + generateDiffImage)
+    if (testCanonical || updateCanonical)
+    {
+        char last[512];
+        std::snprintf(last, sizeof last, "%s_%04d.png", outputPrefix.c_str(), totalFrames - 1);
+        if (updateCanonical)
+        {
+            std::printf("\n=== Updating Canonical Image ===\n");
+            std::ifstream src(last, std::ios::binary);
+            std::ofstream dst(canonicalImagePath, std::ios::binary);
+            if (src.is_open() && dst.is_open() && (dst << src.rdbuf())) std::printf("Canonical image updated: %s\n", canonicalImagePath.c_str());
+            else std::fprintf(stderr, "Failed to update canonical image\n");
+        }
+        if (testCanonical)
+        {
+            std::printf("\n=== Canonical Image Testing ===\n");
+            std::ifstream canon(canonicalImagePath, std::ios::binary), test(last, std::ios::binary);
+            if (!canon.is_open()) std::printf("Warning: Canonical image not found at %s\nUse --update-canonical to create it from current render\n", canonicalImagePath.c_str());
+            else if (!test.is_open()) std::fprintf(stderr, "Error: Test image not found at %s\n", last);
+            else
+            {
+                std::printf("Comparing: %s vs %s\n", last, canonicalImagePath.c_str());
+                VptImageDiffResult r;
+                const std::string diffPath = outputPrefix + "_diff.png";
+                const int rc = vpt_image_diff_files(last, canonicalImagePath.c_str(), &r, diffPath.c_str());
+                if (rc != VPT_OK) std::fprintf(stderr, "Failed to compare the images (different sizes or unreadable)\n");
+                else
+                {
+                    std::printf("=== Image Comparison Results ===\nDifferent pixels: %d / %d (%.2f%%)\nRMSE: %.4f\nSSIM: %.6f\n", r.differentPixels, r.totalPixels,
+                                r.pixelDifferenceRatio * 100.0f, r.rmse, r.ssim);
+                    std::printf("Assessment: %s\n", r.isIdentical ? "IDENTICAL" : r.isVeryClose ? "VERY CLOSE (excellent match)" : r.isClose ? "CLOSE (good match)"
+                                                                                                                               : "DIFFERENT (significant differences detected)");
+                    std::printf("Difference visualization saved to: %s\n", diffPath.c_str());
+                    if (!r.isIdentical && !r.isVeryClose)
+                    {
+                        std::printf("\nWarning: Significant differences detected from canonical image!\nThis may indicate a regression or intentional change.\n");
+                        if (!r.isClose) std::printf("Consider investigating the differences.\n");
+                    }
+                    else std::printf("\nImage matches canonical reference within acceptable tolerance.\n");
+                }
+            }
+        }
+    }
     return 0;
 }

@@ -42,7 +42,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files"]
 
 
 def pack_textures(textures, slots, tex_size):
@@ -82,6 +82,28 @@ def load_materials(materials_yaml, blocks_yaml=None, max_materials=256):
         raise VptError("vpt_load_materials failed (%d)" % rc)
     names = [tuple(bytes(paths[i, k]).split(b"\0")[0].decode() for k in range(4)) for i in range(n.value)]
     return mats[:n.value].copy(), b2m, names
+
+
+IMAGE_DIFF_DTYPE = np.dtype([("differentPixels", "<i4"), ("totalPixels", "<i4"), ("pixelDifferenceRatio", "<f4"), ("rmse", "<f4"), ("ssim", "<f4"),
+                             ("isIdentical", "<i4"), ("isVeryClose", "<i4"), ("isClose", "<i4")])
+
+
+def image_diff(a, b, channels=3):
+    """vpt_image_diff on two (h,w) uint32 RGBA8 images -> dict of ImageDiffResult fields."""
+    a = np.ascontiguousarray(a, np.uint32); b = np.ascontiguousarray(b, np.uint32)
+    r = np.zeros(1, IMAGE_DIFF_DTYPE)
+    rc = lib().vpt_image_diff(_p(a), _p(b), a.shape[1], a.shape[0], channels, _p(r))
+    if rc != 0:
+        raise VptError("vpt_image_diff failed (%d)" % rc)
+    return {k: r[k][0].item() for k in IMAGE_DIFF_DTYPE.names}
+
+
+def image_diff_files(path_a, path_b, diff_png=None):
+    r = np.zeros(1, IMAGE_DIFF_DTYPE)
+    rc = lib().vpt_image_diff_files(path_a.encode(), path_b.encode(), _p(r), diff_png.encode() if diff_png else None)
+    if rc != 0:
+        raise VptError("vpt_image_diff_files failed (%d)" % rc)
+    return {k: r[k][0].item() for k in IMAGE_DIFF_DTYPE.names}
 
 
 def build_mip_chain(level0):

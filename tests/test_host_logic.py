@@ -225,3 +225,40 @@ def test_world_chunk_files_roundtrip(tmp_path):
     assert rc == 0 and ok == 2 and bad == 3
     assert np.array_equal(got[:32768], ids[:32768]) and (got[32768:3 * 32768] == 255).all() and np.array_equal(got[3 * 32768:], ids[3 * 32768:])
     assert vpt.load_world(str(tmp_path / "nope.yaml"), str(tmp_path), chunks, got)[0] != 0
+
+
+def test_image_diff_matches_reference_golden(tmp_path):
+    """vpt_image_diff (the --test-canonical comparison of the offline entry) against the fixture generated by the reference's
+    own ImageDiff.cpp (tests/golden/imagediff_ref.json, made by tests/golden/make_golden.py), in memory and through PNG files."""
+    import json
+    import vpt
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "imagediff_ref.json")))
+
+    def words(img):
+        u = img.astype(np.uint32)
+        return u[..., 0] | (u[..., 1] << 8) | (u[..., 2] << 16) | (np.uint32(255) << 24)
+    for i, c in enumerate(cases):
+        r = np.random.default_rng(c["seed"])
+        a = r.integers(0, 256, (c["h"], c["w"], 3), dtype=np.uint8)
+        a = (a.astype(np.float32) * 0.25 + np.linspace(0, 180, c["w"], dtype=np.float32)[None, :, None]).astype(np.uint8)
+        b = np.clip(a.astype(np.int32) + r.integers(-c["noise"], c["noise"] + 1, a.shape), 0, 255).astype(np.uint8)
+        got = vpt.image_diff(words(a), words(b), 3)
+        assert got["differentPixels"] == c["differentPixels"] and got["totalPixels"] == c["w"] * c["h"]
+        assert abs(got["rmse"] - c["rmse"]) <= 1e-3 * max(1.0, c["rmse"])
+        assert abs(got["ssim"] - c["ssim"]) <= 1e-4
+        assert (bool(got["isIdentical"]), bool(got["isVeryClose"]), bool(got["isClose"])) == (c["isIdentical"], c["isVeryClose"], c["isClose"])
+        if i < 3:
+            PIL = pytest.importorskip("PIL.Image")
+            pa, pb, pd = str(tmp_path / "a.png"), str(tmp_path / "b.png"), str(tmp_path / "d.png")
+            PIL.fromarray(a, "RGB").save(pa); PIL.fromarray(b, "RGB").save(pb)
+            got2 = vpt.image_diff_files(pa, pb, pd)
+            assert got2 == got
+            d = np.asarray(PIL.open(pd).convert("RGB")).astype(np.int32)
+            want = np.minimum(np.abs(a.astype(np.int32) - b.astype(np.int32)) * 3, 255)   # ImageDiff.cpp:161-180
+            assert np.array_equal(d, want)
+    with pytest.raises(vpt.VptError):
+        vpt.image_diff_files(str(tmp_path / "a.png"), str(tmp_path / "missing.png"))
+    PIL = pytest.importorskip("PIL.Image")
+    PIL.fromarray(np.zeros((5, 7, 3), np.uint8), "RGB").save(str(tmp_path / "s.png"))
+    with pytest.raises(vpt.VptError):
+        vpt.image_diff_files(str(tmp_path / "a.png"), str(tmp_path / "s.png"))      # different sizes

@@ -141,3 +141,28 @@ def test_vpt_offline_scripted_edits(tmp_path, flag, frames, expect):
     else:
         assert (removed, placed) == (1, 2)                          # place (frame 3), remove (frame 6), place (frame 9)
     assert os.path.exists(str(tmp_path / "o_0003.png"))
+
+
+@pytest.mark.gpu
+def test_vpt_offline_canonical_image_flow(tmp_path):
+    """mainOffline's --update-canonical / --test-canonical (mainOffline.cpp:422-497): the last frame becomes the canonical image,
+    a second identical run is IDENTICAL to it (the render is deterministic), a run with other settings is reported as different."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "real-time-path-tracing-voxel-blocks_b200")
+    (tmp_path / "scene.yaml").write_text("camera:\n  position: [35.6184, 11.8733, 42.0387]\n  direction: [-0.321564, -0.0129988, -0.946799]\n  up: [0, 1, 0]\n  fov: 90\n")
+    (tmp_path / "settings.yaml").write_text("denoising:\n  atrousIterationNum: 1\npostprocess:\n  manualExposure: 0.8\n")
+    canon = str(tmp_path / "canonical.png")
+    base = [os.path.join(pkg, "vpt_offline"), "--width", "192", "--height", "128", "--frames", "4", "--scene", str(tmp_path / "scene.yaml"),
+            "--settings", str(tmp_path / "settings.yaml"), "--tables", os.path.join(pkg, "data", "bluenoise_tables.bin"),
+            "--sky-tables", os.path.join(pkg, "data", "sky_tables.bin"), "--canonical-image", canon]
+    r0 = subprocess.run(base + ["--output", str(tmp_path / "a"), "--test-canonical"], capture_output=True, text=True, timeout=300)
+    assert r0.returncode == 0 and "Canonical image not found" in r0.stdout, r0.stdout[-2000:]
+    r1 = subprocess.run(base + ["--output", str(tmp_path / "a"), "--update-canonical"], capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0 and "Canonical image updated" in r1.stdout and os.path.exists(canon), r1.stdout[-2000:]
+    r2 = subprocess.run(base + ["--output", str(tmp_path / "b"), "--test-canonical"], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0 and "Assessment: IDENTICAL" in r2.stdout, r2.stdout[-2000:]
+    assert "Image matches canonical reference" in r2.stdout and os.path.exists(str(tmp_path / "b_diff.png"))
+    r3 = subprocess.run(base + ["--output", str(tmp_path / "c"), "--test-canonical", "--exposure", "3.0"], capture_output=True, text=True, timeout=300)
+    assert r3.returncode == 0 and "Assessment: IDENTICAL" not in r3.stdout and "Different pixels:" in r3.stdout, r3.stdout[-2000:]
