@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <string>
 #include <vector>
@@ -103,6 +104,9 @@ int main(int argc, char *argv[])
     std::string assetsDir, dataRoot = "."; // --assets: materials.yaml/blocks.yaml directory (reference: data/assets); texture paths resolve against --data-root
     bool useTextures = true;
     bool testCanonical = false, updateCanonical = false; // mainOffline.cpp:41-42, 422-497
+    // PerformanceTracker::saveReport (renderer/util/PerformanceTracker.h:98-175): one summary line per run, appended. The reference
+    // always writes ../../data/perf/performance_report.txt; here only when --perf-report names the file.
+    std::string runComment = "default run", perfReportPath;
     std::string canonicalImagePath = "../../data/canonical/canonical_render.png"; // the reference's default (mainOffline.cpp:41)
     // scripted block edits (mainOffline.cpp:43-51, 168-188, 279-393): clicks are consumed by the next frame's VoxelEngine::update
     bool enableTestSequence = false, enableRemovalStressTest = false, enableCircularRemovalTest = false;
@@ -134,7 +138,8 @@ int main(int argc, char *argv[])
         else if (arg == "--test-canonical" || arg == "--test") testCanonical = true;
         else if (arg == "--update-canonical") updateCanonical = true;
         else if (arg == "--canonical-image" && i + 1 < argc) canonicalImagePath = argv[++i];
-        else if (arg == "--comment" && i + 1 < argc) ++i;
+        else if (arg == "--comment" && i + 1 < argc) runComment = argv[++i];
+        else if (arg == "--perf-report" && i + 1 < argc) perfReportPath = argv[++i];
         else if (arg == "--test-sequence") enableTestSequence = true;
         else if (arg == "--test-remove20") enableRemovalStressTest = true;
         else if (arg == "--test-remove-circle") enableCircularRemovalTest = true;
@@ -154,6 +159,7 @@ int main(int argc, char *argv[])
                         "  --test-canonical --update-canonical --canonical-image <path> --comment <text>\n"
                         "  --test-sequence --test-remove20 --test-remove-circle   scripted block edits through the picker (vpt_pick_voxel + vpt_set_voxel)\n"
                         "  --spp <int> --bounces <total> <diffuse> --chunks <x> <y> <z> --exposure <f> --settings <file> --tables <file> --sky-tables <file>\n"
+                        "  --perf-report <file>  append the run summary line of PerformanceTracker::saveReport (with --comment)\n"
                         "  --assets <dir>  materials.yaml + blocks.yaml (reference: data/assets) with their textures under --data-root <dir> (default .); --no-textures\n"
                         "  --world-chunks <dir>  load the chunk files the scene lists (WorldSceneManager::LoadScene)   --save-world <dir>  write them\n", argv[0]);
             return 0;
@@ -308,6 +314,7 @@ int main(int argc, char *argv[])
     int iterationIndex = 0; // GlobalSettings::iterationIndex, reset for a fresh offline run (mainOffline.cpp:252)
     double traceMs = 0, denoiseMs = 0;
     const auto t0 = std::chrono::steady_clock::now();
+    std::vector<double> frameWallMs; double lastWallMs = 0.0;
     for (int f = 0; f < totalFrames; ++f)
     {
         const int frameNumber = f + 1;
@@ -352,6 +359,10 @@ int main(int argc, char *argv[])
         VptTimings tm;
         CHECK(vpt_get_timings(ctx, &tm));
         traceMs += tm.trace_ms + tm.resolve_ms; denoiseMs += tm.denoise_total_ms;
+        {
+            const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            frameWallMs.push_back(now - lastWallMs); lastWallMs = now;
+        }
         if (std::find(savedFrames.begin(), savedFrames.end(), frameNumber) != savedFrames.end())
         {
             // PostProcessor::run's deterministic part (FilmicToneMapping with the manual exposure) + the PNG conversion of
@@ -393,6 +404,32 @@ int main(int argc, char *argv[])
     const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::printf("Rendering completed successfully!\nAverage per frame: path trace %.3f ms, denoiser %.3f ms (device), whole %.3f ms (wall)\n",
                 traceMs / totalFrames, denoiseMs / totalFrames, wall / totalFrames);
+    if (!perfReportPath.empty() && !frameWallMs.empty())
+    {
+        std::ifstream probe(perfReportPath);
+        const bool fresh = !probe.is_open() || probe.peek() == std::ifstream::traits_type::eof();
+        probe.close();
+        std::ofstream rep(perfReportPath, std::ios::app);
+        if (rep.is_open())
+        {
+            if (fresh)
+                rep << "# Performance Report - Real-time Path Tracing Voxel Renderer (Run Summary)\n"
+                    << "# Format: Timestamp         | Frames | Resolution | WholeFrame | StdDev | ScenePrep | RendererUpd | PathTrace | Denoiser | PostProc | Comment\n"
+                    << "# ===============================================================================================================================\n";
+            double avg = 0.0, var = 0.0;
+            for (double v : frameWallMs) avg += v;
+            avg /= (double)frameWallMs.size();
+            for (double v : frameWallMs) var += (v - avg) * (v - avg);
+            const double sd = std::sqrt(var / (double)frameWallMs.size());
+            char stamp[32]; const std::time_t tt = std::time(nullptr); std::strftime(stamp, sizeof stamp, "%Y-%m-%d %H:%M:%S", std::localtime(&tt));
+            char line[512];
+            const std::string res = std::to_string(width) + "x" + std::to_string(height);
+            std::snprintf(line, sizeof line, "%-19s | %6zu | %-10s | %10.2f | %6.2f | %9.2f | %11.2f | %9.2f | %8.2f | %8.2f | %s\n", stamp, frameWallMs.size(), res.c_str(), avg, sd,
+                          0.0, 0.0, traceMs / totalFrames, denoiseMs / totalFrames, 0.0, runComment.c_str());
+            rep << line;
+            std::printf("Performance data saved to: %s\n", perfReportPath.c_str());
+        }
+    }
     vpt_destroy(ctx);
     // canonical image testing / updating on the last frame (mainOffline.cpp:422-497; ImageDiff::compare + generateDiffImage)
     if (testCanonical || updateCanonical)

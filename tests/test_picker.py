@@ -159,7 +159,12 @@ def test_vpt_offline_canonical_image_flow(tmp_path):
             "--sky-tables", os.path.join(pkg, "data", "sky_tables.bin"), "--canonical-image", canon]
     r0 = subprocess.run(base + ["--output", str(tmp_path / "a"), "--test-canonical"], capture_output=True, text=True, timeout=300)
     assert r0.returncode == 0 and "Canonical image not found" in r0.stdout, r0.stdout[-2000:]
-    r1 = subprocess.run(base + ["--output", str(tmp_path / "a"), "--update-canonical"], capture_output=True, text=True, timeout=300)
+    rep = str(tmp_path / "perf.txt")
+    r1 = subprocess.run(base + ["--output", str(tmp_path / "a"), "--update-canonical", "--perf-report", rep, "--comment", "unit test run"],
+                        capture_output=True, text=True, timeout=300)
+    lines = open(rep).read().splitlines()
+    assert lines[0].startswith("# Performance Report") and len(lines) == 4 and lines[3].endswith("unit test run") and "192x128" in lines[3]
+    assert lines[3].count("|") == 10
     assert r1.returncode == 0 and "Canonical image updated" in r1.stdout and os.path.exists(canon), r1.stdout[-2000:]
     r2 = subprocess.run(base + ["--output", str(tmp_path / "b"), "--test-canonical"], capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0 and "Assessment: IDENTICAL" in r2.stdout, r2.stdout[-2000:]
