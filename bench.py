@@ -9,7 +9,10 @@ Denoiser::run (firefly, temporal, history fix/clamp, 4 spatial passes, composite
 configs[1]: VoxelSceneGen noise terrain (16 chunks), 1920x1080, 4 spp, bounce limits 3/1, shipped denoiser settings.
 At N GPUs the spp loop is sharded (rank r renders samples r, r+N, ... of 4N spp), the fp32 accumulation buffers are
 summed with ncclAllReduce over NVLink and rank 0 denoises: per-GPU work is fixed -> "scaling": "weak".
+The camera follows SURVEY 8d cfg2: blocks of 8 static frames, then 8 frames with yaw += 0.5 deg/frame.
 Metric: Grays/s (device-counted traversal calls per second, whole job), ms/frame in ms_per_step.
+The `cpu_baseline` leg renders the first frames of the same schedule on the CPU oracle AND on a fresh GPU context and
+compares them plane by plane: the `parity` block of the line.
 """
 import argparse
 import json
@@ -81,6 +84,34 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class Cfg2Cameras:
+    """8 frames with a static camera, then 8 frames with yaw += 0.5 deg/frame (prevCam != cam: the reprojection paths
+    of the temporal ReSTIR pass and of TemporalAccumulation), repeated; the sweep direction alternates so the view stays on the
+    same terrain. frame -> (cam, prevCam)."""
+
+    def __init__(self, vpt, cam0):
+        self.vpt, self.cam, self.f = vpt, cam0, 0
+
+    @staticmethod
+    def moving(f):
+        return (f // 8) % 2 == 1
+
+    def next(self):
+        prev = self.cam
+        if self.moving(self.f):
+            sign = 1.0 if (self.f // 16) % 2 == 0 else -1.0
+            self.cam = self.vpt.camera_set_yaw_pitch(prev, prev[15] + np.float32(sign * 0.5 * np.pi / 180.0), prev[16])
+        self.f += 1
+        return self.cam, prev
+
+
 def make_inputs():
     import common
     inp = common.scene_inputs(CHUNKS)
@@ -101,6 +132,8 @@ def run_reference(args):
     import vpt
     import vpt_scenes as S
     O.build()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: this arm must use every host core it can, whatever the launcher
+    O.set_threads(host_cores())
     inp = common.scene_inputs(CHUNKS, noise_fn=O.perlin_noise_chunks, alias_fn=O.build_alias_table)
     p = S.default_denoising_params()
     threads = O.max_threads()
@@ -123,12 +156,16 @@ def run_reference(args):
             break
         scale *= 2
     frame = 1
+    cams = Cfg2Cameras(O, cam)
+    cams.f = 1
     for _ in range(max(args.warmup - 1, 0)):
-        o.render(cam, cam, frame); o.denoise(p, cam, cam, frame, frame + 1); frame += 1
+        c_, p_ = cams.next()
+        o.render(c_, p_, frame); o.denoise(p, c_, p_, frame, frame + 1); frame += 1
     rays = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.render(cam, cam, frame); o.denoise(p, cam, cam, frame, frame + 1); frame += 1
+        c_, p_ = cams.next()
+        o.render(c_, p_, frame); o.denoise(p, c_, p_, frame, frame + 1); frame += 1
         rays += o.counters()[0]
     dt = time.perf_counter() - t0
     value = rays / dt / 1e9
@@ -146,17 +183,71 @@ def run_reference(args):
 def workload_config(n):
     return {"workload": "cfg2: VoxelSceneGen noise terrain 16 chunks (4x1x4), 1920x1080, %d spp (%d per GPU), bounce limits %d/%d, "
                         "ReSTIR DI, full denoiser chain (global_settings.yaml: 4 spatial passes)" % (SPP * n, SPP, TOTAL_BOUNCE, DIFFUSE_BOUNCE),
+            "camera": "SURVEY 8d cfg2 schedule: blocks of 8 static frames and 8 frames with yaw += 0.5 deg/frame (prevCam != cam), sweep direction alternating",
             "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_total": SPP * n, "chunks": list(CHUNKS),
             "parallelism": ("spp-sharded x%d (%s) + ncclAllReduce(sum) of the accumulation buffer; rank 0 denoises"
                             % (n, "every rank: 1 ReSTIR sample + 3 plain samples, rank-local ReSTIR state" if LOCAL_OWNER else "one ReSTIR sample in total, on rank 0")) if n > 1 else "single GPU",
             "l2_policy": "working set 0.74 GB/frame (356 B/px of planes) > 126 MB L2: inputs larger than L2, no explicit flush"}
 
 
+def parity_and_cpu_baseline(inp, p, n_static=2, n_moving=2):
+    """The `cpu_baseline` leg, which is also the bench's self-check: a FRESH context renders the first frames of the cfg2 schedule
+    (static, then yaw += 0.5 deg/frame) in lockstep with the CPU oracle on the same inputs. The oracle's render + denoise calls are
+    what is timed (the baseline); every frame is then compared plane by plane (the parity block of the JSON line)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import common
+    import imagediff
+    import oracle as O
+    import vpt
+    O.set_threads(host_cores())
+    threads = O.max_threads()
+    g = common.setup(vpt.Vpt(WIDTH, HEIGHT, int(os.environ.get("LOCAL_RANK", "0"))), inp, spp=SPP, total=TOTAL_BOUNCE, diffuse=DIFFUSE_BOUNCE)
+    o = common.setup(O.Oracle(WIDTH, HEIGHT), inp, spp=SPP, total=TOTAL_BOUNCE, diffuse=DIFFUSE_BOUNCE)
+    cam = common.scene_camera(WIDTH, HEIGHT, CHUNKS)
+    prev = cam
+    par = {"frames": 0, "camera": "%d static + %d moving (yaw += 0.5 deg/frame)" % (n_static, n_moving), "primary_exact": True, "gbuffer_exact": True,
+           "history_length_exact": True, "radiance_mre": 0.0, "tail_gt_1e-3": 0.0, "denoised_mre": 0.0, "denoised_tail_gt_1e-3": 0.0, "imagediff": []}
+    cpu_s, rays = 0.0, 0
+    for f in range(n_static + n_moving):
+        if f >= n_static:
+            cam = vpt.camera_set_yaw_pitch(prev, prev[15] + np.float32(0.5 * np.pi / 180.0), prev[16])
+        t0 = time.perf_counter()
+        o.render(cam, prev, f)
+        cpu_s += time.perf_counter() - t0
+        g.render(cam, prev, f)
+        par["primary_exact"] &= bool(np.array_equal(g.read("PrimaryHits"), o.read("PrimaryHits")))
+        for name in ("Depth", "Material", "NormalRoughness", "GeoNormalThinfilm", "MaterialParameter", "Albedo"):
+            par["gbuffer_exact"] &= bool(np.array_equal(g.read(name), o.read(name)))
+        mre, tail, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+        par["radiance_mre"] = max(par["radiance_mre"], mre); par["tail_gt_1e-3"] = max(par["tail_gt_1e-3"], tail)
+        t0 = time.perf_counter()
+        o.denoise(p, cam, prev, f, f + 1)
+        cpu_s += time.perf_counter() - t0
+        g.denoise(p, cam, prev, f, f + 1)
+        par["history_length_exact"] &= bool(np.array_equal(g.read("HistoryLength"), o.read("HistoryLength")))
+        a, b = g.read("IlluminationOutput"), o.read("IlluminationOutput")
+        dm, dtail, _ = common.rel_err_stats(a[..., :3], b[..., :3])
+        par["denoised_mre"] = max(par["denoised_mre"], dm); par["denoised_tail_gt_1e-3"] = max(par["denoised_tail_gt_1e-3"], dtail)
+        r = imagediff.compare(imagediff.to_png8(a), imagediff.to_png8(b))
+        par["imagediff"].append("IDENTICAL" if r["isIdentical"] else "VERY CLOSE" if r["isVeryClose"] else "CLOSE" if r["isClose"] else "DIFFERENT")
+        rays += o.counters()[0]
+        par["frames"] += 1
+        prev = cam
+    par["ok"] = bool(par["primary_exact"] and par["gbuffer_exact"] and par["history_length_exact"] and par["radiance_mre"] <= 1e-3
+                     and all(c in ("IDENTICAL", "VERY CLOSE") for c in par["imagediff"]))
+    g.close()
+    nfr = par["frames"]
+    cpu = {"value": rays / cpu_s / 1e9, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_frame": cpu_s / nfr * 1e3,
+           "sample": "%d full 1080p frames of the same workload (4 spp trace + denoiser chain; %s), oracle on %d OpenMP threads"
+                     % (nfr, par["camera"], threads)}
+    return cpu, par
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -188,7 +279,7 @@ def main():
         uid = torch.from_numpy(vpt.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
         dist.broadcast(uid, 0)
         g.comm_init(rank, world, uid.cpu().numpy())
-    cam = common.scene_camera(WIDTH, HEIGHT, CHUNKS)
+    cams = Cfg2Cameras(vpt, common.scene_camera(WIDTH, HEIGHT, CHUNKS))
     p = S.default_denoising_params()
     stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local_rank))
     out_host = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
@@ -197,13 +288,14 @@ def main():
 
     def step(read_back):
         f = state["frame"]
+        cam, prev = cams.next()  # cfg2: blocks of 8 static / 8 moving frames
         if world == 1:
-            g.render(cam, cam, f)
-            g.denoise(p, cam, cam, f, f + 1)
+            g.render(cam, prev, f)
+            g.denoise(p, cam, prev, f, f + 1)
         else:
-            vpt_shard.render_sharded(g, cam, cam, f, rank, world, lambda c: c.comm_allreduce_illumination(), local_owner=LOCAL_OWNER)
+            vpt_shard.render_sharded(g, cam, prev, f, rank, world, lambda c: c.comm_allreduce_illumination(), local_owner=LOCAL_OWNER)
             if rank == 0:
-                g.denoise(p, cam, cam, f, f + 1)
+                g.denoise(p, cam, prev, f, f + 1)
         if read_back and rank == 0:
             # D2H of this frame's result into pinned memory, pipelined behind the frame (the next frame's denoiser waits for
             # it on the device); completed before the timed region ends
@@ -217,18 +309,17 @@ def main():
         torch.cuda.synchronize()
 
     def timed(read_back, steps):
-        rays = 0
-        stage = {}
         barrier()
+        g.total_rays(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local_rank)
         sampler.start()
         e0.record(stream)
         t0 = time.perf_counter()
+        n_moving = 0
         for _ in range(steps):
+            n_moving += 1 if Cfg2Cameras.moving(cams.f) else 0
             step(read_back)
-            if not read_back:
-                pass
         if read_back and rank == 0:
             g.read_wait()
         e1.record(stream)
@@ -238,39 +329,41 @@ def main():
         sampler.join()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device="cuda")
+        rays_t = torch.tensor([float(g.total_rays())], device="cuda", dtype=torch.float64)  # device-counted, summed over the loop
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall, sampler.summary()
+            dist.all_reduce(rays_t)
+        return float(t.item()), wall, sampler.summary(), float(rays_t.item()), n_moving
 
     # throughput runs: per-stage event records and the DDA step counter off
     g.set_profiling(False)
     for _ in range(args.warmup):
         step(False)
-    # per-step ray counts are deterministic for a static camera after warm-up; read them once per timed loop end
-    ms_dev, wall, clocks = timed(False, args.steps)
-    rays_step = g.counters()[0]
-    rays_t = torch.tensor([float(rays_step)], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(rays_t)
-    rays_all = float(rays_t.item())
-    value = rays_all * args.steps / (ms_dev * 1e-3) / 1e9
+    ms_dev, wall, clocks, rays_all, n_moving = timed(False, args.steps)
+    value = rays_all / (ms_dev * 1e-3) / 1e9
 
     # e2e: same steps through the public API with the result read back to pinned host memory every frame
-    ms_e2e, wall_e2e, _ = timed(True, args.steps)
-    e2e_value = rays_all * args.steps / (wall_e2e) / 1e9
+    ms_e2e, wall_e2e, _, rays_e2e, _ = timed(True, args.steps)
+    e2e_value = rays_e2e / wall_e2e / 1e9
 
-    # per-kernel breakdown: a few extra frames with CUDA-event stage timing + step counting on (not part of the timed runs)
+    # per-kernel breakdown: one more 16-frame cycle (8 static + 8 moving) with CUDA-event stage timing + step counting on (not part of
+    # the timed runs); the best frame of each half is reported
     g.set_profiling(True)
-    tim = None
-    steps_frame = 0
-    for _ in range(3):
+    best = {False: None, True: None}
+    steps_frame = rays_step = 0
+    while cams.f % 16 != 0:
+        step(False)
+    for _ in range(16):
+        mv = Cfg2Cameras.moving(cams.f)
         step(False)
         if rank == 0:
             t_ = g.timings()
-            if tim is None or t_["trace_ms"] + t_["denoise_total_ms"] < tim["trace_ms"] + tim["denoise_total_ms"]:
-                tim = t_
-            steps_frame = g.counters()[1]
+            if best[mv] is None or t_["trace_ms"] + t_["denoise_total_ms"] < best[mv]["trace_ms"] + best[mv]["denoise_total_ms"]:
+                best[mv] = t_
+            if not mv:
+                rays_step, steps_frame = g.counters()
     g.set_profiling(False)
+    tim = best[False]
 
     if rank != 0:
         if dist is not None:
@@ -279,57 +372,58 @@ def main():
 
     peak, peak_src = load_peaks()
     npix = WIDTH * HEIGHT
-    stages = [("trace_dda_x%d" % tim["trace_dda_launches"], tim["trace_dda_ms"], None),
-              ("trace_shade_x%d" % tim["trace_shade_launches"], tim["trace_shade_ms"] + tim["resolve_ms"], None), ("prep_firefly_sky", tim["firefly_ms"], "firefly"), ("temporal", tim["temporal_ms"], "temporal"),
-              ("history_fix", tim["history_fix_ms"], "history_fix"), ("history_clamp", tim["history_clamp_ms"], "history_clamp"),
-              ("atrous_smem", tim["atrous_smem_ms"], "atrous_smem"), ("atrous_x%d" % tim["atrous_passes"], tim["atrous_ms"], "atrous"),
-              ("composite", tim["composite_ms"], "composite")]
-    total_stage = sum(s[1] for s in stages)
-    kernels = []
-    for name, ms, key in stages:
-        k = {"name": name, "ms": round(ms, 4), "share": round(ms / total_stage, 4) if total_stage > 0 else None}
-        if key:
-            mult = tim["atrous_passes"] if key == "atrous" else 1
-            extra = (16, 52) if key == "atrous" else (0, 0)   # the last pass carries the composite
-            k["algorithmic_bytes"] = (PASS_BYTES[key][0] * mult + extra[0]) * npix
-            k["gbs"] = round(k["algorithmic_bytes"] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
-            k["gbs_ref_layout"] = round((PASS_BYTES[key][1] * mult + extra[1]) * npix / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
-        kernels.append(k)
+
+    def kernel_table(tim):
+        stages = [("trace_dda_x%d" % tim["trace_dda_launches"], tim["trace_dda_ms"], None),
+                  ("trace_shade_x%d" % tim["trace_shade_launches"], tim["trace_shade_ms"] + tim["resolve_ms"], None), ("prep_firefly_sky", tim["firefly_ms"], "firefly"),
+                  ("temporal", tim["temporal_ms"], "temporal"), ("history_fix", tim["history_fix_ms"], "history_fix"), ("history_clamp", tim["history_clamp_ms"], "history_clamp"),
+                  ("atrous_smem", tim["atrous_smem_ms"], "atrous_smem"), ("atrous_x%d" % tim["atrous_passes"], tim["atrous_ms"], "atrous"),
+                  ("composite", tim["composite_ms"], "composite")]
+        total_stage = sum(s[1] for s in stages)
+        kernels = []
+        for name, ms, key in stages:
+            k = {"name": name, "ms": round(ms, 4), "share": round(ms / total_stage, 4) if total_stage > 0 else None}
+            if key:
+                mult = tim["atrous_passes"] if key == "atrous" else 1
+                extra = (16, 52) if key == "atrous" else (0, 0)   # the last pass carries the composite
+                k["algorithmic_bytes"] = (PASS_BYTES[key][0] * mult + extra[0]) * npix
+                k["gbs"] = round(k["algorithmic_bytes"] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
+                k["gbs_ref_layout"] = round((PASS_BYTES[key][1] * mult + extra[1]) * npix / (ms * 1e-3) / 1e9, 1) if ms > 0 else None
+            kernels.append(k)
+        return kernels
+
+    kernels = kernel_table(tim)
     den = [k for k in kernels if "gbs" in k and k["ms"] > 0.01 and k["algorithmic_bytes"] > 0 and not k["name"].startswith("history_fix")]
     top = max(den, key=lambda k: k["ms"] / (tim["atrous_passes"] if k["name"].startswith("atrous_x") else 1))
     launches = tim["atrous_passes"] if top["name"].startswith("atrous_x") else 1
     achieved = top["algorithmic_bytes"] / launches / (top["ms"] / launches * 1e-3) / 1e9
     chain_bytes = sum(k["algorithmic_bytes"] for k in den)
     chain_ms = tim["denoise_total_ms"]
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(top["name"].split("_x")[0])
+            tj = json.load(open(tp))
+            traffic = tj.get(top["name"].split("_x")[0])
+            traffic_src = tj.get("_capture")
         except Exception:
             traffic = None
+    ref_layout_bytes = 612 * npix  # the reference's fp32 layout, shipped settings
+    mv = best[True]
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src,
-                "note": "dominant DENOISER kernel (the metric's HBM figure); traversal is shared-memory/issue bound (see trace{} and kernels[])",
+                "traffic": traffic, "traffic_capture": traffic_src, "peak_source": peak_src,
+                "note": "dominant DENOISER kernel (the metric's HBM figure), static-camera frame; traversal is shared-memory/issue bound (see trace{} and kernels[])",
                 "denoiser_chain": {"algorithmic_bytes": chain_bytes, "ms": round(chain_ms, 4), "gbs": round(chain_bytes / (chain_ms * 1e-3) / 1e9, 1),
-                                   "frac": round(chain_bytes / (chain_ms * 1e-3) / 1e9 / peak, 4)}}
+                                   "frac": round(chain_bytes / (chain_ms * 1e-3) / 1e9 / peak, 4),
+                                   "ref_layout_bytes": ref_layout_bytes, "frac_ref_layout": round(ref_layout_bytes / (chain_ms * 1e-3) / 1e9 / peak, 4)},
+                "denoiser_chain_moving_camera": None if mv is None else {
+                    "ms": round(mv["denoise_total_ms"], 4), "temporal_ms": round(mv["temporal_ms"], 4),
+                    "frac": round(chain_bytes / (mv["denoise_total_ms"] * 1e-3) / 1e9 / peak, 4)}}
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:
         try:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import oracle as O
-            o = common.setup(O.Oracle(WIDTH, HEIGHT), inp, spp=SPP, total=TOTAL_BOUNCE, diffuse=DIFFUSE_BOUNCE)
-            threads = O.max_threads()
-            o.render(cam, cam, 0); o.denoise(p, cam, cam, 0, 1)
-            t0 = time.perf_counter()
-            r = 0
-            nfr = 0
-            while time.perf_counter() - t0 < 12.0 and nfr < 8:
-                o.render(cam, cam, nfr + 1); o.denoise(p, cam, cam, nfr + 1, nfr + 2); r += o.counters()[0]; nfr += 1
-            dt = time.perf_counter() - t0
-            cpu_baseline = {"value": r / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_frame": dt / nfr * 1e3,
-                            "sample": "%d full 1080p frames of the same workload (4 spp trace + denoiser chain), oracle on %d OpenMP threads" % (nfr, threads)}
+            cpu_baseline, parity = parity_and_cpu_baseline(inp, p)
         except Exception as ex:  # the baseline is reported, never required for the product path
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
@@ -342,10 +436,16 @@ def main():
             trace_eff = json.load(open(ep))
         except Exception:
             trace_eff = None
+
+    def trace_block(t):
+        return {"ms": round(t["trace_ms"] + t["resolve_ms"], 4), "dda_ms": round(t["trace_dda_ms"], 4), "shade_ms": round(t["trace_shade_ms"], 4),
+                "denoise_ms": round(t["denoise_total_ms"], 4), "temporal_ms": round(t["temporal_ms"], 4)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world),
-            "gpixel_samples_per_s": npix * total_spp * args.steps / (ms_dev * 1e-3) / 1e9, "rays_per_frame": rays_all,
+            "camera_schedule": {"static_steps": args.steps - n_moving, "moving_steps": n_moving, "static": trace_block(tim), "moving": None if mv is None else trace_block(mv)},
+            "gpixel_samples_per_s": npix * total_spp * args.steps / (ms_dev * 1e-3) / 1e9, "rays_per_frame": rays_all / args.steps,
             "dda_steps_per_ray": (steps_frame / rays_step) if rays_step else None,
             "trace": {"ms": round(tim["trace_ms"] + tim["resolve_ms"], 4), "dda_ms": round(tim["trace_dda_ms"], 4),
                       "shade_ms": round(tim["trace_shade_ms"], 4), "dda_grays_per_s": round(rays_step / (tim["trace_dda_ms"] * 1e-3) / 1e9, 3) if tim["trace_dda_ms"] > 0 else None,
@@ -355,7 +455,7 @@ def main():
                     "h2d_bytes_per_step": 2 * 212 + 68 + 64, "d2h_bytes_per_step": npix * 16,
                     "note": "vpt_render + vpt_denoise + vpt_read_buffer_async(IlluminationOutput) into pinned host memory each frame (double-buffered, every copy complete inside the timed region); inputs per frame are "
                             "the two cameras + parameter blocks (scene is resident, as in the reference)"},
-            "roofline": roofline, "trace_efficiency_ncu": trace_eff, "kernels": kernels, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "trace_efficiency_ncu": trace_eff, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

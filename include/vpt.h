@@ -316,6 +316,10 @@ int vpt_write_reservoirs(vpt_ctx *ctx, int parity, const VptReservoir *host, siz
 void *vpt_device_ptr(vpt_ctx *ctx, VptBufferName name);
 /* Device-side counters of the last render: traversal calls (rays) and voxel steps. */
 int vpt_get_counters(vpt_ctx *ctx, uint64_t *rays, uint64_t *steps);
+/* Traversal calls summed over every render since the context was created (or since the last call with reset != 0): lets a
+ * frame loop be timed without a per-frame read-back. No reference counterpart (the reference counts nothing); the convention is
+ * SURVEY 8d's: one per optixTraverse site reached (RayGen.cu:49, closesthit.cu:458, 616, 745, 801). */
+int vpt_get_total_rays(vpt_ctx *ctx, uint64_t *rays, int reset);
 int vpt_get_timings(vpt_ctx *ctx, VptTimings *out);
 /* Toggle CUDA-event stage timing and the DDA step counter (default on; adds event records between kernels and one
  * add per DDA step). Throughput runs switch it off. */

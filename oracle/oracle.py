@@ -93,6 +93,13 @@ def camera_update(cam):
     return cam
 
 
+def camera_set_yaw_pitch(cam, yaw, pitch):
+    cam = cam.copy()
+    cam[15] = np.float32(yaw)
+    cam[16] = np.float32(pitch)
+    return camera_update(cam)
+
+
 def camera_from_scene(width, height, pos, direction, fov_deg):
     cam = np.zeros(CAMERA_FLOATS, np.float32)
     pos = np.asarray(pos, np.float32)

@@ -85,6 +85,7 @@ struct vpt_ctx
     size_t waveBudget = (size_t)16u << 20;
     // staging for vpt_denoise_external
     void *pinned = nullptr; size_t pinnedBytes = 0;
+    uint8_t *rgb8 = nullptr; // vpt_tonemap's 8-bit plane
     // profiling
     bool profiling = true;
     cudaEvent_t ev[EV_COUNT] = {};
@@ -96,6 +97,17 @@ struct vpt_ctx
     void *ncclComm = nullptr; int rank = 0, nranks = 1;
     size_t npix() const { return (size_t)width * height; }
 };
+
+static int createImpl(vpt_ctx *c);
+static void destroyComm(vpt_ctx *c);
+// a pipelined read-back (vpt_read_buffer_async) still in flight: the stream waits for it on the device before anything overwrites a
+// plane it may be reading
+static cudaError_t waitPendingCopy(vpt_ctx *c)
+{
+    if (!c->copyPending) return cudaSuccess;
+    c->copyPending = false; c->copyPendingTraceWritten = false;
+    return cudaStreamWaitEvent(c->stream, c->copyDone, 0);
+}
 
 extern "C" {
 
@@ -116,6 +128,16 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     vpt_ctx *c = new vpt_ctx();
     c->device = device; c->width = width; c->height = height; c->smCount = prop.multiProcessorCount;
     c->smemOptIn = prop.sharedMemPerBlockOptin;
+    const int rc = createImpl(c);
+    if (rc != VPT_OK) { const std::string keep = g_lastError; vpt_destroy(c); g_lastError = keep; return rc; } // nothing leaks on a partial create
+    *out = c;
+    return VPT_OK;
+}
+
+} // extern "C"
+
+static int createImpl(vpt_ctx *c)
+{
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->copyReady, cudaEventDisableTiming));
@@ -155,18 +177,22 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     }
     CU(cudaEventCreateWithFlags(&c->traceStreams.fork, cudaEventDisableTiming));
     CU(cudaStreamSynchronize(c->stream));
-    *out = c;
     return VPT_OK;
 }
+
+extern "C" {
 
 void vpt_destroy(vpt_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    for (int i = 0; i < 2; ++i) if (c->traceStreams.part[i]) cudaStreamSynchronize(c->traceStreams.part[i]);
+    destroyComm(c);
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
                     c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
-                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList};
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList, c->rgb8};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
     {
@@ -175,14 +201,24 @@ void vpt_destroy(vpt_ctx *c)
     }
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i <= TraceProfile::kMax; ++i) if (c->traceProf.ev[i]) cudaEventDestroy(c->traceProf.ev[i]);
     for (auto &p : c->atrousEv) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (int i = 0; i < 2; ++i)
+    {
+        if (c->traceStreams.join[i]) cudaEventDestroy(c->traceStreams.join[i]);
+        if (c->traceStreams.part[i]) cudaStreamDestroy(c->traceStreams.part[i]);
+    }
+    if (c->traceStreams.fork) cudaEventDestroy(c->traceStreams.fork);
+    if (c->copyReady) cudaEventDestroy(c->copyReady);
+    if (c->copyDone) cudaEventDestroy(c->copyDone);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int vpt_sync(vpt_ctx *c)
 {
-    if (c && c->copyStream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->copyStream); c->copyPending = false; }
+    if (c && c->copyStream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->copyStream); c->copyPending = false; c->copyPendingTraceWritten = false; }
     if (!c) return fail(VPT_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
@@ -294,7 +330,7 @@ int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_
     if (!c || !m || !b2m || count <= 0) return fail(VPT_ERR_ARG, "vpt_set_materials: bad argument");
     for (int i = 0; i < 256; ++i) if (b2m[i] >= count) return fail(VPT_ERR_ARG, "vpt_set_materials: blockToMaterial index out of range");
     CU(cudaSetDevice(c->device));
-    if (c->materials) cudaFree(c->materials);
+    if (c->materials) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->materials); c->materials = nullptr; }
     CU(cudaMalloc((void **)&c->materials, (size_t)count * sizeof(VptMaterial)));
     c->nMaterials = count;
     c->nTextures = 0; c->texSpecular = false; // texture slots are per material: vpt_set_textures must follow
@@ -313,7 +349,9 @@ int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *s
     if (!c || !sky || !sun || !skyAlias || !sunAlias || !sunDir || skyW <= 0 || skyH <= 0 || sunW <= 0 || sunH <= 0)
         return fail(VPT_ERR_ARG, "vpt_set_sky: bad argument");
     CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
     for (void *p : {(void *)c->sky, (void *)c->sun, (void *)c->skyAlias, (void *)c->sunAlias}) if (p) cudaFree(p);
+    c->sky = c->sun = nullptr; c->skyAlias = c->sunAlias = nullptr;
     const size_t ns = (size_t)skyW * skyH, nu = (size_t)sunW * sunH;
     CU(cudaMalloc((void **)&c->sky, ns * 16)); CU(cudaMalloc((void **)&c->sun, nu * 16));
     CU(cudaMalloc((void **)&c->skyAlias, ns * sizeof(VptAliasBin))); CU(cudaMalloc((void **)&c->sunAlias, nu * sizeof(VptAliasBin)));
@@ -431,6 +469,9 @@ int vpt_read_sky(vpt_ctx *c, float *skyRGBA, float *sunRGBA, float *sunDir3)
 int vpt_set_trace_params(vpt_ctx *c, int spp, int totalBounceLimit, int diffuseBounceLimit, int enableRestir)
 {
     if (!c || spp < 1 || totalBounceLimit < 1 || diffuseBounceLimit < 1) return fail(VPT_ERR_ARG, "vpt_set_trace_params: bad argument");
+    // every depth round owns three DDA count/cursor pairs and one active-list counter of the per-part counter block (vpt_wave.cu:
+    // kCntList, kCntWords); 16 is also the reference UI's range for the bounce sliders
+    if (totalBounceLimit > 16 || diffuseBounceLimit > 16) return fail(VPT_ERR_ARG, "vpt_set_trace_params: bounce limits above 16 are not supported");
     c->spp = spp; c->totalBounceLimit = totalBounceLimit; c->diffuseBounceLimit = diffuseBounceLimit; c->enableRestir = enableRestir ? 1 : 0;
     return VPT_OK;
 }
@@ -443,7 +484,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     if (!c->sky) return fail(VPT_ERR_STATE, "vpt_render: no sky (vpt_set_sky)");
     if ((int)cam->resolution[0] != c->width || (int)cam->resolution[1] != c->height) return fail(VPT_ERR_ARG, "vpt_render: camera resolution != context size");
     CU(cudaSetDevice(c->device));
-    if (c->copyPending && c->copyPendingTraceWritten) { CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0)); c->copyPending = false; }
+    if (c->copyPending && c->copyPendingTraceWritten) CU(waitPendingCopy(c));
     c->cur ^= 1;
     TraceArgs a;
     std::memset(&a, 0, sizeof a);
@@ -495,8 +536,11 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.resPrev = c->reservoirs + (size_t)((iterationIndex + 1) & 1) * c->npix();
     a.primaryHits = c->primaryHits;
     a.counters = c->counters;
-    CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->counters, 0, 2 * sizeof(unsigned long long), c->stream)); // [0] rays, [1] steps of this frame; [2] = running total of rays
     if (c->profiling) CU(cudaEventRecord(c->ev[EV_TRACE0], c->stream));
+    // more ranks than samples: this shard renders nothing, so its term of the cross-rank sum must be zero (no wave runs, so no
+    // accumulate pass would otherwise overwrite the previous frame's image)
+    if (shardSamples == 0) CU(cudaMemsetAsync(c->illumination, 0, c->npix() * sizeof(float4), c->stream));
     int launches = 0;
     c->traceProf.enabled = c->profiling;
     CU(launchTrace(a, c->wave.maxSamplesInWave, c->stream, c->overlapParts ? &c->traceStreams : nullptr, c->smCount, c->smemOptIn, &launches, &c->traceProf));
@@ -646,7 +690,7 @@ int vpt_denoise(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, c
     if (!c || !p || !cam || !prevCam) return fail(VPT_ERR_ARG, "vpt_denoise: null argument");
     CU(cudaSetDevice(c->device));
     // a pipelined read-back of the previous frame's planes must finish before this chain overwrites them (device-side wait)
-    if (c->copyPending) { CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0)); c->copyPending = false; }
+    CU(waitPendingCopy(c));
     return denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, 0, c->height, c->profiling, false);
 }
 
@@ -714,7 +758,7 @@ int vpt_read_buffer_async(vpt_ctx *c, VptBufferName name, void *host, size_t byt
     c->copyPending = true;
     // planes the trace writes must also survive until the copy is done; IlluminationOutput and the history planes are
     // only touched by the denoiser, so their copy may overlap the whole next trace
-    c->copyPendingTraceWritten = !(name == VPT_BUF_IlluminationOutput || name == VPT_BUF_IlluminationPing || name == VPT_BUF_IlluminationPong ||
+    c->copyPendingTraceWritten |= !(name == VPT_BUF_IlluminationOutput || name == VPT_BUF_IlluminationPing || name == VPT_BUF_IlluminationPong ||
                                    name == VPT_BUF_PrevIllumination || name == VPT_BUF_PrevFastIllumination || name == VPT_BUF_HistoryLength ||
                                    name == VPT_BUF_PrevHistoryLength);
     return VPT_OK;
@@ -724,7 +768,7 @@ int vpt_read_wait(vpt_ctx *c)
     if (!c) return fail(VPT_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->copyStream));
-    c->copyPending = false;
+    c->copyPending = false; c->copyPendingTraceWritten = false;
     return VPT_OK;
 }
 int vpt_write_buffer(vpt_ctx *c, VptBufferName name, const void *host, size_t bytes)
@@ -735,6 +779,7 @@ int vpt_write_buffer(vpt_ctx *c, VptBufferName name, const void *host, size_t by
     if (rc) return rc;
     if (have != bytes) return fail(VPT_ERR_ARG, "vpt_write_buffer: size mismatch");
     CU(cudaSetDevice(c->device));
+    CU(waitPendingCopy(c));
     CU(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return VPT_OK;
@@ -763,6 +808,7 @@ int vpt_denoise_external(vpt_ctx *c, const VptDenoisingParams *p, const VptCamer
     if (!c || !p || !cam || !prevCam || !illumination || !depth || !normalRoughness || !material || !albedo || !outputRGBA)
         return fail(VPT_ERR_ARG, "vpt_denoise_external: null argument");
     CU(cudaSetDevice(c->device));
+    CU(waitPendingCopy(c));
     c->cur ^= 1;
     const size_t n = c->npix();
     GSet &g = c->gb[c->cur];
@@ -784,13 +830,17 @@ int vpt_tonemap(vpt_ctx *c, const VptToneMappingParams *p, uint8_t *rgb8, float 
     CU(cudaSetDevice(c->device));
     const size_t n = c->npix();
     // ping is free between frames (it is rewritten by the next denoise): LDR float plane; the bytes go after it
+    CU(waitPendingCopy(c)); // the LDR plane lives in ping
     uint8_t *d8 = nullptr;
-    if (rgb8) CU(cudaMalloc((void **)&d8, n * 3));
+    if (rgb8)
+    {
+        if (!c->rgb8) CU(cudaMalloc((void **)&c->rgb8, n * 3)); // allocated once, at the first 8-bit read-out
+        d8 = c->rgb8;
+    }
     CU(launchTonemap(c->illumOutput, c->width, c->height, *p, d8, rgbaLDR ? c->ping : nullptr, c->stream));
     if (rgb8) CU(cudaMemcpyAsync(rgb8, d8, n * 3, cudaMemcpyDeviceToHost, c->stream));
     if (rgbaLDR) CU(cudaMemcpyAsync(rgbaLDR, c->ping, n * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (d8) CU(cudaFree(d8));
     return VPT_OK;
 }
 
@@ -802,6 +852,18 @@ int vpt_get_counters(vpt_ctx *c, uint64_t *rays, uint64_t *steps)
     CU(cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *rays = h[0]; *steps = h[1];
+    return VPT_OK;
+}
+
+int vpt_get_total_rays(vpt_ctx *c, uint64_t *rays, int reset)
+{
+    if (!c || !rays) return fail(VPT_ERR_ARG, "vpt_get_total_rays: null argument");
+    unsigned long long h = 0;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(&h, c->counters + 2, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CU(cudaMemsetAsync(c->counters + 2, 0, sizeof h, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *rays = h;
     return VPT_OK;
 }
 
@@ -861,6 +923,7 @@ struct NcclApi
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -873,12 +936,17 @@ bool loadNccl()
     if (!h) { g_lastError = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
 #define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { g_lastError = std::string("libnccl: missing ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast")
-    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString") SYM(CommDestroy, "ncclCommDestroy")
 #undef SYM
     g_nccl.handle = h;
     return true;
 }
 } // namespace
+static void destroyComm(vpt_ctx *c)
+{
+    if (c->ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->ncclComm);
+    c->ncclComm = nullptr;
+}
 #define NC(call)                                                                                                    \
     do {                                                                                                            \
         ncclResult_t r_ = (call);                                                                                   \
@@ -936,29 +1004,42 @@ int vpt_comm_broadcast_gbuffer(vpt_ctx *c, int iterationIndex)
     return VPT_OK;
 }
 
-// Halo exchange of `rows` rows of a plane with the bands above and below (elemFloats floats per pixel).
+// Halo exchange of `rows` rows of a plane with the bands above and below (elemFloats floats per pixel). Every band is at least
+// `rows` high (vpt_denoise_band checks the deepest halo the settings imply against the smallest band), so both sides of a pair
+// always move exactly `rows` rows: the send and receive counts agree by construction.
 static int haloExchange(vpt_ctx *c, void *plane, int elemFloats, int rowBegin, int rowEnd, int rows)
 {
     if (c->nranks == 1 || rows <= 0) return VPT_OK;
     ncclComm_t comm = (ncclComm_t)c->ncclComm;
-    const size_t rowFloats = (size_t)c->width * elemFloats;
+    const size_t rowFloats = (size_t)c->width * elemFloats, n = (size_t)rows * rowFloats;
     float *base = (float *)plane;
     const int up = c->rank - 1, down = c->rank + 1; // band r owns rows [r*H/n, (r+1)*H/n): "up" = lower row indices
     NC(g_nccl.GroupStart());
     if (up >= 0)
     {
-        const int r = std::min(rows, rowBegin);
-        NC(g_nccl.Send(base + (size_t)rowBegin * rowFloats, (size_t)std::min(rows, rowEnd - rowBegin) * rowFloats, ncclFloat, up, comm, c->stream));
-        NC(g_nccl.Recv(base + (size_t)(rowBegin - r) * rowFloats, (size_t)r * rowFloats, ncclFloat, up, comm, c->stream));
+        NC(g_nccl.Send(base + (size_t)rowBegin * rowFloats, n, ncclFloat, up, comm, c->stream));
+        NC(g_nccl.Recv(base + (size_t)(rowBegin - rows) * rowFloats, n, ncclFloat, up, comm, c->stream));
     }
     if (down < c->nranks)
     {
-        const int r = std::min(rows, c->height - rowEnd);
-        NC(g_nccl.Send(base + (size_t)(rowEnd - std::min(rows, rowEnd - rowBegin)) * rowFloats, (size_t)std::min(rows, rowEnd - rowBegin) * rowFloats, ncclFloat, down, comm, c->stream));
-        NC(g_nccl.Recv(base + (size_t)rowEnd * rowFloats, (size_t)r * rowFloats, ncclFloat, down, comm, c->stream));
+        NC(g_nccl.Send(base + (size_t)(rowEnd - rows) * rowFloats, n, ncclFloat, down, comm, c->stream));
+        NC(g_nccl.Recv(base + (size_t)rowEnd * rowFloats, n, ncclFloat, down, comm, c->stream));
     }
     NC(g_nccl.GroupEnd());
     return VPT_OK;
+}
+
+// Deepest halo (rows) the chain exchanges for these settings: the 32-row history guard, HistoryFix's 2 x 9, and the widest a-trous
+// reach (step + the hashed jitter of step / 4 + 1 for step > 4).
+static int maxHaloRows(const VptDenoisingParams *p)
+{
+    int rows = 32;
+    if (p->enableSpatialFiltering && p->atrousIterationNum > 0)
+    {
+        const int step = 1 << (p->atrousIterationNum * 2 - 1); // steps 2, 4, ..., 2^(2k-1)
+        rows = std::max(rows, step + (step > 4 ? step / 4 + 1 : 0));
+    }
+    return rows;
 }
 
 // Row-band sharded Denoiser::run: every rank holds full-size planes but only its band
@@ -971,7 +1052,16 @@ int vpt_denoise_band(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *c
     if (rowBegin < 0 || rowEnd > c->height || rowBegin >= rowEnd || (rowBegin & 3)) return fail(VPT_ERR_ARG, "vpt_denoise_band: band must start on a multiple of 4 rows");
     if (c->nranks > 1 && !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_denoise_band: communicator not initialised");
     if (p->enableHitDistanceReconstruction || p->enablePrePass) return fail(VPT_ERR_ARG, "vpt_denoise_band: unsupported pass enabled");
+    if (c->nranks > 1)
+    {
+        // one-hop exchange only: the deepest halo must fit the smallest band of an n-way split (bands are H/n rounded to 4 rows)
+        const int smallest = std::min(rowEnd - rowBegin, c->height / c->nranks - 3);
+        if (maxHaloRows(p) > smallest)
+            return fail(VPT_ERR_ARG, "vpt_denoise_band: the settings need a " + std::to_string(maxHaloRows(p)) + "-row halo but a band has only " +
+                                         std::to_string(smallest) + " rows (lower atrousIterationNum or use fewer ranks)");
+    }
     CU(cudaSetDevice(c->device));
+    CU(waitPendingCopy(c));
     return denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, rowBegin, rowEnd, false, c->nranks > 1);
 }
 

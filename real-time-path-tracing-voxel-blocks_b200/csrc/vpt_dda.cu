@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         r64 += __shfl_down_sync(kFull, r64, off);
         s64 += __shfl_down_sync(kFull, s64, off);
     }
-    if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); if (kStats) atomicAdd(a.counters + 1, s64); }
+    if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); atomicAdd(a.counters + 2, r64); if (kStats) atomicAdd(a.counters + 1, s64); } // [2]: running total over frames
 }
 
 template <bool kSmem, bool kClosest, bool kStats>

@@ -153,7 +153,7 @@ struct FireflyPatch
 struct TraceProfile
 {
     static constexpr int kMax = 96;
-    cudaEvent_t ev[kMax + 1]; // ev[0] = start, ev[i+1] = after launch i
+    cudaEvent_t ev[kMax + 1] = {}; // ev[0] = start, ev[i+1] = after launch i
     int kind[kMax];
     int n = 0;
     bool enabled = false;

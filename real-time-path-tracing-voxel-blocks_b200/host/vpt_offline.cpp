@@ -439,9 +439,15 @@ int main(int argc, char *argv[])
         if (updateCanonical)
         {
             std::printf("\n=== Updating Canonical Image ===\n");
+            // the destination is opened (= truncated) only once the source is known to be readable
             std::ifstream src(last, std::ios::binary);
-            std::ofstream dst(canonicalImagePath, std::ios::binary);
-            if (src.is_open() && dst.is_open() && (dst << src.rdbuf())) std::printf("Canonical image updated: %s\n", canonicalImagePath.c_str());
+            bool ok = src.is_open();
+            if (ok)
+            {
+                std::ofstream dst(canonicalImagePath, std::ios::binary);
+                ok = dst.is_open() && (dst << src.rdbuf());
+            }
+            if (ok) std::printf("Canonical image updated: %s\n", canonicalImagePath.c_str());
             else std::fprintf(stderr, "Failed to update canonical image\n");
         }
         if (testCanonical)

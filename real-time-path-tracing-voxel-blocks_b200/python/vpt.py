@@ -42,7 +42,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays"]
 
 
 def pack_textures(textures, slots, tex_size):
@@ -479,6 +479,11 @@ class Vpt:
         r, s = C.c_uint64(), C.c_uint64()
         _check(self.L.vpt_get_counters(self.ctx, C.byref(r), C.byref(s)), "vpt_get_counters")
         return r.value, s.value
+
+    def total_rays(self, reset=False):
+        r = C.c_uint64()
+        _check(self.L.vpt_get_total_rays(self.ctx, C.byref(r), 1 if reset else 0), "vpt_get_total_rays")
+        return r.value
 
     def timings(self):
         t = np.zeros(1, TIMINGS_DTYPE)

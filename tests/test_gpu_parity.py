@@ -419,3 +419,19 @@ def test_emissive_material_early_out_matches_oracle(libs):
         assert m <= 1e-3 and outl <= 1e-2, (f, m, outl)
     ill = g.read("Illumination")[..., :3]
     assert (np.abs(ill - np.float32([5.0, 4.0, 3.0])).max(-1) < 1e-6).mean() > 0.02   # emissive pixels are there
+
+
+def test_shard_with_no_samples_contributes_zero(libs):
+    """More ranks than samples (e.g. 8 GPUs at 4 spp): a rank whose shard is empty must add ZERO to the cross-rank sum, not the
+    image its previous frame left in the accumulation buffer."""
+    vpt, _ = libs
+    W, H = 96, 64
+    inp = common.scene_inputs((2, 1, 2))
+    g = common.setup(vpt.Vpt(W, H), inp, spp=2, total=3, diffuse=1)
+    cam = common.scene_camera(W, H)
+    g.render(cam, cam, 0)
+    assert np.abs(g.read("Illumination")[..., :3]).max() > 0
+    g.render_shard(cam, cam, 1, 2, 4)     # rank 2 of 4 at 2 spp: samples {2, 6, ...} of [0, 2) -> none
+    assert not g.read("Illumination").any()
+    with pytest.raises(vpt.VptError):
+        g.set_trace_params(1, 17, 1, 1)   # bounce limits above 16 would alias the per-depth queue counters
