@@ -320,6 +320,8 @@ int vpt_get_counters(vpt_ctx *ctx, uint64_t *rays, uint64_t *steps);
  * frame loop be timed without a per-frame read-back. No reference counterpart (the reference counts nothing); the convention is
  * SURVEY 8d's: one per optixTraverse site reached (RayGen.cu:49, closesthit.cu:458, 616, 745, 801). */
 int vpt_get_total_rays(vpt_ctx *ctx, uint64_t *rays, int reset);
+/* Debug counter: shared-memory tile loads of the denoiser whose completion barrier timed out (0 in a healthy build). */
+int vpt_debug_tma_timeouts(void);
 int vpt_get_timings(vpt_ctx *ctx, VptTimings *out);
 /* Toggle CUDA-event stage timing and the DDA step counter (default on; adds event records between kernels and one
  * add per DDA step). Throughput runs switch it off. */

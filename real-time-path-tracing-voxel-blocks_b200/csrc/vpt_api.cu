@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,6 +87,7 @@ struct vpt_ctx
     // staging for vpt_denoise_external
     void *pinned = nullptr; size_t pinnedBytes = 0;
     uint8_t *rgb8 = nullptr; // vpt_tonemap's 8-bit plane
+    bool dnGather = false;   // VPT_DN_GATHER=1: the per-thread gather kernels instead of the shared-memory tile kernels (A/B runs)
     // profiling
     bool profiling = true;
     cudaEvent_t ev[EV_COUNT] = {};
@@ -128,6 +130,7 @@ int vpt_create(int device, int width, int height, vpt_ctx **out)
     vpt_ctx *c = new vpt_ctx();
     c->device = device; c->width = width; c->height = height; c->smCount = prop.multiProcessorCount;
     c->smemOptIn = prop.sharedMemPerBlockOptin;
+    { const char *e = std::getenv("VPT_DN_GATHER"); c->dnGather = e && e[0] == '1'; }
     const int rc = createImpl(c);
     if (rc != VPT_OK) { const std::string keep = g_lastError; vpt_destroy(c); g_lastError = keep; return rc; } // nothing leaks on a partial create
     *out = c;
@@ -630,7 +633,11 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
             if ((rc = halo(c->pong, 4, 2))) return rc;
         }
         CU(rec(EV_HFIX));
-        if (p->enableHistoryClamping) { CU(launchHistoryClamping(d)); launches++; finalBuf = 3; c->ranClamp = true; }
+        if (p->enableHistoryClamping)
+        {
+            if (c->dnGather || !tileClampEnabled()) CU(launchHistoryClamping(d)); else CU(launchHistoryClampingCols(d));
+            launches++; finalBuf = 3; c->ranClamp = true;
+        }
         CU(rec(EV_HCLAMP));
     }
     else { CU(rec(EV_TEMPORAL)); CU(rec(EV_HFIX)); CU(rec(EV_HCLAMP)); }
@@ -638,7 +645,12 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
     if (p->enableSpatialFiltering)
     {
         if ((rc = halo(c->prevIllum, 4, 2))) return rc;
-        CU(launchAtrousSmem(d, c->prevIllum, c->ping)); launches++; finalBuf = 1; c->ranSpatial = true;
+        {
+            bool tiled = false;
+            if (!c->dnGather) CU(launchAtrousSmemTiled(d, c->prevIllum, c->ping, &tiled));
+            if (!tiled) CU(launchAtrousSmem(d, c->prevIllum, c->ping));
+        }
+        launches++; finalBuf = 1; c->ranSpatial = true;
         CU(rec(EV_ASMEM));
         if (p->atrousIterationNum > 0)
         {
@@ -649,7 +661,9 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
                 int r2 = halo(in, 4, hrows);
                 if (r2) return r2;
                 // the last pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky fused)
-                cudaError_t e = launchAtrous(d, in, last ? c->illumOutput : out, (unsigned)iterationIndex, (unsigned)step, last);
+                bool tiled = false;
+                cudaError_t e = c->dnGather ? cudaSuccess : launchAtrousTiled(d, in, last ? c->illumOutput : out, (unsigned)iterationIndex, (unsigned)step, last, &tiled);
+                if (e == cudaSuccess && !tiled) e = launchAtrous(d, in, last ? c->illumOutput : out, (unsigned)iterationIndex, (unsigned)step, last);
                 if (e != cudaSuccess) return fail(VPT_ERR_CUDA, cudaGetErrorString(e));
                 launches++; c->atrousPasses++;
                 return VPT_OK;
@@ -854,6 +868,9 @@ int vpt_get_counters(vpt_ctx *c, uint64_t *rays, uint64_t *steps)
     *rays = h[0]; *steps = h[1];
     return VPT_OK;
 }
+
+/* debug: tile loads (TMA) of the denoiser whose completion barrier timed out since the process started; 0 in a healthy build */
+int vpt_debug_tma_timeouts(void) { return (int)debugTmaTimeouts(); }
 
 int vpt_get_total_rays(vpt_ctx *c, uint64_t *rays, int reset)
 {

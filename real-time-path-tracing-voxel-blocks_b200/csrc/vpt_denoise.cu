@@ -359,14 +359,6 @@ __global__ void __launch_bounds__(256) historyFixKernel(const __grid_constant__ 
 // 5x5 mean / sigma of the responsive history (YCoCg) and of the noisy input, colour-box clamp, anti-lag, history write
 // (HistoryClamping.h:27-219). The per-pixel transforms are staged once in shared memory for the 36x12 tile and summed
 // separably (5 horizontal + 5 vertical taps per channel instead of 25 taps each redoing the transform).
-struct ClampArgs
-{
-    int W, H, rowBegin, rowEnd;
-    const float4 *illum, *ping, *pong;
-    const float *depth, *histLen;
-    float4 *prevIllum, *prevFast;
-    float *prevHistLen;
-};
 constexpr int kClampTW = kBX + 4, kClampTH = kBY + 4;
 #ifndef VPT_HCLAMP_MINB
 #define VPT_HCLAMP_MINB 1
@@ -467,35 +459,6 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_HCLAMP_MINB) historyClampKernel(
 }
 
 // ------------------------------------------------------------------------------------------------ à-trous
-struct AtrousArgs
-{
-    int W, H, rowBegin, rowEnd;
-    DnView view;
-    float phiLuminance, depthThreshold, lobeAngleFraction;
-    unsigned frameIndex, step;
-    float nParamFull; // GetNormalWeightParam2(1, lobe fraction) of a pixel with historyLength >= 5 (launch-uniform), from the host
-    const float4 *in, *G;
-    const uint32_t *MQ;
-    const float *histLen;
-    const float4 *albedo; // composite variant
-    float4 *out;
-};
-// per-centre constants of the tangent-plane test: dist(tap) = | zs_tap * (A0 + x*Ax + y*Ay) - c0 |
-struct PlaneTest { float A0, Ax, Ay, c0, thr; };
-VPT_DEV PlaneTest planeTest(const DnView &v, int x, int y, f3 cn, float zs, float depthThreshold)
-{
-    const f3 vc = viewVec(v, (float)x, (float)y);
-    PlaneTest p;
-    p.A0 = dot(F3(v.M0[0], v.M0[1], v.M0[2]), cn); p.Ax = dot(F3(v.Mx[0], v.Mx[1], v.Mx[2]), cn); p.Ay = dot(F3(v.My[0], v.My[1], v.My[2]), cn);
-    p.c0 = zs * dot(vc, cn);
-    p.thr = depthThreshold * (zs * sqrtf(dot(vc, vc))); // depthThreshold * z
-    return p;
-}
-VPT_DEV bool planeNear(const PlaneTest &p, float zsTap, float x, float y)
-{
-    return fabsf(fmaf(zsTap, fmaf(y, p.Ay, fmaf(x, p.Ax, p.A0)), -p.c0)) < p.thr;
-}
-
 // AtrousSmem (AtrousSmem.h:66-303): first spatial pass on the freshly written history.
 #ifndef VPT_AFIRST_MINB
 #define VPT_AFIRST_MINB 3 // measured: 1 (101 regs) 72.5 us, 2 72.7, 3 (80 regs) 64.5, 4 (64 regs, spills) 71.7
@@ -664,17 +627,7 @@ VPT_DEV void atrousBody(const AtrousArgs &a, int x, int y)
         {
             const int t = half * 4 + k;
             constexpr float k3[2] = {0.44198f, 0.27901f};
-            float w = k3[tx[t] & 1] * k3[ty[t] & 1];
-            w = (ok[k] && sg[k].w < kSkyZs && (sm[k] & 0xffffu) == cMat && planeNear(pt, sg[k].w, fx[k], fy[k])) ? w : 0.0f;
-            w *= normalWeight(dot(cn, F3(sg[k].x, sg[k].y, sg[k].z)), nParam);
-            if (w > 1e-4f)
-            {
-                const f4 v = F4(sv[k]);
-                const float lumW = fabsf(cLum - luminance(xyz(v))) * phiInv;
-                w *= __expf(-lumW);
-                sumW += w;
-                sum += f4{w, w, w, w * w} * v;
-            }
+            atrousTap(pt, cn, cMat, nParam, cLum, phiInv, ok[k], k3[tx[t] & 1] * k3[ty[t] & 1], sg[k], sm[k], sv[k], fx[k], fy[k], sumW, sum);
         }
     }
     const f4 res = sum / f4{sumW, sumW, sumW, sumW * sumW};
@@ -886,7 +839,7 @@ cudaError_t launchHistoryClamping(const DenoiseLaunch &d)
     historyClampKernel<<<gridFor(d), kBlock, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
-static AtrousArgs atrousArgs(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step)
+AtrousArgs makeAtrousArgs(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step)
 {
     AtrousArgs a;
     a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd; a.view = d.view;
@@ -909,14 +862,14 @@ static AtrousArgs atrousArgs(const DenoiseLaunch &d, const float4 *in, float4 *o
 }
 cudaError_t launchAtrousSmem(const DenoiseLaunch &d, const float4 *in, float4 *out)
 {
-    atrousFirstKernel<<<gridFor(d), kBlock, 0, d.stream>>>(atrousArgs(d, in, out, 0, 1));
+    atrousFirstKernel<<<gridFor(d), kBlock, 0, d.stream>>>(makeAtrousArgs(d, in, out, 0, 1));
     return cudaGetLastError();
 }
 cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step, bool composite)
 {
     const dim3 grid((d.width + kBX - 1) / kBX, (d.rowEnd - d.rowBegin + kAtrousBY - 1) / kAtrousBY), block(kBX, kAtrousBY);
-    if (composite) atrousKernel<true><<<grid, block, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
-    else atrousKernel<false><<<grid, block, 0, d.stream>>>(atrousArgs(d, in, out, frameIndex, step));
+    if (composite) atrousKernel<true><<<grid, block, 0, d.stream>>>(makeAtrousArgs(d, in, out, frameIndex, step));
+    else atrousKernel<false><<<grid, block, 0, d.stream>>>(makeAtrousArgs(d, in, out, frameIndex, step));
     return cudaGetLastError();
 }
 cudaError_t launchHitDist(const DenoiseLaunch &d)

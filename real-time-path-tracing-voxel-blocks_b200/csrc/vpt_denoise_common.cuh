@@ -95,6 +95,71 @@ VPT_DEV uint32_t seqExplode(uint32_t x)
     return x;
 }
 
+// ---- argument blocks shared by the gather kernels (vpt_denoise.cu) and the shared-memory tile kernels (vpt_dn_tiles.cu)
+struct AtrousArgs
+{
+    int W, H, rowBegin, rowEnd;
+    DnView view;
+    float phiLuminance, depthThreshold, lobeAngleFraction;
+    unsigned frameIndex, step;
+    float nParamFull; // GetNormalWeightParam2(1, lobe fraction) of a pixel with historyLength >= 5 (launch-uniform), from the host
+    const float4 *in, *G;
+    const uint32_t *MQ;
+    const float *histLen;
+    const float4 *albedo; // composite variant
+    float4 *out;
+};
+// per-centre constants of the tangent-plane test: dist(tap) = | zs_tap * (A0 + x*Ax + y*Ay) - c0 |
+struct PlaneTest { float A0, Ax, Ay, c0, thr; };
+VPT_DEV PlaneTest planeTest(const DnView &v, int x, int y, f3 cn, float zs, float depthThreshold)
+{
+    const f3 vc = viewVec(v, (float)x, (float)y);
+    PlaneTest p;
+    p.A0 = dot(F3(v.M0[0], v.M0[1], v.M0[2]), cn); p.Ax = dot(F3(v.Mx[0], v.Mx[1], v.Mx[2]), cn); p.Ay = dot(F3(v.My[0], v.My[1], v.My[2]), cn);
+    p.c0 = zs * dot(vc, cn);
+    p.thr = depthThreshold * (zs * sqrtf(dot(vc, vc))); // depthThreshold * z
+    return p;
+}
+VPT_DEV bool planeNear(const PlaneTest &p, float zsTap, float x, float y)
+{
+    return fabsf(fmaf(zsTap, fmaf(y, p.Ay, fmaf(x, p.Ax, p.A0)), -p.c0)) < p.thr;
+}
+#ifndef VPT_ATAP_BRANCH
+#define VPT_ATAP_BRANCH 0 // skipping the normal weight where the tap's normal equals the centre's (weight exactly 1): measured slower as a
+                          // per-thread branch (three passes 142 vs 128 us at 1080p)
+#endif
+// One edge-stopped tap of an a-trous pass (Atrous.h:76-140), shared by the gather and the tile kernel so that both data paths
+// run the very same arithmetic. kern = the 3x3 kernel weight, ok = the tap is inside the image.
+//  * the weighted sums are explicit FMAs (the f4 operators left 4 FMUL + 4 FADD per tap: 7 % of the pass, ncu r2e).
+VPT_DEV void atrousTap(const PlaneTest &pt, f3 cn, uint32_t cMat, float nParam, float cLum, float phiInv, bool ok, float kern, float4 sg, uint32_t sm,
+                       float4 sv, float fx, float fy, float &sumW, f4 &sum)
+{
+    float w = (ok && sg.w < kSkyZs && (sm & 0xffffu) == cMat && planeNear(pt, sg.w, fx, fy)) ? kern : 0.0f;
+    const float d = dot(cn, F3(sg.x, sg.y, sg.z));
+#if VPT_ATAP_BRANCH
+    if (d < 1.0f) w *= normalWeight(d, nParam);
+#else
+    w *= normalWeight(d, nParam);
+#endif
+    if (w > 1e-4f)
+    {
+        const float lumW = fabsf(cLum - luminance(xyz(sv))) * phiInv;
+        w *= __expf(-lumW);
+        sumW += w;
+        sum.x = fmaf(w, sv.x, sum.x); sum.y = fmaf(w, sv.y, sum.y); sum.z = fmaf(w, sv.z, sum.z); sum.w = fmaf(w * w, sv.w, sum.w);
+    }
+}
+
+struct ClampArgs
+{
+    int W, H, rowBegin, rowEnd;
+    const float4 *illum, *ping, *pong;
+    const float *depth, *histLen;
+    float4 *prevIllum, *prevFast;
+    float *prevHistLen;
+};
+AtrousArgs makeAtrousArgs(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step); // host (vpt_denoise.cu)
+
 #define PIXEL_GUARD(W_, rowBegin_, rowEnd_)                       \
     const int x = blockIdx.x * kBX + threadIdx.x;                 \
     const int y = (rowBegin_) + blockIdx.y * kBY + threadIdx.y;   \

@@ -222,6 +222,14 @@ cudaError_t launchHistoryClamping(const DenoiseLaunch &d);
 cudaError_t launchAtrousSmem(const DenoiseLaunch &d, const float4 *in, float4 *out);
 cudaError_t launchAtrous(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step, bool composite);
 cudaError_t launchCompositeNonSky(const DenoiseLaunch &d, const float4 *finalBuf);
+// Shared-memory tile versions (vpt_dn_tiles.cu: TMA + mbarrier halo tiles; column-walking history clamp). *handled = false when the
+// shape is outside what the tiles cover (a-trous steps other than 2/4/8, widths that are not a multiple of 4): the caller then
+// uses the gather kernel above.
+cudaError_t launchAtrousTiled(const DenoiseLaunch &d, const float4 *in, float4 *out, unsigned frameIndex, unsigned step, bool composite, bool *handled);
+cudaError_t launchAtrousSmemTiled(const DenoiseLaunch &d, const float4 *in, float4 *out, bool *handled);
+cudaError_t launchHistoryClampingCols(const DenoiseLaunch &d);
+bool tileClampEnabled();
+unsigned debugTmaTimeouts(); // tile loads that timed out since the process started (0 unless a tensor map / byte count is wrong)
 cudaError_t launchFrame0Init(const DenoiseLaunch &d);
 cudaError_t launchHitDist(const DenoiseLaunch &d);                 // IlluminationBuffer.w -> IlluminationPing (default off)
 cudaError_t launchPrePass(const DenoiseLaunch &d, int frameIndex); // IlluminationPing -> IlluminationBuffer (default off)

@@ -18,6 +18,21 @@
 
 namespace vpt {
 
+// ------------------------------------------------------------------------------------------------ taps
+// kIn: the caller has established that every tap of the pixel's footprint lies inside the image, so the clamp-to-edge of the
+// reference's surface reads (cudaBoundaryModeClamp) is the identity and is skipped: a tap is then base + compile-time offset.
+// 52 taps per pixel -> ~260 fewer integer instructions on all but the border ring (ncu r1l: the pass is issue-bound).
+template <bool kIn> VPT_DEV f4 tap4(const float4 *b, int W, int H, int x, int y)
+{
+    if (!kIn) { x = clampi(x, 0, W - 1); y = clampi(y, 0, H - 1); }
+    return F4(__ldg(b + (y * W + x)));
+}
+template <bool kIn> VPT_DEV float tap1(const float *b, int W, int H, int x, int y)
+{
+    if (!kIn) { x = clampi(x, 0, W - 1); y = clampi(y, 0, H - 1); }
+    return __ldg(b + (y * W + x));
+}
+
 // ------------------------------------------------------------------------------------------------ samplers
 VPT_DEV void bilinearSetup(f2 uv, int W, int H, f2 &f, int &tx0, int &ty0)
 {
@@ -32,7 +47,7 @@ VPT_DEV f4 bilinearWeight(f2 uv, int W, int H)
     f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
     return {w0.x * w0.y, w1.x * w0.y, w0.x * w1.y, w1.x * w1.y};
 }
-VPT_DEV f4 sampleBilinearCustom4(const float4 *tex, f2 uv, int W, int H, f4 cw)
+template <bool kIn> VPT_DEV f4 sampleBilinearCustom4(const float4 *tex, f2 uv, int W, int H, f4 cw)
 {
     f2 f; int x0, y0; bilinearSetup(uv, W, H, f, x0, y0);
     f2 w1 = f, w0 = {1.0f - f.x, 1.0f - f.y};
@@ -42,7 +57,7 @@ VPT_DEV f4 sampleBilinearCustom4(const float4 *tex, f2 uv, int W, int H, f4 cw)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
-        f4 v = ld4(tex, W, H, xs[i], ys[i]);
+        f4 v = tap4<kIn>(tex, W, H, xs[i], ys[i]);
         float w = max1f(ws[i], 1e-6f);
         sum += w; out += v * w;
     }
@@ -64,7 +79,7 @@ VPT_DEV float sampleBilinearCustom1(const float *tex, f2 uv, int W, int H, f4 cw
     }
     return out / sum;
 }
-VPT_DEV f4 sampleBicubic12(const float4 *tex, f2 uv, int W, int H)
+template <bool kIn> VPT_DEV f4 sampleBicubic12(const float4 *tex, f2 uv, int W, int H)
 {
     f2 f; int x1, y1; bilinearSetup(uv, W, H, f, x1, y1);
     f2 f2_ = f * f, f3_ = f2_ * f;
@@ -79,7 +94,7 @@ VPT_DEV f4 sampleBicubic12(const float4 *tex, f2 uv, int W, int H)
                           w0.x * w2.y, w1.x * w2.y, w2.x * w2.y, w3.x * w2.y, w1.x * w3.y, w2.x * w3.y};
     f4 out = F4(0.0f); float sum = 0;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { sum += ws[i]; out += ld4(tex, W, H, xs[i], ys[i]) * ws[i]; }
+    for (int i = 0; i < 12; ++i) { sum += ws[i]; out += tap4<kIn>(tex, W, H, xs[i], ys[i]) * ws[i]; }
     return out / sum;
 }
 VPT_DEV f3 sampleSmoothStep3(const float4 *tex, f2 uv, int W, int H)
@@ -119,7 +134,7 @@ VPT_DEV f4 exBilinearWeight(const ExBilinear &b)
     return {ex::mulf(w0x, w0y), ex::mulf(w1x, w0y), ex::mulf(w0x, w1y), ex::mulf(w1x, w1y)};
 }
 // sampleBilinearCustom1 (Sampler.h:452-498): custom tap weights floored at 1e-6, normalised
-VPT_DEV float exSampleBilinearCustom1(const float *tex, const ExBilinear &b, int W, int H, f4 cw)
+template <bool kIn> VPT_DEV float exSampleBilinearCustom1(const float *tex, const ExBilinear &b, int W, int H, f4 cw)
 {
     const f4 bw = exBilinearWeight(b);
     const int xs[4] = {b.x0, b.x0 + 1, b.x0, b.x0 + 1}, ys[4] = {b.y0, b.y0, b.y0 + 1, b.y0 + 1};
@@ -128,7 +143,7 @@ VPT_DEV float exSampleBilinearCustom1(const float *tex, const ExBilinear &b, int
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
-        const float v = ld1(tex, W, H, xs[i], ys[i]);
+        const float v = tap1<kIn>(tex, W, H, xs[i], ys[i]);
         const float w = max1f(ws[i], 1e-6f);
         sum = ex::addf(sum, w); out = ex::addf(out, ex::mulf(v, w));
     }
@@ -137,7 +152,7 @@ VPT_DEV float exSampleBilinearCustom1(const float *tex, const ExBilinear &b, int
 
 VPT_DEV f3 exAdd3(f3 a, f3 b) { return {ex::addf(a.x, b.x), ex::addf(a.y, b.y), ex::addf(a.z, b.z)}; }
 VPT_DEV f3 exScale3(f3 a, float s) { return {ex::mulf(a.x, s), ex::mulf(a.y, s), ex::mulf(a.z, s)}; }
-VPT_DEV f3 exDiv3(f3 a, float s) { return {ex::divf(a.x, s), ex::divf(a.y, s), ex::divf(a.z, s)}; }
+VPT_DEV f3 exDiv3(f3 a, float s) { const ex::rcpx k = ex::rcpPrepare(s); return {ex::divBy(k, a.x), ex::divBy(k, a.y), ex::divBy(k, a.z)}; }
 // Quat (LinearMath.h:1311-1366) in the exact class: an axis-aligned voxel scene is full of EXACT cancellations (a 3x3 normal
 // average perpendicular to the history normal gives dot == 0), so the sign test below must round like the oracle
 VPT_DEV quat exQmul(quat p, quat q)
@@ -149,12 +164,13 @@ VPT_DEV f3 exQrotate(quat q, f3 v) { return exQmul(exQmul(q, quat{v, 0.0f}), qua
 VPT_DEV float exParallaxInPixels(f3 X, f2 uvZero, f3 camPos, const float *worldToUv, f2 rectSize)
 {
     const f3 h = ex::mulMat3(worldToUv, ex::normalize(exSub3(X, camPos)));
-    const float dx = ex::mulf(ex::subf(ex::divf(h.x, h.z), uvZero.x), rectSize.x), dy = ex::mulf(ex::subf(ex::divf(h.y, h.z), uvZero.y), rectSize.y);
+    const ex::rcpx k = ex::rcpPrepare(h.z);
+    const float dx = ex::mulf(ex::subf(ex::divBy(k, h.x), uvZero.x), rectSize.x), dy = ex::mulf(ex::subf(ex::divBy(k, h.y), uvZero.y), rectSize.y);
     return __fsqrt_rn(ex::addf(ex::mulf(dx, dx), ex::mulf(dy, dy)));
 }
 
 // SampleBicubicSmoothStep (Sampler.h:652-698), xyz only
-VPT_DEV f3 exSampleSmoothStep3(const float4 *tex, const ExBilinear &b, int W, int H)
+template <bool kIn> VPT_DEV f3 exSampleSmoothStep3(const float4 *tex, const ExBilinear &b, int W, int H)
 {
     const float fx2 = ex::mulf(b.fx, b.fx), fy2 = ex::mulf(b.fy, b.fy), fx3 = ex::mulf(fx2, b.fx), fy3 = ex::mulf(fy2, b.fy);
     const float w1x = ex::addf(ex::mulf(-2.0f, fx3), ex::mulf(3.0f, fx2)), w1y = ex::addf(ex::mulf(-2.0f, fy3), ex::mulf(3.0f, fy2));
@@ -163,7 +179,7 @@ VPT_DEV f3 exSampleSmoothStep3(const float4 *tex, const ExBilinear &b, int W, in
     const float ws[4] = {ex::mulf(w0x, w0y), ex::mulf(w1x, w0y), ex::mulf(w0x, w1y), ex::mulf(w1x, w1y)};
     f3 out = F3(0.0f); float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { sum = ex::addf(sum, ws[i]); out = exAdd3(out, exScale3(xyz(ld4(tex, W, H, xs[i], ys[i])), ws[i])); }
+    for (int i = 0; i < 4; ++i) { sum = ex::addf(sum, ws[i]); out = exAdd3(out, exScale3(xyz(tap4<kIn>(tex, W, H, xs[i], ys[i])), ws[i])); }
     return exDiv3(out, sum);
 }
 
@@ -185,27 +201,25 @@ struct TemporalArgs
 #ifndef VPT_TEMPORAL_MINB
 #define VPT_TEMPORAL_MINB 4 // measured: 2 -> 223 us, 3 (80 regs) -> 176, 4 (64 regs) -> 162, 5 -> 162
 #endif
-__global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(const __grid_constant__ TemporalArgs a)
+// Everything after the reprojected footprint is known. kIn: every tap of the pixel (its 3x3 normal neighbourhood and the 4x4
+// previous-frame footprint around (bx, by)) lies inside the image — warp-uniform, see the kernel.
+struct TemporalPre
 {
-    const int W = a.W, H = a.H;
-    PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
-    const float z = __ldg(a.depth + pix);
-    if (z > a.denoisingRange) return;
-    const Cam cam = loadCam(a.cam), prevCam = loadCam(a.prevCam);
+    int x, y; size_t pix; float z;
+    f3 n, viewVec, worldPos, Vprev; float NoV; f2 prevUV; ExBilinear bil;
+};
+template <bool kIn> VPT_DEV void temporalRest(const TemporalArgs &a, const TemporalPre &t)
+{
+    const int W = a.W, H = a.H, x = t.x, y = t.y;
+    const size_t pix = t.pix;
+    const float z = t.z;
+    const f3 n = t.n, worldPos = t.worldPos, Vprev = t.Vprev;
+    const float NoV = t.NoV;
+    const f2 prevUV = t.prevUV;
+    const ExBilinear bil = t.bil;
+    const f3 camPosV = F3(a.cam.pos[0], a.cam.pos[1], a.cam.pos[2]), prevCamPos = F3(a.prevCam.pos[0], a.prevCam.pos[1], a.prevCam.pos[2]);
     // launch-uniform: rotation between the previous and current view directions, evaluated on the host (hostRotationBetween)
     const quat prevToCur = {F3(a.prevToCur[0], a.prevToCur[1], a.prevToCur[2]), a.prevToCur[3]};
-    const f3 n = xyz(__ldg(a.normalRough + pix));
-    // ---- exact class: the chain that decides historyLength
-    const f2 curUV = {ex::mulf(ex::addf(float(x), 0.5f), cam.invResX), ex::mulf(ex::addf(float(y), 0.5f), cam.invResY)};
-    const f3 viewVec = ex::normalize(ex::mulMat3(a.cam.uvToWorld, F3(curUV.x, curUV.y, 1.0f)));
-    const f3 worldPos = ex::pointAt(cam.pos, viewVec, z);
-    const f3 V = -ex::normalize(viewVec);
-    const float NoV = fabsf(ex::dot(n, V));
-    const f3 prevWorldPos = worldPos;
-    const f3 Vprev = ex::normalize(exSub3(prevWorldPos, prevCam.pos));
-    const f3 hUv = ex::mulMat3(a.prevCam.worldToUv, Vprev);
-    const f2 prevUV = {ex::divf(hUv.x, hUv.z), ex::divf(hUv.y, hUv.z)};
-    const ExBilinear bil = exBilinearSetup(prevUV, W, H);
     // ---- fast class from here on, except where noted
     const f3 illum = xyz(__ldg(a.illum + pix));
     f3 nAvg = n;
@@ -215,13 +229,14 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
         for (int j = -1; j <= 1; ++j)
         {
             if (i == 0 && j == 0) continue;
-            nAvg = exAdd3(nAvg, xyz(ld4(a.normalRough, W, H, x + i, y + j)));
+            nAvg = exAdd3(nAvg, xyz(tap4<kIn>(a.normalRough, W, H, x + i, y + j)));
         }
     nAvg = exDiv3(nAvg, 9.0f);
     const float m1 = luminance(illum), m2 = m1 * m1;
     // ---- exact class: everything a tap-validity decision depends on (parallax, disocclusion thresholds, expected depth)
     const f2 pixelUv = {ex::mulf(ex::addf(float(x), 0.5f), a.invW), ex::mulf(ex::addf(float(y), 0.5f), a.invH)};
-    const f3 camDelta = exSub3(prevCam.pos, cam.pos);
+    const f3 prevWorldPos = worldPos;
+    const f3 camDelta = exSub3(prevCamPos, camPosV);
     const f2 rect = {(float)W, (float)H};
     float par1, par2;
     if (a.staticCamera)
@@ -235,12 +250,12 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     }
     else
     {
-        par1 = exParallaxInPixels(exAdd3(prevWorldPos, camDelta), pixelUv, prevCam.pos, a.prevCam.worldToUv, rect);
-        par2 = exParallaxInPixels(exSub3(prevWorldPos, camDelta), prevUV, cam.pos, a.cam.worldToUv, rect);
+        par1 = exParallaxInPixels(exAdd3(prevWorldPos, camDelta), pixelUv, prevCamPos, a.prevCam.worldToUv, rect);
+        par2 = exParallaxInPixels(exSub3(prevWorldPos, camDelta), prevUV, camPosV, a.cam.worldToUv, rect);
     }
     const float parMax = fmaxr(par1, par2);
     const float disThr = a.disThr; // lerp(threshold + 1.5/H, alternate + 1.5/H, 0): launch-uniform, from the host
-    const f3 toPrev = exSub3(prevWorldPos, prevCam.pos);
+    const f3 toPrev = exSub3(prevWorldPos, prevCamPos);
     const float estPrevDepth = __fsqrt_rn(ex::dot(toPrev, toPrev));
     const int bx = bil.x0, by = bil.y0;
     const float pixelSize = ex::mulf(a.unproject, z); // unproject = tanHalfFov.x / (resolution.x / 2), from the host
@@ -265,19 +280,19 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
 #pragma unroll
         for (int j = 0; j < 2; ++j)
         {
-            float pz = ld1(a.prevDepth, W, H, bx + bic[i][j][0], by + bic[i][j][1]);
+            float pz = tap1<kIn>(a.prevDepth, W, H, bx + bic[i][j][0], by + bic[i][j][1]);
             bicubicValid *= fabsf(ex::subf(pz, estPrevDepth)) > thr[i] ? 0.0f : 1.0f;
         }
     float tv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
     {
-        float pz = ld1(a.prevDepth, W, H, bx + bilTap[i][0], by + bilTap[i][1]);
+        float pz = tap1<kIn>(a.prevDepth, W, H, bx + bilTap[i][0], by + bilTap[i][1]);
         float v = fabsf(ex::subf(pz, estPrevDepth)) > thr[i] ? 0.0f : 1.0f;
         bicubicValid *= v; tv[i] = v;
     }
     f4 tapsValid = {tv[0], tv[1], tv[2], tv[3]};
-    const f3 prevNFlat = ex::normalize(exSampleSmoothStep3(a.prevNormalRough, bil, W, H));
+    const f3 prevNFlat = ex::normalize(exSampleSmoothStep3<kIn>(a.prevNormalRough, bil, W, H));
     // identity rotation (static camera: q = (0,0,0,1) exactly): q v q^-1 = v up to the sign of a zero, which the sign test
     // below cannot see; launch-uniform branch
     const f3 prevNRot = ex::normalize(a.identityRotation ? prevNFlat : exQrotate(prevToCur, prevNFlat));
@@ -287,13 +302,13 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     f4 prevIllum; f3 prevFast;
     if (useBicubic)
     {
-        prevIllum = sampleBicubic12(a.prevIllum, prevUV, W, H);
-        prevFast = xyz(sampleBicubic12(a.prevFast, prevUV, W, H));
+        prevIllum = sampleBicubic12<kIn>(a.prevIllum, prevUV, W, H);
+        prevFast = xyz(sampleBicubic12<kIn>(a.prevFast, prevUV, W, H));
     }
     else
     {
-        prevIllum = sampleBilinearCustom4(a.prevIllum, prevUV, W, H, tapsValid);
-        prevFast = xyz(sampleBilinearCustom4(a.prevFast, prevUV, W, H, tapsValid));
+        prevIllum = sampleBilinearCustom4<kIn>(a.prevIllum, prevUV, W, H, tapsValid);
+        prevFast = xyz(sampleBilinearCustom4<kIn>(a.prevFast, prevUV, W, H, tapsValid));
     }
     prevIllum = max4f(prevIllum, F4(0.0f));
     prevFast = max3f(prevFast, F3(0.0f));
@@ -303,7 +318,7 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
     float footprintQuality = (bicubicValid > 0) ? 1.0f : ex::addf(ex::addf(ex::addf(bw.x, bw.y), bw.z), bw.w);
     float historyLength;
     if (dot4(tapsValid, F4(1.0f)) == 0.0f) { reprojFound = 0.0f; footprintQuality = 0.0f; historyLength = 0.0f; }
-    else historyLength = exSampleBilinearCustom1(a.prevHistLen, bil, W, H, tapsValid);
+    else historyLength = exSampleBilinearCustom1<kIn>(a.prevHistLen, bil, W, H, tapsValid);
     historyLength = ex::addf(historyLength, 1.0f);
     const float NoVprev = fabsf(ex::dot(n, Vprev));
     float sizeQuality = ex::divf(ex::addf(NoVprev, 1e-3f), ex::addf(NoV, 1e-3f));
@@ -327,6 +342,38 @@ __global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(co
         base = __shfl_sync(m, base, leader);
         a.fixList[base + __popc(m & ((1u << lane) - 1u))] = (int)pix;
     }
+}
+
+__global__ void __launch_bounds__(kBX *kBY, VPT_TEMPORAL_MINB) temporalKernel(const __grid_constant__ TemporalArgs a)
+{
+    const int W = a.W, H = a.H;
+    PIXEL_GUARD(W, a.rowBegin, a.rowEnd)
+    const float z = __ldg(a.depth + pix);
+    if (z > a.denoisingRange) return;
+    TemporalPre t;
+    t.x = x; t.y = y; t.pix = pix; t.z = z;
+    t.n = xyz(__ldg(a.normalRough + pix));
+    // ---- exact class: the chain that decides historyLength
+    const f3 camPosV = F3(a.cam.pos[0], a.cam.pos[1], a.cam.pos[2]), prevCamPos = F3(a.prevCam.pos[0], a.prevCam.pos[1], a.prevCam.pos[2]);
+    const f2 curUV = {ex::mulf(ex::addf(float(x), 0.5f), a.cam.inversedResolution[0]), ex::mulf(ex::addf(float(y), 0.5f), a.cam.inversedResolution[1])};
+    t.viewVec = ex::normalize(ex::mulMat3(a.cam.uvToWorld, F3(curUV.x, curUV.y, 1.0f)));
+    t.worldPos = ex::pointAt(camPosV, t.viewVec, z);
+    const f3 V = -ex::normalize(t.viewVec);
+    t.NoV = fabsf(ex::dot(t.n, V));
+    t.Vprev = ex::normalize(exSub3(t.worldPos, prevCamPos));
+    const f3 hUv = ex::mulMat3(a.prevCam.worldToUv, t.Vprev);
+    {
+        const ex::rcpx k = ex::rcpPrepare(hUv.z);
+        t.prevUV = {ex::divBy(k, hUv.x), ex::divBy(k, hUv.y)};
+    }
+    t.bil = exBilinearSetup(t.prevUV, W, H);
+    // Every tap in range (the pixel's 3x3 normals and the 4x4 footprint of the reprojection)? Then no tap needs the clamp-to-edge:
+    // decided per WARP so the two instances never diverge (border warps and large reprojections take the clamped one).
+    const int bx = t.bil.x0, by = t.bil.y0;
+    // (one pixel of slack: the fast-class bilinearSetup of the 12-tap fetch may floor to the neighbouring texel of the exact-class one)
+    const bool in = x >= 1 && x + 1 < W && y >= 1 && y + 1 < H && bx >= 2 && bx + 3 < W && by >= 2 && by + 3 < H;
+    if (__all_sync(__activemask(), in)) temporalRest<true>(a, t);
+    else temporalRest<false>(a, t);
 }
 
 // Quat::rotationBetween (LinearMath.h:1311-1366) on the host (same IEEE operations: products and sums rounded one by one, error-free transforms through
