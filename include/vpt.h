@@ -60,6 +60,17 @@ typedef struct VptMaterial
     int32_t pad;
 } VptMaterial;
 
+/* renderer/shaders/Light.h:13-24 (LightInfo): a packed triangle light — centroid, fp16 edge lengths, fp16 radiance, oct-encoded
+ * unit edge directions (TriangleLight::Store / Create, Light.h:84-136). */
+typedef struct VptLightInfo
+{
+    float center[3];
+    uint32_t scalars;
+    uint32_t radiance[2];
+    uint32_t direction1;
+    uint32_t direction2;
+} VptLightInfo;
+
 /* renderer/shaders/AliasTable.h:11-16 */
 typedef struct VptAliasBin
 {
@@ -320,6 +331,13 @@ int vpt_get_counters(vpt_ctx *ctx, uint64_t *rays, uint64_t *steps);
  * frame loop be timed without a per-frame read-back. No reference counterpart (the reference counts nothing); the convention is
  * SURVEY 8d's: one per optixTraverse site reached (RayGen.cu:49, closesthit.cu:458, 616, 745, 801). */
 int vpt_get_total_rays(vpt_ctx *ctx, uint64_t *rays, int reset);
+/* Local emissive lights. Replaces, on this path, launchGenerateLightInfos + buildAliasTable (voxelengine/VoxelEngine.cu:53-192), which
+ * the reference runs over the triangles of its emissive instanced meshes whenever the scene changes; here the lights are the exposed
+ * faces of emissive voxels (two triangles per face; voxel order x + W*(z + D*y), face 0..5, triangle 0, 1) and the list is brought up to
+ * date by the first vpt_render after vpt_set_grid / vpt_generate_terrain / vpt_set_voxel / vpt_set_materials. Returns the number of
+ * lights (after refreshing the list), < 0 on error; lights / alias (count entries) and faceKeys (count / 2 entries:
+ * (linear voxel << 3) | face) may be NULL or hold at least `capacity` lights. */
+int vpt_get_lights(vpt_ctx *ctx, VptLightInfo *lights, VptAliasBin *alias, uint32_t *faceKeys, int capacity);
 /* Debug counter: shared-memory tile loads of the denoiser whose completion barrier timed out (0 in a healthy build). */
 int vpt_debug_tma_timeouts(void);
 int vpt_get_timings(vpt_ctx *ctx, VptTimings *out);

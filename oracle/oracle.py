@@ -168,6 +168,19 @@ def tonemap(hdr_rgba, params):
     return rgb8, ldr
 
 
+LIGHT_DTYPE = np.dtype([("center", "<f4", 3), ("scalars", "<u4"), ("radiance", "<u4", 2), ("direction1", "<u4"), ("direction2", "<u4")])
+
+
+def f32_to_f16_bits(f):
+    lib().orc_f32_to_f16_bits.argtypes = [C.c_float]; lib().orc_f32_to_f16_bits.restype = C.c_uint32
+    return int(lib().orc_f32_to_f16_bits(float(f)))
+
+
+def f16_bits_to_f32(h):
+    lib().orc_f16_bits_to_f32.argtypes = [C.c_uint32]; lib().orc_f16_bits_to_f32.restype = C.c_float
+    return float(lib().orc_f16_bits_to_f32(int(h)))
+
+
 def set_threads(n):
     lib().orc_set_threads(int(n))
 
@@ -312,6 +325,14 @@ class Oracle:
         r, s = C.c_uint64(), C.c_uint64()
         self.L.orc_get_counters(self.ctx, C.byref(r), C.byref(s))
         return r.value, s.value
+
+    def lights(self):
+        """(LightInfo[n], AliasBin[n], faceKeys[n/2]) of the local emissive lights (exposed faces of emissive voxels)."""
+        n = int(self.L.orc_light_count(self.ctx))
+        li = np.zeros(n, LIGHT_DTYPE); al = np.zeros(n, ALIAS_DTYPE); keys = np.zeros(n // 2, np.uint32)
+        if n:
+            self.L.orc_get_lights(self.ctx, _p(li), _p(al), _p(keys))
+        return li, al, keys
 
     def dda(self, origin, direction, tmin=0.0, tmax=1.0e27):
         o = np.asarray(origin, np.float32)

@@ -58,12 +58,14 @@ int orc_set_grid(orc_ctx *c, int cx, int cy, int cz, const uint8_t *ids)
     c->sc.grid.cx = cx; c->sc.grid.cy = cy; c->sc.grid.cz = cz;
     c->sc.grid.ids.assign(ids, ids + (size_t)cx * cy * cz * 32768);
     c->sc.havePrevGrid = false; // a new world has no previous state
+    c->sc.lightsStale = true;
     return 0;
 }
 int orc_generate_terrain(orc_ctx *c, int cx, int cy, int cz, const float *noise)
 {
     generateTerrain(c->sc.grid, cx, cy, cz, noise);
     c->sc.havePrevGrid = false;
+    c->sc.lightsStale = true;
     return 0;
 }
 int orc_get_grid(orc_ctx *c, uint8_t *out, size_t bytes)
@@ -78,12 +80,14 @@ int orc_set_voxel(orc_ctx *c, int x, int y, int z, int id)
     if (x < 0 || y < 0 || z < 0 || x >= g.W() || y >= g.H() || z >= g.D()) return 1;
     if (!c->sc.havePrevGrid) { c->sc.prevGrid = g; c->sc.havePrevGrid = true; } // the world the previous render saw
     g.ids[g.index(x, y, z)] = (uint8_t)id;
+    c->sc.lightsStale = true;
     return 0;
 }
 int orc_set_materials(orc_ctx *c, const Material *m, int n, const uint16_t *blockToMaterial)
 {
     c->sc.materials.assign(m, m + n);
     std::memcpy(c->sc.blockToMaterial, blockToMaterial, 256 * sizeof(uint16_t));
+    c->sc.lightsStale = true;
     return 0;
 }
 int orc_set_sky(orc_ctx *c, const float *sky, int skyW, int skyH, const float *sun, int sunW, int sunH,
@@ -194,6 +198,7 @@ static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int
 {
     Scene &sc = c->sc;
     sc.cur ^= 1;
+    prepareLightRemap(sc);
     uint64_t rays = 0, steps = 0;
 #pragma omp parallel for schedule(dynamic, 2) reduction(+ : rays, steps)
     for (int y = 0; y < sc.height; ++y)
@@ -304,6 +309,25 @@ int orc_write_reservoirs(orc_ctx *c, int parity, const void *in, size_t bytes)
     std::memcpy(c->sc.reservoirs.data() + (size_t)(parity & 1) * n, in, bytes);
     return 0;
 }
+// local emissive lights (orc_lights.h): count, then the list / alias table / face keys as the next render will see them
+int orc_light_count(orc_ctx *c)
+{
+    refreshLights(c->sc);
+    return (int)c->sc.lights.lights.size();
+}
+int orc_get_lights(orc_ctx *c, LightInfo *lights, AliasBin *alias, uint32_t *faceKeys)
+{
+    const int n = orc_light_count(c);
+    if (lights) std::memcpy(lights, c->sc.lights.lights.data(), (size_t)n * sizeof(LightInfo));
+    if (alias) std::memcpy(alias, c->sc.lights.alias.data(), (size_t)n * sizeof(AliasBin));
+    if (faceKeys) std::memcpy(faceKeys, c->sc.lights.faceKeys.data(), (size_t)(n / 2) * sizeof(uint32_t));
+    return n;
+}
+// fp16 / octahedral helpers, exposed for the known-answer tests against numpy
+uint32_t orc_f32_to_f16_bits(float f) { return f32ToF16Bits(f); }
+float orc_f16_bits_to_f32(uint32_t h) { return f16BitsToF32(h); }
+uint32_t orc_ndir_to_oct(const float *n) { return ndirToOctUnorm32(F3(n[0], n[1], n[2])); }
+void orc_oct_to_ndir(uint32_t u, float *out) { const f3 d = octToNdirUnorm32(u); out[0] = d.x; out[1] = d.y; out[2] = d.z; }
 void orc_get_counters(orc_ctx *c, uint64_t *rays, uint64_t *steps) { *rays = c->sc.rayCount; *steps = c->sc.stepCount; }
 
 // ---- stand-alone helpers

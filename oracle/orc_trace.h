@@ -15,8 +15,10 @@
 //    VoxelSceneGen.cu:192-199: 0 Up(+y) 1 Down(-y) 2 Left(-x) 3 Right(+x) 4 Back(+z) 5 Front(-z).
 //  * Spawn point: hit point with the face coordinate snapped exactly onto the integer plane, pushed
 //    kSpawnEps = 2^-10 along the geometric normal (replaces SelfIntersectionAvoidance, closesthit.cu:40-73).
-//  * Textures, ray-cone LOD, thin-film, local emissive triangle lights and the motion vector of animated
-//    meshes are outside this build's scenes (static cube voxels): motionWS == 0.
+//  * Thin-film and the motion vector of animated meshes are outside this build's scenes (static cube voxels;
+//    SURVEY §8a S4/S5, §8f): motionWS == 0. Local emissive lights are the exposed faces of emissive voxels
+//    (orc_lights.h) instead of the triangles of emissive instanced meshes; from the light list on, the reference's
+//    arithmetic (closesthit.cu:330-375, 470-600, 616-626, 736-755, 801-820; Restir.h:48-79, 383-415).
 //  * C++ leaves the evaluation order of rand2/rand4's constructor arguments unspecified; nvcc evaluates
 //    left to right, which is what is restated here (x = first dimension drawn).
 //  * New parameters (SURVEY "five facts" #2): spp (sample index = iterationIndex*spp + k; sample 0 owns the
@@ -24,6 +26,7 @@
 //    totalBounceLimit / diffuseBounceLimit. spp=1, limits 3/1 is exactly the reference.
 #pragma once
 #include "orc_scene.h"
+#include "orc_lights.h"
 
 namespace orc {
 
@@ -425,7 +428,32 @@ struct Scene
     std::vector<Reservoir> reservoirs;    // 2 * W*H, parity = iterationIndex & 1
     std::vector<int32_t> primaryHits;     // x,y,z,face per pixel (face -1 = miss), sample 0
     uint64_t rayCount = 0, stepCount = 0; // statistics of the last render
+    // local emissive lights (orc_lights.h): rebuilt by the first render after the grid or the materials changed
+    LightList lights;
+    std::vector<int> prevLightToCur; int prevNumLights = 0;
+    std::vector<uint32_t> renderedKeys; // face keys of the list the last render used
+    bool lightsStale = true;       // grid / materials changed since the list was built
+    bool lightsStateDirty = false; // this render's previous-frame reservoirs hold ids of the previous list (Restir.h:52)
 };
+// the list as the next render will see it
+inline void refreshLights(Scene &sc)
+{
+    if (!sc.lightsStale) return;
+    sc.lights = LightList();
+    buildLightList(sc.grid, sc.materials, sc.blockToMaterial, sc.lights);
+    sc.lightsStale = false;
+}
+// at the start of a render (single-threaded): if the list differs from the one the previous render used, the stored reservoirs
+// hold stale light ids -> previous -> current id table (Restir.h:60-75), lightsStateDirty for this frame
+inline void prepareLightRemap(Scene &sc)
+{
+    refreshLights(sc);
+    sc.lightsStateDirty = sc.renderedKeys != sc.lights.faceKeys;
+    if (!sc.lightsStateDirty) return;
+    buildLightRemap(sc.renderedKeys, sc.lights.faceKeys, sc.prevLightToCur);
+    sc.prevNumLights = (int)sc.renderedKeys.size() * 2;
+    sc.renderedKeys = sc.lights.faceKeys;
+}
 
 struct Surface
 {
@@ -563,8 +591,46 @@ inline void finalizeResampling(Reservoir &r, float num, float den)
 }
 inline f2 reservoirUV(const Reservoir &r) { return {float(r.uvData & 0xffff) / float(0xffff), float(r.uvData >> 16) / float(0xffff)}; }
 
-inline bool lightSampleFromReservoir(const Sky &sky, LightSample &ls, const Reservoir &r)
+// TriangleLight::calcSample / calcSolidAnglePdf (Light.h:54-82)
+inline LightSample triangleLightSample(const TriangleLight &t, f2 random, f3 viewerPosition)
 {
+    LightSample r;
+    const f3 bary = sampleTriangle(random);
+    r.position = t.base + t.edge1 * bary.y + t.edge2 * bary.z;
+    r.normal = t.normal;
+    f3 L = r.position - viewerPosition;
+    const float Ldist = length(L);
+    L = L / Ldist;
+    const float areaPdf = 1.0f / t.surfaceArea;
+    const float cosTheta = saturate(dot(L, -r.normal));
+    r.solidAnglePdf = areaPdf * (Ldist * Ldist) / cosTheta; // PdfAtoW
+    r.radiance = t.radiance;
+    r.lightType = LightLocalTriangle;
+    return r;
+}
+// direction and far end of a visibility ray towards a light sample (closesthit.cu:616-617, 743-744, 801-802)
+inline f3 lightRayDir(const LightSample &ls, f3 from) { return ls.lightType == LightLocalTriangle ? normalize(ls.position - from) : ls.position; }
+inline float lightRayTmax(const LightSample &ls, f3 from, float extraRayOffset)
+{
+    return ls.lightType == LightLocalTriangle ? length(ls.position - from) - 0.01f - extraRayOffset : kRayMax;
+}
+// LoadDIReservoir's id remap (Restir.h:48-79)
+inline Reservoir remapReservoir(const Scene &sc, Reservoir r)
+{
+    if (!sc.lightsStateDirty) return r;
+    const uint32_t prevIdx = r.lightData & kLightIndexMask;
+    if (prevIdx >= kSunLight) return r;
+    if (sc.prevNumLights > 0 && prevIdx < (uint32_t)sc.prevNumLights)
+    {
+        const int curIdx = sc.prevLightToCur[prevIdx];
+        if (curIdx < 0 || curIdx >= (int)sc.lights.lights.size()) return emptyReservoir();
+        r.lightData = (r.lightData & ~kLightIndexMask) | (uint32_t)curIdx;
+    }
+    return r;
+}
+inline bool lightSampleFromReservoir(const Scene &sc, LightSample &ls, const Reservoir &r, const Surface &surface, bool hasLocal)
+{
+    const Sky &sky = sc.sky;
     uint32_t li = r.lightData & kLightIndexMask;
     f2 uv = reservoirUV(r);
     if (li == kSkyLight)
@@ -576,6 +642,11 @@ inline bool lightSampleFromReservoir(const Sky &sky, LightSample &ls, const Rese
     {
         int x = clampi(int(uv.x * sky.sunW), 0, sky.sunW - 1), y = clampi(int(uv.y * sky.sunH), 0, sky.sunH - 1);
         ls = createSunLightSample(sky, y * sky.sunW + x);
+    }
+    else if (hasLocal && li < (uint32_t)sc.lights.lights.size())
+    {
+        ls = triangleLightSample(createTriangleLight(sc.lights.lights[li]), uv, surface.pos);
+        return true;
     }
     return li < kInvalidLight;
 }
@@ -805,13 +876,28 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
     LightSample lightSample;
     Reservoir ris = emptyReservoir();
     const bool skipSun = (dot(s.normal, sky.sunDir) < 0.0f || dot(s.geoNormal, sky.sunDir) < 0.0f);
-    const int nLocal = 0; // local emissive triangle lights: out of scope
+    const LightList &ll = sc.lights;
+    const int numLights = (int)ll.lights.size();
+    const int nLocal = numLights > 0 ? 8 : 0; // closesthit.cu:330
     const int nSun = skipSun ? 0 : 1, nSky = 1, nBrdf = 1;
     const int nMis = nLocal + nSun + nSky + nBrdf;
     const float localMisW = float(nLocal) / nMis, sunMisW = float(nSun) / nMis, skyMisW = float(nSky) / nMis, brdfMisW = float(nBrdf) / nMis;
 
     Reservoir localRes = emptyReservoir();
     LightSample localSample;
+    for (int i = 0; i < nLocal; ++i) // closesthit.cu:350-375
+    {
+        float sourcePdf;
+        const int lightIndex = (int)aliasSample(ll.alias, c.rnd(), sourcePdf);
+        if (lightIndex >= numLights) continue;
+        const f2 uv = c.rnd2();
+        const LightSample cand = triangleLightSample(createTriangleLight(ll.lights[lightIndex]), uv, s.pos);
+        const float blended = lightBrdfMisWeight(s, cand, sourcePdf, localMisW, false, brdfMisW);
+        const float targetPdf = targetPdfForSurface(cand, s);
+        const float risRnd = c.rnd();
+        if (blended != 0.0f)
+            if (streamSample(localRes, (uint32_t)lightIndex, uv, risRnd, targetPdf, 1.0f / blended)) localSample = cand;
+    }
     finalizeResampling(localRes, 1.0f, (float)nMis);
     localRes.M = 1;
 
@@ -862,9 +948,28 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
         disneySample(c.rnd4(), s.normal, s.geoNormal, s.wo, s.albedo, s.metallic, s.translucency, s.roughness, sampleDir, dummy, brdfPdf, trans);
         if (brdfPdf > 0.0f)
         {
-            // BSDF-light ray (closesthit.cu:458-468): any geometry hit -> no light (no emissive blocks), miss -> sky
+            // BSDF-light ray (closesthit.cu:458-468, __closesthit__bsdf_light :854-901): miss -> sky / sun disk, an emissive
+            // voxel face -> that face's triangle light, any other geometry -> no light
             Hit sh = c.trace(frontPos, sampleDir, 0.0f, FLT_MAX);
-            if (!sh.hit)
+            if (sh.hit && nLocal > 0 && sh.face < 6 && sc.materials[sc.blockToMaterial[sh.id]].isEmissive)
+            {
+                // which of the face's two triangles, and the hit's barycentrics (optixGetTriangleBarycentrics)
+                f3 A, eu, ev;
+                faceFrame(sh.face, sh.x, sh.y, sh.z, A, eu, ev);
+                const f3 P = hitPoint(sh, frontPos, sampleDir);
+                const float fs = dot(P - A, eu), ft = dot(P - A, ev);
+                const int tri = (fs + ft <= 1.0f) ? 0 : 1;
+                const f2 bary = tri == 0 ? f2{fs, ft} : f2{1.0f - fs, 1.0f - ft};
+                const int li = findLight(ll, (uint32_t)(sh.x + sc.grid.W() * (sh.z + sc.grid.D() * sh.y)), sh.face, tri);
+                if (li >= 0 && li < numLights)
+                {
+                    lightIndex = (uint32_t)li;
+                    uv = inverseTriangleSample(bary);
+                    cand = triangleLightSample(createTriangleLight(ll.lights[li]), uv, s.pos);
+                    lightSourcePdf = ll.alias[li].p;
+                }
+            }
+            else if (!sh.hit)
             {
                 if (equalAreaMapConeInv(uv, sky.sunDir, sampleDir, sunCosThetaMax()))
                 {
@@ -918,7 +1023,7 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
     bool isLightVisible = false;
     if (lightSample.lightType != LightInvalid && isValidReservoir(ris))
     {
-        Hit vh = c.trace(frontPos, lightSample.position, 0.0f, kRayMax);
+        Hit vh = c.trace(frontPos, lightRayDir(lightSample, s.pos), 0.0f, lightRayTmax(lightSample, s.pos, 0.0f));
         isLightVisible = !vh.hit;
         if (!isLightVisible) { ris.lightData = 0; ris.weightSum = 0; }
     }
@@ -957,14 +1062,14 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
             bool rOk = fabsf(s.roughness - ts.roughness) <= 0.5f * fmaxr(s.roughness, ts.roughness);
             if (!(nOk && dOk && rOk)) continue;
             cached |= (1u << i);
-            Reservoir pr = sc.reservoirs[prevBase + (size_t)idx.y * sc.width + idx.x];
+            Reservoir pr = remapReservoir(sc, sc.reservoirs[prevBase + (size_t)idx.y * sc.width + idx.x]);
             if (std::isnan(pr.weightSum) || std::isinf(pr.weightSum)) pr = emptyReservoir();
             if (pr.M > mCap) pr.M = mCap;
             float neighborWeight = 0;
             LightSample cand;
             if (isValidReservoir(pr))
             {
-                if (!lightSampleFromReservoir(sky, cand, pr)) pr = emptyReservoir();
+                if (!lightSampleFromReservoir(sc, cand, pr, s, nLocal > 0)) pr = emptyReservoir();
                 neighborWeight = targetPdfForSurface(cand, s);
             }
             if (combineReservoirs(restir, pr, c.rnd(), neighborWeight)) { lightSample = cand; selectedLoopIdx = i; }
@@ -979,16 +1084,16 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
                 Surface ts;
                 getPrevSurface(c, ts, idx);
                 LightSample atNeighbor;
-                lightSampleFromReservoir(sky, atNeighbor, restir);
+                lightSampleFromReservoir(sc, atNeighbor, restir, ts, nLocal > 0);
                 float ps = targetPdfForSurface(atNeighbor, ts);
                 if (ps > 0 && !(i == 0 && i == selectedLoopIdx))
                 {
                     const float extraRayOffset = 0.01f + 0.01f * ts.depth;
-                    // previous BVH == current grid (static scene)
-                    Hit nh = c.tracePrev(ts.pos, lightSample.position, extraRayOffset, kRayMax);
+                    // the ray goes to `lightSample` (the sample at the CURRENT surface), as in the reference (closesthit.cu:743-744)
+                    Hit nh = c.tracePrev(ts.pos, lightRayDir(lightSample, ts.pos), extraRayOffset, lightRayTmax(lightSample, ts.pos, extraRayOffset));
                     if (nh.hit) ps = 0.0f;
                 }
-                Reservoir pr = sc.reservoirs[prevBase + (size_t)idx.y * sc.width + idx.x];
+                Reservoir pr = remapReservoir(sc, sc.reservoirs[prevBase + (size_t)idx.y * sc.width + idx.x]);
                 if (std::isnan(pr.weightSum) || std::isinf(pr.weightSum)) pr = emptyReservoir();
                 if (pr.M > mCap) pr.M = mCap;
                 if (selectedLoopIdx == i) pi = ps;
@@ -998,7 +1103,7 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
         }
         if (lightSample.lightType != LightInvalid)
         {
-            Hit vh = c.trace(frontPos, lightSample.position, 0.0f, kRayMax);
+            Hit vh = c.trace(frontPos, lightRayDir(lightSample, s.pos), 0.0f, lightRayTmax(lightSample, s.pos, 0.0f));
             isLightVisible = !vh.hit;
             if (!isLightVisible) { restir.lightData = 0; restir.weightSum = 0; }
         }
@@ -1007,7 +1112,7 @@ inline void closestHit(PixelCtx &c, RayData &rd, const Hit &h, f3 rayOrig, bool 
     const Reservoir shading = enableReSTIR ? restir : ris;
     if (lightSample.lightType != LightInvalid && isValidReservoir(shading) && isLightVisible)
     {
-        f3 sampleDir = lightSample.position;
+        f3 sampleDir = lightRayDir(lightSample, s.pos);
         const f3 albedo = skipAlbedoInShadowRay ? F3(1.0f) : s.albedo;
         f3 bsdf; float pdf;
         disneyEvaluate(s.normal, s.geoNormal, sampleDir, s.wo, albedo, s.metallic, s.translucency, s.roughness, bsdf, pdf);

@@ -87,6 +87,13 @@ struct vpt_ctx
     // staging for vpt_denoise_external
     void *pinned = nullptr; size_t pinnedBytes = 0;
     uint8_t *rgb8 = nullptr; // vpt_tonemap's 8-bit plane
+    // local emissive lights (host/vpt_lights.cpp): the list is rebuilt by the first render after the grid or the materials changed
+    std::vector<VptMaterial> hostMaterials; uint16_t hostB2m[256] = {};
+    LightList lights; std::vector<int> prevLightToCur; int prevNumLights = 0;
+    std::vector<uint32_t> renderedKeys; // face keys of the list the LAST RENDER used: what the stored reservoirs' light ids refer to
+    bool lightsStale = true, lightsStateDirty = false;
+    VptLightInfo *dLights = nullptr; VptAliasBin *dLightAlias = nullptr; uint32_t *dFaceKeys = nullptr; int *dPrevToCur = nullptr;
+    size_t dLightCap = 0, dRemapCap = 0;
     bool dnGather = false;   // VPT_DN_GATHER=1: the per-thread gather kernels instead of the shared-memory tile kernels (A/B runs)
     // profiling
     bool profiling = true;
@@ -195,7 +202,7 @@ void vpt_destroy(vpt_ctx *c)
     destroyComm(c);
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
                     c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
-                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList, c->rgb8};
+                    c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList, c->rgb8, c->dLights, c->dLightAlias, c->dFaceKeys, c->dPrevToCur};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
     {
@@ -269,6 +276,7 @@ int vpt_set_grid(vpt_ctx *c, int cx, int cy, int cz, const uint8_t *ids)
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->idsChunk, ids, (size_t)cx * cy * cz * 32768, cudaMemcpyHostToDevice, c->stream));
     c->prevSnapshot = false; // a new world has no previous state
+    c->lightsStale = true;
     CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, c->upHDev, &c->upH, cx, cy, cz, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return VPT_OK;
@@ -285,6 +293,7 @@ int vpt_generate_terrain(vpt_ctx *c, int cx, int cy, int cz, const float *noise)
     CU(cudaMemcpyAsync(dNoise, noise, nb, cudaMemcpyHostToDevice, c->stream));
     CU(launchGenerateTerrain(dNoise, c->idsChunk, cx, cy, cz, c->stream));
     c->prevSnapshot = false; // a new world has no previous state
+    c->lightsStale = true;
     CU(launchRepackGrid(c->idsChunk, c->idsLinear, c->occ, c->upHDev, &c->upH, cx, cy, cz, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFree(dNoise));
@@ -313,6 +322,7 @@ int vpt_set_voxel(vpt_ctx *c, int x, int y, int z, int blockId)
         c->upHPrev = c->upH; c->prevSnapshot = true;
     }
     CU(launchSetVoxel(c->idsChunk, c->idsLinear, c->occ, &c->upH, c->cx, c->cy, c->cz, x, y, z, blockId, c->stream));
+    c->lightsStale = true;
     return VPT_OK;
 }
 
@@ -343,6 +353,8 @@ int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_
     CU(cudaMemcpyAsync(c->materials, m, (size_t)count * sizeof(VptMaterial), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->blockToMaterial, b2m, 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->hostMaterials.assign(m, m + count); std::memcpy(c->hostB2m, b2m, sizeof c->hostB2m);
+    c->lightsStale = true;
     return VPT_OK;
 }
 
@@ -479,6 +491,69 @@ int vpt_set_trace_params(vpt_ctx *c, int spp, int totalBounceLimit, int diffuseB
     return VPT_OK;
 }
 
+// Bring the local-light list up to date (the reference rebuilds its LightInfo buffer + alias table on every scene update,
+// VoxelEngine.cu:53-192, synchronously). Only scenes with an emissive material pay for the grid read-back.
+static int refreshLights(vpt_ctx *c)
+{
+    if (!c->lightsStale) return VPT_OK;
+    c->lightsStale = false;
+    bool anyEmissive = false;
+    for (const VptMaterial &m : c->hostMaterials) anyEmissive = anyEmissive || m.isEmissive != 0;
+    c->lights = LightList();
+    if (anyEmissive && c->idsChunk)
+    {
+        std::vector<uint8_t> ids((size_t)c->cx * c->cy * c->cz * 32768);
+        CU(cudaMemcpyAsync(ids.data(), c->idsChunk, ids.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        buildLightList(ids.data(), c->cx, c->cy, c->cz, c->hostMaterials.data(), (int)c->hostMaterials.size(), c->hostB2m, c->lights);
+    }
+    const size_t n = c->lights.lights.size();
+    if (n > c->dLightCap)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        for (void *p : {(void *)c->dLights, (void *)c->dLightAlias, (void *)c->dFaceKeys}) if (p) cudaFree(p);
+        c->dLights = nullptr; c->dLightAlias = nullptr; c->dFaceKeys = nullptr; c->dLightCap = 0;
+        const size_t cap = n + n / 2 + 64;
+        CU(cudaMalloc((void **)&c->dLights, cap * sizeof(VptLightInfo)));
+        CU(cudaMalloc((void **)&c->dLightAlias, cap * sizeof(VptAliasBin)));
+        CU(cudaMalloc((void **)&c->dFaceKeys, cap / 2 * sizeof(uint32_t) + 4));
+        c->dLightCap = cap;
+    }
+    if (n)
+    {
+        CU(cudaMemcpyAsync(c->dLights, c->lights.lights.data(), n * sizeof(VptLightInfo), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->dLightAlias, c->lights.alias.data(), n * sizeof(VptAliasBin), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->dFaceKeys, c->lights.faceKeys.data(), c->lights.faceKeys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream)); // pageable sources
+    }
+    return VPT_OK;
+}
+// Before a render: if the list differs from the one the previous render used, the stored reservoirs hold stale light ids — upload
+// the previous -> current id table (Restir.h:60-75) and raise lightsStateDirty for this frame.
+static int prepareLightRemap(vpt_ctx *c)
+{
+    c->lightsStateDirty = c->renderedKeys != c->lights.faceKeys;
+    if (!c->lightsStateDirty) return VPT_OK;
+    buildLightRemap(c->renderedKeys, c->lights.faceKeys, c->prevLightToCur);
+    c->prevNumLights = (int)c->renderedKeys.size() * 2;
+    if (c->prevLightToCur.size() > c->dRemapCap)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->dPrevToCur) cudaFree(c->dPrevToCur);
+        c->dPrevToCur = nullptr; c->dRemapCap = 0;
+        const size_t cap = c->prevLightToCur.size() * 2 + 64;
+        CU(cudaMalloc((void **)&c->dPrevToCur, cap * sizeof(int)));
+        c->dRemapCap = cap;
+    }
+    if (!c->prevLightToCur.empty())
+    {
+        CU(cudaMemcpyAsync(c->dPrevToCur, c->prevLightToCur.data(), c->prevLightToCur.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->renderedKeys = c->lights.faceKeys; // from this render on the reservoirs speak the new ids
+    return VPT_OK;
+}
+
 static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, bool resolve, bool localOwner = false)
 {
     if (!c || !cam || !prevCam || sampleBegin < 0 || sampleStep < 1) return fail(VPT_ERR_ARG, "vpt_render: bad argument");
@@ -488,6 +563,7 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     if ((int)cam->resolution[0] != c->width || (int)cam->resolution[1] != c->height) return fail(VPT_ERR_ARG, "vpt_render: camera resolution != context size");
     CU(cudaSetDevice(c->device));
     if (c->copyPending && c->copyPendingTraceWritten) CU(waitPendingCopy(c));
+    { int rcl = refreshLights(c); if (!rcl) rcl = prepareLightRemap(c); if (rcl) return rcl; }
     c->cur ^= 1;
     TraceArgs a;
     std::memset(&a, 0, sizeof a);
@@ -533,6 +609,9 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.skyW = c->skyW; a.skyH = c->skyH; a.sunW = c->sunW; a.sunH = c->sunH;
     a.sunDir[0] = c->sunDir[0]; a.sunDir[1] = c->sunDir[1]; a.sunDir[2] = c->sunDir[2];
     a.sunCosThetaMax = cosf(0.51f * 3.1415926535897932384626422832795028841971f / 180.0f / 2.0f); // miss.cu:46-47, host libm like the oracle
+    a.lv.lights = c->dLights; a.lv.alias = c->dLightAlias; a.lv.faceKeys = c->dFaceKeys; a.lv.prevToCur = c->dPrevToCur;
+    a.lv.numLights = (int)c->lights.lights.size(); a.lv.numFaces = (int)c->lights.faceKeys.size();
+    a.lv.prevNumLights = c->prevNumLights; a.lv.stateDirty = c->lightsStateDirty ? 1 : 0;
     a.cur = c->gb[c->cur].ptrs(); a.prev = c->gb[c->cur ^ 1].ptrs();
     a.illumination = c->illumination;
     a.resCur = c->reservoirs + (size_t)(iterationIndex & 1) * c->npix();
@@ -869,8 +948,33 @@ int vpt_get_counters(vpt_ctx *c, uint64_t *rays, uint64_t *steps)
     return VPT_OK;
 }
 
+/* debug: raw read of a wavefront-state plane of the last wave (which: 0 candC, 1 ris, 2 rstA, 3 rstB, 4 lightA, 5 light2A); 16 bytes per entry */
+int vpt_debug_read_wave(vpt_ctx *c, int which, void *host, size_t entries)
+{
+    if (!c || !host || !c->wave.arena) return fail(VPT_ERR_STATE, "vpt_debug_read_wave: no wave state");
+    const void *src[] = {c->wave.wb.candC, c->wave.wb.ris, c->wave.wb.rstA, c->wave.wb.rstB, c->wave.wb.lightA, c->wave.wb.light2A};
+    if (which < 0 || which > 5) return fail(VPT_ERR_ARG, "vpt_debug_read_wave: unknown plane");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(host, src[which], entries * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+
 /* debug: tile loads (TMA) of the denoiser whose completion barrier timed out since the process started; 0 in a healthy build */
 int vpt_debug_tma_timeouts(void) { return (int)debugTmaTimeouts(); }
+
+int vpt_get_lights(vpt_ctx *c, VptLightInfo *lights, VptAliasBin *alias, uint32_t *faceKeys, int capacity)
+{
+    if (!c) { fail(VPT_ERR_ARG, "vpt_get_lights: null context"); return -1; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { fail(VPT_ERR_CUDA, "vpt_get_lights: cudaSetDevice"); return -1; }
+    if (refreshLights(c) != VPT_OK) return -1;
+    const int n = (int)c->lights.lights.size();
+    if (n > capacity && (lights || alias || faceKeys)) { fail(VPT_ERR_ARG, "vpt_get_lights: capacity too small"); return -1; }
+    if (lights) std::memcpy(lights, c->lights.lights.data(), (size_t)n * sizeof(VptLightInfo));
+    if (alias) std::memcpy(alias, c->lights.alias.data(), (size_t)n * sizeof(VptAliasBin));
+    if (faceKeys) std::memcpy(faceKeys, c->lights.faceKeys.data(), c->lights.faceKeys.size() * sizeof(uint32_t));
+    return n;
+}
 
 int vpt_get_total_rays(vpt_ctx *c, uint64_t *rays, int reset)
 {

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
     };
 
     // per-lane DDA state
-    float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f;
+    float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f, tmax = kRayMax;
     int lin = parkLin, dX = 0, dY = 0, dZ = 0, lastD = 0;
     uint32_t meta = 0, result = 0;
     bool live = false;
@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         if (pending)
         {
             int x, y, z;
-            const bool shell = decode(finLin, x, y, z);
+            // a solid voxel first met at or beyond the ray's far end is no hit (the oracle's walk stops at tCur >= tmax; every voxel
+            // before that one was empty, so stopping there or walking on to the first solid voxel decides the same)
+            const bool shell = decode(finLin, x, y, z) || finT >= tmax; // (the lane's tmax is only replaced by the re-arm below)
             if (kClosest)
             {
                 uint32_t packed = kHitMiss;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                 const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
                 tX = __uint_as_float(q0.x); tY = __uint_as_float(q0.y); tZ = __uint_as_float(q0.z); tCur = __uint_as_float(q0.w);
                 dtX = __uint_as_float(q1.x); dtY = __uint_as_float(q1.y); dtZ = __uint_as_float(q1.z); tmin = __uint_as_float(q1.w);
-                lin = (int)q2.x; meta = q2.y; result = q2.z;
+                lin = (int)q2.x; meta = q2.y; result = q2.z; tmax = __uint_as_float(q2.w);
                 dX = (meta & 1u) ? 1 : -1;
                 dY = (meta & 2u) ? strideY : -strideY;
                 dZ = (meta & 4u) ? Wp : -Wp;

@@ -16,12 +16,12 @@ struct PreparedRay // 3 x 16 bytes
     int lin;         // padded linear voxel index of the start voxel
     uint32_t meta;   // bits 0..2: step is +1 along x,y,z; bits 4..6: face id if the start voxel is the hit (6 = none)
     uint32_t result; // slot the result is written to
-    uint32_t pad;
+    float tmax;      // far end (visibility rays towards a local light stop 0.01 before it, closesthit.cu:616-617); kRayMax = none
 };
 constexpr uint32_t kHitMiss = 0xFFFFFFFFu;
 
 // Returns false when the ray never enters the grid (the caller records a miss itself).
-VPT_DEV bool prepareRay(const GridView &g, f3 o, f3 d, float tmin, uint32_t result, PreparedRay &r)
+VPT_DEV bool prepareRay(const GridView &g, f3 o, f3 d, float tmin, uint32_t result, PreparedRay &r, float tmax = kRayMax)
 {
     const int W = g.W, H = g.H, D = g.D;
     int x = (int)floorf(o.x), y = (int)floorf(o.y), z = (int)floorf(o.z);
@@ -78,7 +78,7 @@ VPT_DEV bool prepareRay(const GridView &g, f3 o, f3 d, float tmin, uint32_t resu
     else if (hitAxis == 2) face0 = pz ? 5u : 4u;
     r.meta = (px ? 1u : 0u) | (py ? 2u : 0u) | (pz ? 4u : 0u) | (face0 << 4);
     r.result = result;
-    r.pad = 0u;
+    r.tmax = tmax;
     return true;
 }
 
@@ -87,7 +87,7 @@ VPT_DEV void storePreparedRay(uint4 *queue, unsigned pos, const PreparedRay &r)
     uint4 *q = queue + (size_t)pos * 3;
     q[0] = make_uint4(__float_as_uint(r.tMaxX), __float_as_uint(r.tMaxY), __float_as_uint(r.tMaxZ), __float_as_uint(r.tCur));
     q[1] = make_uint4(__float_as_uint(r.tDeltaX), __float_as_uint(r.tDeltaY), __float_as_uint(r.tDeltaZ), __float_as_uint(r.tmin));
-    q[2] = make_uint4((uint32_t)r.lin, r.meta, r.result, 0u);
+    q[2] = make_uint4((uint32_t)r.lin, r.meta, r.result, __float_as_uint(r.tmax));
 }
 
 } // namespace vpt

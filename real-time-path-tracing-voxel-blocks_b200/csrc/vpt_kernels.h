@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include "../../include/vpt.h"
 #include "vpt_fastdiv.h"
+#include "vpt_lights.h"
 
 namespace vpt {
 
@@ -55,7 +56,8 @@ struct WaveBuffers
     float4 *surfD;      // textured scenes only: albedo rgb, metallic
     uint32_t *pflag;    // path flags (vpt_wave.cu: F_*)
     float4 *candA;      // sun idx, sun weightSum, sun targetPdf, sky idx
-    float4 *candB;      // sky weightSum, sky targetPdf
+    float4 *candB;      // sky weightSum, sky targetPdf, local-light uv (unquantised)
+    uint4 *candC;       // local lights: selected light index (or 0xFFFFFFFF), weightSum bits, targetPdf bits
     float4 *dir1;       // direction of the BSDF-candidate ray
     uint4 *ris;         // lightData, uvData, weightSum, targetPdf (M == 1)
     float4 *lightA;     // selected light sample: direction xyz, solidAnglePdf
@@ -102,6 +104,7 @@ struct TraceArgs
     const int4 *matTexSlots;
     const float *matTexMip0Size;
     int nTextures;
+    LightView lv;                // local emissive lights (numLights == 0: none, and no stage does anything for them)
     GBufferPtrs cur, prev;
     float4 *illumination;
     VptReservoir *resCur;

@@ -20,6 +20,7 @@
 // Arithmetic: the exact class (vpt::ex::) up to and including every DDA set-up; shading is the fast class
 // (vpt_math.cuh). RNG dimensions are consumed in exactly the reference's order (randIdx travels in the path flags).
 #include "vpt_dda.cuh"
+#include <cuda_fp16.h>
 
 #ifndef VPT_FN
 #define VPT_FN __device__ __forceinline__
@@ -273,6 +274,86 @@ VPT_DEV VptReservoir emptyReservoir() { VptReservoir r; r.lightData = 0; r.uvDat
 VPT_DEV bool isValidReservoir(const VptReservoir &r) { return r.lightData != 0; }
 VPT_DEV bool sameDir(f3 a, f3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
+// ------------------------------------------------------------------------------------------------ local emissive lights
+// TriangleLight (renderer/shaders/Light.h:44-137) over the host-built list of emissive voxel faces (host/vpt_lights.cpp).
+struct TriLight { f3 base, edge1, edge2, radiance, normal; float surfaceArea; };
+VPT_DEV float halfToFloat(uint32_t bits) { return __half2float(__ushort_as_half((unsigned short)(bits & 0xffffu))); }
+VPT_DEV f3 octToNdirUnorm32(uint32_t u) // LinearMath.h:2069-2089
+{
+    const float px = saturate(float(u & 0xffffu) / 0xfffe) * 2.0f - 1.0f, py = saturate(float(u >> 16) / 0xfffe) * 2.0f - 1.0f;
+    f3 n = {px, py, 1.0f - fabsf(px) - fabsf(py)};
+    const float t = fmaxf(0.0f, -n.z);
+    n.x += n.x >= 0.0f ? -t : t;
+    n.y += n.y >= 0.0f ? -t : t;
+    return normalize(n);
+}
+VPT_DEV TriLight createTriLight(const VptLightInfo *li) // TriangleLight::Create (Light.h:84-122): two 16-byte loads
+{
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(li)), b = __ldg(reinterpret_cast<const uint4 *>(li) + 1);
+    TriLight t;
+    t.edge1 = octToNdirUnorm32(b.z) * halfToFloat(a.w);
+    t.edge2 = octToNdirUnorm32(b.w) * halfToFloat(a.w >> 16);
+    t.base = F3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)) - (t.edge1 + t.edge2) / 3.0f;
+    t.radiance = {halfToFloat(b.x), halfToFloat(b.x >> 16), halfToFloat(b.y)};
+    const f3 n = cross(t.edge1, t.edge2);
+    const float len = length(n);
+    if (len > 0.0f) { t.surfaceArea = 0.5f * len; t.normal = n / len; }
+    else { t.surfaceArea = 0.0f; t.normal = F3(0.0f); }
+    return t;
+}
+VPT_DEV LightSample triLightSample(const TriLight &t, f2 random, f3 viewer) // calcSample + calcSolidAnglePdf (Light.h:54-82), SampleTriangle, PdfAtoW
+{
+    LightSample r;
+    const float sq = sqrtf(random.x);
+    const float by = sq * (1.0f - random.y), bz = sq * random.y;
+    r.position = t.base + t.edge1 * by + t.edge2 * bz;
+    f3 L = r.position - viewer;
+    const float Ldist = length(L);
+    L = L / Ldist;
+    const float cosTheta = saturate(dot(L, -t.normal));
+    r.solidAnglePdf = (1.0f / t.surfaceArea) * (Ldist * Ldist) / cosTheta;
+    r.radiance = t.radiance;
+    r.lightType = LightLocalTriangle;
+    return r;
+}
+// direction and far end of a visibility ray towards a light sample (closesthit.cu:616-617, 743-744, 801-802)
+template <bool kLights> VPT_DEV f3 lightRayDir(const LightSample &ls, f3 from)
+{
+    return (kLights && ls.lightType == LightLocalTriangle) ? normalize(ls.position - from) : ls.position;
+}
+template <bool kLights> VPT_DEV float lightRayTmax(const LightSample &ls, f3 from, float extraRayOffset)
+{
+    return (kLights && ls.lightType == LightLocalTriangle) ? length(ls.position - from) - 0.01f - extraRayOffset : kRayMax;
+}
+// light index of (voxel, face, triangle): binary search of the ascending face keys, like the instance -> light table that
+// __closesthit__bsdf_light searches (closesthit.cu:870-895); -1 = not a light
+VPT_DEV int findLight(const LightView &lv, uint32_t lin, int face, int tri)
+{
+    const uint32_t key = (lin << 3) | (uint32_t)face;
+    int left = 0, right = lv.numFaces - 1;
+    while (left <= right)
+    {
+        const int mid = (left + right) >> 1;
+        const uint32_t v = __ldg(lv.faceKeys + mid);
+        if (v == key) return 2 * mid + tri;
+        if (v < key) left = mid + 1; else right = mid - 1;
+    }
+    return -1;
+}
+VPT_DEV void faceFrameDev(int face, int x, int y, int z, f3 &A, f3 &u, f3 &v)
+{
+    const float fx = (float)x, fy = (float)y, fz = (float)z;
+    switch (face)
+    {
+    case 0: A = {fx, fy + 1.0f, fz}; u = {0, 0, 1}; v = {1, 0, 0}; break;
+    case 1: A = {fx, fy, fz}; u = {1, 0, 0}; v = {0, 0, 1}; break;
+    case 2: A = {fx, fy, fz}; u = {0, 0, 1}; v = {0, 1, 0}; break;
+    case 3: A = {fx + 1.0f, fy, fz}; u = {0, 1, 0}; v = {0, 0, 1}; break;
+    case 4: A = {fx, fy, fz + 1.0f}; u = {1, 0, 0}; v = {0, 1, 0}; break;
+    default: A = {fx, fy, fz}; u = {0, 1, 0}; v = {1, 0, 0}; break;
+    }
+}
+
 // Per-thread shading context: pixel, sample index and the RNG dimension counter (RandGen.h:21-45).
 struct Ctx
 {
@@ -380,7 +461,7 @@ struct Ctx
         return luminance(refl);
     }
     VPT_DEV float targetPdfForSurface(const LightSample &ls, const Surface &s) const { return evalCandidate(s, ls, 0.0f, 0.0f, 0.0f, nullptr); }
-    VPT_FN bool lightSampleFromReservoir(LightSample &ls, const VptReservoir &r) const
+    template <bool kLights> VPT_FN bool lightSampleFromReservoir(LightSample &ls, const VptReservoir &r, f3 surfacePos) const
     {
         uint32_t li = r.lightData & kLightIndexMask;
         f2 uv = {float(r.uvData & 0xffff) / float(0xffff), float(r.uvData >> 16) / float(0xffff)};
@@ -393,6 +474,11 @@ struct Ctx
         {
             int x = clampi(int(uv.x * a.sunW), 0, a.sunW - 1), y = clampi(int(uv.y * a.sunH), 0, a.sunH - 1);
             ls = createSunLightSample(y * a.sunW + x);
+        }
+        else if (kLights && li < (uint32_t)a.lv.numLights) // hasLocalLights && lightIndex < numLights (Restir.h:404-410)
+        {
+            ls = triLightSample(createTriLight(a.lv.lights + li), uv, surfacePos);
+            return true;
         }
         return li < kInvalidLight;
     }
@@ -746,14 +832,14 @@ __global__ void __launch_bounds__(kShadeThreads) genKernel(const __grid_constant
     if (!want)
     {
         r.tMaxX = r.tMaxY = r.tMaxZ = r.tCur = 0.0f; r.tDeltaX = r.tDeltaY = r.tDeltaZ = r.tmin = 0.0f;
-        r.lin = 0; r.meta = 6u << 4; r.result = (uint32_t)p; r.pad = 0u;
+        r.lin = 0; r.meta = 6u << 4; r.result = (uint32_t)p; r.tmax = kRayMax;
     }
     storePreparedRay(a.wb.queue, (unsigned)idx, r);
 }
 
 // ------------------------------------------------------------------------------------------------ S1
 // __miss__radiance, and __closesthit__radiance up to the BSDF-candidate ray (closesthit.cu:96-468).
-template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_MINB) shade1Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
@@ -886,8 +972,33 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
                     const f3 sunD = c.sunDir();
                     const bool skipSun = (dot(s.normal, sunD) < 0.0f || dot(s.geoNormal, sunD) < 0.0f);
                     const int nSun = skipSun ? 0 : 1;
-                    const int nMis = nSun + 2;
-                    const float sunMisW = float(nSun) / nMis, skyMisW = 1.0f / nMis, brdfMisW = 1.0f / nMis;
+                    constexpr int nLocal = kLights ? 8 : 0; // closesthit.cu:330: 8 when the scene has lights (kLights: a separate instance, so scenes without lights carry none of this)
+                    const int nMis = nLocal + nSun + 2;
+                    const float localMisW = float(nLocal) / nMis, sunMisW = float(nSun) / nMis, skyMisW = 1.0f / nMis, brdfMisW = 1.0f / nMis;
+
+                    // local-light candidates (closesthit.cu:347-375): alias-sampled light, point on its triangle, RIS stream
+                    if (nLocal > 0)
+                    {
+                        VptReservoir localRes = emptyReservoir();
+                        int localIdx = -1;
+                        f2 localUv = {0.0f, 0.0f};
+#pragma unroll 1
+                        for (int i = 0; i < nLocal; ++i)
+                        {
+                            float sourcePdf;
+                            const int li = (int)c.aliasSample(a.lv.alias, a.lv.numLights, c.rnd(), sourcePdf);
+                            if (li >= a.lv.numLights) continue;
+                            const f2 uv = c.rnd2();
+                            const LightSample cand = triLightSample(createTriLight(a.lv.lights + li), uv, s.pos);
+                            float blended;
+                            const float targetPdf = c.evalCandidate(s, cand, sourcePdf, localMisW, brdfMisW, &blended);
+                            const float risRnd = c.rnd();
+                            if (blended != 0.0f && streamSample(localRes, (uint32_t)li, uv, risRnd, targetPdf, 1.0f / blended)) { localIdx = li; localUv = uv; }
+                        }
+                        finalizeResampling(localRes, 1.0f, (float)nMis);
+                        a.wb.candC[p] = make_uint4((uint32_t)localIdx, __float_as_uint(localRes.weightSum), __float_as_uint(localRes.targetPdf), 0u); // integer plane: the index never passes through a float register (-ftz)
+                        a.wb.candB[p].z = localUv.x; a.wb.candB[p].w = localUv.y;
+                    }
 
                     // sun candidate (closesthit.cu:380-420; Restir.h:221-250)
                     VptReservoir sunRes = emptyReservoir();
@@ -925,7 +1036,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
                     }
                     finalizeResampling(skyRes, 1.0f, (float)nMis);
                     a.wb.candA[p] = make_float4(__int_as_float(sunIdx), sunRes.weightSum, sunRes.targetPdf, __int_as_float(skyIdx));
-                    a.wb.candB[p] = make_float4(skyRes.weightSum, skyRes.targetPdf, 0.0f, 0.0f);
+                    a.wb.candB[p].x = skyRes.weightSum; a.wb.candB[p].y = skyRes.targetPdf; // (.zw: the local light's uv, above)
                     // BSDF candidate: sample a direction and cast the BSDF-light ray (closesthit.cu:452-468)
                     f3 sampleDir, dummy; float brdfPdf; bool trans = false;
                     disneySample(c.rnd4(), s.normal, s.geoNormal, s.wo, s.albedo, s.metallic, s.translucency, s.roughness, sampleDir, dummy, brdfPdf, trans);
@@ -935,7 +1046,9 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
                         nf |= F_RAY1;
                         a.wb.dir1[p] = make_float4(sampleDir.x, sampleDir.y, sampleDir.z, 0.0f);
                         want = prepareRay(a.grid, frontPos, sampleDir, 0.0f, (uint32_t)p, r);
-                        if (!want) a.wb.vis1[p] = 0;
+                        // scenes with local lights trace this ray in closest-hit mode (which emissive face it hits matters,
+                        // __closesthit__bsdf_light): its result then lands in hitPacked / hitT, which S1 has consumed by now
+                        if (!want) { if (kLights) a.wb.hitPacked[p] = kHitMiss; else a.wb.vis1[p] = 0; }
                     }
                     if (a.enableRestir && gbufferPass) nf |= F_RESTIR;
                 }
@@ -980,7 +1093,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_SHADE_
 
 // ------------------------------------------------------------------------------------------------ S2
 // RIS: classify the BSDF candidate, merge the three reservoirs, cast the winner's visibility ray (closesthit.cu:470-634).
-template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MINB) shade2Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
@@ -999,13 +1112,28 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MIN
         const f3 sunD = c.sunDir();
         const bool skipSun = (dot(s.normal, sunD) < 0.0f || dot(s.geoNormal, sunD) < 0.0f);
         const int nSun = skipSun ? 0 : 1;
-        const int nMis = nSun + 2;
-        const float localMisW = 0.0f / nMis, sunMisW = float(nSun) / nMis, skyMisW = 1.0f / nMis, brdfMisW = 1.0f / nMis;
+        constexpr bool hasLights = kLights;
+        const int nLocal = hasLights ? 8 : 0;
+        const int nMis = nLocal + nSun + 2;
+        const float localMisW = float(nLocal) / nMis, sunMisW = float(nSun) / nMis, skyMisW = 1.0f / nMis, brdfMisW = 1.0f / nMis;
 
         const float4 ca = __ldg(a.wb.candA + p), cb = __ldg(a.wb.candB + p);
         const int sunIdx = __float_as_int(ca.x), skyIdx = __float_as_int(ca.w);
         VptReservoir localRes = emptyReservoir();
-        finalizeResampling(localRes, 1.0f, (float)nMis);
+        int localIdx = -1;
+        if (hasLights)
+        {
+            const uint4 cc = __ldg(a.wb.candC + p);
+            localIdx = (int)cc.x;
+            localRes.weightSum = __uint_as_float(cc.y); localRes.targetPdf = __uint_as_float(cc.z); // already finalised by S1
+            if (localIdx >= 0)
+            {
+                localRes.lightData = (uint32_t)localIdx | kLightValidBit;
+                localRes.uvData = (uint32_t)(saturate(cb.z) * 0xffff) | ((uint32_t)(saturate(cb.w) * 0xffff) << 16);
+            }
+        }
+        else
+            finalizeResampling(localRes, 1.0f, (float)nMis);
         localRes.M = 1;
         VptReservoir sunRes = emptyReservoir();
         sunRes.weightSum = ca.y; sunRes.targetPdf = ca.z; sunRes.M = 1;
@@ -1035,13 +1163,42 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MIN
         LightSample brdfSample = noLight();
         const bool haveRay1 = (fl & F_RAY1) != 0;
         const f3 sampleDir = haveRay1 ? xyz(__ldg(a.wb.dir1 + p)) : F3(0.0f);
-        const bool ray1Hit = haveRay1 ? (a.wb.vis1[p] != 0) : true;
+        const uint32_t hp1 = (haveRay1 && hasLights) ? a.wb.hitPacked[p] : kHitMiss;
+        const bool ray1Hit = haveRay1 ? (hasLights ? hp1 != kHitMiss : a.wb.vis1[p] != 0) : true;
         {
             float lightSourcePdf = 0.0f;
             uint32_t lightIndex = kInvalidLight;
             f2 uv = {0, 0};
             LightSample cand = noLight();
-            if (haveRay1 && !ray1Hit)
+            if (haveRay1 && ray1Hit && hasLights && (hp1 & 7u) < 6u)
+            {
+                // the BSDF ray ended on a voxel: an emissive one is a light (__closesthit__bsdf_light, closesthit.cu:854-901) — which of
+                // the face's two triangles, and the hit's barycentrics
+                const int lin = (int)(hp1 >> 3), face = (int)(hp1 & 7u);
+                const VptMaterial *hm = a.materials + __ldg(a.blockToMaterial + __ldg(a.grid.idsLinear + lin));
+                if (__ldg(&hm->isEmissive))
+                {
+                    uint32_t hxu, yzu, hzu, hyu;
+                    a.grid.divW.div((uint32_t)lin, yzu, hxu);
+                    a.grid.divD.div(yzu, hyu, hzu);
+                    f3 A, eu, ev;
+                    faceFrameDev(face, (int)hxu, (int)hyu, (int)hzu, A, eu, ev);
+                    const f3 P = hitPoint((int)hxu, (int)hyu, (int)hzu, face, a.wb.hitT[p], s.pos, sampleDir);
+                    const float fs = dot(P - A, eu), ft = dot(P - A, ev);
+                    const int tri = (fs + ft <= 1.0f) ? 0 : 1;
+                    const f2 bary = tri == 0 ? f2{fs, ft} : f2{1.0f - fs, 1.0f - ft};
+                    const int li = findLight(a.lv, (uint32_t)lin, face, tri);
+                    if (li >= 0 && li < a.lv.numLights)
+                    {
+                        lightIndex = (uint32_t)li;
+                        const float sq = 1.0f - (1.0f - bary.x - bary.y); // InverseTriangleSample (LinearMath.h:2059-2064)
+                        uv = {sq * sq, bary.y / sq};
+                        cand = triLightSample(createTriLight(a.lv.lights + li), uv, s.pos);
+                        lightSourcePdf = __ldg(&a.lv.alias[li].p);
+                    }
+                }
+            }
+            else if (haveRay1 && !ray1Hit)
             {
                 if (equalAreaMapConeInv(uv, sunD, sampleDir, a.sunCosThetaMax))
                 {
@@ -1090,6 +1247,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MIN
         if (selBrdf) lightSample = brdfSample;
         else if (selSky) { if (skyIdx >= 0) lightSample = c.createSkyLightSample(skyIdx); }
         else if (selSun) { if (sunIdx >= 0) lightSample = c.createSunLightSample(sunIdx); }
+        else if (localIdx >= 0) lightSample = triLightSample(createTriLight(a.lv.lights + localIdx), f2{cb.z, cb.w}, s.pos); // localSample, recomputed
 
         fl &= ~(0xffu << kRandShift);
         fl |= ((uint32_t)c.randIdx << kRandShift);
@@ -1100,14 +1258,14 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S2_MIN
             {
                 fl |= F_VISHAVE1;
                 // identical (origin, direction) -> identical result: reuse the BSDF-candidate ray instead of re-tracing it
-                if (haveRay1 && sameDir(sampleDir, lightSample.position))
+                if (haveRay1 && lightSample.lightType != LightLocalTriangle && sameDir(sampleDir, lightSample.position))
                 {
                     if (!ray1Hit) fl |= F_VIS;
                     else { ris.lightData = 0; ris.weightSum = 0; }
                 }
                 else
                 {
-                    want = prepareRay(a.grid, s.pos, lightSample.position, 0.0f, (uint32_t)p, r);
+                    want = prepareRay(a.grid, s.pos, lightRayDir<kLights>(lightSample, s.pos), 0.0f, (uint32_t)p, r, lightRayTmax<kLights>(lightSample, s.pos, 0.0f));
                     if (want) fl |= F_RAY2;
                     else fl |= F_VIS; // never enters the grid: visible
                 }
@@ -1128,9 +1286,19 @@ VPT_DEV VptReservoir loadRis(const TraceArgs &a, int p)
     r.lightData = v.x; r.uvData = v.y; r.weightSum = __uint_as_float(v.z); r.targetPdf = __uint_as_float(v.w); r.M = 1;
     return r;
 }
-VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float mCap)
+template <bool kLights> VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float mCap)
 {
     VptReservoir pr = loadReservoir(a.resPrev + (size_t)iy * a.width + ix);
+    if (kLights && a.lv.stateDirty) // LoadDIReservoir (Restir.h:48-79): the light list changed since the reservoir was written
+    {
+        const uint32_t prevIdx = pr.lightData & kLightIndexMask;
+        if (prevIdx < kSunLight && a.lv.prevNumLights > 0 && prevIdx < (uint32_t)a.lv.prevNumLights)
+        {
+            const int curIdx = __ldg(a.lv.prevToCur + prevIdx);
+            if (curIdx < 0 || curIdx >= a.lv.numLights) pr = emptyReservoir();
+            else pr.lightData = (pr.lightData & ~kLightIndexMask) | (uint32_t)curIdx;
+        }
+    }
     if (isnan(pr.weightSum) || isinf(pr.weightSum)) pr = emptyReservoir();
     if (pr.M > mCap) pr.M = mCap;
     return pr;
@@ -1146,7 +1314,7 @@ VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &a, int ix, int iy, float
 #else
 #define VPT_S3_LOOP _Pragma("unroll 1")
 #endif
-template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
+template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThreads, VPT_S3_MINB) shade3Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx; // sample 0 of the wave: path == slot
@@ -1198,7 +1366,7 @@ VPT_S3_LOOP
             Surface ts;
             // the candidate's reservoir travels with its surface planes (same pixel): requested before the validation
             const bool inView = ix >= 0 && iy >= 0 && ix < a.width && iy < a.height; // getPrevSurface's own test
-            VptReservoir pr = inView ? loadPrevReservoir(a, ix, iy, mCap) : emptyReservoir();
+            VptReservoir pr = inView ? loadPrevReservoir<kLights>(a, ix, iy, mCap) : emptyReservoir();
             if (!c.getPrevSurface(ts, ix, iy)) continue;
             const bool nOk = dot(s.normal, ts.geoNormal) >= 0.5f;
             const bool dOk = fabsf(expectedPrevDepth - ts.depth) <= 0.1f * fmaxr(expectedPrevDepth, ts.depth);
@@ -1209,7 +1377,7 @@ VPT_S3_LOOP
             LightSample cand = noLight();
             if (isValidReservoir(pr))
             {
-                if (!c.lightSampleFromReservoir(cand, pr)) pr = emptyReservoir();
+                if (!c.template lightSampleFromReservoir<kLights>(cand, pr, s.pos)) pr = emptyReservoir();
                 neighborWeight = c.targetPdfForSurface(cand, s);
             }
             if (combineReservoirs(restir, pr, c.rnd(), neighborWeight)) { lightSample = cand; selectedLoopIdx = i; }
@@ -1227,20 +1395,21 @@ VPT_S3_LOOP
                 Surface ts;
                 c.getPrevSurface(ts, ix, iy);
                 LightSample atNeighbor = noLight();
-                c.lightSampleFromReservoir(atNeighbor, restir);
+                c.template lightSampleFromReservoir<kLights>(atNeighbor, restir, ts.pos);
                 ps[i] = c.targetPdfForSurface(atNeighbor, ts);
                 if (ps[i] > 0 && !(i == 0 && i == selectedLoopIdx))
                 {
                     const float extraRayOffset = 0.01f + 0.01f * ts.depth;
                     PreparedRay pr_;
-                    if (prepareRay(a.grid, ts.pos, lightSample.position, extraRayOffset, (uint32_t)(p * 3 + i), pr_))
+                    // towards `lightSample`, the sample at the CURRENT surface, as in the reference (closesthit.cu:743-744)
+                    if (prepareRay(a.grid, ts.pos, lightRayDir<kLights>(lightSample, ts.pos), extraRayOffset, (uint32_t)(p * 3 + i), pr_, lightRayTmax<kLights>(lightSample, ts.pos, extraRayOffset)))
                     {
                         rays[nWant++] = pr_;
                         rayMask |= (1u << i);
                     }
                     else a.wb.vis3[p * 3 + i] = 0;
                 }
-                pm[i] = loadPrevReservoir(a, ix, iy, mCap).M;
+                pm[i] = loadPrevReservoir<kLights>(a, ix, iy, mCap).M;
             }
         }
         a.wb.rstA[p] = make_uint4(restir.lightData, restir.uvData, __float_as_uint(restir.weightSum), __float_as_uint(restir.targetPdf));
@@ -1258,7 +1427,7 @@ VPT_S3_LOOP
 
 // ------------------------------------------------------------------------------------------------ S4
 // Bias-corrected normalisation and the final visibility ray (closesthit.cu:760-820).
-__global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
+template <bool kLights> __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_constant__ TraceArgs a, unsigned *qCount)
 {
     const int idx = blockIdx.x * kShadeThreads + threadIdx.x;
     const int p = a.slotBase + idx;
@@ -1300,8 +1469,13 @@ __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_const
             const f3 dirRis = xyz(__ldg(a.wb.lightA + p));
             const bool haveRay1 = (fl & F_RAY1) != 0;
             bool known = false, visible = false;
+            // (a local light's `position` is a point, an environment light's a direction: equal bits = the same ray from this surface)
             if ((fl & F_VISHAVE1) && sameDir(dirRis, lightSample.position)) { known = true; visible = risVis; }
-            else if (haveRay1 && sameDir(xyz(__ldg(a.wb.dir1 + p)), lightSample.position)) { known = true; visible = a.wb.vis1[p] == 0; }
+            else if (haveRay1 && lightSample.lightType != LightLocalTriangle && sameDir(xyz(__ldg(a.wb.dir1 + p)), lightSample.position))
+            {
+                known = true;
+                visible = kLights ? a.wb.hitPacked[p] == kHitMiss : a.wb.vis1[p] == 0; // ray #1 ran in closest-hit mode when lights exist
+            }
             if (known)
             {
                 if (visible) fl |= F_VIS;
@@ -1310,7 +1484,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_const
             else
             {
                 const float4 sa = __ldg(a.wb.surfA + p);
-                want = prepareRay(a.grid, xyz(sa), lightSample.position, 0.0f, (uint32_t)p, r);
+                want = prepareRay(a.grid, xyz(sa), lightRayDir<kLights>(lightSample, xyz(sa)), 0.0f, (uint32_t)p, r, lightRayTmax<kLights>(lightSample, xyz(sa), 0.0f));
                 if (want) fl |= F_RAY5;
                 else fl |= F_VIS;
             }
@@ -1324,7 +1498,7 @@ __global__ void __launch_bounds__(kShadeThreads) shade4Kernel(const __grid_const
 
 // ------------------------------------------------------------------------------------------------ S5
 // Shade with the surviving reservoir, store it, accumulate, spawn the continuation ray (closesthit.cu:822-851, RayGen.cu:71-84).
-template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
+template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MINB) shade5Kernel(const __grid_constant__ TraceArgs a, int depth, const int *__restrict__ list,
                                                               const unsigned *__restrict__ listCount, int *__restrict__ nextList,
                                                               unsigned *nextCount, unsigned *qCount)
 {
@@ -1372,7 +1546,7 @@ template <bool kTex> __global__ void __launch_bounds__(kShadeThreads, VPT_S5_MIN
             }
             if (lightSample.lightType != LightInvalid && isValidReservoir(shading) && visible)
             {
-                const f3 sampleDir = lightSample.position;
+                const f3 sampleDir = lightRayDir<kLights>(lightSample, s.pos);
                 const f3 albedo = (depth == 0) ? F3(1.0f) : s.albedo; // first hit is demodulated (closesthit.cu:301)
                 f3 bsdf; float pdf;
                 disneyEvaluate(s.normal, s.geoNormal, sampleDir, s.wo, albedo, s.metallic, s.roughness, bsdf, pdf);
@@ -1460,7 +1634,7 @@ static void carveAll(char *base, WaveBuffers &wb, int nSlots, int samples)
     char *cur = base;
     carve(cur, wb.dirT, N); carve(cur, wb.org, N); carve(cur, wb.hitT, N); carve(cur, wb.hitPacked, N);
     carve(cur, wb.surfA, N); carve(cur, wb.surfB, N); carve(cur, wb.surfC, N); carve(cur, wb.surfD, N); carve(cur, wb.pflag, N);
-    carve(cur, wb.candA, N); carve(cur, wb.candB, N); carve(cur, wb.dir1, N);
+    carve(cur, wb.candA, N); carve(cur, wb.candB, N); carve(cur, wb.candC, N); carve(cur, wb.dir1, N);
     carve(cur, wb.ris, N); carve(cur, wb.lightA, N); carve(cur, wb.lightB, N);
     carve(cur, wb.vis1, N); carve(cur, wb.vis2, N); carve(cur, wb.vis4, N);
     carve(cur, wb.rad, N); carve(cur, wb.thr, N); carve(cur, wb.nextD, N); carve(cur, wb.bop, N);
@@ -1503,8 +1677,8 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
     // gain — a shading kernel's thousands of pending CTAs keep back-filling the SMs, so the other part's 1024-thread
     // DDA CTA (173 KiB of shared memory) only gets in at the tail. One part unless the caller passes side streams.
     const int nParts = (overlap && nTiles >= 2) ? 2 : 1;
-    const bool tex = a.nTextures > 0;
-#define KTEX(k) (tex ? k<true> : k<false>)
+    const bool tex = a.nTextures > 0, lights = a.lv.numLights > 0;
+#define KTEX(k) (tex ? (lights ? k<true, true> : k<true, false>) : (lights ? k<false, true> : k<false, false>))
 #define VPT_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
     for (int first = 0; first < shardSamples; first += maxSamplesInWave)
     {
@@ -1550,14 +1724,14 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
                 const unsigned *listCount = cnt + kCntList + depth;
                 VPT_TRY(dda(pair, true, nullptr)); ++pair;
                 KTEX(shade1Kernel)<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
-                VPT_TRY(dda(pair, false, a.wb.vis1)); ++pair;
+                VPT_TRY(dda(pair, lights, a.wb.vis1)); ++pair; // BSDF-candidate ray: which emissive face it hits matters when lights exist
                 KTEX(shade2Kernel)<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, cnt + 2 * pair); ++nl; mark(1, st);
                 VPT_TRY(dda(pair, false, a.wb.vis2)); ++pair;
                 if (depth == 0 && restirWave)
                 {
                     KTEX(shade3Kernel)<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
                     VPT_TRY(dda(pair, false, a.wb.vis3, true)); ++pair;
-                    shade4Kernel<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
+                    (lights ? shade4Kernel<true> : shade4Kernel<false>)<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
                     VPT_TRY(dda(pair, false, a.wb.vis4)); ++pair;
                 }
                 KTEX(shade5Kernel)<<<gridPaths, kShadeThreads, 0, st>>>(a, depth, list, listCount, nextList, cnt + kCntList + depth + 1, cnt + 2 * pair); ++nl; mark(1, st);

@@ -29,6 +29,7 @@ TIMINGS_DTYPE = np.dtype([("trace_ms", "<f4"), ("resolve_ms", "<f4"), ("firefly_
                           ("history_fix_ms", "<f4"), ("history_clamp_ms", "<f4"), ("atrous_smem_ms", "<f4"), ("atrous_ms", "<f4"),
                           ("composite_ms", "<f4"), ("denoise_total_ms", "<f4"), ("atrous_passes", "<i4"), ("kernel_launches", "<i4"),
                           ("trace_dda_ms", "<f4"), ("trace_shade_ms", "<f4"), ("trace_dda_launches", "<i4"), ("trace_shade_launches", "<i4")])
+LIGHT_DTYPE = np.dtype([("center", "<f4", 3), ("scalars", "<u4"), ("radiance", "<u4", 2), ("direction1", "<u4"), ("direction2", "<u4")])
 CAMERA_FLOATS = 53
 
 # every symbol include/vpt.h declares (checked by the CPU test-suite against the built library)
@@ -42,7 +43,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays", "vpt_debug_tma_timeouts"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays", "vpt_debug_tma_timeouts", "vpt_get_lights"]
 
 
 def pack_textures(textures, slots, tex_size):
@@ -479,6 +480,16 @@ class Vpt:
         r, s = C.c_uint64(), C.c_uint64()
         _check(self.L.vpt_get_counters(self.ctx, C.byref(r), C.byref(s)), "vpt_get_counters")
         return r.value, s.value
+
+    def lights(self):
+        """(VptLightInfo[n], VptAliasBin[n], faceKeys[n/2]): the local emissive lights as the next render will see them."""
+        n = int(self.L.vpt_get_lights(self.ctx, None, None, None, 0))
+        if n < 0:
+            raise VptError("vpt_get_lights failed: %s" % lib().vpt_last_error().decode())
+        li = np.zeros(n, LIGHT_DTYPE); al = np.zeros(n, ALIAS_DTYPE); keys = np.zeros(n // 2, np.uint32)
+        if n and int(self.L.vpt_get_lights(self.ctx, _p(li), _p(al), _p(keys), n)) != n:
+            raise VptError("vpt_get_lights failed: %s" % lib().vpt_last_error().decode())
+        return li, al, keys
 
     def total_rays(self, reset=False):
         r = C.c_uint64()

@@ -9,5 +9,5 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -linein
 for f in denoise dn_tiles; do $NV -prec-div=false -prec-sqrt=false -ftz=true $EXTRA -c csrc/vpt_$f.cu -o $B/vpt_$f.o & done
 $NV -prec-div=false -prec-sqrt=false $EXTRA -c csrc/vpt_temporal.cu -o $B/vpt_temporal.o &
 wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o libvpt_$NAME.so build/vpt_wave.o build/vpt_dda.o $B/vpt_denoise.o $B/vpt_dn_tiles.o $B/vpt_temporal.o build/vpt_sky.o build/vpt_grid.o build/vpt_api.o build/vpt_host.o -ldl
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o libvpt_$NAME.so build/vpt_wave.o build/vpt_dda.o $B/vpt_denoise.o $B/vpt_dn_tiles.o $B/vpt_temporal.o build/vpt_sky.o build/vpt_grid.o build/vpt_api.o build/vpt_host.o build/vpt_lights.o -ldl
 echo built libvpt_$NAME.so

@@ -12,5 +12,5 @@ $NV -prec-div=false -prec-sqrt=false $EXTRA -c csrc/vpt_temporal.cu -o $B/vpt_te
 $NV -fmad=false $EXTRA -c csrc/vpt_grid.cu -o $B/vpt_grid.o &
 $NV -fmad=false -DVPT_FAST_MATH=0 $EXTRA -c csrc/vpt_sky.cu -o $B/vpt_sky.o &
 wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o libvpt_$NAME.so $B/vpt_wave.o $B/vpt_dda.o $B/vpt_denoise.o $B/vpt_temporal.o $B/vpt_sky.o $B/vpt_grid.o $B/vpt_api.o build/vpt_host.o -ldl
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o libvpt_$NAME.so $B/vpt_wave.o $B/vpt_dda.o $B/vpt_denoise.o $B/vpt_temporal.o $B/vpt_sky.o $B/vpt_grid.o $B/vpt_api.o build/vpt_host.o build/vpt_lights.o -ldl
 echo built libvpt_$NAME.so
