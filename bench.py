@@ -185,8 +185,9 @@ def workload_config(n):
                         "ReSTIR DI, full denoiser chain (global_settings.yaml: 4 spatial passes)" % (SPP * n, SPP, TOTAL_BOUNCE, DIFFUSE_BOUNCE),
             "camera": "SURVEY 8d cfg2 schedule: blocks of 8 static frames and 8 frames with yaw += 0.5 deg/frame (prevCam != cam), sweep direction alternating",
             "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_total": SPP * n, "chunks": list(CHUNKS),
-            "parallelism": ("spp-sharded x%d (%s) + ncclAllReduce(sum) of the accumulation buffer; rank 0 denoises"
-                            % (n, "every rank: 1 ReSTIR sample + 3 plain samples, rank-local ReSTIR state" if LOCAL_OWNER else "one ReSTIR sample in total, on rank 0")) if n > 1 else "single GPU",
+            "parallelism": ("spp-sharded x%d (%s) + ncclAllReduce(sum) of the accumulation buffer; %s"
+                            % (n, "every rank: 1 ReSTIR sample + 3 plain samples, rank-local ReSTIR state" if LOCAL_OWNER else "one ReSTIR sample in total, on rank 0",
+                               "row-band denoise on every rank (extended bands, one history exchange per frame), bands gathered on rank 0" if LOCAL_OWNER else "rank 0 denoises")) if n > 1 else "single GPU",
             "l2_policy": "working set 0.74 GB/frame (356 B/px of planes) > 126 MB L2: inputs larger than L2, no explicit flush"}
 
 
@@ -243,6 +244,206 @@ def parity_and_cpu_baseline(inp, p, n_static=2, n_moving=2):
     return cpu, par
 
 
+# ------------------------------------------------------------------------------------------------ configs[2..4]
+OTHER = {
+    "cfg3": dict(workload="cfg3: denoiser chain alone on a synthetic G-buffer + noisy radiance, 3840x2160, shipped settings (4 spatial passes), row-band sharded "
+                          "(extended bands, one history exchange per frame)", W=3840, H=2160, scaling="strong"),
+    "cfg4": dict(workload="cfg4: 4K offline render, 64 spp in total, bounce limits 4/1, 2x1x2-chunk scene, spp-sharded with ncclAllReduce(sum) of the accumulation "
+                          "buffers (one ReSTIR sample in total, on rank 0: bit-comparable to one GPU), rank 0 denoises", W=3840, H=2160, spp=64, limits=(4, 1),
+                 chunks=(2, 1, 2), scaling="strong"),
+    "cfg5": dict(workload="cfg5: large procedural world 32x8x32 chunks (1024x256x1024 voxels, masks walked through L2), 7680x4320, 256 spp in total, bounce "
+                          "limits 8/2, spp-sharded with ncclAllReduce(sum), rank 0 denoises", W=7680, H=4320, spp=256, limits=(8, 2), chunks=(32, 8, 32), scaling="strong"),
+}
+
+
+def run_other_config(args):
+    import torch
+    import common
+    import vpt
+    import vpt_scenes as S
+    import vpt_shard
+    cfg = OTHER[args.config]
+    W, H = cfg["W"], cfg["H"]
+    rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    args.warmup = max(args.warmup, 3)
+    p = S.default_denoising_params()
+    npix = W * H
+    peak, peak_src = load_peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def comm(g):
+        if world > 1:
+            uid = torch.from_numpy(vpt.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+            dist.broadcast(uid, 0)
+            g.comm_init(rank, world, uid.cpu().numpy())
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out_host = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    if args.config == "cfg3":
+        g = vpt.Vpt(W, H, local_rank)
+        comm(g)
+        stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local_rank))
+        cam = vpt.camera_init(W, H); cam[6:9] = (0.0, 6.0, 0.0); cam = vpt.camera_set_yaw_pitch(cam, 0.0, 0.0)
+        base = S.synthetic_gbuffer(W, H, 0)
+        # the G-buffer is static; four noisy radiance planes stay on the device and are swapped in per frame (device-to-device)
+        noisy = [torch.from_numpy(np.ascontiguousarray(S.synthetic_gbuffer(W, H, f)["Illumination"])).cuda() for f in range(4)]
+        r0, r1 = vpt.band_rows(H, world, rank)
+        state = {"f": 0}
+
+        def step(read_back, timed_events=None):
+            f = state["f"]
+            g.begin_external_frame()
+            if f < 2:   # the G-buffer is static: once into each of the two ping-pong sets
+                for name in ("Depth", "NormalRoughness", "Material", "Albedo"):
+                    g.write(name, base[name])
+            g.write_device("Illumination", noisy[f & 3].data_ptr(), noisy[f & 3].numel() * 4)
+            if timed_events is not None:
+                timed_events[0].record(stream)
+            if world == 1:
+                g.denoise(p, cam, cam, f, f + 1)
+            else:
+                g.denoise_band(p, cam, cam, f, f + 1, r0, r1)
+                g.comm_gather_output(0)
+            if timed_events is not None:
+                timed_events[1].record(stream)
+            if read_back and rank == 0:
+                g.read_async("IlluminationOutput", out_host[f & 1])
+            state["f"] = f + 1
+
+        g.set_profiling(False)
+        for _ in range(args.warmup):
+            step(False)
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        sampler = ClockSampler(local_rank); sampler.start()
+        for k in range(args.steps):
+            step(False, evs[k])
+        barrier()
+        sampler.stop_flag = True; sampler.join()
+        ms_dev = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(True)
+        if rank == 0:
+            g.read_wait()
+        barrier()
+        wall = time.perf_counter() - t0
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+        chain_bytes = sum((PASS_BYTES[k][0] * (3 if k == "atrous" else 1)) for k in ("firefly", "temporal", "history_clamp", "atrous_smem", "atrous")) * npix + 16 * npix
+        ms = ms_dev / args.steps
+        gbs = chain_bytes / (ms * 1e-3) / 1e9
+        line = {"metric": "denoiser chain GB/s (algorithmic bytes / time, whole job) and ms/frame at 3840x2160", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": cfg["workload"], "width": W, "height": H, "l2_policy": "planes of 133 MB each > 126 MB L2: inputs larger than L2, no explicit flush",
+                           "timed": "CUDA events around vpt_denoise / vpt_denoise_band + vpt_comm_gather_output of every frame, summed, max over ranks; the per-frame swap of the noisy "
+                                    "plane (device-to-device) is outside the events"},
+                "roofline": {"kernel": "denoiser chain", "bound": "hbm", "achieved": round(gbs / world, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / world / peak, 4),
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_frame": chain_bytes, "ref_layout_bytes": 612 * npix,
+                             "frac_ref_layout": round(612 * npix / (ms * 1e-3) / 1e9 / world / peak, 4), "note": "per-GPU share of the aggregate against one GPU's HBM peak"},
+                "clocks": sampler.summary(), "gpu_launches": 12 * args.steps,
+                "e2e": {"value": chain_bytes / (wall / args.steps) / 1e9, "unit": "GB/s", "ms_per_step": wall / args.steps * 1e3, "h2d_bytes_per_step": 2 * 212 + 68,
+                        "d2h_bytes_per_step": npix * 16, "note": "wall clock of the same loop with IlluminationOutput read back into pinned host memory every frame (includes the "
+                        "device-to-device swap of the noisy plane and the G-buffer ping-pong copies)"}}
+        print(json.dumps(line))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- cfg4 / cfg5: spp-sharded render of ONE image, strong scaling
+    spp, (total, diffuse), chunks = cfg["spp"], cfg["limits"], cfg["chunks"]
+    inp = common.scene_inputs(chunks)
+    g = common.setup(vpt.Vpt(W, H, local_rank), inp, spp=spp, total=total, diffuse=diffuse)
+    comm(g)
+    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local_rank))
+    if chunks[0] >= 32:
+        cam = vpt.camera_from_scene(W, H, [512.0, 200.0, 512.0], [-0.321564, -0.35, -0.946799], 90.0)
+    else:
+        cam = common.scene_camera(W, H, chunks)
+    state = {"f": 0}
+
+    def step(read_back):
+        f = state["f"]
+        if world == 1:
+            g.render(cam, cam, f)
+        else:
+            vpt_shard.render_sharded(g, cam, cam, f, rank, world, lambda c: c.comm_allreduce_illumination(), local_owner=False)
+        if rank == 0:
+            g.denoise(p, cam, cam, f, f + 1)
+            if read_back:
+                g.read_async("IlluminationOutput", out_host[f & 1])
+        state["f"] = f + 1
+
+    def timed(read_back, steps):
+        barrier()
+        g.total_rays(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank); sampler.start()
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(read_back)
+        if read_back and rank == 0:
+            g.read_wait()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        sampler.stop_flag = True; sampler.join()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        rays_t = torch.tensor([float(g.total_rays())], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(rays_t)
+        return ms, wall, sampler.summary(), float(rays_t.item())
+
+    g.set_profiling(False)
+    for _ in range(args.warmup):
+        step(False)
+    ms_dev, wall, clocks, rays = timed(False, args.steps)
+    ms_e2e, wall_e2e, _, rays_e2e = timed(True, args.steps)
+    g.set_profiling(True)
+    step(False)
+    tim = g.timings() if rank == 0 else None
+    steps_ray = (g.counters()[1] / max(g.counters()[0], 1)) if rank == 0 else None
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    line = {"metric": "Grays/s (%s; ms/frame in ms_per_step)" % args.config, "value": rays / (ms_dev * 1e-3) / 1e9, "unit": "Grays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "width": W, "height": H, "spp_total": spp, "chunks": list(chunks), "bounce_limits": [total, diffuse],
+                       "l2_policy": "frame planes + wavefront state far larger than the 126 MB L2: no explicit flush"},
+            "gpixel_samples_per_s": npix * spp * args.steps / (ms_dev * 1e-3) / 1e9, "rays_per_frame": rays / args.steps, "dda_steps_per_ray_rank0": steps_ray,
+            "rank0_frame": {"trace_ms": round(tim["trace_ms"] + tim["resolve_ms"], 3), "dda_ms": round(tim["trace_dda_ms"], 3), "shade_ms": round(tim["trace_shade_ms"], 3),
+                            "denoise_ms": round(tim["denoise_total_ms"], 3)},
+            "roofline": {"kernel": "denoiser chain (rank 0)", "bound": "hbm", "achieved": round(528 * npix / (tim["denoise_total_ms"] * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(528 * npix / (tim["denoise_total_ms"] * 1e-3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "note": "the trace is shared-memory / L2 and issue bound (Grays/s is its figure); the HBM-bound part of the frame is the denoiser chain"},
+            "clocks": clocks, "gpu_launches": tim["kernel_launches"] * args.steps,
+            "e2e": {"value": rays_e2e / wall_e2e / 1e9, "unit": "Grays/s", "ms_per_step": wall_e2e / args.steps * 1e3, "h2d_bytes_per_step": 2 * 212 + 68 + 64,
+                    "d2h_bytes_per_step": npix * 16}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -250,9 +451,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[1..4]; cfg2 is the metric's workload and what the driver runs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "cfg2":
+        return run_other_config(args)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -292,8 +497,11 @@ def main():
         if world == 1:
             g.render(cam, prev, f)
             g.denoise(p, cam, prev, f, f + 1)
+        elif LOCAL_OWNER:
+            # the two SURVEY 8e rows composed: spp-sharded trace, NCCL sum, row-band denoise on every rank, bands gathered on rank 0
+            vpt_shard.frame_banded(g, p, cam, prev, f, rank, world, lambda c: c.comm_allreduce_illumination(), HEIGHT)
         else:
-            vpt_shard.render_sharded(g, cam, prev, f, rank, world, lambda c: c.comm_allreduce_illumination(), local_owner=LOCAL_OWNER)
+            vpt_shard.render_sharded(g, cam, prev, f, rank, world, lambda c: c.comm_allreduce_illumination(), local_owner=False)
             if rank == 0:
                 g.denoise(p, cam, prev, f, f + 1)
         if read_back and rank == 0:

@@ -314,6 +314,9 @@ int vpt_denoise_external(vpt_ctx *ctx, const VptDenoisingParams *params, const V
 /* ---- outputs. BufferManager::GetBuffer2D (renderer/core/BufferManager.h:84) + OfflineBackend::storeFrameInBatch. */
 int vpt_read_buffer(vpt_ctx *ctx, VptBufferName name, void *host, size_t bytes);
 int vpt_write_buffer(vpt_ctx *ctx, VptBufferName name, const void *host, size_t bytes);
+/* The same from DEVICE memory of this GPU (a caller that owns a CUDA context in the process, e.g. a frame producer): an asynchronous
+ * device-to-device copy ordered on the context's stream. No reference counterpart (its producers write the surfaces in place). */
+int vpt_write_buffer_device(vpt_ctx *ctx, VptBufferName name, const void *device, size_t bytes);
 /* Pipelined read-back (OfflineBackend::storeFrameInBatch without stalling the frame loop): the copy is queued on a copy
  * stream behind everything submitted so far and returns at once; `host` should be pinned. The next vpt_denoise /
  * vpt_render that would overwrite the plane waits for the copy on the DEVICE, so the transfer overlaps the next frame's
@@ -353,10 +356,21 @@ int vpt_comm_init(vpt_ctx *ctx, int rank, int nranks, const uint8_t *id128);
 int vpt_comm_allreduce_illumination(vpt_ctx *ctx);
 /* Broadcast the sample-0 G-buffer, depth and current reservoir plane from rank 0 (so any rank can denoise). */
 int vpt_comm_broadcast_gbuffer(vpt_ctx *ctx, int iterationIndex);
-/* Row-band sharded denoiser (config 3): this rank owns rows [rowBegin,rowEnd) (multiples of 4); halo rows are
- * exchanged with the neighbouring bands by ncclSend/ncclRecv between passes. */
+/* Row-band sharded Denoiser::run (the reference runs one GPU). Rank r of the communicator owns the rows vpt_band_rows gives
+ * it (boundaries at multiples of 4: the firefly filter's 8x4 tiles) and leaves its band of IlluminationOutput exact — bit-identical
+ * to the single-GPU chain. Every rank runs the whole chain, with no exchange, on its band extended by the depth of the chain's
+ * dependency cone; one grouped ncclSend/ncclRecv per frame then brings in the history rows (PrevIllumination,
+ * PrevFastIllumination, PrevHistoryLength) the next frame's temporal pass needs from the two neighbours. Inputs (Illumination and
+ * the current G-buffer) must be valid on the band +- vpt_band_input_halo(params) rows. VPT_ERR_ARG when a band is smaller than
+ * the rows a neighbour must supply, or when the camera pair can reproject further than the 32-row history guard. */
 int vpt_denoise_band(vpt_ctx *ctx, const VptDenoisingParams *params, const VptCamera *camera, const VptCamera *prevCamera,
                      int frameNum, int iterationIndex, int rowBegin, int rowEnd);
+/* Rows [rowBegin,rowEnd) of rank `rank` of `nranks` for an image of `height` rows (host only). */
+void vpt_band_rows(int height, int nranks, int rank, int *rowBegin, int *rowEnd);
+/* Rows either side of its band on which a rank's inputs must be valid for vpt_denoise_band with these settings (host only). */
+int vpt_band_input_halo(const VptDenoisingParams *params);
+/* The bands of IlluminationOutput collected on rank `root` (one grouped exchange): the frame a caller reads back. */
+int vpt_comm_gather_output(vpt_ctx *ctx, int root);
 
 /* ---- host-side helpers mirroring the reference's host code (no device work) */
 /* Camera::init / Camera::update (renderer/shaders/Camera.h:29-99). */

@@ -658,10 +658,9 @@ int vpt_render(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int i
 }
 int vpt_begin_external_frame(vpt_ctx *c) { if (!c) return VPT_ERR_ARG; c->cur ^= 1; return VPT_OK; }
 
-static int haloExchange(vpt_ctx *c, void *plane, int elemFloats, int rowBegin, int rowEnd, int rows);
-
-// Denoiser::run (renderer/denoising/Denoiser.cu:24-408) over rows [rowBegin,rowEnd). band: this rank owns only those rows
-//  and exchanges halo rows with its neighbours between passes; inputs are valid on the band plus a guard.
+// Denoiser::run (renderer/denoising/Denoiser.cu:24-408) over rows [rowBegin,rowEnd). band: the rows are one rank's EXTENDED band
+// (vpt_denoise_band): the chain runs without any exchange and its result is exact on the rows whose whole dependency
+// cone lies inside [rowBegin,rowEnd) — the band proper; the packed G-buffer is prepared on a guard around the rows.
 static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
                         int rowBegin, int rowEnd, bool timing, bool band)
 {
@@ -675,7 +674,6 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
     const int usedIter = iterationIndex > 0 ? iterationIndex - 1 : 0;
     d.b.reservoirs = c->reservoirs + (size_t)(usedIter & 1) * c->npix();
     auto rec = [&](int e) -> cudaError_t { return timing ? cudaEventRecord(c->ev[e], c->stream) : cudaSuccess; };
-    auto halo = [&](void *plane, int elemFloats, int rows) -> int { return band ? haloExchange(c, plane, elemFloats, rowBegin, rowEnd, rows) : VPT_OK; };
     int launches = 0, rc;
     c->ranFirefly = c->ranTemporal = c->ranFix = c->ranClamp = c->ranSpatial = false;
     c->atrousPasses = 0;
@@ -685,7 +683,6 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
     const int prep0 = band ? std::max(0, rowBegin - guard) : rowBegin, prep1 = band ? std::min(c->height, rowEnd + guard) : rowEnd;
     CU(launchPrep(d, prep0, prep1, p->enableFireflyFilter != 0, c->patches, c->maxPatches));
     launches += p->enableFireflyFilter ? 3 : 1; c->ranFirefly = true;
-    if (p->enableFireflyFilter && (rc = halo(c->illumination, 4, 2))) return rc; // 5x5 noisy moments in HistoryClamping
     CU(rec(EV_FIREFLY));
     int finalBuf = 0;
     // HitDistReconstruction -> Ping, PrePass Ping -> Illumination (Denoiser.cu:86-119; off in the shipped settings). Their
@@ -695,21 +692,15 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
     if (frameNum == 0)
     {
         CU(launchFrame0Init(d)); launches++;
-        if ((rc = halo(c->prevIllum, 4, 2))) return rc;
     }
     CU(rec(EV_SKY));
     if (p->enableTemporalAccumulation && frameNum > 0)
     {
-        // band mode: static camera or small motion — history taps stay within the guard band exchanged at the end of the last frame
         CU(launchTemporal(d)); launches++; finalBuf = 1; c->ranTemporal = true;
-        if ((rc = halo(c->historyLength, 1, 18))) return rc;
-        if ((rc = halo(c->ping, 4, 18))) return rc; // HistoryFix stride <= 9, 2 taps
-        if ((rc = halo(c->pong, 4, 2))) return rc;
         CU(rec(EV_TEMPORAL));
         if (p->enableHistoryFix)
         {
             CU(launchHistoryFix(d, c->smCount)); launches++; finalBuf = 2; c->ranFix = true;
-            if ((rc = halo(c->pong, 4, 2))) return rc;
         }
         CU(rec(EV_HFIX));
         if (p->enableHistoryClamping)
@@ -723,7 +714,6 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
     bool composited = false;
     if (p->enableSpatialFiltering)
     {
-        if ((rc = halo(c->prevIllum, 4, 2))) return rc;
         {
             bool tiled = false;
             if (!c->dnGather) CU(launchAtrousSmemTiled(d, c->prevIllum, c->ping, &tiled));
@@ -736,9 +726,6 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
             int idx = 1, step = 1 << idx;
             const int maxIt = p->atrousIterationNum * 2;
             auto pass = [&](float4 *in, float4 *out, bool last) -> int {
-                const int hrows = step + (step > 4 ? step / 4 + 1 : 0);
-                int r2 = halo(in, 4, hrows);
-                if (r2) return r2;
                 // the last pass multiplies by albedo and writes IlluminationOutput (BufferCopyNonSky fused)
                 bool tiled = false;
                 cudaError_t e = c->dnGather ? cudaSuccess : launchAtrousTiled(d, in, last ? c->illumOutput : out, (unsigned)iterationIndex, (unsigned)step, last, &tiled);
@@ -766,13 +753,7 @@ static int denoiseChain(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera
         CU(launchCompositeNonSky(d, fin)); launches++;
     }
     CU(rec(EV_COMP));
-    if (band)
-    {
-        // history for the next frame's temporal pass: guard band of 32 rows (bicubic footprint + small camera motion)
-        if ((rc = halo(c->prevIllum, 4, 32))) return rc;
-        if ((rc = halo(c->prevFastIllum, 4, 32))) return rc;
-        if ((rc = halo(c->prevHistoryLength, 1, 32))) return rc;
-    }
+    (void)rc;
     c->launchesDenoise = launches;
     c->haveDenoise = timing;
     return VPT_OK;
@@ -875,6 +856,18 @@ int vpt_write_buffer(vpt_ctx *c, VptBufferName name, const void *host, size_t by
     CU(waitPendingCopy(c));
     CU(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return VPT_OK;
+}
+int vpt_write_buffer_device(vpt_ctx *c, VptBufferName name, const void *device, size_t bytes)
+{
+    if (!c || !device) return fail(VPT_ERR_ARG, "vpt_write_buffer_device: null argument");
+    void *p; size_t have;
+    int rc = planeInfo(c, name, &p, &have);
+    if (rc) return rc;
+    if (have != bytes) return fail(VPT_ERR_ARG, "vpt_write_buffer_device: size mismatch");
+    CU(cudaSetDevice(c->device));
+    CU(waitPendingCopy(c));
+    CU(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToDevice, c->stream)); // stays asynchronous: ordered on the context's stream
     return VPT_OK;
 }
 int vpt_read_reservoirs(vpt_ctx *c, int parity, VptReservoir *host, size_t bytes)
@@ -1125,65 +1118,146 @@ int vpt_comm_broadcast_gbuffer(vpt_ctx *c, int iterationIndex)
     return VPT_OK;
 }
 
-// Halo exchange of `rows` rows of a plane with the bands above and below (elemFloats floats per pixel). Every band is at least
-// `rows` high (vpt_denoise_band checks the deepest halo the settings imply against the smallest band), so both sides of a pair
-// always move exactly `rows` rows: the send and receive counts agree by construction.
-static int haloExchange(vpt_ctx *c, void *plane, int elemFloats, int rowBegin, int rowEnd, int rows)
+} // extern "C"
+
+// ---- row-band sharded Denoiser::run
+// Every rank runs the WHOLE chain, without any exchange, on its band extended by E rows either side, E = the depth of the chain's
+// dependency cone: HistoryFix 2 x 9 taps, HistoryClamping 5 x 5, the first a-trous pass (halo 2) and every a-trous step (step +
+// hashed jitter), plus HitDistReconstruction (2) / PrePass (31) when enabled. Rows of the extension are computed with a truncated
+// cone and are simply not used: the band proper is exact — bit-identical to the single-GPU chain. The only data a rank lacks for the
+// NEXT frame is the history (PrevIllumination, PrevFastIllumination, PrevHistoryLength) outside the rows where its own copy is
+// exact (band +- 20: HistoryFix + HistoryClamping): one grouped exchange per frame with the two neighbours brings in the rows
+// [band - E - 32, band - 20) and [band + 20, band + E + 32) — the extension plus the 32-row guard of the temporal pass's reprojected
+// taps. One NCCL launch per frame instead of the 13 per-pass halo exchanges of the first version (which were launch-latency bound:
+// a 4K band at 8 GPUs is ~0.15 ms of kernels).
+static int chainDepthRows(const VptDenoisingParams *p)
 {
-    if (c->nranks == 1 || rows <= 0) return VPT_OK;
-    ncclComm_t comm = (ncclComm_t)c->ncclComm;
-    const size_t rowFloats = (size_t)c->width * elemFloats, n = (size_t)rows * rowFloats;
-    float *base = (float *)plane;
-    const int up = c->rank - 1, down = c->rank + 1; // band r owns rows [r*H/n, (r+1)*H/n): "up" = lower row indices
-    NC(g_nccl.GroupStart());
-    if (up >= 0)
+    int d = 0;
+    if (p->enableHitDistanceReconstruction) d += 2;
+    if (p->enablePrePass) d += 31;
+    if (p->enableTemporalAccumulation) d += (p->enableHistoryFix ? 18 : 0) + (p->enableHistoryClamping ? 2 : 0);
+    if (p->enableSpatialFiltering)
     {
-        NC(g_nccl.Send(base + (size_t)rowBegin * rowFloats, n, ncclFloat, up, comm, c->stream));
-        NC(g_nccl.Recv(base + (size_t)(rowBegin - rows) * rowFloats, n, ncclFloat, up, comm, c->stream));
+        d += 2;
+        // the chain runs steps 2^1 .. 2^(2n+1) for atrousIterationNum = n > 0 (Denoiser.cu:296-352)
+        for (int idx = 1; p->atrousIterationNum > 0 && idx <= 2 * p->atrousIterationNum + 1; ++idx) { const int step = 1 << idx; d += step + (step > 4 ? step / 4 : 0); }
     }
-    if (down < c->nranks)
+    return (d + 3) & ~3; // band boundaries are multiples of 4 rows (firefly tiles): so is the extension
+}
+constexpr int kHistoryExact = 20; // a rank's own history planes are exact on its band +- 20 rows
+constexpr int kTemporalGuard = 32;
+
+extern "C" void vpt_band_rows(int height, int nranks, int rank, int *rowBegin, int *rowEnd)
+{
+    // python/vpt_shard.row_bands: boundaries at multiples of 4 rows
+    auto bound = [&](int r) { return r >= nranks ? height : ((int)((long long)height * r / nranks) / 4) * 4; };
+    if (rowBegin) *rowBegin = bound(rank);
+    if (rowEnd) *rowEnd = bound(rank + 1);
+}
+extern "C" int vpt_band_input_halo(const VptDenoisingParams *p) { return p ? chainDepthRows(p) + kTemporalGuard : -1; }
+
+// history planes of the next frame: rows [b0 - E - guard, b0 - exact) from the band above, [b1 + exact, b1 + E + guard) from below
+static int historyExchange(vpt_ctx *c, int b0, int b1, int E)
+{
+    if (c->nranks == 1) return VPT_OK;
+    ncclComm_t comm = (ncclComm_t)c->ncclComm;
+    const int H = c->height, W = c->width;
+    struct Plane { void *ptr; int floats; } planes[3] = {{c->prevIllum, 4}, {c->prevFastIllum, 4}, {c->prevHistoryLength, 1}};
+    const int up = c->rank - 1, down = c->rank + 1;
+    NC(g_nccl.GroupStart());
+    for (const Plane &pl : planes)
     {
-        NC(g_nccl.Send(base + (size_t)(rowEnd - rows) * rowFloats, n, ncclFloat, down, comm, c->stream));
-        NC(g_nccl.Recv(base + (size_t)rowEnd * rowFloats, n, ncclFloat, down, comm, c->stream));
+        float *base = (float *)pl.ptr;
+        const size_t rowFloats = (size_t)W * pl.floats;
+        if (up >= 0)
+        {
+            // the band above needs [b0 + exact, b0 + E + guard) of mine; I need [b0 - E - guard, b0 - exact) of its rows
+            const int s0 = std::min(H, b0 + kHistoryExact), s1 = std::min(H, b0 + E + kTemporalGuard);
+            const int r0 = std::max(0, b0 - E - kTemporalGuard), r1 = std::max(0, b0 - kHistoryExact);
+            if (s1 > s0) NC(g_nccl.Send(base + (size_t)s0 * rowFloats, (size_t)(s1 - s0) * rowFloats, ncclFloat, up, comm, c->stream));
+            if (r1 > r0) NC(g_nccl.Recv(base + (size_t)r0 * rowFloats, (size_t)(r1 - r0) * rowFloats, ncclFloat, up, comm, c->stream));
+        }
+        if (down < c->nranks)
+        {
+            const int s0 = std::max(0, b1 - E - kTemporalGuard), s1 = std::max(0, b1 - kHistoryExact);
+            const int r0 = std::min(H, b1 + kHistoryExact), r1 = std::min(H, b1 + E + kTemporalGuard);
+            if (s1 > s0) NC(g_nccl.Send(base + (size_t)s0 * rowFloats, (size_t)(s1 - s0) * rowFloats, ncclFloat, down, comm, c->stream));
+            if (r1 > r0) NC(g_nccl.Recv(base + (size_t)r0 * rowFloats, (size_t)(r1 - r0) * rowFloats, ncclFloat, down, comm, c->stream));
+        }
     }
     NC(g_nccl.GroupEnd());
     return VPT_OK;
 }
 
-// Deepest halo (rows) the chain exchanges for these settings: the 32-row history guard, HistoryFix's 2 x 9, and the widest a-trous
-// reach (step + the hashed jitter of step / 4 + 1 for step > 4).
-static int maxHaloRows(const VptDenoisingParams *p)
+// largest reprojection shift (pixel rows / columns) the camera pair can produce for geometry at >= 4 units: rotation + translation
+static float reprojectionBound(const VptCamera *cam, const VptCamera *prev, int height)
 {
-    int rows = 32;
-    if (p->enableSpatialFiltering && p->atrousIterationNum > 0)
-    {
-        const int step = 1 << (p->atrousIterationNum * 2 - 1); // steps 2, 4, ..., 2^(2k-1)
-        rows = std::max(rows, step + (step > 4 ? step / 4 + 1 : 0));
-    }
-    return rows;
+    const float d = cam->dir[0] * prev->dir[0] + cam->dir[1] * prev->dir[1] + cam->dir[2] * prev->dir[2];
+    const float angle = std::acos(std::fmin(1.0f, std::fmax(-1.0f, d)));
+    const float dx = cam->pos[0] - prev->pos[0], dy = cam->pos[1] - prev->pos[1], dz = cam->pos[2] - prev->pos[2];
+    const float move = std::sqrt(dx * dx + dy * dy + dz * dz);
+    const float pixelsPerRadian = (float)height / (2.0f * std::atan(cam->tanHalfFov[1]));
+    return (angle + std::atan(move / 4.0f)) * pixelsPerRadian;
 }
 
-// Row-band sharded Denoiser::run: every rank holds full-size planes but only its band
-// [rowBegin,rowEnd) (+ halos) is valid. Inputs (Illumination + current G-buffer) must be valid on the band plus
-// 32 guard rows either side (the caller uploads them that way); history planes are exchanged as they are produced.
+extern "C" {
+
+// Row-band sharded Denoiser::run: every rank holds full-size planes; rank r owns the rows [rowBegin,rowEnd) (vpt_band_rows)
+// and leaves its band of IlluminationOutput exact. Inputs (Illumination + the current G-buffer) must be valid on the band +-
+// vpt_band_input_halo(params) rows (the spp-sharded renderer leaves them valid everywhere).
 int vpt_denoise_band(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *cam, const VptCamera *prevCam, int frameNum, int iterationIndex,
                      int rowBegin, int rowEnd)
 {
     if (!c || !p || !cam || !prevCam) return fail(VPT_ERR_ARG, "vpt_denoise_band: null argument");
     if (rowBegin < 0 || rowEnd > c->height || rowBegin >= rowEnd || (rowBegin & 3)) return fail(VPT_ERR_ARG, "vpt_denoise_band: band must start on a multiple of 4 rows");
     if (c->nranks > 1 && !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_denoise_band: communicator not initialised");
-    if (p->enableHitDistanceReconstruction || p->enablePrePass) return fail(VPT_ERR_ARG, "vpt_denoise_band: unsupported pass enabled");
+    const int E = chainDepthRows(p);
     if (c->nranks > 1)
     {
-        // one-hop exchange only: the deepest halo must fit the smallest band of an n-way split (bands are H/n rounded to 4 rows)
-        const int smallest = std::min(rowEnd - rowBegin, c->height / c->nranks - 3);
-        if (maxHaloRows(p) > smallest)
-            return fail(VPT_ERR_ARG, "vpt_denoise_band: the settings need a " + std::to_string(maxHaloRows(p)) + "-row halo but a band has only " +
+        // one-hop exchange: what a neighbour sends must lie in the rows where its own history is exact (its band +- 20)
+        int smallest = c->height;
+        for (int r = 0; r < c->nranks; ++r) { int a, b; vpt_band_rows(c->height, c->nranks, r, &a, &b); smallest = std::min(smallest, b - a); }
+        if (E + kTemporalGuard - kHistoryExact > smallest)
+            return fail(VPT_ERR_ARG, "vpt_denoise_band: the settings need " + std::to_string(E + kTemporalGuard - kHistoryExact) + " history rows from a neighbour but the smallest band has " +
                                          std::to_string(smallest) + " rows (lower atrousIterationNum or use fewer ranks)");
+        if (p->enableTemporalAccumulation && frameNum > 0 && reprojectionBound(cam, prevCam, c->height) > (float)kTemporalGuard)
+            return fail(VPT_ERR_ARG, "vpt_denoise_band: the camera moved too far for the 32-row history guard of the band-sharded temporal pass");
     }
     CU(cudaSetDevice(c->device));
     CU(waitPendingCopy(c));
-    return denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, rowBegin, rowEnd, false, c->nranks > 1);
+    const bool sharded = c->nranks > 1;
+    const int e0 = sharded ? std::max(0, rowBegin - E) : rowBegin, e1 = sharded ? std::min(c->height, rowEnd + E) : rowEnd;
+    const int rc = denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, e0, e1, false, sharded);
+    if (rc) return rc;
+    return sharded ? historyExchange(c, rowBegin, rowEnd, E) : VPT_OK;
+}
+
+// The bands of IlluminationOutput collected on rank `root` (one grouped send / receive): the frame a caller reads back.
+int vpt_comm_gather_output(vpt_ctx *c, int root)
+{
+    if (!c || !c->ncclComm) return fail(VPT_ERR_STATE, "vpt_comm_gather_output: communicator not initialised");
+    if (root < 0 || root >= c->nranks) return fail(VPT_ERR_ARG, "vpt_comm_gather_output: bad root");
+    CU(cudaSetDevice(c->device));
+    ncclComm_t comm = (ncclComm_t)c->ncclComm;
+    float *base = (float *)c->illumOutput;
+    const size_t rowFloats = (size_t)c->width * 4;
+    NC(g_nccl.GroupStart());
+    if (c->rank == root)
+    {
+        for (int r = 0; r < c->nranks; ++r)
+        {
+            if (r == root) continue;
+            int a, b; vpt_band_rows(c->height, c->nranks, r, &a, &b);
+            NC(g_nccl.Recv(base + (size_t)a * rowFloats, (size_t)(b - a) * rowFloats, ncclFloat, r, comm, c->stream));
+        }
+    }
+    else
+    {
+        int a, b; vpt_band_rows(c->height, c->nranks, c->rank, &a, &b);
+        NC(g_nccl.Send(base + (size_t)a * rowFloats, (size_t)(b - a) * rowFloats, ncclFloat, root, comm, c->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return VPT_OK;
 }
 
 } // extern "C"

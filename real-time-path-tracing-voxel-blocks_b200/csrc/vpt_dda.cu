@@ -46,7 +46,7 @@ constexpr int kChunk = VPT_DDA_CHUNK;        // rays reserved per warp per atomi
 constexpr int kRefillBelow = VPT_DDA_REFILL; // re-arm idle lanes when <= this many lanes are live
 constexpr unsigned kFull = 0xffffffffu;
 
-template <bool kSmem, bool kClosest, bool kStats>
+template <bool kSmem, bool kClosest, bool kStats, bool kTmax>
 __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constant__ DdaArgs a)
 {
     extern __shared__ uint32_t occS[];
@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
             int x, y, z;
             // a solid voxel first met at or beyond the ray's far end is no hit (the oracle's walk stops at tCur >= tmax; every voxel
             // before that one was empty, so stopping there or walking on to the first solid voxel decides the same)
-            const bool shell = decode(finLin, x, y, z) || finT >= tmax; // (the lane's tmax is only replaced by the re-arm below)
+            const bool shell = decode(finLin, x, y, z) || (kTmax && finT >= tmax); // (the lane's tmax is only replaced by the re-arm below;
+            // kTmax: only the visibility launches of scenes with local lights carry a finite far end)
             if (kClosest)
             {
                 uint32_t packed = kHitMiss;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                 const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
                 tX = __uint_as_float(q0.x); tY = __uint_as_float(q0.y); tZ = __uint_as_float(q0.z); tCur = __uint_as_float(q0.w);
                 dtX = __uint_as_float(q1.x); dtY = __uint_as_float(q1.y); dtZ = __uint_as_float(q1.z); tmin = __uint_as_float(q1.w);
-                lin = (int)q2.x; meta = q2.y; result = q2.z; tmax = __uint_as_float(q2.w);
+                lin = (int)q2.x; meta = q2.y; result = q2.z; if (kTmax) tmax = __uint_as_float(q2.w);
                 dX = (meta & 1u) ? 1 : -1;
                 dY = (meta & 2u) ? strideY : -strideY;
                 dZ = (meta & 4u) ? Wp : -Wp;
@@ -222,33 +223,41 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
     if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); atomicAdd(a.counters + 2, r64); if (kStats) atomicAdd(a.counters + 1, s64); } // [2]: running total over frames
 }
 
-template <bool kSmem, bool kClosest, bool kStats>
+template <bool kSmem, bool kClosest, bool kStats, bool kTmax>
 static cudaError_t launchDdaT(const DdaArgs &a, cudaStream_t s, int smCount)
 {
     size_t smem = 0;
     if (kSmem)
     {
         smem = (size_t)a.grid.occWords * 4;
-        cudaError_t e = cudaFuncSetAttribute(ddaKernel<kSmem, kClosest, kStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ddaKernel<kSmem, kClosest, kStats, kTmax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    ddaKernel<kSmem, kClosest, kStats><<<smCount, kDdaThreads, smem, s>>>(a);
+    ddaKernel<kSmem, kClosest, kStats, kTmax><<<smCount, kDdaThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, cudaStream_t s, int smCount)
+cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, bool farEnd, cudaStream_t s, int smCount)
 {
     const int sel = (occInSmem ? 4 : 0) | (closest ? 2 : 0) | (countSteps ? 1 : 0);
+    if (farEnd && !closest) // finite tmax only exists on visibility rays
+        switch (sel)
+        {
+        case 0: return launchDdaT<false, false, false, true>(a, s, smCount);
+        case 1: return launchDdaT<false, false, true, true>(a, s, smCount);
+        case 4: return launchDdaT<true, false, false, true>(a, s, smCount);
+        default: return launchDdaT<true, false, true, true>(a, s, smCount);
+        }
     switch (sel)
     {
-    case 0: return launchDdaT<false, false, false>(a, s, smCount);
-    case 1: return launchDdaT<false, false, true>(a, s, smCount);
-    case 2: return launchDdaT<false, true, false>(a, s, smCount);
-    case 3: return launchDdaT<false, true, true>(a, s, smCount);
-    case 4: return launchDdaT<true, false, false>(a, s, smCount);
-    case 5: return launchDdaT<true, false, true>(a, s, smCount);
-    case 6: return launchDdaT<true, true, false>(a, s, smCount);
-    default: return launchDdaT<true, true, true>(a, s, smCount);
+    case 0: return launchDdaT<false, false, false, false>(a, s, smCount);
+    case 1: return launchDdaT<false, false, true, false>(a, s, smCount);
+    case 2: return launchDdaT<false, true, false, false>(a, s, smCount);
+    case 3: return launchDdaT<false, true, true, false>(a, s, smCount);
+    case 4: return launchDdaT<true, false, false, false>(a, s, smCount);
+    case 5: return launchDdaT<true, false, true, false>(a, s, smCount);
+    case 6: return launchDdaT<true, true, false, false>(a, s, smCount);
+    default: return launchDdaT<true, true, true, false>(a, s, smCount);
     }
 }
 

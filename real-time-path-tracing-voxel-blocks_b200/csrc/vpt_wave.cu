@@ -1709,7 +1709,7 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
                 d.hitT = a.wb.hitT; d.hitPacked = a.wb.hitPacked; d.vis = vis; d.grid = a.grid; d.counters = a.counters;
                 if (prevWorld && a.occPrev) { d.grid.occ = a.occPrev; d.grid.upH = a.upHPrev; } // closesthit.cu:736-755: prevTopObject
                 ++nl;
-                cudaError_t e = launchDda(d, closest, smem, stats, st, smCount);
+                cudaError_t e = launchDda(d, closest, smem, stats, a.lv.numLights > 0, st, smCount);
                 mark(0, st);
                 return e;
             };

@@ -43,7 +43,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays", "vpt_debug_tma_timeouts", "vpt_get_lights"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays", "vpt_debug_tma_timeouts", "vpt_get_lights", "vpt_band_rows", "vpt_band_input_halo", "vpt_comm_gather_output", "vpt_write_buffer_device"]
 
 
 def pack_textures(textures, slots, tex_size):
@@ -290,6 +290,17 @@ def load_scene_config(path):
                 chunks=tuple(int(v) for v in chunks), loaded=(rc == 0))
 
 
+def band_rows(height, nranks, rank):
+    a, b = C.c_int(), C.c_int()
+    lib().vpt_band_rows(height, nranks, rank, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def band_input_halo(params):
+    p = np.ascontiguousarray(params)
+    return int(lib().vpt_band_input_halo(_p(p)))
+
+
 def comm_unique_id():
     buf = np.zeros(128, np.uint8)
     _check(lib().vpt_comm_unique_id(_p(buf)), "vpt_comm_unique_id")
@@ -507,6 +518,12 @@ class Vpt:
 
     def comm_allreduce_illumination(self):
         _check(self.L.vpt_comm_allreduce_illumination(self.ctx), "vpt_comm_allreduce_illumination")
+
+    def write_device(self, name, device_ptr, nbytes):
+        _check(self.L.vpt_write_buffer_device(self.ctx, BUF[name], C.c_void_p(int(device_ptr)), C.c_size_t(int(nbytes))), "vpt_write_buffer_device(%s)" % name)
+
+    def comm_gather_output(self, root=0):
+        _check(self.L.vpt_comm_gather_output(self.ctx, root), "vpt_comm_gather_output")
 
     def comm_broadcast_gbuffer(self, iteration_index):
         _check(self.L.vpt_comm_broadcast_gbuffer(self.ctx, iteration_index), "vpt_comm_broadcast_gbuffer")

@@ -38,3 +38,18 @@ def render_sharded(ctx, cam, prev_cam, iteration_index, rank, nranks, allreduce_
         ctx.render_shard(cam, prev_cam, iteration_index, begin, step)
     allreduce_sum(ctx)
     ctx.resolve()
+
+
+def frame_banded(ctx, params, cam, prev_cam, frame, rank, nranks, allreduce_sum, height, gather=True):
+    """One frame of the composed multi-GPU path (both rows): every rank renders its samples with a rank-local owner
+    (its own G-buffer, reservoirs and ReSTIR pass), the accumulation buffers are summed over the ranks, and every rank denoises its
+    row band (vpt_denoise_band: no exchange inside the chain, one history exchange per frame); the bands of the output are
+    collected on rank 0."""
+    begin, step = sample_shard(rank, nranks)
+    ctx.render_shard_local(cam, prev_cam, frame, begin, step)
+    allreduce_sum(ctx)
+    ctx.resolve()
+    b = row_bands(height, nranks)
+    ctx.denoise_band(params, cam, prev_cam, frame, frame + 1, b[rank], b[rank + 1])
+    if gather and nranks > 1:
+        ctx.comm_gather_output(0)
