@@ -1050,7 +1050,7 @@ bool loadNccl()
     if (!h) { g_lastError = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
 #define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { g_lastError = std::string("libnccl: missing ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast")
-    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString") SYM(CommDestroy, "ncclCommAbort")
 #undef SYM
     g_nccl.handle = h;
     return true;
@@ -1058,6 +1058,8 @@ bool loadNccl()
 } // namespace
 static void destroyComm(vpt_ctx *c)
 {
+    // ncclCommAbort: frees the communicator without any handshake with the peers (the context's streams are already drained), so a rank
+    // that tears down while its peers are still reporting — or have died — can never block here
     if (c->ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->ncclComm);
     c->ncclComm = nullptr;
 }
@@ -1227,7 +1229,7 @@ int vpt_denoise_band(vpt_ctx *c, const VptDenoisingParams *p, const VptCamera *c
     CU(waitPendingCopy(c));
     const bool sharded = c->nranks > 1;
     const int e0 = sharded ? std::max(0, rowBegin - E) : rowBegin, e1 = sharded ? std::min(c->height, rowEnd + E) : rowEnd;
-    const int rc = denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, e0, e1, false, sharded);
+    const int rc = denoiseChain(c, p, cam, prevCam, frameNum, iterationIndex, e0, e1, c->profiling, sharded); // (per-pass times: of the extended band)
     if (rc) return rc;
     return sharded ? historyExchange(c, rowBegin, rowEnd, E) : VPT_OK;
 }
