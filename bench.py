@@ -248,8 +248,8 @@ def parity_and_cpu_baseline(inp, p, n_static=2, n_moving=2):
 OTHER = {
     "cfg3": dict(workload="cfg3: denoiser chain alone on a synthetic G-buffer + noisy radiance, 3840x2160, shipped settings (4 spatial passes), row-band sharded "
                           "(extended bands, one history exchange per frame)", W=3840, H=2160, scaling="strong"),
-    "cfg4": dict(workload="cfg4: 4K offline render, 64 spp in total, bounce limits 4/1, 2x1x2-chunk scene, spp-sharded with ncclAllReduce(sum) of the accumulation "
-                          "buffers (one ReSTIR sample in total, on rank 0: bit-comparable to one GPU), rank 0 denoises", W=3840, H=2160, spp=64, limits=(4, 1),
+    "cfg4": dict(workload="cfg4: 4K offline render, 64 spp in total, bounce limits 4/1, 2x1x2-chunk scene, spp-sharded in cost-balanced contiguous ranges (rank 0 renders sample 0 with the ReSTIR pass and denoises, so it gets fewer plain samples) with "
+                          "ncclAllReduce(sum) of the accumulation buffers; one ReSTIR sample in total: bit-comparable to one GPU", W=3840, H=2160, spp=64, limits=(4, 1),
                  chunks=(2, 1, 2), scaling="strong"),
     "cfg5": dict(workload="cfg5: large procedural world 32x8x32 chunks (1024x256x1024 voxels, masks walked through L2), 7680x4320, 256 spp in total, bounce "
                           "limits 8/2, spp-sharded with ncclAllReduce(sum), rank 0 denoises", W=7680, H=4320, spp=256, limits=(8, 2), chunks=(32, 8, 32), scaling="strong"),
@@ -390,7 +390,7 @@ def run_other_config(args):
         if world == 1:
             g.render(cam, cam, f)
         else:
-            vpt_shard.render_sharded(g, cam, cam, f, rank, world, lambda c: c.comm_allreduce_illumination(), local_owner=False)
+            vpt_shard.render_balanced(g, cam, cam, f, rank, world, spp, lambda c: c.comm_allreduce_illumination())
         if rank == 0:
             g.denoise(p, cam, cam, f, f + 1)
             if read_back:

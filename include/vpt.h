@@ -292,6 +292,11 @@ int vpt_render(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamer
  * the un-normalised radiance SUM in Illumination; vpt_resolve divides by spp (after the cross-GPU sum). */
 int vpt_render_shard(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamera, int iterationIndex,
                      int sampleBegin, int sampleStep);
+/* Contiguous form: samples sampleBegin .. sampleBegin + sampleCount - 1 (clipped to spp; sampleCount 0 = an empty shard that
+ * contributes zero). Lets a caller size the shards by COST: the rank that renders sample 0 also runs the temporal ReSTIR pass
+ * (about 1.5 plain samples of extra work) and, in the offline flow, the denoiser — python/vpt_shard.py:balanced_ranges. */
+int vpt_render_range(vpt_ctx *ctx, const VptCamera *camera, const VptCamera *prevCamera, int iterationIndex,
+                     int sampleBegin, int sampleCount);
 /* Same shard, but its FIRST sample (sampleBegin) owns this context's G-buffer, reservoir plane and temporal ReSTIR pass — every
  * rank then runs the reference's whole per-frame algorithm (RayGen.cu:102-181: one ReSTIR sample + spp-1 plain samples) on its own
  * sample subset with rank-local ReSTIR state ("keep it rank-local"), so the ranks do equal work. The sum over ranks is

@@ -281,6 +281,9 @@ class Oracle:
     def render_shard(self, cam, prev_cam, iteration_index, sample_begin, sample_step):
         self.L.orc_render_shard(self.ctx, _p(cam), _p(prev_cam), iteration_index, sample_begin, sample_step)
 
+    def render_range(self, cam, prev_cam, iteration_index, sample_begin, sample_count):
+        assert self.L.orc_render_range(self.ctx, _p(cam), _p(prev_cam), iteration_index, sample_begin, sample_count) == 0
+
     def render_shard_local(self, cam, prev_cam, iteration_index, sample_begin, sample_step):
         self.L.orc_render_shard_local(self.ctx, _p(cam), _p(prev_cam), iteration_index, sample_begin, sample_step)
 

@@ -184,7 +184,7 @@ int orc_set_trace_params(orc_ctx *c, int spp, int totalBounceLimit, int diffuseB
 
 // OptixRenderer::render for the sample shard {k = sampleBegin, sampleBegin+sampleStep, ...}.
 // Leaves the un-normalised radiance SUM in Illumination (w = primary distance on the shard owning k=0).
-static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, int ownerSample);
+static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, int ownerSample, int sampleLimit = 0);
 int orc_render_shard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
 {
     return renderShard(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, 0);
@@ -194,7 +194,13 @@ int orc_render_shard_local(orc_ctx *c, const Camera *cam, const Camera *prevCam,
 {
     return renderShard(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, sampleBegin);
 }
-static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, int ownerSample)
+// contiguous form (vpt_render_range): samples sampleBegin .. sampleBegin + sampleCount - 1; 0 samples = an empty shard
+int orc_render_range(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleCount)
+{
+    if (sampleCount == 0) return renderShard(c, cam, prevCam, iterationIndex, c->sc.tp.spp, 1, 0);
+    return renderShard(c, cam, prevCam, iterationIndex, sampleBegin, 1, 0, sampleCount);
+}
+static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, int ownerSample, int sampleLimit)
 {
     Scene &sc = c->sc;
     sc.cur ^= 1;
@@ -205,7 +211,7 @@ static int renderShard(orc_ctx *c, const Camera *cam, const Camera *prevCam, int
         for (int x = 0; x < sc.width; ++x)
         {
             f4 acc;
-            renderPixel(sc, *cam, *prevCam, iterationIndex, x, y, sampleBegin, sampleStep, &acc, rays, steps, ownerSample);
+            renderPixel(sc, *cam, *prevCam, iterationIndex, x, y, sampleBegin, sampleStep, &acc, rays, steps, ownerSample, sampleLimit);
             sc.illumination[(size_t)y * sc.width + x] = acc;
         }
     sc.rayCount = rays; sc.stepCount = steps;

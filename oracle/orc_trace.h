@@ -1174,14 +1174,15 @@ inline f3 tracePath(PixelCtx &c, bool ownsGBuffer, float &primaryDist)
 // `sampleBegin/sampleStep` shard the spp loop (multi-GPU: rank r renders k = r, r+n, ...). ownerSample = the sample that owns
 // the G-buffer / reservoir / ReSTIR pass: 0 (the reference), or sampleBegin for a rank-local owner.
 inline void renderPixel(Scene &sc, const Camera &cam, const Camera &prevCam, int iterationIndex, int px, int py,
-                        int sampleBegin, int sampleStep, f4 *accumOut, uint64_t &rays, uint64_t &steps, int ownerSample = 0)
+                        int sampleBegin, int sampleStep, f4 *accumOut, uint64_t &rays, uint64_t &steps, int ownerSample = 0, int sampleLimit = 0)
 {
     PixelCtx c{&sc, &cam, &prevCam, px, py, iterationIndex, 0, 0, 0, 0, 0};
     const int spp = sc.tp.spp;
     f3 sum = F3(0.0f);
     float depth0 = kRayMax;
     bool haveDepth = false;
-    for (int k = sampleBegin; k < spp; k += sampleStep)
+    int done = 0;
+    for (int k = sampleBegin; k < spp && (sampleLimit <= 0 || done < sampleLimit); k += sampleStep, ++done)
     {
         c.sampleIndex = iterationIndex * spp + k;
         c.prevSampleIndex = (iterationIndex - 1) * spp + ownerSample; // the previous frame's owner sample (its G-buffer jitter)

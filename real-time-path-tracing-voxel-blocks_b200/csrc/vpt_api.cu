@@ -554,7 +554,8 @@ static int prepareLightRemap(vpt_ctx *c)
     return VPT_OK;
 }
 
-static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, bool resolve, bool localOwner = false)
+static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep, bool resolve, bool localOwner = false,
+                      int sampleLimit = 0)
 {
     if (!c || !cam || !prevCam || sampleBegin < 0 || sampleStep < 1) return fail(VPT_ERR_ARG, "vpt_render: bad argument");
     if (!c->occ) return fail(VPT_ERR_STATE, "vpt_render: no voxel grid (vpt_set_grid / vpt_generate_terrain)");
@@ -590,7 +591,9 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     a.countSteps = c->countSteps;
     a.resolveSpp = (resolve && c->spp > 1) ? (float)c->spp : 0.0f;
     // wave size: as many samples per wave as fit a 16 M-path budget
-    const int shardSamples = sampleBegin < c->spp ? (c->spp - sampleBegin + sampleStep - 1) / sampleStep : 0;
+    int shardSamples = sampleBegin < c->spp ? (c->spp - sampleBegin + sampleStep - 1) / sampleStep : 0;
+    if (sampleLimit > 0 && shardSamples > sampleLimit) shardSamples = sampleLimit;
+    a.sampleLimit = sampleLimit;
     int samplesPerWave = (int)(c->waveBudget / (size_t)a.nSlots);
     if (samplesPerWave < 1) samplesPerWave = 1;
     if (samplesPerWave > shardSamples) samplesPerWave = shardSamples > 0 ? shardSamples : 1;
@@ -650,6 +653,12 @@ int vpt_render_shard(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam,
 int vpt_render_shard_local(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleStep)
 {
     return renderImpl(c, cam, prevCam, iterationIndex, sampleBegin, sampleStep, false, true);
+}
+int vpt_render_range(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex, int sampleBegin, int sampleCount)
+{
+    if (sampleCount < 0) return fail(VPT_ERR_ARG, "vpt_render_range: negative sample count");
+    if (sampleCount == 0) return renderImpl(c, cam, prevCam, iterationIndex, c ? c->spp : 0, 1, false); // an empty shard: contributes zero
+    return renderImpl(c, cam, prevCam, iterationIndex, sampleBegin, 1, false, false, sampleCount);
 }
 int vpt_render(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam, int iterationIndex)
 {

@@ -86,6 +86,7 @@ struct TraceArgs
     int width, height;
     int iterationIndex, spp, totalBounceLimit, diffuseBounceLimit, enableRestir;
     int sampleBegin, sampleStep;
+    int sampleLimit;             // > 0: at most this many samples of the shard (vpt_render_range)
     const uint32_t *occPrev; int upHPrev; // masks of the world as the previous render saw it (nullptr: unchanged); bias rays only
     int ownerSample; // the sample that owns the G-buffer, the reservoir and the temporal ReSTIR pass: 0, or sampleBegin with a rank-local owner
     GridView grid;

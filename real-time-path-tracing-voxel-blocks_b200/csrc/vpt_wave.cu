@@ -1668,7 +1668,8 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
     auto mark = [&](int kind, cudaStream_t st) {
         if (timing && prof->n < TraceProfile::kMax) { prof->kind[prof->n] = kind; cudaEventRecord(prof->ev[prof->n + 1], st); ++prof->n; }
     };
-    const int shardSamples = a.sampleBegin < a.spp ? (a.spp - a.sampleBegin + a.sampleStep - 1) / a.sampleStep : 0;
+    int shardSamples = a.sampleBegin < a.spp ? (a.spp - a.sampleBegin + a.sampleStep - 1) / a.sampleStep : 0;
+    if (a.sampleLimit > 0 && shardSamples > a.sampleLimit) shardSamples = a.sampleLimit;
     a.occInSmem = ((size_t)a.grid.occWords * 4 + 1024 <= smemOptIn) ? 1 : 0;
     const bool smem = a.occInSmem != 0, stats = a.countSteps != 0;
     const WaveBuffers wb0 = a.wb;

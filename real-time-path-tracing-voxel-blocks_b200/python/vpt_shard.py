@@ -53,3 +53,28 @@ def frame_banded(ctx, params, cam, prev_cam, frame, rank, nranks, allreduce_sum,
     ctx.denoise_band(params, cam, prev_cam, frame, frame + 1, b[rank], b[rank + 1])
     if gather and nranks > 1:
         ctx.comm_gather_output(0)
+
+
+def balanced_ranges(spp, nranks, owner_extra=2.3):
+    """Contiguous sample ranges [(begin, count)] per rank for ONE image of `spp` samples (strong scaling, cfg4 / cfg5), sized by cost:
+    rank 0 renders sample 0, whose temporal ReSTIR pass is worth ~1.5 plain samples, and denoises the frame (~0.8 at 4K / 64 spp), so
+    it gets `owner_extra` fewer plain samples than the others. Every sample is rendered exactly once whatever the split."""
+    if nranks == 1:
+        return [(0, spp)]
+    per = (spp + owner_extra) / nranks                      # cost units per rank
+    first = max(1, min(spp, int(round(per - owner_extra))))
+    rest = spp - first
+    counts = [first] + [rest // (nranks - 1) + (1 if i < rest % (nranks - 1) else 0) for i in range(nranks - 1)]
+    out, b = [], 0
+    for c in counts:
+        out.append((b, c))
+        b += c
+    return out
+
+
+def render_balanced(ctx, cam, prev_cam, iteration_index, rank, nranks, spp, allreduce_sum, owner_extra=2.3):
+    """Strong-scaling frame: cost-balanced contiguous sample ranges, sum over ranks, resolve."""
+    begin, count = balanced_ranges(spp, nranks, owner_extra)[rank]
+    ctx.render_range(cam, prev_cam, iteration_index, begin, count)
+    allreduce_sum(ctx)
+    ctx.resolve()

@@ -128,3 +128,63 @@ def test_spp_sharding_local_owner_gloo_world2():
     assert res[1] <= 1e-5, res                      # all-reduced sum == the two shards added up (fp32 summation order)
     assert res[2] and other[1]                      # BOTH ranks own a G-buffer
     assert res[3] > 0.3 and other[2] > 0.3          # ... and keep ReSTIR reservoirs of their own
+
+
+def _worker_balanced(rank, world, port, q):
+    """Cost-balanced contiguous sample ranges (vpt_shard.render_balanced, the cfg4 / cfg5 strong-scaling split)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "real-time-path-tracing-voxel-blocks_b200", "python"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import common
+    import oracle as O
+    import vpt_scenes as S
+    import vpt_shard
+    O.set_threads(2)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    W, H, spp = 96, 64, 6
+    inp = common.scene_inputs((2, 1, 2), noise_fn=O.perlin_noise_chunks, alias_fn=O.build_alias_table)
+    o = common.setup(O.Oracle(W, H), inp, spp=spp, total=3, diffuse=1)
+    cam = O.camera_from_scene(W, H, S.SCENE_CAMERA["position"], S.SCENE_CAMERA["direction"], 90.0)
+
+    def allreduce(ctx):
+        t = torch.from_numpy(ctx.read("Illumination"))
+        dist.all_reduce(t)
+        ctx.write("Illumination", t.numpy())
+
+    for f in range(2):
+        vpt_shard.render_balanced(o, cam, cam, f, rank, world, spp, allreduce)
+    got = o.read("Illumination")
+    if rank == 0:
+        full = common.setup(O.Oracle(W, H), inp, spp=spp, total=3, diffuse=1)
+        for f in range(2):
+            full.render(cam, cam, f)
+        ref = full.read("Illumination")
+        q.put(("result", float(np.abs(got[..., :3] - ref[..., :3]).max()), bool(np.array_equal(got[..., 3], ref[..., 3])), vpt_shard.balanced_ranges(spp, world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_balanced_sample_ranges_gloo_world2():
+    sys.path.insert(0, os.path.join(ROOT, "real-time-path-tracing-voxel-blocks_b200", "python"))
+    import vpt_shard
+    for spp, n in ((64, 8), (64, 4), (64, 2), (256, 8), (4, 8), (8, 8), (1, 3), (5, 1)):
+        r = vpt_shard.balanced_ranges(spp, n)
+        assert len(r) == n and r[0][0] == 0 and sum(c for _, c in r) == spp
+        assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(n - 1))
+        assert r[0][1] >= 1                                     # rank 0 always renders sample 0 (the G-buffer / ReSTIR sample)
+        if n > 1 and spp >= 4 * n:
+            assert r[0][1] < max(c for _, c in r[1:])           # ... and fewer plain samples than the others
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30000 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker_balanced, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[1] < 1e-5 and res[2], res     # the two ranges add up to the full render (fp32 summation order); depth from the sample-0 rank
+    assert res[3][0][1] + res[3][1][1] == 6
