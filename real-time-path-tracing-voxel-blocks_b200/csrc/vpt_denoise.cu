@@ -836,6 +836,8 @@ cudaError_t launchHistoryClamping(const DenoiseLaunch &d)
     a.W = d.width; a.H = d.height; a.rowBegin = d.rowBegin; a.rowEnd = d.rowEnd;
     a.depth = d.b.cur.depth; a.illum = d.b.illumination; a.ping = d.b.ping; a.pong = d.b.pong; a.histLen = d.b.historyLength;
     a.prevIllum = d.b.prevIllum; a.prevFast = d.b.prevFastIllum; a.prevHistLen = d.b.prevHistoryLength;
+    // (a 32 x 16 tile with two rows per thread — 6 instead of 10 row loads for the vertical sums — was measured: 71.7 vs 69.6 us at 1080p,
+    // 239.6 vs 243.7 us at 4K; not kept)
     historyClampKernel<<<gridFor(d), kBlock, 0, d.stream>>>(a);
     return cudaGetLastError();
 }
