@@ -348,6 +348,9 @@ int vpt_get_total_rays(vpt_ctx *ctx, uint64_t *rays, int reset);
 int vpt_get_lights(vpt_ctx *ctx, VptLightInfo *lights, VptAliasBin *alias, uint32_t *faceKeys, int capacity);
 /* Debug counter: shared-memory tile loads of the denoiser whose completion barrier timed out (0 in a healthy build). */
 int vpt_debug_tma_timeouts(void);
+/* Debug: raw read-back of one 16-byte-per-path plane of the last wave's state (which: 0 candidate C, 1 RIS state, 2 / 3 stored
+ * reservoir A / B, 4 light sample A, 5 second light sample A); entries <= the paths of a wave. tools/lights_debug.py. */
+int vpt_debug_read_wave(vpt_ctx *ctx, int which, void *host, size_t entries);
 int vpt_get_timings(vpt_ctx *ctx, VptTimings *out);
 /* Toggle CUDA-event stage timing and the DDA step counter (default on; adds event records between kernels and one
  * add per DDA step). Throughput runs switch it off. */

@@ -956,6 +956,7 @@ int vpt_debug_read_wave(vpt_ctx *c, int which, void *host, size_t entries)
     if (!c || !host || !c->wave.arena) return fail(VPT_ERR_STATE, "vpt_debug_read_wave: no wave state");
     const void *src[] = {c->wave.wb.candC, c->wave.wb.ris, c->wave.wb.rstA, c->wave.wb.rstB, c->wave.wb.lightA, c->wave.wb.light2A};
     if (which < 0 || which > 5) return fail(VPT_ERR_ARG, "vpt_debug_read_wave: unknown plane");
+    if (entries > (size_t)c->wave.nSlots * (size_t)c->wave.maxSamplesInWave) return fail(VPT_ERR_ARG, "vpt_debug_read_wave: more entries than the wave has paths");
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(host, src[which], entries * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -43,7 +43,7 @@ EXPORTS = [
     "vpt_build_alias_table", "vpt_load_denoising_settings", "vpt_default_denoising_params", "vpt_load_scene_config",
     "vpt_debug_fastdiv", "vpt_generate_sky", "vpt_read_sky", "vpt_sky_size", "vpt_sky_state",
     "vpt_chunk_hash", "vpt_save_world", "vpt_load_world", "vpt_set_wave_budget", "vpt_read_buffer_async", "vpt_read_wait", "vpt_tonemap", "vpt_default_tonemapping_params", "vpt_load_tonemapping_settings", "vpt_load_sky_settings",
-    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays", "vpt_debug_tma_timeouts", "vpt_get_lights", "vpt_band_rows", "vpt_band_input_halo", "vpt_comm_gather_output", "vpt_write_buffer_device", "vpt_render_range"]
+    "vpt_set_textures", "vpt_mip_chain_texels", "vpt_build_mip_chain", "vpt_load_materials", "vpt_load_png_rgba8", "vpt_pick_voxel", "vpt_render_shard_local", "vpt_image_diff", "vpt_image_diff_files", "vpt_get_total_rays", "vpt_debug_tma_timeouts", "vpt_debug_read_wave", "vpt_get_lights", "vpt_band_rows", "vpt_band_input_halo", "vpt_comm_gather_output", "vpt_write_buffer_device", "vpt_render_range"]
 
 
 def pack_textures(textures, slots, tex_size):
