@@ -42,9 +42,32 @@ constexpr int kDdaThreads = VPT_DDA_THREADS;
 #ifndef VPT_DDA_BREAK
 #define VPT_DDA_BREAK 1
 #endif
+// The step is bound by the ALU pipe, not by issue slots: LOP3 / SHF / SEL / FSEL / FSETP / ISETP / FMNMX all go to the alu pipe
+// (one warp instruction per 2 cycles per SM sub-partition), FADD / IMAD to the fma pipe. The select form below compiles to
+// 12 alu + 4 fma instructions of 18: 24 alu cycles per step = the 73 % issue-slot utilisation ncu reports (r2p capture).
+// VPT_DDA_PRED: the same decision as ONE 3-input minimum (FMNMX3) and equality predicates — Z wins ties, then Y, then X, exactly
+// the nested '<' of VoxelEngine.cu:1133-1162 — with predicated FADD / IADD instead of selects: 16 instructions, 9 alu.
+// (Zero signs: an axis' tMax is only ever -0, never +0 — (boundary - o)/d is zero only for a negative step — so the minimum
+// returns the same bits as the select.)
+// VPT_DDA_BYTE: the shared-memory mask is staged byte-swapped and read with LDS.U8 at lin >> 3 (one alu instruction instead of
+// SHF + LOP3); the byte is replicated over the word by an IMAD (fma pipe) so the shift-by-lin sign test stays as it is.
+#ifndef VPT_DDA_PRED
+#define VPT_DDA_PRED 1
+#endif
+#ifndef VPT_DDA_BYTE
+#define VPT_DDA_BYTE 1
+#endif
 constexpr int kChunk = VPT_DDA_CHUNK;        // rays reserved per warp per atomic
 constexpr int kRefillBelow = VPT_DDA_REFILL; // re-arm idle lanes when <= this many lanes are live
 constexpr unsigned kFull = 0xffffffffu;
+
+// one mask byte replicated over the word: the shift-by-lin sign test then finds bit 7 - (lin & 7) of it wherever lin & 31 points
+__device__ __forceinline__ uint32_t repByte(uint32_t b)
+{
+    uint32_t w;
+    asm("mul.lo.u32 %0, %1, 0x01010101;" : "=r"(w) : "r"(b)); // IMAD (fma pipe), not PRMT / shifts (alu pipe)
+    return w;
+}
 
 template <bool kSmem, bool kClosest, bool kStats, bool kTmax>
 __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constant__ DdaArgs a)
@@ -55,7 +78,15 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         const uint4 *src = reinterpret_cast<const uint4 *>(a.grid.occ);
         uint4 *dst = reinterpret_cast<uint4 *>(occS);
         const int n4 = a.grid.occWords >> 2; // occWords is a multiple of 4
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        {
+            uint4 w = __ldg(src + i);
+#if VPT_DDA_BYTE
+            // byte-swapped: voxel k of a word (bit 31-k) then lives in byte k >> 3 of the word, i.e. at byte address lin >> 3
+            w.x = __byte_perm(w.x, 0u, 0x0123u); w.y = __byte_perm(w.y, 0u, 0x0123u); w.z = __byte_perm(w.z, 0u, 0x0123u); w.w = __byte_perm(w.w, 0u, 0x0123u);
+#endif
+            dst[i] = w;
+        }
         __syncthreads();
     }
     const uint32_t *__restrict__ occG = a.grid.occ;
@@ -78,7 +109,12 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
 
     // per-lane DDA state
     float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f, tmax = kRayMax;
-    int lin = parkLin, dX = 0, dY = 0, dZ = 0, lastD = 0;
+    int lin = parkLin, dX = 0, dY = 0, dZ = 0;
+#if VPT_DDA_PRED
+    int linB = parkLin; // the voxel before lin (lin - linB = the last step; equal: no step taken yet)
+#else
+    int lastD = 0;
+#endif
     uint32_t meta = 0, result = 0;
     bool live = false;
     // a finished ray's result is written later, together with the other idle lanes (convergent), not inside the step loop
@@ -148,7 +184,11 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                 dX = (meta & 1u) ? 1 : -1;
                 dY = (meta & 2u) ? strideY : -strideY;
                 dZ = (meta & 4u) ? Wp : -Wp;
+#if VPT_DDA_PRED
+                linB = lin;
+#else
                 lastD = 0;
+#endif
                 live = true;
                 ++raysAcc;
             }
@@ -158,6 +198,69 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         if (idle == kFull) break; // nothing live and nothing left to take
 
         // ---- step loop
+#if VPT_DDA_PRED
+        // Two voxel registers that swap roles every step (linB = step(lin), lin = step(linB)): the voxel before the current one
+        // — what the entry face of a hit follows from — is then simply the other register, at no instruction per step.
+        for (;;)
+        {
+            bool leave = false;
+#pragma unroll
+            for (int u = 0; u < (kClosest ? VPT_DDA_UNROLL : VPT_DDA_UNROLL_ANY) / 2; ++u)
+            {
+#define VPT_DDA_LOADWORD(L) \
+    (kSmem ? (VPT_DDA_BYTE ? repByte(reinterpret_cast<const uint8_t *>(occS)[(unsigned)(L) >> 3]) : occS[(unsigned)(L) >> 5]) \
+           : __ldg(occG + ((unsigned)(L) >> 5)))
+// advance the axis with the smallest tMax (ties: Z, then Y, then X = X<Y ? (X<Z ? X : Z) : (Y<Z ? Y : Z)); TO = FROM + its step
+#define VPT_DDA_ADVANCE(FROM, TO)                                                                  \
+    do {                                                                                           \
+        asm("{\n\t.reg .pred pz, pnz, py, px;\n\t"                                                \
+            "min.f32 %0, %2, %3, %4;\n\t"                                                          \
+            "setp.eq.f32 pz|pnz, %4, %0;\n\t"                                                      \
+            "setp.eq.and.f32 py|px, %3, %0, pnz;\n\t"                                              \
+            "@px add.rn.f32 %2, %2, %5;\n\t"                                                       \
+            "@py add.rn.f32 %3, %3, %6;\n\t"                                                       \
+            "@pz add.rn.f32 %4, %4, %7;\n\t"                                                       \
+            "@px add.s32 %1, %8, %9;\n\t"                                                          \
+            "@py add.s32 %1, %8, %10;\n\t"                                                         \
+            "@pz add.s32 %1, %8, %11;\n\t}"                                                        \
+            : "=f"(tCur), "=r"(TO), "+f"(tX), "+f"(tY), "+f"(tZ)                                   \
+            : "f"(dtX), "f"(dtY), "f"(dtZ), "r"(FROM), "r"(dX), "r"(dY), "r"(dZ));                 \
+        if (kStats) stepsAcc += live ? 1u : 0u;                                                    \
+    } while (0)
+// mask words are bit-reversed: voxel k of a word sits at bit 31-k. A set bit = solid voxel or shell: once per ray (twice for
+// a ray whose origin voxel lies before tmin). Leaving the unrolled block on it closes the divergent region once per block,
+// not once per step, and a finished lane has nothing to do before the next ballot anyway.
+#define VPT_DDA_TEST(CUR, PRV, SWAPBACK)                                                           \
+    if ((int)(VPT_DDA_LOADWORD(CUR) << ((CUR) & 31)) < 0)                                          \
+    {                                                                                              \
+        bool fin = tCur >= tmin;                                                                   \
+        if (!fin) { int x, y, z; fin = decode(CUR, x, y, z); }                                     \
+        if (fin)                                                                                   \
+        {                                                                                          \
+            finLin = CUR; finT = tCur; finD = (CUR) - (PRV);                                       \
+            pending = true;                                                                        \
+            live = false;                                                                          \
+            lin = parkLin; linB = parkLin; dX = 0; dY = 0; dZ = 0; /* parked: steps in place on an empty spare word */ \
+        }                                                                                          \
+        else                                                                                       \
+        {                                                                                          \
+            VPT_DDA_ADVANCE(CUR, PRV);                                                             \
+            if (SWAPBACK) { const int t_ = linB; linB = lin; lin = t_; }                           \
+        }                                                                                          \
+        leave = true;                                                                              \
+        break;                                                                                     \
+    }
+                VPT_DDA_TEST(lin, linB, true)
+                VPT_DDA_ADVANCE(lin, linB);
+                VPT_DDA_TEST(linB, lin, false)
+                VPT_DDA_ADVANCE(linB, lin);
+            }
+            (void)leave;
+            const unsigned act = __ballot_sync(kFull, live);
+            if (act == 0u) break;
+            if (!exhausted && __popc(act) <= kRefillBelow) break;
+        }
+#else
         for (;;)
         {
 #pragma unroll
@@ -211,6 +314,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
             if (act == 0u) break;
             if (!exhausted && __popc(act) <= kRefillBelow) break;
         }
+#endif
     }
     // statistics: one atomic pair per warp
     unsigned long long r64 = raysAcc, s64 = stepsAcc;
@@ -221,6 +325,257 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         s64 += __shfl_down_sync(kFull, s64, off);
     }
     if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); atomicAdd(a.counters + 2, r64); if (kStats) atomicAdd(a.counters + 1, s64); } // [2]: running total over frames
+}
+
+// ------------------------------------------------------------------------------------------------ branch-free engine
+// What the profile of the kernel above says (ncu r3b): 26 warp-instructions per warp-step although the step itself is 16 —
+// a warp of ~24 live rays retires about one ray per step, and every retirement runs its bookkeeping (record the hit, park the
+// lane, leave the unrolled block) as a divergent region for that one lane. ddaFlatKernel has NO branch inside a block of steps:
+//  * "alive" is a predicate that is threaded through the block (each step's hit test produces the next step's alive); every
+//    instruction of a finished lane is predicated off, so its registers simply keep the state of the step that ended it;
+//  * the step advances into a CANDIDATE voxel (nxt = cur + step) and tests that, with the two voxel registers swapping roles
+//    every step: a finished lane holds the hit voxel in one and the voxel before it in the other (the entry face follows from
+//    their difference); which is which follows from the sign of that difference when the ray retires;
+//  * tCur = min(tX, tY, tZ) is predicated on alive as well, so it stays the entry time of the hit voxel.
+// The block is one asm statement (PTX predicates cannot cross statements). Same decisions, same roundings, same results as
+// ddaKernel: 16 instructions per step, nothing per retirement.
+// tmin > 0 (only the bias rays of the temporal ReSTIR pass): a solid voxel entered before tmin ends the block like a hit and
+// is resolved after it — not the shell: the ray walks on from it.
+#ifndef VPT_DDA_FLAT
+#define VPT_DDA_FLAT 1
+#endif
+#ifndef VPT_DDA_FLAT_BLOCK
+#define VPT_DDA_FLAT_BLOCK 16 // steps per block, any-hit launches
+#endif
+#ifndef VPT_DDA_FLAT_BLOCK_CLOSEST
+#define VPT_DDA_FLAT_BLOCK_CLOSEST 8
+#endif
+#ifndef VPT_DDA_FLAT_CLOSEST
+#define VPT_DDA_FLAT_CLOSEST 0 // closest-hit launches (coherent primary rays) on the branch-free engine too
+#endif
+// %0-%2 tX tY tZ, %3 tCur, %4 %5 the two voxel registers, %6 alive, %7 step counter; %8-%10 tDelta, %11-%13 voxel strides,
+// %14 mask base (shared).
+// Written the way ptxas keeps it (it turns a predicated min into min + select and the second output of a two-output setp into a
+// PLOP3): one FSETP per predicate, each ANDed with alive; the next step's alive comes straight out of the mask test (ISETP.GE.AND).
+// TC = per-instance extras: the tCur commit, only in the instances that look at the hit time (closest hits, rays with a near or
+// far end); the step counter of vpt_get_counters, only while statistics are on.
+#define VPT_FS(PA, PN, CUR, NXT, TC)                               \
+    "min.f32 tn, %0, %1, %2;\n\t"                                  \
+    TC(PA)                                                         \
+    "setp.eq.and.f32 pz, %2, tn, " PA ";\n\t"                      \
+    "setp.neu.and.f32 pnz, %2, tn, " PA ";\n\t"                    \
+    "setp.eq.and.f32 py, %1, tn, pnz;\n\t"                         \
+    "setp.neu.and.f32 px, %1, tn, pnz;\n\t"                        \
+    "@px add.s32 " NXT ", " CUR ", %11;\n\t"                       \
+    "@py add.s32 " NXT ", " CUR ", %12;\n\t"                       \
+    "@pz add.s32 " NXT ", " CUR ", %13;\n\t"                       \
+    "@px add.rn.f32 %0, %0, %8;\n\t"                               \
+    "@py add.rn.f32 %1, %1, %9;\n\t"                               \
+    "@pz add.rn.f32 %2, %2, %10;\n\t"                              \
+    "shr.u32 ad, " NXT ", 3;\n\t"                                  \
+    "add.u32 ad, ad, %14;\n\t"                                     \
+    "ld.shared.u8 wb, [ad];\n\t"                                   \
+    "mul.lo.u32 wb, wb, 0x01010101;\n\t"                           \
+    "shf.l.wrap.b32 wb, 0, wb, " NXT ";\n\t"                       \
+    "setp.ge.and.s32 " PN ", wb, 0, " PA ";\n\t"
+#define VPT_TC_ON(PA) "selp.f32 %3, tn, %3, " PA ";\n\t"
+#define VPT_TC_OFF(PA)
+#define VPT_TC_ON_STATS(PA) VPT_TC_ON(PA) "@" PA " add.u32 %7, %7, 1;\n\t"
+#define VPT_TC_OFF_STATS(PA) "@" PA " add.u32 %7, %7, 1;\n\t"
+#define VPT_FS2(TC) VPT_FS("p0", "p1", "%4", "%5", TC) VPT_FS("p1", "p0", "%5", "%4", TC)
+#define VPT_FS8(TC) VPT_FS2(TC) VPT_FS2(TC) VPT_FS2(TC) VPT_FS2(TC)
+#define VPT_FLAT_BLOCK(STEPS)                                                                                        \
+    asm volatile("{\n\t.reg .pred p0, p1, pz, pnz, py, px;\n\t.reg .u32 ad, wb;\n\t.reg .f32 tn;\n\t"                \
+                 "setp.ne.s32 p0, %6, 0;\n\t" STEPS "selp.s32 %6, 1, 0, p0;\n\t}"                                    \
+                 : "+f"(tX), "+f"(tY), "+f"(tZ), "+f"(tCur), "+r"(linA), "+r"(linB), "+r"(alive), "+r"(stepsAcc)     \
+                 : "f"(dtX), "f"(dtY), "f"(dtZ), "r"(dX), "r"(dY), "r"(dZ), "r"(base))
+#if VPT_DDA_FLAT_BLOCK == 32
+#define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#elif VPT_DDA_FLAT_BLOCK == 24
+#define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#elif VPT_DDA_FLAT_BLOCK == 8
+#define VPT_FS_ANY(TC) VPT_FS8(TC)
+#else
+#define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC)
+#endif
+#if VPT_DDA_FLAT_BLOCK_CLOSEST == 8
+#define VPT_FS_CLOSEST(TC) VPT_FS8(TC)
+#elif VPT_DDA_FLAT_BLOCK_CLOSEST == 16
+#define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC)
+#elif VPT_DDA_FLAT_BLOCK_CLOSEST == 24
+#define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#else
+#define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#endif
+
+template <bool kClosest, bool kTmax, bool kTmin, bool kStats>
+__global__ void __launch_bounds__(kDdaThreads, 1) ddaFlatKernel(const __grid_constant__ DdaArgs a)
+{
+    extern __shared__ uint32_t occS[];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.grid.occ);
+        uint4 *dst = reinterpret_cast<uint4 *>(occS);
+        const int n4 = a.grid.occWords >> 2; // occWords is a multiple of 4
+        for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        {
+            uint4 w = __ldg(src + i);
+            // byte-swapped: voxel k of a word (bit 31-k) then lives in byte k >> 3 of the word, i.e. at byte address lin >> 3
+            w.x = __byte_perm(w.x, 0u, 0x0123u); w.y = __byte_perm(w.y, 0u, 0x0123u); w.z = __byte_perm(w.z, 0u, 0x0123u); w.w = __byte_perm(w.w, 0u, 0x0123u);
+            dst[i] = w;
+        }
+        __syncthreads();
+    }
+    const uint8_t *occB = reinterpret_cast<const uint8_t *>(occS);
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(occS);
+    auto solid = [&](int l) -> bool { return ((uint32_t)occB[(unsigned)l >> 3] << (l & 7)) & 0x80u; };
+    const unsigned count = __ldg(a.count);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int Wp = a.grid.Wp, Dp = a.grid.Dp, W = a.grid.W, H = a.grid.H, D = a.grid.D;
+    const int strideY = Wp * Dp;
+    const int parkLin = a.grid.parkLin, maskBits = a.grid.maskWords * 32, upH = a.grid.upH;
+    auto decode = [&](int l, int &x, int &y, int &z) -> bool {
+        const bool up = l >= maskBits;
+        if (up) l -= maskBits;
+        uint32_t r, xp, yp, zp;
+        a.grid.divWp.div((uint32_t)l, r, xp);
+        a.grid.divDp.div(r, yp, zp);
+        x = (int)xp - 1; y = (int)yp - 1; z = (int)zp - 1;
+        return (unsigned)x >= (unsigned)W || (unsigned)z >= (unsigned)D || (unsigned)y >= (unsigned)(up ? upH : H);
+    };
+
+    float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f, tmax = kRayMax;
+    int linA = parkLin, linB = parkLin, dX = 0, dY = 0, dZ = 0;
+    int alive = 0;      // the lane's ray is still walking
+    bool armed = false; // the lane holds a ray (walking, or finished and not yet retired)
+    uint32_t meta = 0, result = 0;
+    unsigned chunkPos = 0, chunkEnd = 0;
+    bool exhausted = (count == 0);
+    unsigned raysAcc = 0, stepsAcc = 0;
+    // a finished lane holds the voxel that ended it in one register and the voxel before it in the other: the later one is a
+    // forward step (dX, dY or dZ, signed) ahead. (Not "the solid one": a ray with a near end may have walked through solid voxels.)
+    auto aheadA = [&]() -> bool { const int d = linA - linB; return d == 0 || d == dX || d == dY || d == dZ; };
+
+    for (;;)
+    {
+        // ---- retire finished rays (all idle lanes together, convergent)
+        if (armed && !alive)
+        {
+            // which register holds the hit voxel: the one that is a forward step ahead of the other (equal: the start voxel itself)
+            const bool hitA = aheadA();
+            const int finLin = hitA ? linA : linB, finD = hitA ? linA - linB : linB - linA;
+            int x, y, z;
+            // a solid voxel first met at or beyond the ray's far end is no hit (see ddaKernel)
+            const bool shell = decode(finLin, x, y, z) || (kTmax && tCur >= tmax);
+            if (kClosest)
+            {
+                uint32_t packed = kHitMiss;
+                if (!shell)
+                {
+                    uint32_t face = (meta >> 4) & 7u;
+                    if (finD != 0)
+                    {
+                        const int ax = finD < 0 ? -finD : finD;
+                        if (ax == 1) face = (meta & 1u) ? 2u : 3u;
+                        else if (ax == strideY) face = (meta & 2u) ? 1u : 0u;
+                        else face = (meta & 4u) ? 5u : 4u;
+                    }
+                    packed = ((uint32_t)((y * D + z) * W + x) << 3) | face;
+                }
+                a.hitT[result] = shell ? kRayMax : tCur;
+                a.hitPacked[result] = packed;
+            }
+            else
+                a.vis[result] = shell ? (uint8_t)0 : (uint8_t)1;
+            armed = false;
+        }
+        // ---- re-arm idle lanes
+        unsigned idle = __ballot_sync(kFull, !armed);
+        while (idle != 0 && !exhausted)
+        {
+            if (chunkPos >= chunkEnd)
+            {
+                unsigned b0 = 0;
+                if (lane == 0) b0 = atomicAdd(a.cursor, (unsigned)kChunk);
+                b0 = __shfl_sync(kFull, b0, 0);
+                if (b0 >= count) { exhausted = true; break; }
+                chunkPos = b0;
+                chunkEnd = min(b0 + (unsigned)kChunk, count);
+            }
+            const unsigned avail = chunkEnd - chunkPos;
+            const unsigned rank = __popc(idle & ltMask);
+            const bool take = !armed && rank < avail;
+            if (take)
+            {
+                const uint4 *q = a.queue + (size_t)(chunkPos + rank) * 3;
+                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                tX = __uint_as_float(q0.x); tY = __uint_as_float(q0.y); tZ = __uint_as_float(q0.z); tCur = __uint_as_float(q0.w);
+                dtX = __uint_as_float(q1.x); dtY = __uint_as_float(q1.y); dtZ = __uint_as_float(q1.z); if (kTmin) tmin = __uint_as_float(q1.w);
+                linA = (int)q2.x; linB = linA; meta = q2.y; result = q2.z; if (kTmax) tmax = __uint_as_float(q2.w);
+                dX = (meta & 1u) ? 1 : -1;
+                dY = (meta & 2u) ? strideY : -strideY;
+                dZ = (meta & 4u) ? Wp : -Wp;
+                // a solid start voxel is the hit (entry face from the prepared ray) unless the ray has not reached tmin yet
+                alive = (solid(linA) && !(kTmin && tCur < tmin)) ? 0 : 1;
+                armed = true;
+                ++raysAcc;
+            }
+            chunkPos += min((unsigned)__popc(idle), avail);
+            idle = __ballot_sync(kFull, !armed);
+        }
+        if (idle == kFull) break; // nothing armed and nothing left to take
+
+        // ---- step loop
+        for (;;)
+        {
+            if (kStats)
+            {
+                if (kClosest) VPT_FLAT_BLOCK(VPT_FS_CLOSEST(VPT_TC_ON_STATS));
+                else if (kTmax || kTmin) VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_ON_STATS));
+                else VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_OFF_STATS));
+            }
+            else
+            {
+                if (kClosest) VPT_FLAT_BLOCK(VPT_FS_CLOSEST(VPT_TC_ON));
+                else if (kTmax || kTmin) VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_ON));
+                else VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_OFF));
+            }
+            if (kTmin)
+            {
+                // ended on a solid voxel entered before tmin: not a hit unless it is the shell — walk on from it
+                const bool early = armed && !alive && tCur < tmin;
+                if (__any_sync(kFull, early) && early)
+                {
+                    const int cur = aheadA() ? linA : linB;
+                    int x, y, z;
+                    if (!decode(cur, x, y, z)) { linA = cur; linB = cur; alive = 1; }
+                }
+            }
+            const unsigned act = __ballot_sync(kFull, alive != 0);
+            if (act == 0u) break;
+            if (!exhausted && __popc(act) <= kRefillBelow) break;
+        }
+    }
+    unsigned long long r64 = raysAcc, s64 = stepsAcc;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        r64 += __shfl_down_sync(kFull, r64, off);
+        if (kStats) s64 += __shfl_down_sync(kFull, s64, off);
+    }
+    if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); atomicAdd(a.counters + 2, r64); if (kStats) atomicAdd(a.counters + 1, s64); } // [2]: running total over frames
+}
+
+template <bool kClosest, bool kTmax, bool kTmin>
+static cudaError_t launchFlatT(const DdaArgs &a, bool stats, cudaStream_t s, int smCount)
+{
+    const size_t smem = (size_t)a.grid.occWords * 4;
+    cudaError_t e = stats ? cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (stats) ddaFlatKernel<kClosest, kTmax, kTmin, true><<<smCount, kDdaThreads, smem, s>>>(a);
+    else ddaFlatKernel<kClosest, kTmax, kTmin, false><<<smCount, kDdaThreads, smem, s>>>(a);
+    return cudaGetLastError();
 }
 
 template <bool kSmem, bool kClosest, bool kStats, bool kTmax>
@@ -237,8 +592,17 @@ static cudaError_t launchDdaT(const DdaArgs &a, cudaStream_t s, int smCount)
     return cudaGetLastError();
 }
 
-cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, bool farEnd, cudaStream_t s, int smCount)
+cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, bool farEnd, bool nearEnd, cudaStream_t s, int smCount)
 {
+#if VPT_DDA_FLAT
+    // the branch-free engine: every launch whose mask is in shared memory (closest hits only with VPT_DDA_FLAT_CLOSEST)
+    if (occInSmem && !(closest && !VPT_DDA_FLAT_CLOSEST))
+    {
+        if (closest) return launchFlatT<true, false, false>(a, countSteps, s, smCount);
+        if (farEnd) return nearEnd ? launchFlatT<false, true, true>(a, countSteps, s, smCount) : launchFlatT<false, true, false>(a, countSteps, s, smCount);
+        return nearEnd ? launchFlatT<false, false, true>(a, countSteps, s, smCount) : launchFlatT<false, false, false>(a, countSteps, s, smCount);
+    }
+#endif
     const int sel = (occInSmem ? 4 : 0) | (closest ? 2 : 0) | (countSteps ? 1 : 0);
     if (farEnd && !closest) // finite tmax only exists on visibility rays
         switch (sel)

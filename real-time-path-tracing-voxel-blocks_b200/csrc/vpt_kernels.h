@@ -184,7 +184,7 @@ struct DdaArgs
     GridView grid;
     unsigned long long *counters;
 };
-cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, bool farEnd, cudaStream_t s, int smCount); // farEnd: rays carry a finite tmax
+cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, bool farEnd, bool nearEnd, cudaStream_t s, int smCount); // farEnd: rays carry a finite tmax; nearEnd: a tmin > 0
 
 // upH (device int): highest solid y + 1, maintained by the repack / set-voxel kernels; the upward mask is rebuilt from it
 // sky generator (vpt_sky.cu)

@@ -1704,13 +1704,13 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
             queueBase += (size_t)(a.partPaths > a.partSlots * 3 ? a.partPaths : a.partSlots * 3);
             listBase += (size_t)a.partPaths;
             unsigned *cnt = a.wb.cnt;
-            auto dda = [&](int pair, bool closest, uint8_t *vis, bool prevWorld = false) -> cudaError_t {
+            auto dda = [&](int pair, bool closest, uint8_t *vis, bool prevWorld = false, bool nearEnd = false) -> cudaError_t {
                 DdaArgs d;
                 d.queue = a.wb.queue; d.count = cnt + 2 * pair; d.cursor = cnt + 2 * pair + 1;
                 d.hitT = a.wb.hitT; d.hitPacked = a.wb.hitPacked; d.vis = vis; d.grid = a.grid; d.counters = a.counters;
                 if (prevWorld && a.occPrev) { d.grid.occ = a.occPrev; d.grid.upH = a.upHPrev; } // closesthit.cu:736-755: prevTopObject
                 ++nl;
-                cudaError_t e = launchDda(d, closest, smem, stats, a.lv.numLights > 0, st, smCount);
+                cudaError_t e = launchDda(d, closest, smem, stats, a.lv.numLights > 0, nearEnd, st, smCount);
                 mark(0, st);
                 return e;
             };
@@ -1731,7 +1731,7 @@ cudaError_t launchTrace(TraceArgs &a, int maxSamplesInWave, cudaStream_t s, cons
                 if (depth == 0 && restirWave)
                 {
                     KTEX(shade3Kernel)<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
-                    VPT_TRY(dda(pair, false, a.wb.vis3, true)); ++pair;
+                    VPT_TRY(dda(pair, false, a.wb.vis3, true, true)); ++pair; // the bias rays start extraRayOffset along the ray (tmin > 0)
                     (lights ? shade4Kernel<true> : shade4Kernel<false>)<<<gridSlots, kShadeThreads, 0, st>>>(a, cnt + 2 * pair); ++nl; mark(1, st);
                     VPT_TRY(dda(pair, false, a.wb.vis4)); ++pair;
                 }

@@ -175,3 +175,36 @@ def test_lantern_scene_matches_oracle_with_edits(oracle_lib):
                 c.set_voxel(x + 1, y + 1, z, LANTERN)
         prev = cam
         cam = vpt.camera_set_yaw_pitch(cam, cam[15] + np.float32(0.4 * np.pi / 180.0), cam[16])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanterns", [False, True])
+def test_throughput_path_is_bit_identical_to_the_instrumented_path(lanterns):
+    """vpt_set_profiling(0) — what bench.py times — selects the kernel instances without the step counter and the per-launch
+    events. Same engine, same results: every plane, the reservoirs and the ray count are bit-identical to the instrumented
+    (default) path the other parity tests run, with and without local lights (finite-tmax visibility rays, closest-hit BSDF rays)."""
+    import vpt
+    W, H = 320, 192
+    inp = lantern_inputs() if lanterns else common.scene_inputs((2, 1, 2))
+    a = common.setup(vpt.Vpt(W, H), inp, spp=3, total=3, diffuse=1)
+    b = common.setup(vpt.Vpt(W, H), inp, spp=3, total=3, diffuse=1)
+    b.set_profiling(False)
+    p = S.default_denoising_params()
+    cam = common.scene_camera(W, H)
+    prev = cam
+    for f in range(3):
+        for c in (a, b):
+            c.render(cam, prev, f)
+        for name in ("PrimaryHits", "Depth", "Material", "NormalRoughness", "GeoNormalThinfilm", "MaterialParameter", "Albedo", "Illumination"):
+            assert a.read(name).tobytes() == b.read(name).tobytes(), (f, name)
+        assert a.read_reservoirs(f & 1).tobytes() == b.read_reservoirs(f & 1).tobytes(), f
+        assert a.counters()[0] == b.counters()[0], f
+        assert a.counters()[1] > 10 * a.counters()[0] and b.counters()[1] == 0   # steps are only counted on the instrumented path
+        for c in (a, b):
+            c.denoise(p, cam, prev, f, f + 1)
+        for name in ("HistoryLength", "IlluminationOutput"):
+            assert a.read(name).tobytes() == b.read(name).tobytes(), (f, name)
+        if f == 0 and lanterns:
+            assert len(place_lanterns([a, b], a.read("PrimaryHits"), W, H, [(0.5, 0.55), (0.3, 0.7), (0.75, 0.6)])) >= 2
+        prev = cam
+        cam = vpt.camera_set_yaw_pitch(cam, cam[15] + np.float32(0.4 * np.pi / 180.0), cam[16])
