@@ -384,11 +384,11 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
 #define VPT_TC_OFF_STATS(PA) "@" PA " add.u32 %7, %7, 1;\n\t"
 #define VPT_FS2(TC) VPT_FS("p0", "p1", "%4", "%5", TC) VPT_FS("p1", "p0", "%5", "%4", TC)
 #define VPT_FS8(TC) VPT_FS2(TC) VPT_FS2(TC) VPT_FS2(TC) VPT_FS2(TC)
-#define VPT_FLAT_BLOCK(STEPS)                                                                                        \
+#define VPT_FLAT_BLOCK(R, STEPS)                                                                                     \
     asm volatile("{\n\t.reg .pred p0, p1, pz, pnz, py, px;\n\t.reg .u32 ad, wb;\n\t.reg .f32 tn;\n\t"                \
                  "setp.ne.s32 p0, %6, 0;\n\t" STEPS "selp.s32 %6, 1, 0, p0;\n\t}"                                    \
-                 : "+f"(tX), "+f"(tY), "+f"(tZ), "+f"(tCur), "+r"(linA), "+r"(linB), "+r"(alive), "+r"(stepsAcc)     \
-                 : "f"(dtX), "f"(dtY), "f"(dtZ), "r"(dX), "r"(dY), "r"(dZ), "r"(base))
+                 : "+f"(R.tX), "+f"(R.tY), "+f"(R.tZ), "+f"(R.tCur), "+r"(R.linA), "+r"(R.linB), "+r"(R.alive), "+r"(R.steps) \
+                 : "f"(R.dtX), "f"(R.dtY), "f"(R.dtZ), "r"(R.dX), "r"(R.dY), "r"(R.dZ), "r"(base))
 #if VPT_DDA_FLAT_BLOCK == 32
 #define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
 #elif VPT_DDA_FLAT_BLOCK == 24
@@ -408,7 +408,23 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
 #define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
 #endif
 
-template <bool kClosest, bool kTmax, bool kTmin, bool kStats>
+// kRays rays per lane: each is an independent dependency chain (min -> compare -> add -> LDS -> test -> next step's alive), and a
+// block of steps is straight-line code, so ptxas interleaves the lane's rays and one warp covers its own latencies the way two
+// warps would — the shared-memory masks leave room for one 1024-thread CTA per SM, this doubles the chains in flight.
+#ifndef VPT_DDA_RAYS
+#define VPT_DDA_RAYS 1 // measured: 2 rays per lane 0.816 vs 0.793 ms of DDA per frame (a warp of 64 slots refills less often; the engine is alu/issue bound, not latency bound)
+#endif
+struct LaneRay
+{
+    float tX, tY, tZ, dtX, dtY, dtZ, tCur, tmin, tmax;
+    int linA, linB, dX, dY, dZ;
+    int alive;      // the ray is still walking
+    bool armed;     // the slot holds a ray (walking, or finished and not yet retired)
+    uint32_t meta, result;
+    unsigned steps;
+};
+
+template <bool kClosest, bool kTmax, bool kTmin, bool kStats, int kRays>
 __global__ void __launch_bounds__(kDdaThreads, 1) ddaFlatKernel(const __grid_constant__ DdaArgs a)
 {
     extern __shared__ uint32_t occS[];
@@ -444,119 +460,144 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaFlatKernel(const __grid_con
         return (unsigned)x >= (unsigned)W || (unsigned)z >= (unsigned)D || (unsigned)y >= (unsigned)(up ? upH : H);
     };
 
-    float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f, tmax = kRayMax;
-    int linA = parkLin, linB = parkLin, dX = 0, dY = 0, dZ = 0;
-    int alive = 0;      // the lane's ray is still walking
-    bool armed = false; // the lane holds a ray (walking, or finished and not yet retired)
-    uint32_t meta = 0, result = 0;
+    LaneRay rays[kRays];
+#pragma unroll
+    for (int k = 0; k < kRays; ++k)
+    {
+        LaneRay &R = rays[k];
+        R.tX = R.tY = R.tZ = R.dtX = R.dtY = R.dtZ = R.tCur = R.tmin = 0.0f; R.tmax = kRayMax;
+        R.linA = R.linB = parkLin; R.dX = R.dY = R.dZ = 0; R.alive = 0; R.armed = false; R.meta = R.result = 0; R.steps = 0;
+    }
     unsigned chunkPos = 0, chunkEnd = 0;
     bool exhausted = (count == 0);
-    unsigned raysAcc = 0, stepsAcc = 0;
-    // a finished lane holds the voxel that ended it in one register and the voxel before it in the other: the later one is a
+    unsigned raysAcc = 0;
+    // a finished slot holds the voxel that ended it in one register and the voxel before it in the other: the later one is a
     // forward step (dX, dY or dZ, signed) ahead. (Not "the solid one": a ray with a near end may have walked through solid voxels.)
-    auto aheadA = [&]() -> bool { const int d = linA - linB; return d == 0 || d == dX || d == dY || d == dZ; };
+    auto aheadA = [&](const LaneRay &R) -> bool { const int d = R.linA - R.linB; return d == 0 || d == R.dX || d == R.dY || d == R.dZ; };
 
     for (;;)
     {
-        // ---- retire finished rays (all idle lanes together, convergent)
-        if (armed && !alive)
+#pragma unroll
+        for (int k = 0; k < kRays; ++k)
         {
-            // which register holds the hit voxel: the one that is a forward step ahead of the other (equal: the start voxel itself)
-            const bool hitA = aheadA();
-            const int finLin = hitA ? linA : linB, finD = hitA ? linA - linB : linB - linA;
-            int x, y, z;
-            // a solid voxel first met at or beyond the ray's far end is no hit (see ddaKernel)
-            const bool shell = decode(finLin, x, y, z) || (kTmax && tCur >= tmax);
-            if (kClosest)
+            LaneRay &R = rays[k];
+            // ---- retire finished rays (all idle lanes together, convergent)
+            if (R.armed && !R.alive)
             {
-                uint32_t packed = kHitMiss;
-                if (!shell)
+                const bool hitA = aheadA(R);
+                const int finLin = hitA ? R.linA : R.linB, finD = hitA ? R.linA - R.linB : R.linB - R.linA;
+                int x, y, z;
+                // a solid voxel first met at or beyond the ray's far end is no hit (see ddaKernel)
+                const bool shell = decode(finLin, x, y, z) || (kTmax && R.tCur >= R.tmax);
+                if (kClosest)
                 {
-                    uint32_t face = (meta >> 4) & 7u;
-                    if (finD != 0)
+                    uint32_t packed = kHitMiss;
+                    if (!shell)
                     {
-                        const int ax = finD < 0 ? -finD : finD;
-                        if (ax == 1) face = (meta & 1u) ? 2u : 3u;
-                        else if (ax == strideY) face = (meta & 2u) ? 1u : 0u;
-                        else face = (meta & 4u) ? 5u : 4u;
+                        uint32_t face = (R.meta >> 4) & 7u;
+                        if (finD != 0)
+                        {
+                            const int ax = finD < 0 ? -finD : finD;
+                            if (ax == 1) face = (R.meta & 1u) ? 2u : 3u;
+                            else if (ax == strideY) face = (R.meta & 2u) ? 1u : 0u;
+                            else face = (R.meta & 4u) ? 5u : 4u;
+                        }
+                        packed = ((uint32_t)((y * D + z) * W + x) << 3) | face;
                     }
-                    packed = ((uint32_t)((y * D + z) * W + x) << 3) | face;
+                    a.hitT[R.result] = shell ? kRayMax : R.tCur;
+                    a.hitPacked[R.result] = packed;
                 }
-                a.hitT[result] = shell ? kRayMax : tCur;
-                a.hitPacked[result] = packed;
+                else
+                    a.vis[R.result] = shell ? (uint8_t)0 : (uint8_t)1;
+                R.armed = false;
             }
-            else
-                a.vis[result] = shell ? (uint8_t)0 : (uint8_t)1;
-            armed = false;
+            // ---- re-arm idle slots
+            unsigned idle = __ballot_sync(kFull, !R.armed);
+            while (idle != 0 && !exhausted)
+            {
+                if (chunkPos >= chunkEnd)
+                {
+                    unsigned b0 = 0;
+                    if (lane == 0) b0 = atomicAdd(a.cursor, (unsigned)kChunk);
+                    b0 = __shfl_sync(kFull, b0, 0);
+                    if (b0 >= count) { exhausted = true; break; }
+                    chunkPos = b0;
+                    chunkEnd = min(b0 + (unsigned)kChunk, count);
+                }
+                const unsigned avail = chunkEnd - chunkPos;
+                const unsigned rank = __popc(idle & ltMask);
+                const bool take = !R.armed && rank < avail;
+                if (take)
+                {
+                    const uint4 *q = a.queue + (size_t)(chunkPos + rank) * 3;
+                    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+                    R.tX = __uint_as_float(q0.x); R.tY = __uint_as_float(q0.y); R.tZ = __uint_as_float(q0.z); R.tCur = __uint_as_float(q0.w);
+                    R.dtX = __uint_as_float(q1.x); R.dtY = __uint_as_float(q1.y); R.dtZ = __uint_as_float(q1.z); if (kTmin) R.tmin = __uint_as_float(q1.w);
+                    R.linA = (int)q2.x; R.linB = R.linA; R.meta = q2.y; R.result = q2.z; if (kTmax) R.tmax = __uint_as_float(q2.w);
+                    R.dX = (R.meta & 1u) ? 1 : -1;
+                    R.dY = (R.meta & 2u) ? strideY : -strideY;
+                    R.dZ = (R.meta & 4u) ? Wp : -Wp;
+                    // a solid start voxel is the hit (entry face from the prepared ray) unless the ray has not reached tmin yet
+                    R.alive = (solid(R.linA) && !(kTmin && R.tCur < R.tmin)) ? 0 : 1;
+                    R.armed = true;
+                    ++raysAcc;
+                }
+                chunkPos += min((unsigned)__popc(idle), avail);
+                idle = __ballot_sync(kFull, !R.armed);
+            }
         }
-        // ---- re-arm idle lanes
-        unsigned idle = __ballot_sync(kFull, !armed);
-        while (idle != 0 && !exhausted)
         {
-            if (chunkPos >= chunkEnd)
-            {
-                unsigned b0 = 0;
-                if (lane == 0) b0 = atomicAdd(a.cursor, (unsigned)kChunk);
-                b0 = __shfl_sync(kFull, b0, 0);
-                if (b0 >= count) { exhausted = true; break; }
-                chunkPos = b0;
-                chunkEnd = min(b0 + (unsigned)kChunk, count);
-            }
-            const unsigned avail = chunkEnd - chunkPos;
-            const unsigned rank = __popc(idle & ltMask);
-            const bool take = !armed && rank < avail;
-            if (take)
-            {
-                const uint4 *q = a.queue + (size_t)(chunkPos + rank) * 3;
-                const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-                tX = __uint_as_float(q0.x); tY = __uint_as_float(q0.y); tZ = __uint_as_float(q0.z); tCur = __uint_as_float(q0.w);
-                dtX = __uint_as_float(q1.x); dtY = __uint_as_float(q1.y); dtZ = __uint_as_float(q1.z); if (kTmin) tmin = __uint_as_float(q1.w);
-                linA = (int)q2.x; linB = linA; meta = q2.y; result = q2.z; if (kTmax) tmax = __uint_as_float(q2.w);
-                dX = (meta & 1u) ? 1 : -1;
-                dY = (meta & 2u) ? strideY : -strideY;
-                dZ = (meta & 4u) ? Wp : -Wp;
-                // a solid start voxel is the hit (entry face from the prepared ray) unless the ray has not reached tmin yet
-                alive = (solid(linA) && !(kTmin && tCur < tmin)) ? 0 : 1;
-                armed = true;
-                ++raysAcc;
-            }
-            chunkPos += min((unsigned)__popc(idle), avail);
-            idle = __ballot_sync(kFull, !armed);
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < kRays; ++k) any = any || rays[k].armed;
+            if (!__any_sync(kFull, any)) break; // nothing armed and nothing left to take
         }
-        if (idle == kFull) break; // nothing armed and nothing left to take
 
         // ---- step loop
         for (;;)
         {
-            if (kStats)
+#pragma unroll
+            for (int k = 0; k < kRays; ++k)
             {
-                if (kClosest) VPT_FLAT_BLOCK(VPT_FS_CLOSEST(VPT_TC_ON_STATS));
-                else if (kTmax || kTmin) VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_ON_STATS));
-                else VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_OFF_STATS));
-            }
-            else
-            {
-                if (kClosest) VPT_FLAT_BLOCK(VPT_FS_CLOSEST(VPT_TC_ON));
-                else if (kTmax || kTmin) VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_ON));
-                else VPT_FLAT_BLOCK(VPT_FS_ANY(VPT_TC_OFF));
-            }
-            if (kTmin)
-            {
-                // ended on a solid voxel entered before tmin: not a hit unless it is the shell — walk on from it
-                const bool early = armed && !alive && tCur < tmin;
-                if (__any_sync(kFull, early) && early)
+                LaneRay &R = rays[k];
+                if (kStats)
                 {
-                    const int cur = aheadA() ? linA : linB;
-                    int x, y, z;
-                    if (!decode(cur, x, y, z)) { linA = cur; linB = cur; alive = 1; }
+                    if (kClosest) VPT_FLAT_BLOCK(R, VPT_FS_CLOSEST(VPT_TC_ON_STATS));
+                    else if (kTmax || kTmin) VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_ON_STATS));
+                    else VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_OFF_STATS));
+                }
+                else
+                {
+                    if (kClosest) VPT_FLAT_BLOCK(R, VPT_FS_CLOSEST(VPT_TC_ON));
+                    else if (kTmax || kTmin) VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_ON));
+                    else VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_OFF));
                 }
             }
-            const unsigned act = __ballot_sync(kFull, alive != 0);
-            if (act == 0u) break;
-            if (!exhausted && __popc(act) <= kRefillBelow) break;
+            unsigned nAlive = 0;
+#pragma unroll
+            for (int k = 0; k < kRays; ++k)
+            {
+                LaneRay &R = rays[k];
+                if (kTmin)
+                {
+                    // ended on a solid voxel entered before tmin: not a hit unless it is the shell — walk on from it
+                    const bool early = R.armed && !R.alive && R.tCur < R.tmin;
+                    if (__any_sync(kFull, early) && early)
+                    {
+                        const int cur = aheadA(R) ? R.linA : R.linB;
+                        int x, y, z;
+                        if (!decode(cur, x, y, z)) { R.linA = cur; R.linB = cur; R.alive = 1; }
+                    }
+                }
+                nAlive += __popc(__ballot_sync(kFull, R.alive != 0));
+            }
+            if (nAlive == 0u) break;
+            if (!exhausted && nAlive <= (unsigned)(kRefillBelow * kRays)) break;
         }
     }
-    unsigned long long r64 = raysAcc, s64 = stepsAcc;
+    unsigned long long r64 = raysAcc, s64 = 0;
+#pragma unroll
+    for (int k = 0; k < kRays; ++k) s64 += rays[k].steps;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
     {
@@ -570,11 +611,11 @@ template <bool kClosest, bool kTmax, bool kTmin>
 static cudaError_t launchFlatT(const DdaArgs &a, bool stats, cudaStream_t s, int smCount)
 {
     const size_t smem = (size_t)a.grid.occWords * 4;
-    cudaError_t e = stats ? cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = stats ? cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, true, VPT_DDA_RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, false, VPT_DDA_RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (stats) ddaFlatKernel<kClosest, kTmax, kTmin, true><<<smCount, kDdaThreads, smem, s>>>(a);
-    else ddaFlatKernel<kClosest, kTmax, kTmin, false><<<smCount, kDdaThreads, smem, s>>>(a);
+    if (stats) ddaFlatKernel<kClosest, kTmax, kTmin, true, VPT_DDA_RAYS><<<smCount, kDdaThreads, smem, s>>>(a);
+    else ddaFlatKernel<kClosest, kTmax, kTmin, false, VPT_DDA_RAYS><<<smCount, kDdaThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 

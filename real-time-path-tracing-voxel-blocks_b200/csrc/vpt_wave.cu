@@ -977,6 +977,7 @@ template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThrea
                     const float localMisW = float(nLocal) / nMis, sunMisW = float(nSun) / nMis, skyMisW = 1.0f / nMis, brdfMisW = 1.0f / nMis;
 
                     // local-light candidates (closesthit.cu:347-375): alias-sampled light, point on its triangle, RIS stream
+                    f2 candUv = {0.0f, 0.0f};
                     if (nLocal > 0)
                     {
                         VptReservoir localRes = emptyReservoir();
@@ -997,7 +998,7 @@ template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThrea
                         }
                         finalizeResampling(localRes, 1.0f, (float)nMis);
                         a.wb.candC[p] = make_uint4((uint32_t)localIdx, __float_as_uint(localRes.weightSum), __float_as_uint(localRes.targetPdf), 0u); // integer plane: the index never passes through a float register (-ftz)
-                        a.wb.candB[p].z = localUv.x; a.wb.candB[p].w = localUv.y;
+                        candUv = localUv;
                     }
 
                     // sun candidate (closesthit.cu:380-420; Restir.h:221-250)
@@ -1036,7 +1037,9 @@ template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThrea
                     }
                     finalizeResampling(skyRes, 1.0f, (float)nMis);
                     a.wb.candA[p] = make_float4(__int_as_float(sunIdx), sunRes.weightSum, sunRes.targetPdf, __int_as_float(skyIdx));
-                    a.wb.candB[p].x = skyRes.weightSum; a.wb.candB[p].y = skyRes.targetPdf; // (.zw: the local light's uv, above)
+                    // one full 16-byte store (.zw: the local light's uv): two 8-byte halves leave every 32-byte sector half written,
+                    // which costs a fill read of the sector at the L2 (133 MB per frame, ncu r2p: S1 read 374 MB for 232 MB of inputs)
+                    a.wb.candB[p] = make_float4(skyRes.weightSum, skyRes.targetPdf, candUv.x, candUv.y);
                     // BSDF candidate: sample a direction and cast the BSDF-light ray (closesthit.cu:452-468)
                     f3 sampleDir, dummy; float brdfPdf; bool trans = false;
                     disneySample(c.rnd4(), s.normal, s.geoNormal, s.wo, s.albedo, s.metallic, s.translucency, s.roughness, sampleDir, dummy, brdfPdf, trans);
@@ -1309,6 +1312,9 @@ template <bool kLights> VPT_DEV VptReservoir loadPrevReservoir(const TraceArgs &
 #ifndef VPT_S3_UNROLL
 #define VPT_S3_UNROLL 0
 #endif
+// Measured and not kept: prefetch.global.L2 / .L1 of the three candidates' 18 scattered sectors before the candidate loop (the loop
+// visits them one after the other: three dependent round trips): S3 327 -> 372 us — the prefetches are extra LSU work and the
+// sectors are evicted or still in flight when the loop gets to them; unrolling the loop: slower as well (register pressure).
 #if VPT_S3_UNROLL
 #define VPT_S3_LOOP _Pragma("unroll")
 #else
