@@ -11,5 +11,5 @@ CMD="python bench.py --steps 2 --warmup 6 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"genKernel|ddaKernel|shade|accumulate|prepKernel|temporalKernel|historyFix|historyClamp|atrous|firefly" -s 115 -c 23 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"genKernel|dda|shade|accumulate|prepKernel|temporalKernel|historyFix|historyClamp|atrous|firefly" -s 115 -c 23 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/pytest_gpu_$TAG.log; tail -2 gpurun_out/smoke_$TAG.log; cat gpurun_out/bench_$TAG.json | cut -c1-600
