@@ -33,9 +33,6 @@ constexpr int kDdaThreads = VPT_DDA_THREADS;
 #ifndef VPT_DDA_UNROLL
 #define VPT_DDA_UNROLL 32 // closest-hit launches (coherent primary rays): 16 -> 0.947, 32 -> 0.933, 48 -> 0.939, 64 -> 0.933 ms of DDA per frame. Both kinds, earlier sweep: measured on B200 (DDA ms/frame): 3 -> 1.196, 4 -> 1.121, 6 -> 1.037, 8 -> 0.993, 12 -> 0.961, 16 -> 0.945, 24 -> 0.946, 32 -> 0.963
 #endif
-#ifndef VPT_DDA_MULHI
-#define VPT_DDA_MULHI 0 // lin >> 5 as IMAD.HI (fma pipe) instead of SHF + LOP3: measured slower (0.983 vs 0.943 ms)
-#endif
 #ifndef VPT_DDA_UNROLL_ANY
 #define VPT_DDA_UNROLL_ANY 16 // any-hit launches (ray lengths vary more): 8 -> 0.981, 12 -> 0.953, 16 -> 0.947, 24 -> 0.951
 #endif
@@ -110,11 +107,12 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
     // per-lane DDA state
     float tX = 0.0f, tY = 0.0f, tZ = 0.0f, dtX = 0.0f, dtY = 0.0f, dtZ = 0.0f, tCur = 0.0f, tmin = 0.0f, tmax = kRayMax;
     int lin = parkLin, dX = 0, dY = 0, dZ = 0;
-#if VPT_DDA_PRED
-    int linB = parkLin; // the voxel before lin (lin - linB = the last step; equal: no step taken yet)
-#else
-    int lastD = 0;
-#endif
+    // kPred: the FMNMX3 / predicated-add step (masks in shared memory). Worlds walked through L1/L2 keep the select form: measured on
+    // the cfg5-shaped trace (tools/cfg5_quick.py): select form 48.3 ms, predicated form 49.0 ms, branch-free engine 49.8 ms per frame.
+    constexpr bool kPred = kSmem && VPT_DDA_PRED;
+    int linB = parkLin; // kPred: the voxel before lin (lin - linB = the last step; equal: no step taken yet)
+    int lastD = 0;      // select form: the last step's stride
+    (void)lastD; (void)linB;
     uint32_t meta = 0, result = 0;
     bool live = false;
     // a finished ray's result is written later, together with the other idle lanes (convergent), not inside the step loop
@@ -184,11 +182,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
                 dX = (meta & 1u) ? 1 : -1;
                 dY = (meta & 2u) ? strideY : -strideY;
                 dZ = (meta & 4u) ? Wp : -Wp;
-#if VPT_DDA_PRED
-                linB = lin;
-#else
-                lastD = 0;
-#endif
+                linB = lin; lastD = 0; // (both forms of "no step taken yet")
                 live = true;
                 ++raysAcc;
             }
@@ -198,7 +192,8 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
         if (idle == kFull) break; // nothing live and nothing left to take
 
         // ---- step loop
-#if VPT_DDA_PRED
+        if (kPred)
+        {
         // Two voxel registers that swap roles every step (linB = step(lin), lin = step(linB)): the voxel before the current one
         // — what the entry face of a hit follows from — is then simply the other register, at no instruction per step.
         for (;;)
@@ -260,20 +255,18 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
             if (act == 0u) break;
             if (!exhausted && __popc(act) <= kRefillBelow) break;
         }
-#else
+        }
+        else
+        {
         for (;;)
         {
 #pragma unroll
             for (int u = 0; u < (kClosest ? VPT_DDA_UNROLL : VPT_DDA_UNROLL_ANY); ++u)
             {
                 uint32_t word;
-#if VPT_DDA_MULHI
-                if (kSmem) word = occS[__umulhi((unsigned)lin, 0x08000000u)]; // lin >> 5 on the fma pipe (the alu pipe is the bottleneck)
-#else
-                if (kSmem) word = occS[(unsigned)lin >> 5];
-#endif
+                if (kSmem) word = VPT_DDA_BYTE ? repByte(reinterpret_cast<const uint8_t *>(occS)[(unsigned)lin >> 3]) : occS[(unsigned)lin >> 5];
                 else word = __ldg(occG + ((unsigned)lin >> 5));
-#define VPT_DDA_ADVANCE()                                                                          \
+#define VPT_DDA_ADVANCE_SEL()                                                                          \
     do {                                                                                           \
         const bool xy = tX < tY;                                                                   \
         const float tA = xy ? tX : tY;                                                             \
@@ -303,18 +296,18 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
 #if VPT_DDA_BREAK
                     // leave the unrolled block: the divergent region then closes once per block, not once per step, and a
                     // finished lane has nothing to do before the next ballot anyway
-                    else VPT_DDA_ADVANCE();
+                    else VPT_DDA_ADVANCE_SEL();
                     break;
 #endif
                 }
                 // advance the axis with the smallest tMax: X<Y ? (X<Z ? X : Z) : (Y<Z ? Y : Z)  ==  A = min(X,Y); A<Z ? A : Z
-                VPT_DDA_ADVANCE();
+                VPT_DDA_ADVANCE_SEL();
             }
             const unsigned act = __ballot_sync(kFull, live);
             if (act == 0u) break;
             if (!exhausted && __popc(act) <= kRefillBelow) break;
         }
-#endif
+        }
     }
     // statistics: one atomic pair per warp
     unsigned long long r64 = raysAcc, s64 = stepsAcc;
@@ -359,7 +352,7 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
 // PLOP3): one FSETP per predicate, each ANDed with alive; the next step's alive comes straight out of the mask test (ISETP.GE.AND).
 // TC = per-instance extras: the tCur commit, only in the instances that look at the hit time (closest hits, rays with a near or
 // far end); the step counter of vpt_get_counters, only while statistics are on.
-#define VPT_FS(PA, PN, CUR, NXT, TC)                               \
+#define VPT_FS(PA, PN, CUR, NXT, TC, LD)                           \
     "min.f32 tn, %0, %1, %2;\n\t"                                  \
     TC(PA)                                                         \
     "setp.eq.and.f32 pz, %2, tn, " PA ";\n\t"                      \
@@ -372,40 +365,40 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaKernel(const __grid_constan
     "@px add.rn.f32 %0, %0, %8;\n\t"                               \
     "@py add.rn.f32 %1, %1, %9;\n\t"                               \
     "@pz add.rn.f32 %2, %2, %10;\n\t"                              \
-    "shr.u32 ad, " NXT ", 3;\n\t"                                  \
-    "add.u32 ad, ad, %14;\n\t"                                     \
-    "ld.shared.u8 wb, [ad];\n\t"                                   \
+    LD(NXT)                                                        \
     "mul.lo.u32 wb, wb, 0x01010101;\n\t"                           \
     "shf.l.wrap.b32 wb, 0, wb, " NXT ";\n\t"                       \
     "setp.ge.and.s32 " PN ", wb, 0, " PA ";\n\t"
+// the mask byte of voxel NXT from the byte-swapped shared-memory copy: byte lin >> 3
+#define VPT_LD_S(NXT) "shr.u32 ad, " NXT ", 3;\n\t" "add.u32 ad, ad, %14;\n\t" "ld.shared.u8 wb, [ad];\n\t"
 #define VPT_TC_ON(PA) "selp.f32 %3, tn, %3, " PA ";\n\t"
 #define VPT_TC_OFF(PA)
 #define VPT_TC_ON_STATS(PA) VPT_TC_ON(PA) "@" PA " add.u32 %7, %7, 1;\n\t"
 #define VPT_TC_OFF_STATS(PA) "@" PA " add.u32 %7, %7, 1;\n\t"
-#define VPT_FS2(TC) VPT_FS("p0", "p1", "%4", "%5", TC) VPT_FS("p1", "p0", "%5", "%4", TC)
-#define VPT_FS8(TC) VPT_FS2(TC) VPT_FS2(TC) VPT_FS2(TC) VPT_FS2(TC)
+#define VPT_FS2(TC, LD) VPT_FS("p0", "p1", "%4", "%5", TC, LD) VPT_FS("p1", "p0", "%5", "%4", TC, LD)
+#define VPT_FS8(TC, LD) VPT_FS2(TC, LD) VPT_FS2(TC, LD) VPT_FS2(TC, LD) VPT_FS2(TC, LD)
 #define VPT_FLAT_BLOCK(R, STEPS)                                                                                     \
     asm volatile("{\n\t.reg .pred p0, p1, pz, pnz, py, px;\n\t.reg .u32 ad, wb;\n\t.reg .f32 tn;\n\t"                \
                  "setp.ne.s32 p0, %6, 0;\n\t" STEPS "selp.s32 %6, 1, 0, p0;\n\t}"                                    \
                  : "+f"(R.tX), "+f"(R.tY), "+f"(R.tZ), "+f"(R.tCur), "+r"(R.linA), "+r"(R.linB), "+r"(R.alive), "+r"(R.steps) \
                  : "f"(R.dtX), "f"(R.dtY), "f"(R.dtZ), "r"(R.dX), "r"(R.dY), "r"(R.dZ), "r"(base))
 #if VPT_DDA_FLAT_BLOCK == 32
-#define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#define VPT_FS_ANY(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD)
 #elif VPT_DDA_FLAT_BLOCK == 24
-#define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#define VPT_FS_ANY(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD)
 #elif VPT_DDA_FLAT_BLOCK == 8
-#define VPT_FS_ANY(TC) VPT_FS8(TC)
+#define VPT_FS_ANY(TC, LD) VPT_FS8(TC, LD)
 #else
-#define VPT_FS_ANY(TC) VPT_FS8(TC) VPT_FS8(TC)
+#define VPT_FS_ANY(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD)
 #endif
 #if VPT_DDA_FLAT_BLOCK_CLOSEST == 8
-#define VPT_FS_CLOSEST(TC) VPT_FS8(TC)
+#define VPT_FS_CLOSEST(TC, LD) VPT_FS8(TC, LD)
 #elif VPT_DDA_FLAT_BLOCK_CLOSEST == 16
-#define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC)
+#define VPT_FS_CLOSEST(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD)
 #elif VPT_DDA_FLAT_BLOCK_CLOSEST == 24
-#define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#define VPT_FS_CLOSEST(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD)
 #else
-#define VPT_FS_CLOSEST(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC) VPT_FS8(TC)
+#define VPT_FS_CLOSEST(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD) VPT_FS8(TC, LD)
 #endif
 
 // kRays rays per lane: each is an independent dependency chain (min -> compare -> add -> LDS -> test -> next step's alive), and a
@@ -560,18 +553,22 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaFlatKernel(const __grid_con
             for (int k = 0; k < kRays; ++k)
             {
                 LaneRay &R = rays[k];
-                if (kStats)
-                {
-                    if (kClosest) VPT_FLAT_BLOCK(R, VPT_FS_CLOSEST(VPT_TC_ON_STATS));
-                    else if (kTmax || kTmin) VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_ON_STATS));
-                    else VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_OFF_STATS));
-                }
-                else
-                {
-                    if (kClosest) VPT_FLAT_BLOCK(R, VPT_FS_CLOSEST(VPT_TC_ON));
-                    else if (kTmax || kTmin) VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_ON));
-                    else VPT_FLAT_BLOCK(R, VPT_FS_ANY(VPT_TC_OFF));
-                }
+#define VPT_FLAT_RUN(BLOCK, LD)                                                                  \
+    do {                                                                                         \
+        if (kStats)                                                                              \
+        {                                                                                        \
+            if (kClosest) BLOCK(R, VPT_FS_CLOSEST(VPT_TC_ON_STATS, LD));                         \
+            else if (kTmax || kTmin) BLOCK(R, VPT_FS_ANY(VPT_TC_ON_STATS, LD));                  \
+            else BLOCK(R, VPT_FS_ANY(VPT_TC_OFF_STATS, LD));                                     \
+        }                                                                                        \
+        else                                                                                     \
+        {                                                                                        \
+            if (kClosest) BLOCK(R, VPT_FS_CLOSEST(VPT_TC_ON, LD));                               \
+            else if (kTmax || kTmin) BLOCK(R, VPT_FS_ANY(VPT_TC_ON, LD));                        \
+            else BLOCK(R, VPT_FS_ANY(VPT_TC_OFF, LD));                                           \
+        }                                                                                        \
+    } while (0)
+                VPT_FLAT_RUN(VPT_FLAT_BLOCK, VPT_LD_S);
             }
             unsigned nAlive = 0;
 #pragma unroll
@@ -607,16 +604,19 @@ __global__ void __launch_bounds__(kDdaThreads, 1) ddaFlatKernel(const __grid_con
     if (lane == 0 && r64) { atomicAdd(a.counters + 0, r64); atomicAdd(a.counters + 2, r64); if (kStats) atomicAdd(a.counters + 1, s64); } // [2]: running total over frames
 }
 
+template <bool kClosest, bool kTmax, bool kTmin, bool kStats>
+static cudaError_t launchFlatK(const DdaArgs &a, cudaStream_t s, int smCount)
+{
+    const size_t smem = (size_t)a.grid.occWords * 4;
+    cudaError_t e = cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, kStats, VPT_DDA_RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ddaFlatKernel<kClosest, kTmax, kTmin, kStats, VPT_DDA_RAYS><<<smCount, kDdaThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
 template <bool kClosest, bool kTmax, bool kTmin>
 static cudaError_t launchFlatT(const DdaArgs &a, bool stats, cudaStream_t s, int smCount)
 {
-    const size_t smem = (size_t)a.grid.occWords * 4;
-    cudaError_t e = stats ? cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, true, VPT_DDA_RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(ddaFlatKernel<kClosest, kTmax, kTmin, false, VPT_DDA_RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (stats) ddaFlatKernel<kClosest, kTmax, kTmin, true, VPT_DDA_RAYS><<<smCount, kDdaThreads, smem, s>>>(a);
-    else ddaFlatKernel<kClosest, kTmax, kTmin, false, VPT_DDA_RAYS><<<smCount, kDdaThreads, smem, s>>>(a);
-    return cudaGetLastError();
+    return stats ? launchFlatK<kClosest, kTmax, kTmin, true>(a, s, smCount) : launchFlatK<kClosest, kTmax, kTmin, false>(a, s, smCount);
 }
 
 template <bool kSmem, bool kClosest, bool kStats, bool kTmax>
@@ -636,7 +636,9 @@ static cudaError_t launchDdaT(const DdaArgs &a, cudaStream_t s, int smCount)
 cudaError_t launchDda(const DdaArgs &a, bool closest, bool occInSmem, bool countSteps, bool farEnd, bool nearEnd, cudaStream_t s, int smCount)
 {
 #if VPT_DDA_FLAT
-    // the branch-free engine: every launch whose mask is in shared memory (closest hits only with VPT_DDA_FLAT_CLOSEST)
+    // the branch-free engine: every any-hit launch whose masks are in shared memory (closest hits only with VPT_DDA_FLAT_CLOSEST).
+    // Worlds walked through L1/L2 stay on ddaKernel: a global-memory instance of the block measured 49.8 vs 48.3 ms per frame on the
+    // cfg5-shaped trace (tools/cfg5_quick.py; the finished lanes' loads are no longer free there) and was removed.
     if (occInSmem && !(closest && !VPT_DDA_FLAT_CLOSEST))
     {
         if (closest) return launchFlatT<true, false, false>(a, countSteps, s, smCount);
