@@ -24,6 +24,9 @@ import time
 
 import numpy as np
 
+# rank 0 prints ONE JSON line on stdout: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO in the environment) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "real-time-path-tracing-voxel-blocks_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))

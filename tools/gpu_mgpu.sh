@@ -7,7 +7,7 @@ for a in "$@"; do
   if [ "$a" = check ]; then $TR --master-port 29511 tools/mgpu_check.py > gpurun_out/${TAG}_mgpu_check_${N}gpu.log 2>&1; grep "\[mgpu\]" gpurun_out/${TAG}_mgpu_check_${N}gpu.log; tail -n 3 gpurun_out/${TAG}_mgpu_check_${N}gpu.log | grep -i error; fi
 done
 $TR --master-port 29512 bench.py --gpus $N --steps 48 --warmup 8 --no-cpu-baseline > gpurun_out/${TAG}_cfg2_${N}gpu.json 2> gpurun_out/${TAG}_cfg2_${N}gpu.err
-$TR --master-port 29513 bench.py --gpus $N --config cfg3 --steps 24 --warmup 6 > gpurun_out/${TAG}_cfg3_${N}gpu.json 2> gpurun_out/${TAG}_cfg3_${N}gpu.err
+[ -n "$SKIP_CFG3" ] || $TR --master-port 29513 bench.py --gpus $N --config cfg3 --steps 24 --warmup 6 > gpurun_out/${TAG}_cfg3_${N}gpu.json 2> gpurun_out/${TAG}_cfg3_${N}gpu.err
 $TR --master-port 29514 bench.py --gpus $N --config cfg4 --steps 4 --warmup 3 > gpurun_out/${TAG}_cfg4_${N}gpu.json 2> gpurun_out/${TAG}_cfg4_${N}gpu.err
 for a in "$@"; do
   if [ "$a" = cfg5 ]; then $TR --master-port 29515 bench.py --gpus $N --config cfg5 --steps 1 --warmup 3 > gpurun_out/${TAG}_cfg5_${N}gpu.json 2> gpurun_out/${TAG}_cfg5_${N}gpu.err; fi
