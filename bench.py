@@ -650,7 +650,7 @@ def main():
         except Exception as ex:  # the baseline is reported, never required for the product path
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
-    # the dominant kernel of the whole step is the DDA engine: issue-bound, so its "roofline" is the issue-slot one (ncu figures
+    # the dominant kernel of the whole step is the DDA engine: ALU-pipe / issue bound, so its "roofline" is the issue-slot one (ncu figures
     # committed under profiles/); reported next to the HBM roofline of the dominant denoiser kernel
     trace_eff = None
     ep = os.path.join(ROOT, "profiles", "trace_efficiency.json")
@@ -672,7 +672,7 @@ def main():
             "dda_steps_per_ray": (steps_frame / rays_step) if rays_step else None,
             "trace": {"ms": round(tim["trace_ms"] + tim["resolve_ms"], 4), "dda_ms": round(tim["trace_dda_ms"], 4),
                       "shade_ms": round(tim["trace_shade_ms"], 4), "dda_grays_per_s": round(rays_step / (tim["trace_dda_ms"] * 1e-3) / 1e9, 3) if tim["trace_dda_ms"] > 0 else None,
-                      "note": "traversal is shared-memory/issue bound, not HBM bound: figures of merit are Grays/s and the ncu warp-execution efficiency / issue utilisation in profiles/"},
+                      "note": "traversal is ALU-pipe / issue bound (16 SASS instructions per voxel step, ~21 of 32 lanes alive per warp-step), not HBM bound: figures of merit are Grays/s and the ncu issue / pipe / alive-lane figures in trace_efficiency_ncu (profiles/)"},
             "clocks": clocks, "gpu_launches": tim["kernel_launches"] * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": wall_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": 2 * 212 + 68 + 64, "d2h_bytes_per_step": npix * 16,
