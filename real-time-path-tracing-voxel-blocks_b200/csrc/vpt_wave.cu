@@ -596,10 +596,13 @@ constexpr int kShadeThreads = VPT_SHADE_THREADS;
 constexpr int kCntWords = 256, kCntList = 128; // cnt[2k], cnt[2k+1] = count / cursor of the k-th DDA launch; cnt[128+d] = active paths at depth d
 
 #ifndef VPT_RESERVE_WARP
-#define VPT_RESERVE_WARP 0
+#define VPT_RESERVE_WARP 1
 #endif
-// Queue reservation. Every thread of the CTA calls it (convergent); n = entries wanted. Default: ONE atomic per CTA (scan over
-// the CTA, three barriers). VPT_RESERVE_WARP=1: one atomic per warp and no barrier (A/B variant).
+// Queue reservation. Every thread of the warp calls it (convergent); n = entries wanted. One atomic per WARP and no barrier: the
+// queue stays dense (what the DDA engine wants) and no warp waits for the CTA. VPT_RESERVE_WARP=0: one atomic per CTA behind a
+// CTA-wide scan with two barriers — 12 % of shade1Kernel's stall samples sat in it (ncu r2p, tools/ncu_lines.py); it was the default
+// while the stages ran 512-thread CTAs. Measured with 128-thread CTAs (stages, ms per frame): per CTA 1.360, per warp 1.333 — the
+// 260 k same-address atomics per launch are not the bottleneck the per-CTA form was built to avoid.
 template <int kSite = 0> VPT_DEV unsigned ctaReserve(unsigned n, unsigned *counter)
 {
 #if VPT_RESERVE_WARP
