@@ -435,3 +435,34 @@ def test_shard_with_no_samples_contributes_zero(libs):
     assert not g.read("Illumination").any()
     with pytest.raises(vpt.VptError):
         g.set_trace_params(1, 17, 1, 1)   # bounce limits above 16 would alias the per-depth queue counters
+
+
+def test_traversal_edge_cases_match_oracle(libs):
+    """The cases a DDA gets wrong first, through both engines (closest-hit primary rays, any-hit shadow / bias rays) against the
+    oracle: views straight down / along an axis / along a face diagonal from half-integer and from INTEGER positions (zero direction
+    components: tDelta = FLT_MAX; symmetric rays: two or three tMax tie, where the nested '<' of VoxelEngine.cu:1133-1162 steps z,
+    then y, then x; an origin on a voxel boundary: tMax = -0), a camera INSIDE the solid terrain (the start voxel is the hit) and
+    one OUTSIDE the grid (entry clip). Primary hits and the G-buffer bit-exact, radiance within tolerance, two frames each so the
+    temporal ReSTIR pass casts its bias rays (tmin > 0, walked from inside the previous frame's surfaces)."""
+    vpt, O = libs
+    W, H = 96, 64
+    inp = common.scene_inputs((2, 1, 2))
+    views = [([32.5, 40.5, 32.5], [0.0, -1.0, 0.0]),        # straight down from above the grid (outside: entry clip through the top)
+             ([32.0, 28.0, 32.0], [0.0, -1.0, 0.0]),        # the same from integer coordinates inside the grid
+             ([2.5, 20.5, 32.5], [1.0, 0.0, 0.0]),          # along +x, level
+             ([60.0, 24.0, 4.0], [-1.0, -1.0, 1.0]),        # body diagonal from integer coordinates: three-way ties
+             ([10.5, 25.5, 10.5], [1.0, -1.0, 0.0]),        # face diagonal
+             ([32.5, 3.5, 32.5], [0.3, 0.1, 0.9]),          # inside the terrain
+             ([-20.0, 30.0, 80.0], [1.0, -0.3, -0.4])]      # outside the grid, looking in
+    for pos, dirn in views:
+        g, o = _pair(libs, W, H, inp, spp=2, total=3, diffuse=1)
+        cam = vpt.camera_from_scene(W, H, pos, dirn, 70.0)
+        for f in range(2):
+            g.render(cam, cam, f); o.render(cam, cam, f)
+            hg, ho = g.read("PrimaryHits"), o.read("PrimaryHits")
+            assert np.array_equal(hg, ho), (pos, dirn, f, int((hg != ho).any(-1).sum()))
+            for name in ("Depth", "NormalRoughness", "Albedo"):
+                assert np.array_equal(g.read(name), o.read(name)), (pos, dirn, f, name)
+            mean_rel, outliers, _ = common.rel_err_stats(g.read("Illumination")[..., :3], o.read("Illumination")[..., :3])
+            assert mean_rel <= 1e-3 and outliers <= 2e-2, (pos, dirn, f, mean_rel, outliers)
+            assert g.counters()[0] <= o.counters()[0] + 50
