@@ -1367,6 +1367,7 @@ template <bool kTex, bool kLights> __global__ void __launch_bounds__(kShadeThrea
         }
         unsigned cached = 0, rayMask = 0;
         int selectedLoopIdx = -1;
+        float pm[3] = {0.0f, 0.0f, 0.0f};
 VPT_S3_LOOP
         for (int i = 0; i < nTemporal; ++i)
         {
@@ -1376,6 +1377,7 @@ VPT_S3_LOOP
             // the candidate's reservoir travels with its surface planes (same pixel): requested before the validation
             const bool inView = ix >= 0 && iy >= 0 && ix < a.width && iy < a.height; // getPrevSurface's own test
             VptReservoir pr = inView ? loadPrevReservoir<kLights>(a, ix, iy, mCap) : emptyReservoir();
+            const float mIn = pr.M;
             if (!c.getPrevSurface(ts, ix, iy)) continue;
             const bool nOk = dot(s.normal, ts.geoNormal) >= 0.5f;
             const bool dOk = fabsf(expectedPrevDepth - ts.depth) <= 0.1f * fmaxr(expectedPrevDepth, ts.depth);
@@ -1389,9 +1391,10 @@ VPT_S3_LOOP
                 if (!c.template lightSampleFromReservoir<kLights>(cand, pr, s.pos)) pr = emptyReservoir();
                 neighborWeight = c.targetPdfForSurface(cand, s);
             }
+            pm[i] = mIn; // the candidate's (capped) M as loaded: the bias-correction pass below needs nothing else of the reservoir
             if (combineReservoirs(restir, pr, c.rnd(), neighborWeight)) { lightSample = cand; selectedLoopIdx = i; }
         }
-        float ps[3] = {0.0f, 0.0f, 0.0f}, pm[3] = {0.0f, 0.0f, 0.0f};
+        float ps[3] = {0.0f, 0.0f, 0.0f};
         const bool valid = isValidReservoir(restir);
         if (valid)
         {
@@ -1418,7 +1421,6 @@ VPT_S3_LOOP
                     }
                     else a.wb.vis3[p * 3 + i] = 0;
                 }
-                pm[i] = loadPrevReservoir<kLights>(a, ix, iy, mCap).M;
             }
         }
         a.wb.rstA[p] = make_uint4(restir.lightData, restir.uvData, __float_as_uint(restir.weightSum), __float_as_uint(restir.targetPdf));
