@@ -262,3 +262,28 @@ def test_image_diff_matches_reference_golden(tmp_path):
     PIL.fromarray(np.zeros((5, 7, 3), np.uint8), "RGB").save(str(tmp_path / "s.png"))
     with pytest.raises(vpt.VptError):
         vpt.image_diff_files(str(tmp_path / "a.png"), str(tmp_path / "s.png"))      # different sizes
+
+
+def test_dda_axis_choice_forms_agree():
+    """The DDA engines pick the axis to step as ONE 3-input minimum plus equality predicates (z wins ties, then y, then x; csrc/vpt_dda.cu)
+    where the oracle / VoxelEngine::performRayTraversal (voxelengine/VoxelEngine.cu:1133-1162) nest two '<' tests. Same axis and the
+    same tCur for every combination of ties, infinities (axis-parallel rays: tMax = tDelta = FLT_MAX) and signed zeros (an origin
+    on a voxel boundary with a negative step gives tMax = -0; +0 never occurs as an axis' tMax)."""
+    rng = np.random.default_rng(5)
+    n = 400_000
+    special = np.array([-0.0, 1.0, 1.5, 2.0, 3.25, 1e-30, np.finfo(np.float32).max], np.float32)
+    t = np.where(rng.random((n, 3)) < 0.5, rng.choice(special, size=(n, 3)), (rng.random((n, 3)) * 4).astype(np.float32)).astype(np.float32)
+    tx, ty, tz = t[:, 0], t[:, 1], t[:, 2]
+    xy = tx < ty
+    ta = np.where(xy, tx, ty)
+    az = ta < tz
+    axis_ref = np.where(az, np.where(xy, 0, 1), 2)
+    tcur_ref = np.where(az, ta, tz)
+    m = np.minimum(np.minimum(tx, ty), tz)
+    pz = tz == m
+    py = (ty == m) & ~pz
+    axis_new = np.where(pz, 2, np.where(py, 1, 0))
+    assert np.array_equal(axis_ref, axis_new)
+    assert np.array_equal(tcur_ref, m)                       # equal as values ...
+    chosen = np.take_along_axis(t, axis_new[:, None], 1)[:, 0]
+    assert np.array_equal(np.signbit(tcur_ref), np.signbit(chosen))   # ... and the reference's tCur carries the chosen axis' sign of zero
