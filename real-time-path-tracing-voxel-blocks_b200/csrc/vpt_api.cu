@@ -58,8 +58,9 @@ struct vpt_ctx
     uint16_t *blockToMaterial = nullptr;
     VptPickResult *pickDev = nullptr;
     uint32_t *texels = nullptr; int4 *texDescs = nullptr, *matTexSlots = nullptr; float *matTexMip0Size = nullptr; int nTextures = 0;
-    float4 *sky = nullptr, *sun = nullptr;
+    float4 *sky = nullptr, *sun = nullptr;      // four views into skyArena
     VptAliasBin *skyAlias = nullptr, *sunAlias = nullptr;
+    void *skyArena = nullptr;
     int skyW = 0, skyH = 0, sunW = 0, sunH = 0;
     float sunDir[3] = {0, 1, 0};
     // trace params
@@ -200,8 +201,8 @@ void vpt_destroy(vpt_ctx *c)
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     for (int i = 0; i < 2; ++i) if (c->traceStreams.part[i]) cudaStreamSynchronize(c->traceStreams.part[i]);
     destroyComm(c);
-    void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->sky, c->sun,
-                    c->skyAlias, c->sunAlias, c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
+    void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->skyArena,
+                    c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
                     c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList, c->rgb8, c->dLights, c->dLightAlias, c->dFaceKeys, c->dPrevToCur};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; ++s)
@@ -358,6 +359,41 @@ int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_
     return VPT_OK;
 }
 
+// Sky / sun maps and their alias tables in ONE allocation, pinned in L2 as far as the device allows: the stages sample them at random
+// (alias bin -> texel, twice per path) while 6 GB of wavefront state stream through the same 126 MB L2 every frame; an access-policy
+// window keeps the 12 MB of tables resident (hit = persisting) instead of letting the stream evict them. A hint: failures are ignored.
+static int allocSkyArena(vpt_ctx *c, size_t ns, size_t nu)
+{
+    if (c->skyArena) cudaFree(c->skyArena);
+    c->skyArena = nullptr; c->sky = c->sun = nullptr; c->skyAlias = c->sunAlias = nullptr;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t oSky = 0, oSkyAlias = oSky + up(ns * 16), oSun = oSkyAlias + up(ns * sizeof(VptAliasBin)), oSunAlias = oSun + up(nu * 16),
+                 total = oSunAlias + up(nu * sizeof(VptAliasBin));
+    CU(cudaMalloc(&c->skyArena, total));
+    char *b = static_cast<char *>(c->skyArena);
+    c->sky = reinterpret_cast<float4 *>(b + oSky); c->skyAlias = reinterpret_cast<VptAliasBin *>(b + oSkyAlias);
+    c->sun = reinterpret_cast<float4 *>(b + oSun); c->sunAlias = reinterpret_cast<VptAliasBin *>(b + oSunAlias);
+#ifndef VPT_NO_L2_WINDOW
+    int maxPersist = 0, maxWindow = 0;
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    if (maxPersist > 0 && maxWindow > 0)
+    {
+        const size_t bytes = total < (size_t)maxWindow ? total : (size_t)maxWindow;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes < (size_t)maxPersist ? bytes : (size_t)maxPersist);
+        cudaStreamAttrValue v = {};
+        v.accessPolicyWindow.base_ptr = c->skyArena;
+        v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = bytes <= (size_t)maxPersist ? 1.0f : (float)maxPersist / (float)bytes;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+        cudaGetLastError(); // a hint only
+    }
+#endif
+    return VPT_OK;
+}
+
 int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *sun, int sunW, int sunH,
                 const VptAliasBin *skyAlias, const VptAliasBin *sunAlias, const float *sunDir)
 {
@@ -365,11 +401,8 @@ int vpt_set_sky(vpt_ctx *c, const float *sky, int skyW, int skyH, const float *s
         return fail(VPT_ERR_ARG, "vpt_set_sky: bad argument");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    for (void *p : {(void *)c->sky, (void *)c->sun, (void *)c->skyAlias, (void *)c->sunAlias}) if (p) cudaFree(p);
-    c->sky = c->sun = nullptr; c->skyAlias = c->sunAlias = nullptr;
     const size_t ns = (size_t)skyW * skyH, nu = (size_t)sunW * sunH;
-    CU(cudaMalloc((void **)&c->sky, ns * 16)); CU(cudaMalloc((void **)&c->sun, nu * 16));
-    CU(cudaMalloc((void **)&c->skyAlias, ns * sizeof(VptAliasBin))); CU(cudaMalloc((void **)&c->sunAlias, nu * sizeof(VptAliasBin)));
+    if (int rc = allocSkyArena(c, ns, nu)) return rc;
     CU(cudaMemcpyAsync(c->sky, sky, ns * 16, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->sun, sun, nu * 16, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->skyAlias, skyAlias, ns * sizeof(VptAliasBin), cudaMemcpyHostToDevice, c->stream));
@@ -434,10 +467,7 @@ int vpt_generate_sky(vpt_ctx *c, const VptSkyParams *params, const float *tables
     const size_t ns = (size_t)skyW * skyH, nu = (size_t)sunW * sunH;
     float configs[90], radiances[10], sunDir[3];
     vpt_sky_state(params, tables, configs, radiances, sunDir);
-    for (void *p : {(void *)c->sky, (void *)c->sun, (void *)c->skyAlias, (void *)c->sunAlias}) if (p) cudaFree(p);
-    c->sky = c->sun = nullptr; c->skyAlias = c->sunAlias = nullptr;
-    CU(cudaMalloc((void **)&c->sky, ns * 16)); CU(cudaMalloc((void **)&c->sun, nu * 16));
-    CU(cudaMalloc((void **)&c->skyAlias, ns * sizeof(VptAliasBin))); CU(cudaMalloc((void **)&c->sunAlias, nu * sizeof(VptAliasBin)));
+    if (int rc = allocSkyArena(c, ns, nu)) return rc;
     float *dPdf = nullptr, *dTab = nullptr;
     CU(cudaMalloc((void **)&dPdf, (ns + nu) * sizeof(float)));
     CU(cudaMalloc((void **)&dTab, 1860 * sizeof(float)));
