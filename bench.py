@@ -24,8 +24,17 @@ import time
 
 import numpy as np
 
-# rank 0 prints ONE JSON line on stdout: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO in the environment) go to stderr
+# rank 0 prints ONE JSON line on stdout. Libraries write there too — NCCL prints its version banner with a plain printf when
+# NCCL_DEBUG=VERSION|WARN is set in the environment (NCCL_DEBUG_FILE is only honoured above that level) — so file descriptor 1 is
+# pointed at stderr for the run and the line goes to the descriptor that was stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "real-time-path-tracing-voxel-blocks_b200", "python"))
@@ -180,7 +189,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference CUDA/OptiX build impossible offline (SURVEY 8c); this is the CPU oracle port of the same path"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n):
@@ -371,7 +380,7 @@ def run_other_config(args):
                 "e2e": {"value": chain_bytes / (wall / args.steps) / 1e9, "unit": "GB/s", "ms_per_step": wall / args.steps * 1e3, "h2d_bytes_per_step": 2 * 212 + 68,
                         "d2h_bytes_per_step": npix * 16, "note": "wall clock of the same loop with IlluminationOutput read back into pinned host memory every frame (includes the "
                         "device-to-device swap of the noisy plane and the G-buffer ping-pong copies)"}}
-        print(json.dumps(line))
+        emit(line)
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -446,7 +455,7 @@ def run_other_config(args):
             "clocks": clocks, "gpu_launches": tim["kernel_launches"] * args.steps,
             "e2e": {"value": rays_e2e / wall_e2e / 1e9, "unit": "Grays/s", "ms_per_step": wall_e2e / args.steps * 1e3, "h2d_bytes_per_step": 2 * 212 + 68 + 64,
                     "d2h_bytes_per_step": npix * 16}}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -679,7 +688,7 @@ def main():
                     "note": "vpt_render + vpt_denoise + vpt_read_buffer_async(IlluminationOutput) into pinned host memory each frame (double-buffered, every copy complete inside the timed region); inputs per frame are "
                             "the two cameras + parameter blocks (scene is resident, as in the reference)"},
             "roofline": roofline, "trace_efficiency_ncu": trace_eff, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
