@@ -5,17 +5,21 @@
 // VoxelEngine::performRayTraversal (/root/reference/voxelengine/VoxelEngine.cu:1133-1162), bit-exact vs the oracle.
 //
 // B200 shape:
-//  * one persistent 1024-thread CTA per SM; the padded 1-bit occupancy mask (86 KiB for the 16-chunk world) is staged
-//    whole in shared memory, so a step is one LDS + bit test; worlds whose mask exceeds shared memory walk it
-//    through L1/L2 (kSmem = false).
+//  * one persistent 1024-thread CTA per SM; the padded 1-bit occupancy masks (2 x 86 KiB for the 16-chunk world) are staged
+//    whole in shared memory, so a step is one LDS + bit test; worlds whose masks exceed shared memory walk them
+//    through L1/L2 (ddaKernel<kSmem = false>).
 //  * the mask has a solid one-voxel shell: leaving the grid is "hitting" the shell — the step loop has NO bounds
-//    arithmetic. 18 SASS instructions per step (words are stored bit-reversed: shift + sign test). Rays with dir.y > 0 walk a second copy of the mask that is solid
-//    from the highest solid voxel up (GridView::upH): they retire as soon as nothing can be above them.
+//    arithmetic. Rays with dir.y > 0 walk a second copy of the mask that is solid from the highest solid voxel up
+//    (GridView::upH): they retire as soon as nothing can be above them.
 //  * warp-level ray compaction: a warp reserves chunks of the prepared-ray queue (one atomic per 64 rays); whenever
-//    at most kRefillBelow lanes still hold a live ray, the idle lanes are re-armed from the queue
+//    at most kRefillBelow lanes still hold a live ray, the idle lanes are retired and re-armed from the queue together
 //    (__ballot_sync/__popc slot assignment), so the step loop runs with most lanes active regardless of how
-//    different the trip counts are. Lanes without a ray are parked on a spare all-zero mask word with zero
-//    strides: they execute the same instructions harmlessly — no per-step predicate.
+//    different the trip counts are.
+//  * two kernels, same decisions and roundings, bit-identical results (DESIGN.md §3 has the profile that led here):
+//      ddaFlatKernel  the any-hit launches: a block of 16 steps without a single branch — "alive" is a predicate threaded
+//                     through the block, a finished lane's instructions are predicated off; 16 SASS instructions per step.
+//      ddaKernel      the closest-hit launch (coherent primary rays) and global-memory masks: a hit leaves the unrolled block;
+//                     lanes without a ray are parked on a spare all-zero mask word with zero strides.
 #include "vpt_dda.cuh"
 
 namespace vpt {
@@ -25,16 +29,16 @@ namespace vpt {
 #endif
 constexpr int kDdaThreads = VPT_DDA_THREADS;
 #ifndef VPT_DDA_CHUNK
-#define VPT_DDA_CHUNK 64 // rays reserved per warp per atomic; measured (DDA ms/frame): 32 -> 0.963, 64 -> 0.923, 128 -> 0.934, 256 -> 0.997
+#define VPT_DDA_CHUNK 64 // rays reserved per warp per atomic; measured (DDA ms/frame): 32 -> 0.844, 64 -> 0.789, 128 -> 0.797 (round-1 engine: 0.963 / 0.923 / 0.934)
 #endif
 #ifndef VPT_DDA_REFILL
 #define VPT_DDA_REFILL 20
 #endif
 #ifndef VPT_DDA_UNROLL
-#define VPT_DDA_UNROLL 32 // closest-hit launches (coherent primary rays): 16 -> 0.947, 32 -> 0.933, 48 -> 0.939, 64 -> 0.933 ms of DDA per frame. Both kinds, earlier sweep: measured on B200 (DDA ms/frame): 3 -> 1.196, 4 -> 1.121, 6 -> 1.037, 8 -> 0.993, 12 -> 0.961, 16 -> 0.945, 24 -> 0.946, 32 -> 0.963
+#define VPT_DDA_UNROLL 32 // closest-hit launches (coherent primary rays), steps per unrolled block: 16 -> 0.798, 32 -> 0.789, 48 -> 0.792 ms of DDA per frame
 #endif
 #ifndef VPT_DDA_UNROLL_ANY
-#define VPT_DDA_UNROLL_ANY 16 // any-hit launches (ray lengths vary more): 8 -> 0.981, 12 -> 0.953, 16 -> 0.947, 24 -> 0.951
+#define VPT_DDA_UNROLL_ANY 16 // any-hit launches on ddaKernel (global-memory masks; shared-memory masks: ddaFlatKernel, VPT_DDA_FLAT_BLOCK)
 #endif
 #ifndef VPT_DDA_BREAK
 #define VPT_DDA_BREAK 1
