@@ -11,7 +11,7 @@
 //                          candidate ray                           rays (<= 3)        ray
 //
 // Stage kernels are one thread per path with NO traversal state (no spills, high occupancy); every ray they spawn is
-// set up once (vpt_dda.cuh: prepareRay) and appended to a queue with one atomic per CTA. The DDA engine (vpt_dda.cu)
+// set up once (vpt_dda.cuh: prepareRay) and appended to a queue with one atomic per warp. The DDA engine (vpt_dda.cu)
 // consumes a queue with warp-level lane re-arming, so traversal runs near full lane occupancy no matter how
 // divergent the trip counts are. S3/S4 run for sample 0 at depth 0 only (the ReSTIR sample, closesthit.cu:636-820);
 // paths that continue past their first hit (specular chains, diffuse limit > 1) loop DDA/S1/DDA/S2/DDA/S5 per depth
