@@ -573,9 +573,9 @@ enum : uint32_t
     F_VISHAVE1 = 1u << 10 // the RIS winner's visibility was resolved (direction = lightA)
 };
 constexpr int kRandShift = 16, kDepthShift = 24, kDiffuseShift = 28;
-// Stage CTAs: 128 threads. Measured on B200 (shading ms/frame, same register budgets): 512 -> 1.710, 256 -> 1.504, 128 -> 1.443,
-// 96 -> 1.473, 64 -> 1.439: the CTA-wide queue reservation (three barriers) stalls fewer warps in a smaller CTA, and 128 keeps
-// the same-address atomics at 65 k per launch. Resident CTAs per SM (register budget) per stage, from the same variant runs:
+// Stage CTAs: 128 threads. Measured on B200 with the per-warp queue reservation (shading ms/frame, same register budgets):
+// 256 -> 1.373, 128 -> 1.328, 64 -> 1.333, 32 -> 1.438 (with the CTA-wide reservation of round 1: 512 -> 1.710, 256 -> 1.504,
+// 128 -> 1.443, 64 -> 1.439). Resident CTAs per SM (register budget) per stage, from the same kind of variant runs:
 // S1/S2 8 (64 regs; 7 -> 1.476, 10 -> 1.566), S3 7 (73 regs; 5 -> 1.485, 6 -> 1.443, 7 -> 1.434), S5 16 (12 -> 1.443, 16 -> 1.439).
 #ifndef VPT_SHADE_THREADS
 #define VPT_SHADE_THREADS 128
