@@ -201,6 +201,7 @@ void vpt_destroy(vpt_ctx *c)
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     for (int i = 0; i < 2; ++i) if (c->traceStreams.part[i]) cudaStreamSynchronize(c->traceStreams.part[i]);
     destroyComm(c);
+    if (c->skyArena) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); } // hand the lines pinned for the sky tables back to the normal L2
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->skyArena,
                     c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
                     c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList, c->rgb8, c->dLights, c->dLightAlias, c->dFaceKeys, c->dPrevToCur};
