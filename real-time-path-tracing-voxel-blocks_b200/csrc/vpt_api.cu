@@ -61,6 +61,8 @@ struct vpt_ctx
     float4 *sky = nullptr, *sun = nullptr;      // four views into skyArena
     VptAliasBin *skyAlias = nullptr, *sunAlias = nullptr;
     void *skyArena = nullptr;
+    size_t skyArenaBytes = 0;
+    const void *l2Base = nullptr; size_t l2Bytes = 0; // what the stream's L2 access-policy window covers now
     int skyW = 0, skyH = 0, sunW = 0, sunH = 0;
     float sunDir[3] = {0, 1, 0};
     // trace params
@@ -201,7 +203,7 @@ void vpt_destroy(vpt_ctx *c)
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     for (int i = 0; i < 2; ++i) if (c->traceStreams.part[i]) cudaStreamSynchronize(c->traceStreams.part[i]);
     destroyComm(c);
-    if (c->skyArena) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); } // hand the lines pinned for the sky tables back to the normal L2
+    if (c->l2Base) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); } // hand the lines pinned by the L2 window back to the normal L2
     void *ptrs[] = {c->sobol, c->scrambling, c->ranking, c->idsChunk, c->idsLinear, c->occ, c->materials, c->blockToMaterial, c->skyArena,
                     c->illumination, c->illumOutput, c->ping, c->pong, c->prevIllum, c->prevFastIllum,
                     c->historyLength, c->prevHistoryLength, c->reservoirs, c->primaryHits, c->counters, c->patches, c->patchCount, c->wave.arena, c->upHDev, c->occPrev, c->pickDev, c->texels, c->texDescs, c->matTexSlots, c->matTexMip0Size, c->dnG, c->dnMQ, c->dnCounters, c->fireflyList, c->fixList, c->rgb8, c->dLights, c->dLightAlias, c->dFaceKeys, c->dPrevToCur};
@@ -360,6 +362,33 @@ int vpt_set_materials(vpt_ctx *c, const VptMaterial *m, int count, const uint16_
     return VPT_OK;
 }
 
+// One L2 access-policy window per context, on its stream (hits persisting, misses streaming). A hint: failures are ignored.
+static void setL2Window(vpt_ctx *c, const void *base, size_t bytes)
+{
+#ifndef VPT_NO_L2_WINDOW
+    if (!base || bytes == 0 || (c->l2Base == base && c->l2Bytes == bytes)) return;
+    int maxPersist = 0, maxWindow = 0;
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    if (maxPersist > 0 && maxWindow > 0)
+    {
+        const size_t win = bytes < (size_t)maxWindow ? bytes : (size_t)maxWindow;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, win < (size_t)maxPersist ? win : (size_t)maxPersist);
+        cudaStreamAttrValue v = {};
+        v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+        v.accessPolicyWindow.num_bytes = win;
+        v.accessPolicyWindow.hitRatio = win <= (size_t)maxPersist ? 1.0f : (float)maxPersist / (float)win;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+        cudaGetLastError();
+    }
+    c->l2Base = base; c->l2Bytes = bytes;
+#else
+    (void)c; (void)base; (void)bytes;
+#endif
+}
+
 // Sky / sun maps and their alias tables in ONE allocation, pinned in L2 as far as the device allows: the stages sample them at random
 // (alias bin -> texel, twice per path) while 6 GB of wavefront state stream through the same 126 MB L2 every frame; an access-policy
 // window keeps the 12 MB of tables resident (hit = persisting) instead of letting the stream evict them. A hint: failures are ignored.
@@ -374,24 +403,8 @@ static int allocSkyArena(vpt_ctx *c, size_t ns, size_t nu)
     char *b = static_cast<char *>(c->skyArena);
     c->sky = reinterpret_cast<float4 *>(b + oSky); c->skyAlias = reinterpret_cast<VptAliasBin *>(b + oSkyAlias);
     c->sun = reinterpret_cast<float4 *>(b + oSun); c->sunAlias = reinterpret_cast<VptAliasBin *>(b + oSunAlias);
-#ifndef VPT_NO_L2_WINDOW
-    int maxPersist = 0, maxWindow = 0;
-    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
-    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-    if (maxPersist > 0 && maxWindow > 0)
-    {
-        const size_t bytes = total < (size_t)maxWindow ? total : (size_t)maxWindow;
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes < (size_t)maxPersist ? bytes : (size_t)maxPersist);
-        cudaStreamAttrValue v = {};
-        v.accessPolicyWindow.base_ptr = c->skyArena;
-        v.accessPolicyWindow.num_bytes = bytes;
-        v.accessPolicyWindow.hitRatio = bytes <= (size_t)maxPersist ? 1.0f : (float)maxPersist / (float)bytes;
-        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
-        cudaGetLastError(); // a hint only
-    }
-#endif
+    c->skyArenaBytes = total;
+    c->l2Base = nullptr; // the old window (if any) pointed into the freed arena: the next render sets it again
     return VPT_OK;
 }
 
@@ -657,6 +670,10 @@ static int renderImpl(vpt_ctx *c, const VptCamera *cam, const VptCamera *prevCam
     // more ranks than samples: this shard renders nothing, so its term of the cross-rank sum must be zero (no wave runs, so no
     // accumulate pass would otherwise overwrite the previous frame's image)
     if (shardSamples == 0) CU(cudaMemsetAsync(c->illumination, 0, c->npix() * sizeof(float4), c->stream));
+    // The L2 window goes to the sky tables: the stages read them at random and the streaming wavefront state would evict them
+    // (stages 1.311 -> 1.292 ms on cfg2). Not for worlds whose traversal masks are walked through L1/L2: those want the whole L2 —
+    // pinning the masks themselves (2 x 33 MiB) measured 51.5 vs 48.3 ms per frame on the cfg5-shaped trace (tools/cfg5_quick.py).
+    if ((size_t)a.grid.occWords * 4 + 1024 <= c->smemOptIn) setL2Window(c, c->skyArena, c->skyArenaBytes);
     int launches = 0;
     c->traceProf.enabled = c->profiling;
     CU(launchTrace(a, c->wave.maxSamplesInWave, c->stream, c->overlapParts ? &c->traceStreams : nullptr, c->smCount, c->smemOptIn, &launches, &c->traceProf));
